@@ -1,0 +1,155 @@
+/*
+ * mumpy_b200.h -- C ABI of libmumpy_b200.so: the sm_100a kernels behind the Mumpy inference forward.
+ *
+ * The reference (yuxiaoxiangyong/Multilateral-Temporal-view-Pyramid-Transformer-for-Video-Inpainting-
+ * Detection) has no native layer: every function below replaces a group of ATen calls made by one
+ * Python method of the reference, cited as <file>:<lines> relative to the reference root.  The Python
+ * mirror classes in the package (same names / ctor / forward / state_dict keys as the reference) are
+ * the only intended callers; INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is DEVICE memory owned by the caller (incl. workspaces);
+ *     the library never allocates, frees, synchronises or keeps references (CUDA-graph capturable);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, a negative MUMPY_ERR_* otherwise; mumpy_last_error() gives the text;
+ *   - token tensors are "canvases": row-major (B, T*H, W, C), frame t in rows [t*H,(t+1)*H)
+ *     (multiTemporalViewEncoder.py:614,707; swinTransformer.py:267); decoder maps are NHWC;
+ *   - dtype codes: MUMPY_F32 / MUMPY_BF16.  MUMPY_F32 GEMMs run exact fp32 FMA kernels (the <=1e-4
+ *     parity mode); MUMPY_BF16 GEMMs run the TMA + tcgen05 + TMEM kernel with fp32 accumulation.
+ *   - no CPU fallback exists anywhere in this library.
+ */
+#ifndef MUMPY_B200_H
+#define MUMPY_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUMPY_F32 0
+#define MUMPY_BF16 1
+
+#define MUMPY_ACT_NONE 0
+#define MUMPY_ACT_GELU 1      /* exact erf GELU (nn.GELU default) */
+#define MUMPY_ACT_RELU 2
+#define MUMPY_ACT_SIGMOID 3
+
+#define MUMPY_OK 0
+#define MUMPY_ERR_ARG (-1)
+#define MUMPY_ERR_CUDA (-2)
+#define MUMPY_ERR_UNSUPPORTED (-3)
+
+/* resample modes of mumpy_resample_nhwc */
+#define MUMPY_RS_IDENTITY 0
+#define MUMPY_RS_UP_ALIGNED 1     /* nn.Upsample(bilinear, align_corners=True)  decoder.py:72,79,86,93 */
+#define MUMPY_RS_UP_HALFPIX 2     /* nn.Upsample(bilinear) default align_corners=False decoder.py:10,136-137 */
+#define MUMPY_RS_AVGPOOL2 3       /* nn.AvgPool2d(2) decoder.py:149..176 */
+#define MUMPY_RS_PIXEL_SHUFFLE2 4 /* nn.PixelShuffle(2) decoder.py:128 */
+
+int mumpy_abi_version(void);
+/* Binds the calling thread to `device` and resolves the driver entry point used to encode TMA maps. */
+int mumpy_init(int device);
+const char *mumpy_last_error(void);
+
+/* nn.Linear / 1x1 conv:  out = act(A . W^T + bias) (+ residual).   swinTransformer.py:45-51,142,164,365;
+ * blocks.py:28-34,56,71; deformableAttention.py:333,361-362,402; multiTemporalViewEncoder.py:283,740;
+ * decoder.py:98-120 (Conv3d k=(3,1,1) as a per-pixel GEMM).
+ * A (M,K) row-major with row stride lda, W (N,K) row-major, both of `ab_dtype`; bias (N) fp32 or NULL;
+ * residual (M,N) fp32 with row stride ldo or NULL (may alias out); out (M,N) of `out_dtype`, row stride ldo. */
+int mumpy_linear(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out,
+                 long ldo, long M, int N, int K, int ab_dtype, int out_dtype, int act, void *stream);
+
+/* nn.LayerNorm over the last dim (eps inside the sqrt).  swinTransformer.py:266,305; blocks.py:88,92. */
+int mumpy_layernorm(const float *x, const float *gamma, const float *beta, void *out, int out_dtype, long rows,
+                    int C, float eps, void *stream);
+
+/* PatchMerging gather + LayerNorm(4C): out row (b, r', c') = LN(cat[x(2r',2c'), x(2r'+1,2c'), x(2r',2c'+1),
+ * x(2r'+1,2c'+1)]).  swinTransformer.py:355-364.  x canvas (B,TH,W,C) fp32 -> out (B*TH/2*W/2, 4C). */
+int mumpy_patch_merge_norm(const float *x, const float *gamma, const float *beta, void *out, int out_dtype, int B,
+                           int TH, int W, int C, float eps, void *stream);
+
+/* Window attention core of WindowAttention.forward (swinTransformer.py:142-163) with the cyclic shift and
+ * window partition/reverse of SwinTransformerBlock.forward (:270-301) folded into the addressing.
+ * qkv (B*TH*W, 3C) canvas order, channel o -> (which=o/C, head=(o%C)/d, o%d); bias (heads,N,N) fp32 =
+ * relative_position_bias_table gathered by relative_position_index; mask (nW,N,N) fp32 or NULL;
+ * out (B*TH*W, C) canvas order; N = ws*ws (<=64), d = C/heads in {32,64}. */
+int mumpy_window_attention(const void *qkv, const float *bias, const float *mask, void *out, int dtype, int B, int TH,
+                           int W, int C, int heads, int ws, int shift, void *stream);
+
+/* Attention.forward core for short sequences (blocks.py:64-70): qkv (Bn*N, 3C) -> out (Bn*N, C), N <= 8. */
+int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, int N, int C, int heads, void *stream);
+
+/* CrossThreeViewTokenize, one view (multiTemporalViewEncoder.py:605-618): Conv3d(3->C, k=s=(kt,4,4)) + LayerNorm.
+ * x (B,T,3,S,S) fp32; w_kc (3*kt*16, C) fp32 = weight.reshape(C,-1).T; out (B, To*(S/4)^2, C) fp32, To = T/kt. */
+int mumpy_tokenize(const float *x, const float *w_kc, const float *bias, const float *gamma, const float *beta,
+                   float *out, int B, int T, int S, int kt, int C, float eps, void *stream);
+
+/* FAF on the middle frame (dct.py:71-79; multiTemporalViewEncoder.py:734).  x (B,T,3,S,S) fp32, frame index
+ * `frame`; dct (S,S) fp32 DCT-II matrix; ws fp32 workspace of 5*B*3*S*S floats; out (B,9,S,S) fp32,
+ * channel = band*3 + rgb; band k keeps lo_k <= i+j <= hi_k, band_lo_hi6 = HOST array {lo0,hi0,lo1,hi1,lo2,hi2}
+ * (read during the call; the only non-device pointer in this ABI). */
+int mumpy_faf(const float *x, const float *dct, float *ws, float *out, int B, int T, int frame, int S,
+              const int *band_lo_hi6, void *stream);
+
+/* SwinDAttention pieces (deformableAttention.py:324-405); windows are addressed on canvases.
+ * offsets: q (B*L1, C) fp32 canvas of the query view -> pix (N1, groups, P, 2) fp32 sampling positions in pixel
+ *          units (y,x) of an aligned-corners ws x ws grid (:334-356).  dw_w (Cg,25), dw_b, ln_g, ln_b (Cg), pw (2,Cg). */
+int mumpy_cva_offsets(const float *q, const float *dw_w, const float *dw_b, const float *ln_g, const float *ln_b,
+                      const float *pw, float *pix, int B, int TH1, int W, int C, int groups, int ws, void *stream);
+/* sample: x2 (B*L2, C) fp32 canvas (after `pre`) -> sampled (N2*P, C) window-major rows of `out_dtype`;
+ *         kv window j uses the offsets of query window qidx(j) (see mumpy_cva_attention). */
+int mumpy_cva_sample(const float *x2, const float *pix, void *sampled, int out_dtype, int B, int TH1, int TH2, int W,
+                     int C, int groups, int ws, int per_clip_pairing, void *stream);
+/* attention: q (B*L1,C) fp32 canvas, kv (N2*P, 2C) window-major of `kv_dtype` -> o (N1*P, C) of `out_dtype`
+ *         o[i] = sum_t softmax(q[qidx(r*i+t)] k[r*i+t]^T * d^-1/2) v[r*i+t], r = N2/N1 (:329-330,364,390-395);
+ *         qidx(j) = j mod N1 (reference, batch-global) or the same map applied inside each clip. */
+int mumpy_cva_attention(const float *q, const void *kv, int kv_dtype, void *o, int out_dtype, int B, int TH1,
+                        int TH2, int W, int C, int heads, int ws, int per_clip_pairing, void *stream);
+/* residual: x_new[b,l,:] = h[b,l,:] + h[b, canvas(l/P, l%P), :] + reinterpret(y)[b,l,:]
+ *         (deformableAttention.py:403 raw reshape; multiTemporalViewEncoder.py:138,284-286). y (N1*P, C) fp32. */
+int mumpy_cva_residual(const float *h, const float *y, float *x_new, int B, int TH1, int W, int C, int ws,
+                       void *stream);
+
+/* Row gather into a column slice of a wider matrix (merge_views_along_channel_axis,
+ * multiTemporalViewEncoder.py:710-718; decoder.py:43-53): for out row r = b*rows_out + q,
+ *   src row = b*rows_src + (q / div) * mul_hi + (q % div) * mul_lo + add. */
+int mumpy_gather_rows(const float *src, int C, void *dst, int dst_dtype, long dst_ld, int dst_col, int B,
+                      int rows_out, int rows_src, int div, int mul_hi, int mul_lo, int add, void *stream);
+
+/* Decoder primitives on NHWC maps (decoder.py:183-225). */
+/* conv (stride 1): in (B,H,W,Cin) row stride ld_in, w (Cout, kh, kw, Cin) fp32, out (B,H,W,Cout) fp32. */
+int mumpy_conv2d_nhwc(const float *in, long ld_in, const float *w, const float *bias, float *out, long ld_out, int B,
+                      int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, void *stream);
+/* im2col for the tensor-core path: out (B*H*W, Kpad) bf16, K order (ky,kx,c), zero padded to Kpad. */
+int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int B, int H, int W, int Cin, int kh, int kw, int ph,
+                      int pw, int Kpad, void *stream);
+/* GroupNorm + activation; stats over (H*W, C/groups) per (b, group); stats_ws: 2*B*groups floats. */
+int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *stats_ws, float *out,
+                         long ld_out, int out_col, int B, int HW, int C, int groups, float eps, int act, void *stream);
+/* out[..., col:col+Cout] = resample(in) (* mul) (+ add); mul/add are (B,Ho,Wo,Cout) contiguous or NULL. */
+int mumpy_resample_nhwc(const float *in, const float *mul, const float *add, float *out, long ld_out, int out_col,
+                        int B, int H, int W, int C, int mode, int scale, void *stream);
+/* out = a * b (+ c) elementwise over n floats (c may be NULL). */
+int mumpy_mul_add(const float *a, const float *b, const float *c, float *out, long n, void *stream);
+/* out = a + b elementwise over n floats (the `shortcut + attn` of CrossSwinBlock, whose un-summed attention
+ * branch is also an output: multiTemporalViewEncoder.py:275-276). */
+int mumpy_add(const float *a, const float *b, float *out, long n, void *stream);
+/* layout changes: NCHW (B,C,H,W) <-> NHWC; `pool2` averages 2x2 blocks first (AvgPool2d on ffinfo). */
+int mumpy_nchw_to_nhwc(const float *in, float *out, long ld_out, int out_col, int B, int C, int H, int W, int pool2,
+                       void *stream);
+int mumpy_nhwc_to_nchw(const float *in, long ld_in, float *out, int B, int C, int H, int W, void *stream);
+/* DAP == mean over groups of `k` consecutive channels (decoder.py:140-143). */
+int mumpy_channel_group_mean(const float *in, float *out, long pixels, int C, int k, void *stream);
+
+/* a20 + measure.py:77-91: thresholded mask (logit > 0 -> 255) and per-clip integer counts
+ * [TP, n_pred, n_gt, n_union] (int64, accumulated with atomics; counts must be zeroed by the caller).
+ * logits (B, HW) fp32; gt (B, HW) uint8 (non-zero = positive) or NULL; mask (B, HW) uint8 or NULL. */
+int mumpy_mask_counts(const float *logits, const unsigned char *gt, unsigned char *mask, long long *counts, int B,
+                      int HW, void *stream);
+
+/* fp32 -> bf16 cast (weight packing). */
+int mumpy_cast_bf16(const float *in, void *out, long n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUMPY_B200_H */

@@ -1,0 +1,72 @@
+"""ctypes binding of libmumpy_b200.so (the C ABI declared in include/mumpy_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a tensor is not on a CUDA device the
+call fails loudly.  Build the library with `python __graft_entry__.py` (or `python -m mumpy_b200.build`).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmumpy_b200.so")
+
+_lib = None
+
+vp, ci, cl, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
+
+# name -> argtypes, exactly the prototypes of include/mumpy_b200.h
+SIGNATURES = {
+    "mumpy_abi_version": [],
+    "mumpy_init": [ci],
+    "mumpy_linear": [vp, cl, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, ci, vp],
+    "mumpy_layernorm": [vp, vp, vp, vp, ci, cl, ci, cf, vp],
+    "mumpy_patch_merge_norm": [vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
+    "mumpy_window_attention": [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_mha_short": [vp, vp, ci, cl, ci, ci, ci, vp],
+    "mumpy_tokenize": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
+    "mumpy_faf": [vp, vp, vp, vp, ci, ci, ci, ci, ctypes.POINTER(ci), vp],
+    "mumpy_cva_offsets": [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_cva_sample": [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_cva_attention": [vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_cva_residual": [vp, vp, vp, ci, ci, ci, ci, ci, vp],
+    "mumpy_gather_rows": [vp, ci, vp, ci, cl, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_conv2d_nhwc": [vp, cl, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_im2col_nhwc": [vp, cl, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_groupnorm_nhwc": [vp, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, cf, ci, vp],
+    "mumpy_resample_nhwc": [vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_mul_add": [vp, vp, vp, vp, cl, vp],
+    "mumpy_add": [vp, vp, vp, cl, vp],
+    "mumpy_nchw_to_nhwc": [vp, vp, cl, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_nhwc_to_nchw": [vp, cl, vp, ci, ci, ci, ci, vp],
+    "mumpy_channel_group_mean": [vp, vp, cl, ci, ci, vp],
+    "mumpy_mask_counts": [vp, vp, vp, vp, ci, ci, vp],
+    "mumpy_cast_bf16": [vp, vp, cl, vp],
+}
+
+
+class MumpyError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MumpyError(
+            "libmumpy_b200.so not found at %s -- build it first (python __graft_entry__.py); "
+            "this package has no CPU/PyTorch fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.argtypes = argtypes
+        fn.restype = ci
+    lib.mumpy_last_error.argtypes = []
+    lib.mumpy_last_error.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mumpy_last_error().decode("utf-8", "replace")
+        raise MumpyError("%s failed (%d): %s" % (what or "libmumpy_b200 call", rc, msg))

@@ -1,0 +1,84 @@
+// Error plumbing, init and the dtype dispatch of mumpy_linear.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace mumpy {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_status(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MUMPY_ERR_CUDA;
+  }
+  return MUMPY_OK;
+}
+
+int resolve_driver_entry_points();
+int linear_f32(const float *A, long lda, const float *W, const float *bias, const float *residual, float *out, long ldo,
+               long M, int N, int K, int act, cudaStream_t st);
+int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, long ldo,
+                long M, int N, int K, int out_dtype, int act, cudaStream_t st);
+
+__global__ void cast_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+}  // namespace mumpy
+
+using namespace mumpy;
+
+extern "C" int mumpy_abi_version(void) { return 1; }
+
+extern "C" const char *mumpy_last_error(void) { return g_err; }
+
+extern "C" int mumpy_init(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    return MUMPY_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return MUMPY_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    set_error("libmumpy_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    return MUMPY_ERR_UNSUPPORTED;
+  }
+  return resolve_driver_entry_points();
+}
+
+extern "C" int mumpy_linear(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out,
+                            long ldo, long M, int N, int K, int ab_dtype, int out_dtype, int act, void *stream) {
+  MUMPY_REQUIRE(A && W && out && M > 0 && N > 0 && K > 0, "linear: bad arguments (M=%ld N=%d K=%d)", M, N, K);
+  if (ab_dtype == MUMPY_F32) {
+    MUMPY_REQUIRE(out_dtype == MUMPY_F32, "linear(fp32): output must be fp32");
+    return linear_f32(static_cast<const float *>(A), lda, static_cast<const float *>(W), bias, residual,
+                      static_cast<float *>(out), ldo, M, N, K, act, as_stream(stream));
+  }
+  if (ab_dtype == MUMPY_BF16) return linear_bf16(A, lda, W, bias, residual, out, ldo, M, N, K, out_dtype, act, as_stream(stream));
+  set_error("linear: unknown dtype %d", ab_dtype);
+  return MUMPY_ERR_ARG;
+}
+
+extern "C" int mumpy_cast_bf16(const float *in, void *out, long n, void *stream) {
+  MUMPY_REQUIRE(in && out && n > 0, "cast_bf16: bad arguments");
+  int blocks = (int)(cdiv(n, 256) < 148 * 8 ? cdiv(n, 256) : 148 * 8);
+  cast_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(in, static_cast<__nv_bfloat16 *>(out), n);
+  return launch_status("cast_bf16");
+}

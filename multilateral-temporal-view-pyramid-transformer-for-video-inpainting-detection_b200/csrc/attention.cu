@@ -1,0 +1,255 @@
+// Attention cores: Swin (shifted-)window attention with relative-position bias and mask, the short-sequence
+// ViT attention of the temporal "global" encoder, and the deformable cross-view attention core.
+// Window partition / reverse / cyclic shift are index maps on the token canvas (window_token_row), never copies.
+// Scores, softmax and P.V are fp32; q/k/v are read as stored (fp32 or bf16).
+#include "common.cuh"
+
+namespace mumpy {
+
+// smem layout for one (window, head): q,k,v [N][D+1] and scores [N][N+1]
+template <int D>
+__host__ __device__ constexpr int attn_smem_floats(int N) { return 3 * N * (D + 1) + N * (N + 1); }
+
+// softmax over rows of S (N x N, row stride N+1); one warp per row
+__device__ __forceinline__ void softmax_rows(float *S, int N, int warp, int nwarps, int lane) {
+  for (int i = warp; i < N; i += nwarps) {
+    float *row = S + i * (N + 1);
+    float m = -INFINITY;
+    for (int j = lane; j < N; j += 32) m = fmaxf(m, row[j]);
+    m = warp_max(m);
+    float s = 0.0f;
+    for (int j = lane; j < N; j += 32) {
+      const float e = expf(row[j] - m);
+      row[j] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    for (int j = lane; j < N; j += 32) row[j] *= inv;
+  }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(128) window_attention_kernel(const T *__restrict__ qkv, const float *__restrict__ bias,
+                                                               const float *__restrict__ mask, T *__restrict__ out, int TH, int W,
+                                                               int C, int ws, int shift) {
+  extern __shared__ float sm[];
+  const int N = ws * ws;
+  float *q = sm, *k = q + N * (D + 1), *v = k + N * (D + 1), *S = v + N * (D + 1);
+  const int nW = (TH / ws) * (W / ws);
+  const int win = blockIdx.x;
+  const int b = win / nW, n = win % nW;
+  const int h = blockIdx.y;
+  const long L = (long)TH * W;
+  const float qscale = (D == 64) ? 0.125f : 0.17677669529663687f;   // head_dim ** -0.5 rounded to fp32
+  for (int e = threadIdx.x; e < N * D; e += blockDim.x) {
+    const int p = e / D, d = e % D;
+    const long row = b * L + window_token_row(n, p, TH, W, ws, shift);
+    const T *src = qkv + row * 3 * C + h * D + d;
+    q[p * (D + 1) + d] = to_f32(src[0]) * qscale;
+    k[p * (D + 1) + d] = to_f32(src[C]);
+    v[p * (D + 1) + d] = to_f32(src[2 * C]);
+  }
+  __syncthreads();
+  const float *bh = bias + (long)h * N * N;
+  const float *mw = mask ? mask + (long)n * N * N : nullptr;
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    const int i = e / N, j = e % N;
+    float acc = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc = fmaf(q[i * (D + 1) + d], k[j * (D + 1) + d], acc);
+    acc += bh[e];
+    if (mw) acc += mw[e];
+    S[i * (N + 1) + j] = acc;
+  }
+  __syncthreads();
+  softmax_rows(S, N, threadIdx.x >> 5, blockDim.x >> 5, threadIdx.x & 31);
+  __syncthreads();
+  for (int e = threadIdx.x; e < N * D; e += blockDim.x) {
+    const int i = e / D, d = e % D;
+    float acc = 0.0f;
+    for (int j = 0; j < N; ++j) acc = fmaf(S[i * (N + 1) + j], v[j * (D + 1) + d], acc);
+    const long row = b * L + window_token_row(n, i, TH, W, ws, shift);
+    out[row * C + h * D + d] = from_f32<T>(acc);
+  }
+}
+
+// blocks.py:55-70 for N <= 8 tokens: one warp per (head, query); lanes span the head dim.
+template <typename T>
+__global__ void __launch_bounds__(128) mha_short_kernel(const T *__restrict__ qkv, T *__restrict__ out, int N, int C, int heads) {
+  const long bn = blockIdx.x;
+  const int d = C / heads;
+  const float scale = 1.0f / sqrtf((float)d);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const T *base = qkv + bn * N * 3 * C;
+  for (int pair = warp; pair < heads * N; pair += nwarps) {
+    const int h = pair / N, i = pair % N;
+    float s[8];
+    const T *qi = base + (long)i * 3 * C + h * d;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] = -INFINITY;
+      if (j < N) {
+        const T *kj = base + (long)j * 3 * C + C + h * d;
+        float a = 0.0f;
+        for (int dd = lane; dd < d; dd += 32) a = fmaf(to_f32(qi[dd]), to_f32(kj[dd]), a);
+        s[j] = warp_sum(a) * scale;
+      }
+    }
+    float m = s[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) m = fmaxf(m, s[j]);
+    float den = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] = (j < N) ? expf(s[j] - m) : 0.0f;
+      den += s[j];
+    }
+    const float inv = 1.0f / den;
+    for (int dd = lane; dd < d; dd += 32) {
+      float a = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < N) a = fmaf(s[j] * inv, to_f32(base[(long)j * 3 * C + 2 * C + h * d + dd]), a);
+      out[(bn * N + i) * C + h * d + dd] = from_f32<T>(a);
+    }
+  }
+}
+
+// query window paired with kv window j (deformableAttention.py:329-330 + :394)
+__device__ __forceinline__ int cva_query_window(int j, int r, int N1, int nW1, int per_clip) {
+  if (!per_clip) return j % N1;
+  const int i = j / r;
+  const int clip = i / nW1;
+  return clip * nW1 + ((i % nW1) * r + j % r) % nW1;
+}
+
+template <typename TKV, typename TO, int D>
+__global__ void __launch_bounds__(128) cva_attention_kernel(const float *__restrict__ q, const TKV *__restrict__ kv, TO *__restrict__ o,
+                                                            int N1, int TH1, int W, int C, int ws, int r, int per_clip) {
+  extern __shared__ float sm[];
+  const int N = ws * ws;
+  float *qs = sm, *ks = qs + N * (D + 1), *vs = ks + N * (D + 1), *S = vs + N * (D + 1);
+  const int i = blockIdx.x;      // output window
+  const int h = blockIdx.y;
+  const int nW1 = (TH1 / ws) * (W / ws);
+  const long L1 = (long)TH1 * W;
+  const float scale = (D == 64) ? 0.125f : 0.17677669529663687f;
+  // each thread owns the same (p,d) outputs across t: accumulate in registers
+  constexpr int kPerThread = (64 * D + 127) / 128;
+  float acc[kPerThread];
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u) acc[u] = 0.0f;
+  for (int t = 0; t < r; ++t) {
+    const int j = r * i + t;
+    const int qw = cva_query_window(j, r, N1, nW1, per_clip);
+    const int qb = qw / nW1, qn = qw % nW1;
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * D; e += blockDim.x) {
+      const int p = e / D, d = e % D;
+      const long qrow = qb * L1 + window_token_row(qn, p, TH1, W, ws, 0);
+      qs[p * (D + 1) + d] = q[qrow * C + h * D + d];
+      const TKV *src = kv + ((long)j * N + p) * 2 * C + h * D + d;
+      ks[p * (D + 1) + d] = to_f32(src[0]);
+      vs[p * (D + 1) + d] = to_f32(src[C]);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+      const int a = e / N, b = e % N;
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(qs[a * (D + 1) + d], ks[b * (D + 1) + d], s);
+      S[a * (N + 1) + b] = s * scale;
+    }
+    __syncthreads();
+    softmax_rows(S, N, threadIdx.x >> 5, blockDim.x >> 5, threadIdx.x & 31);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPerThread; ++u) {
+      const int e = threadIdx.x + u * 128;
+      if (e < N * D) {
+        const int a = e / D, d = e % D;
+        float s = 0.0f;
+        for (int b = 0; b < N; ++b) s = fmaf(S[a * (N + 1) + b], vs[b * (D + 1) + d], s);
+        acc[u] += s;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u) {
+    const int e = threadIdx.x + u * 128;
+    if (e < N * D) {
+      const int p = e / D, d = e % D;
+      o[((long)i * N + p) * C + h * D + d] = from_f32<TO>(acc[u]);
+    }
+  }
+}
+
+template <typename K>
+static int ensure_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return MUMPY_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
+    return MUMPY_ERR_CUDA;
+  }
+  return MUMPY_OK;
+}
+
+}  // namespace mumpy
+
+using namespace mumpy;
+
+extern "C" int mumpy_window_attention(const void *qkv, const float *bias, const float *mask, void *out, int dtype, int B, int TH,
+                                      int W, int C, int heads, int ws, int shift, void *stream) {
+  MUMPY_REQUIRE(qkv && bias && out && B > 0 && heads > 0 && C % heads == 0, "window_attention: bad arguments");
+  MUMPY_REQUIRE(TH % ws == 0 && W % ws == 0 && ws * ws <= 64 && shift >= 0 && shift < ws, "window_attention: bad window geometry");
+  const int D = C / heads;
+  MUMPY_REQUIRE(D == 32 || D == 64, "window_attention: head dim %d unsupported (32 or 64)", D);
+  const int N = ws * ws;
+  dim3 grid((unsigned)(B * (TH / ws) * (W / ws)), (unsigned)heads);
+  cudaStream_t st = as_stream(stream);
+  int rc = MUMPY_OK;
+#define LAUNCH(T, DD)                                                                                                     \
+  {                                                                                                                       \
+    const size_t smem = attn_smem_floats<DD>(N) * sizeof(float);                                                          \
+    rc = ensure_smem(window_attention_kernel<T, DD>, smem);                                                               \
+    if (rc) return rc;                                                                                                    \
+    window_attention_kernel<T, DD><<<grid, 128, smem, st>>>(static_cast<const T *>(qkv), bias, mask, static_cast<T *>(out), TH, W, C, ws, shift); \
+  }
+  if (dtype == MUMPY_BF16) {
+    if (D == 32) LAUNCH(__nv_bfloat16, 32) else LAUNCH(__nv_bfloat16, 64)
+  } else {
+    if (D == 32) LAUNCH(float, 32) else LAUNCH(float, 64)
+  }
+#undef LAUNCH
+  return launch_status("window_attention");
+}
+
+extern "C" int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, int N, int C, int heads, void *stream) {
+  MUMPY_REQUIRE(qkv && out && Bn > 0 && N > 0 && N <= 8 && C % heads == 0, "mha_short: bad arguments (N=%d)", N);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == MUMPY_BF16)
+    mha_short_kernel<__nv_bfloat16><<<(unsigned)Bn, 128, 0, st>>>(static_cast<const __nv_bfloat16 *>(qkv), static_cast<__nv_bfloat16 *>(out), N, C, heads);
+  else
+    mha_short_kernel<float><<<(unsigned)Bn, 128, 0, st>>>(static_cast<const float *>(qkv), static_cast<float *>(out), N, C, heads);
+  return launch_status("mha_short");
+}
+
+extern "C" int mumpy_cva_attention(const float *q, const void *kv, int kv_dtype, void *o, int out_dtype, int B, int TH1, int TH2,
+                                   int W, int C, int heads, int ws, int per_clip_pairing, void *stream) {
+  MUMPY_REQUIRE(q && kv && o && B > 0 && C % heads == 0 && C / heads == 32, "cva_attention: bad arguments (head dim must be 32)");
+  MUMPY_REQUIRE(TH1 % ws == 0 && TH2 % TH1 == 0 && W % ws == 0 && ws * ws <= 64, "cva_attention: bad window geometry");
+  MUMPY_REQUIRE(kv_dtype == out_dtype, "cva_attention: kv and output dtypes must match");
+  const int N = ws * ws;
+  const int N1 = B * (TH1 / ws) * (W / ws);
+  const int r = TH2 / TH1;
+  dim3 grid((unsigned)N1, (unsigned)heads);
+  const size_t smem = attn_smem_floats<32>(N) * sizeof(float);
+  cudaStream_t st = as_stream(stream);
+  if (kv_dtype == MUMPY_BF16)
+    cva_attention_kernel<__nv_bfloat16, __nv_bfloat16, 32><<<grid, 128, smem, st>>>(q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1, TH1, W, C, ws, r, per_clip_pairing);
+  else
+    cva_attention_kernel<float, float, 32><<<grid, 128, smem, st>>>(q, static_cast<const float *>(kv), static_cast<float *>(o), N1, TH1, W, C, ws, r, per_clip_pairing);
+  return launch_status("cva_attention");
+}

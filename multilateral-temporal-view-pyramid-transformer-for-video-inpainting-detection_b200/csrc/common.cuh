@@ -1,0 +1,65 @@
+// Shared helpers for libmumpy_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mumpy_b200.h"
+
+namespace mumpy {
+
+void set_error(const char *fmt, ...);
+int launch_status(const char *what);   // cudaGetLastError -> MUMPY_OK / MUMPY_ERR_CUDA (+ message)
+
+#define MUMPY_REQUIRE(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::mumpy::set_error(__VA_ARGS__);      \
+      return MUMPY_ERR_ARG;                 \
+    }                                       \
+  } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case MUMPY_ACT_GELU: return gelu_erf(v);
+    case MUMPY_ACT_RELU: return fmaxf(v, 0.0f);
+    case MUMPY_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    default: return v;
+  }
+}
+
+// canvas row of token p (0..ws*ws) of window n (0..nW) on a (TH x W) canvas, optionally cyclically
+// shifted: window (wr,wc) position (pr,pc) reads canvas ((7wr+pr+shift) mod TH, (7wc+pc+shift) mod W)
+// (swinTransformer.py:63-66,273,295).
+__device__ __forceinline__ int window_token_row(int n, int p, int TH, int W, int ws, int shift) {
+  const int wpr = W / ws;
+  int r = (n / wpr) * ws + p / ws + shift;
+  int c = (n % wpr) * ws + p % ws + shift;
+  if (r >= TH) r -= TH;
+  if (c >= W) c -= W;
+  return r * W + c;
+}
+
+}  // namespace mumpy

@@ -1,0 +1,199 @@
+// Deformable cross-view attention (SwinDAttention, deformableAttention.py:324-405): offset network, bilinear
+// sampling of the key/value windows and the raw-reshape residual.  All three are HBM/L2-bound gathers on the
+// token canvases; the k/v/out projections run through mumpy_linear and the softmax core is in attention.cu.
+#include "common.cuh"
+
+namespace mumpy {
+
+__device__ __forceinline__ int cva_query_window_s(int j, int r, int N1, int nW1, int per_clip) {
+  if (!per_clip) return j % N1;
+  const int i = j / r;
+  const int clip = i / nW1;
+  return clip * nW1 + ((i % nW1) * r + j % r) % nW1;
+}
+
+// One CTA per (query window, group); one warp per pixel; lanes span the group's channels.
+// conv_offset = dw5x5(pad 2, within the window) -> LayerNorm(Cg) -> GELU -> 1x1 (Cg->2)   (:253-258)
+// pix = ((tanh(o) * (1/ws) * 2 + ref) + 1) / 2 * (ws-1)                                    (:338-356)
+template <int MAXC>   // channels per lane = Cg/32 <= MAXC
+__global__ void __launch_bounds__(128) cva_offsets_kernel(const float *__restrict__ q, const float *__restrict__ dw_w,
+                                                          const float *__restrict__ dw_b, const float *__restrict__ ln_g,
+                                                          const float *__restrict__ ln_b, const float *__restrict__ pw,
+                                                          float *__restrict__ pix, int TH1, int W, int C, int groups, int ws) {
+  extern __shared__ float tile[];   // [P][Cg]
+  const int P = ws * ws;
+  const int Cg = C / groups;
+  const int win = blockIdx.x, g = blockIdx.y;
+  const int nW1 = (TH1 / ws) * (W / ws);
+  const int b = win / nW1, n = win % nW1;
+  const long L1 = (long)TH1 * W;
+  for (int e = threadIdx.x; e < P * Cg; e += blockDim.x) {
+    const int p = e / Cg, c = e % Cg;
+    const long row = b * L1 + window_token_row(n, p, TH1, W, ws, 0);
+    tile[e] = q[row * C + g * Cg + c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int p = warp; p < P; p += nwarps) {
+    const int pi = p / ws, pj = p % ws;
+    float val[MAXC];
+    float s = 0.0f;
+#pragma unroll
+    for (int u = 0; u < MAXC; ++u) {
+      const int c = lane + 32 * u;
+      float acc = 0.0f;
+      if (c < Cg) {
+        for (int a = 0; a < 5; ++a) {
+          const int yy = pi + a - 2;
+          if (yy < 0 || yy >= ws) continue;
+          for (int bb = 0; bb < 5; ++bb) {
+            const int xx = pj + bb - 2;
+            if (xx < 0 || xx >= ws) continue;
+            acc = fmaf(tile[(yy * ws + xx) * Cg + c], dw_w[c * 25 + a * 5 + bb], acc);
+          }
+        }
+        acc += dw_b[c];
+        s += acc;
+      }
+      val[u] = acc;
+    }
+    const float mean = warp_sum(s) / Cg;
+    float v = 0.0f;
+#pragma unroll
+    for (int u = 0; u < MAXC; ++u) {
+      const int c = lane + 32 * u;
+      if (c < Cg) {
+        const float d = val[u] - mean;
+        v = fmaf(d, d, v);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(v) / Cg + 1e-5f);
+    float oy = 0.0f, ox = 0.0f;
+#pragma unroll
+    for (int u = 0; u < MAXC; ++u) {
+      const int c = lane + 32 * u;
+      if (c < Cg) {
+        const float a = gelu_erf((val[u] - mean) * rstd * ln_g[c] + ln_b[c]);
+        oy = fmaf(a, pw[c], oy);
+        ox = fmaf(a, pw[Cg + c], ox);
+      }
+    }
+    oy = warp_sum(oy);
+    ox = warp_sum(ox);
+    if (lane == 0) {
+      const float inv = 1.0f / (float)ws;
+      const float ref_y = ((pi + 0.5f) / ws) * 2.0f - 1.0f;
+      const float ref_x = ((pj + 0.5f) / ws) * 2.0f - 1.0f;
+      const float pos_y = tanhf(oy) * inv * 2.0f + ref_y;
+      const float pos_x = tanhf(ox) * inv * 2.0f + ref_x;
+      float *o = pix + (((long)win * groups + g) * P + p) * 2;
+      o[0] = ((pos_y + 1.0f) / 2.0f) * (ws - 1);
+      o[1] = ((pos_x + 1.0f) / 2.0f) * (ws - 1);
+    }
+  }
+}
+
+// F.grid_sample(bilinear, zeros padding, align_corners=True) of kv window j with the offsets of its query window.
+template <typename OutT>
+__global__ void __launch_bounds__(256) cva_sample_kernel(const float *__restrict__ x2, const float *__restrict__ pix,
+                                                         OutT *__restrict__ sampled, int N1, int TH1, int TH2, int W, int C,
+                                                         int groups, int ws, int per_clip) {
+  const int P = ws * ws;
+  const int Cg = C / groups;
+  const int j = blockIdx.x;
+  const int r = TH2 / TH1;
+  const int nW1 = (TH1 / ws) * (W / ws);
+  const int nW2 = (TH2 / ws) * (W / ws);
+  const int qw = cva_query_window_s(j, r, N1, nW1, per_clip);
+  const int b2 = j / nW2, n2 = j % nW2;
+  const long L2 = (long)TH2 * W;
+  for (int e = threadIdx.x; e < P * C; e += blockDim.x) {
+    const int p = e / C, c = e % C;
+    const int g = c / Cg;
+    const float *pp = pix + (((long)qw * groups + g) * P + p) * 2;
+    const float py = pp[0], px = pp[1];
+    const float fy = floorf(py), fx = floorf(px);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const float wy1 = py - fy, wx1 = px - fx;
+    const float wy0 = 1.0f - wy1, wx0 = 1.0f - wx1;
+    float acc = 0.0f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = y0 + dy, xx = x0 + dx;
+        if (yy < 0 || yy >= ws || xx < 0 || xx >= ws) continue;
+        const long row = b2 * L2 + window_token_row(n2, yy * ws + xx, TH2, W, ws, 0);
+        acc = fmaf(x2[row * C + c], (dy ? wy1 : wy0) * (dx ? wx1 : wx0), acc);
+      }
+    }
+    sampled[((long)j * P + p) * C + c] = from_f32<OutT>(acc);
+  }
+}
+
+// x_new = h + window_partition(h) (window-major, added at flat position) + reinterpret_(C,P)->(P,C)(y)
+__global__ void __launch_bounds__(256) cva_residual_kernel(const float *__restrict__ h, const float *__restrict__ y,
+                                                           float *__restrict__ x_new, long total, int TH1, int W, int C, int ws) {
+  const int P = ws * ws;
+  const long L1 = (long)TH1 * W;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; idx < total; idx += stride) {
+    const int c = (int)(idx % C);
+    const long tok = idx / C;
+    const long b = tok / L1;
+    const int l = (int)(tok % L1);
+    const int n = l / P, p = l % P;
+    const long wrow = b * L1 + window_token_row(n, p, TH1, W, ws, 0);
+    const int f = p * C + c;                 // flat index inside the window's (C,P) channel-major block
+    const int cc = f / P, pp = f % P;
+    const long win = b * (L1 / P) + n;
+    x_new[idx] = h[idx] + h[wrow * C + c] + y[(win * P + pp) * C + cc];
+  }
+}
+
+}  // namespace mumpy
+
+using namespace mumpy;
+
+extern "C" int mumpy_cva_offsets(const float *q, const float *dw_w, const float *dw_b, const float *ln_g, const float *ln_b,
+                                 const float *pw, float *pix, int B, int TH1, int W, int C, int groups, int ws, void *stream) {
+  MUMPY_REQUIRE(q && dw_w && dw_b && ln_g && ln_b && pw && pix && B > 0 && C % groups == 0, "cva_offsets: bad arguments");
+  MUMPY_REQUIRE(TH1 % ws == 0 && W % ws == 0 && ws <= 8, "cva_offsets: bad window geometry");
+  const int Cg = C / groups;
+  MUMPY_REQUIRE(Cg <= 256, "cva_offsets: group width %d > 256 unsupported", Cg);
+  const int N1 = B * (TH1 / ws) * (W / ws);
+  const size_t smem = (size_t)ws * ws * Cg * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(cva_offsets_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("cva_offsets: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+  }
+  dim3 grid((unsigned)N1, (unsigned)groups);
+  cva_offsets_kernel<8><<<grid, 128, smem, as_stream(stream)>>>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, TH1, W, C, groups, ws);
+  return launch_status("cva_offsets");
+}
+
+extern "C" int mumpy_cva_sample(const float *x2, const float *pix, void *sampled, int out_dtype, int B, int TH1, int TH2, int W,
+                                int C, int groups, int ws, int per_clip_pairing, void *stream) {
+  MUMPY_REQUIRE(x2 && pix && sampled && B > 0 && TH2 % TH1 == 0, "cva_sample: bad arguments");
+  const int N1 = B * (TH1 / ws) * (W / ws);
+  const int N2 = B * (TH2 / ws) * (W / ws);
+  cudaStream_t st = as_stream(stream);
+  if (out_dtype == MUMPY_BF16)
+    cva_sample_kernel<__nv_bfloat16><<<N2, 256, 0, st>>>(x2, pix, static_cast<__nv_bfloat16 *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
+  else
+    cva_sample_kernel<float><<<N2, 256, 0, st>>>(x2, pix, static_cast<float *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
+  return launch_status("cva_sample");
+}
+
+extern "C" int mumpy_cva_residual(const float *h, const float *y, float *x_new, int B, int TH1, int W, int C, int ws,
+                                  void *stream) {
+  MUMPY_REQUIRE(h && y && x_new && h != x_new && B > 0, "cva_residual: bad arguments (must be out of place)");
+  const long total = (long)B * TH1 * W * C;
+  const int blocks = (int)(cdiv(total, 256) < 148 * 16 ? cdiv(total, 256) : 148 * 16);
+  cva_residual_kernel<<<blocks, 256, 0, as_stream(stream)>>>(h, y, x_new, total, TH1, W, C, ws);
+  return launch_status("cva_residual");
+}

@@ -1,0 +1,305 @@
+// HBM-bound data-movement kernels: view merges (row gathers), decoder resampling (bilinear up, avg-pool,
+// pixel-shuffle) with fused gate/skip, layout changes, im2col for the tensor-core conv path, DAP and the
+// mask + metric counts.  All are grid-stride, coalesced along the channel (innermost) dimension.
+#include "common.cuh"
+
+namespace mumpy {
+
+static inline int flat_blocks(long total, int threads = 256) {
+  const long b = cdiv(total, threads);
+  return (int)(b < 148 * 16 ? b : 148 * 16);
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ src, int C, OutT *__restrict__ dst, long dst_ld,
+                                                          int dst_col, long total, int rows_out, int rows_src, int div, int mul_hi,
+                                                          int mul_lo, int add) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int c = (int)(i % C);
+    const long r = i / C;
+    const long b = r / rows_out;
+    const int q = (int)(r % rows_out);
+    const long srow = b * rows_src + (q / div) * mul_hi + (q % div) * mul_lo + add;
+    dst[r * dst_ld + dst_col + c] = from_f32<OutT>(src[srow * C + c]);
+  }
+}
+
+__global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ in, long ld_in, __nv_bfloat16 *__restrict__ out, long total,
+                                                     int H, int W, int Cin, int kh, int kw, int ph, int pw, int Kpad) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const int K = kh * kw * Cin;
+  for (; i < total; i += stride) {
+    const int k = (int)(i % Kpad);
+    const long m = i / Kpad;
+    float v = 0.0f;
+    if (k < K) {
+      const int c = k % Cin;
+      const int t = k / Cin;
+      const int kx = t % kw, ky = t / kw;
+      const int x = (int)(m % W);
+      const long r = m / W;
+      const int y = (int)(r % H);
+      const long b = r / H;
+      const int yy = y + ky - ph, xx = x + kx - pw;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = in[((b * H + yy) * W + xx) * ld_in + c];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// source index + weights of nn.Upsample(bilinear) along one axis (ATen area_pixel_compute_source_index)
+__device__ __forceinline__ void bilinear_axis(int o, int n_in, int n_out, int scale, bool aligned, int &i0, int &i1, float &w1) {
+  float src;
+  if (aligned) {
+    const float s = n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f;
+    src = s * o;
+  } else {
+    src = (1.0f / scale) * (o + 0.5f) - 0.5f;
+    if (src < 0.0f) src = 0.0f;
+  }
+  i0 = (int)src;
+  if (i0 > n_in - 1) i0 = n_in - 1;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  w1 = src - i0;
+}
+
+__global__ void __launch_bounds__(256) resample_kernel(const float *__restrict__ in, const float *__restrict__ mul,
+                                                       const float *__restrict__ add, float *__restrict__ out, long ld_out, int out_col,
+                                                       long total, int H, int W, int C, int Ho, int Wo, int Co, int mode, int scale) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int c = (int)(i % Co);
+    long t = i / Co;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const long b = t / Ho;
+    const float *img = in + b * H * W * C;
+    float v;
+    if (mode == MUMPY_RS_IDENTITY) {
+      v = img[((long)ho * W + wo) * C + c];
+    } else if (mode == MUMPY_RS_AVGPOOL2) {
+      const float *p = img + ((long)(2 * ho) * W + 2 * wo) * C + c;
+      v = (p[0] + p[C] + p[(long)W * C] + p[(long)W * C + C]) * 0.25f;
+    } else if (mode == MUMPY_RS_PIXEL_SHUFFLE2) {
+      v = img[((long)(ho >> 1) * W + (wo >> 1)) * C + c * 4 + (ho & 1) * 2 + (wo & 1)];
+    } else {
+      int y0, y1, x0, x1;
+      float wy, wx;
+      const bool aligned = mode == MUMPY_RS_UP_ALIGNED;
+      bilinear_axis(ho, H, Ho, scale, aligned, y0, y1, wy);
+      bilinear_axis(wo, W, Wo, scale, aligned, x0, x1, wx);
+      const float v00 = img[((long)y0 * W + x0) * C + c], v01 = img[((long)y0 * W + x1) * C + c];
+      const float v10 = img[((long)y1 * W + x0) * C + c], v11 = img[((long)y1 * W + x1) * C + c];
+      // ATen upsample_bilinear2d: w0*(w0x*v00 + w1x*v01) + w1*(w0x*v10 + w1x*v11)
+      v = (1.0f - wy) * ((1.0f - wx) * v00 + wx * v01) + wy * ((1.0f - wx) * v10 + wx * v11);
+    }
+    if (mul) v *= mul[i];
+    if (add) v += add[i];
+    out[(i / Co) * ld_out + out_col + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) mul_add_kernel(const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ c,
+                                                      float *__restrict__ out, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = a[i] * b[i];
+    if (c) v += c[i];
+    out[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) add_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = a[i] + b[i];
+}
+
+// in (batch, R, Cc) with row stride ld_in -> out (batch, Cc, R) with row stride ld_out (+ column offset), tiled via smem
+__global__ void __launch_bounds__(256) transpose_kernel(const float *__restrict__ in, long ld_in, long in_batch, float *__restrict__ out,
+                                                        long ld_out, long out_batch, int out_col, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < R && c < Cc) tile[i][tx] = in[b * in_batch + (long)r * ld_in + c];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < R && c < Cc) out[b * out_batch + (long)c * ld_out + out_col + r] = tile[tx][i];
+  }
+}
+
+// NCHW -> NHWC with a fused 2x2 average (ffinfo -> decoder_frequency_0 input)
+__global__ void __launch_bounds__(256) nchw_pool2_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, long ld_out,
+                                                                 int out_col, long total, int C, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {       // i over (b, c, ho, wo): coalesced-ish reads
+    const int wo = (int)(i % Wo);
+    long t = i / Wo;
+    const int ho = (int)(t % Ho);
+    t /= Ho;
+    const int c = (int)(t % C);
+    const long b = t / C;
+    const float *p = in + ((b * C + c) * H + 2 * ho) * W + 2 * wo;
+    const float v = (p[0] + p[1] + p[W] + p[W + 1]) * 0.25f;
+    out[((b * Ho + ho) * Wo + wo) * ld_out + out_col + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) channel_group_mean_kernel(const float *__restrict__ in, float *__restrict__ out, long total, int C,
+                                                                 int k) {
+  const int Co = C / k;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int g = (int)(i % Co);
+    const long p = i / Co;
+    const float *src = in + p * C + g * k;
+    float s = 0.0f;
+    for (int j = 0; j < k; ++j) s += src[j];
+    out[i] = s / (float)k;
+  }
+}
+
+__global__ void __launch_bounds__(256) mask_counts_kernel(const float *__restrict__ logits, const unsigned char *__restrict__ gt,
+                                                          unsigned char *__restrict__ mask, unsigned long long *__restrict__ counts, int HW) {
+  __shared__ unsigned int red[4][8];
+  const int b = blockIdx.y;
+  unsigned int tp = 0, np = 0, ng = 0, nu = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const bool p = logits[(long)b * HW + i] > 0.0f;      // sigmoid(x) > 0.5  <=>  x > 0   (test.py:100-106)
+    if (mask) mask[(long)b * HW + i] = p ? 255 : 0;
+    if (gt) {
+      const bool g = gt[(long)b * HW + i] != 0;
+      tp += (p && g);
+      ng += g;
+      nu += (p || g);
+    }
+    np += p;
+  }
+  unsigned int vals[4] = {tp, np, ng, nu};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    unsigned int v = vals[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[q][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 && counts) {
+    unsigned int s = 0;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    if (s) atomicAdd(&counts[b * 4 + threadIdx.x], (unsigned long long)s);
+  }
+}
+
+}  // namespace mumpy
+
+using namespace mumpy;
+
+extern "C" int mumpy_gather_rows(const float *src, int C, void *dst, int dst_dtype, long dst_ld, int dst_col, int B, int rows_out,
+                                 int rows_src, int div, int mul_hi, int mul_lo, int add, void *stream) {
+  MUMPY_REQUIRE(src && dst && C > 0 && B > 0 && rows_out > 0 && div > 0, "gather_rows: bad arguments");
+  const long total = (long)B * rows_out * C;
+  cudaStream_t st = as_stream(stream);
+  if (dst_dtype == MUMPY_BF16)
+    gather_rows_kernel<__nv_bfloat16><<<flat_blocks(total), 256, 0, st>>>(src, C, static_cast<__nv_bfloat16 *>(dst), dst_ld, dst_col, total, rows_out, rows_src, div, mul_hi, mul_lo, add);
+  else
+    gather_rows_kernel<float><<<flat_blocks(total), 256, 0, st>>>(src, C, static_cast<float *>(dst), dst_ld, dst_col, total, rows_out, rows_src, div, mul_hi, mul_lo, add);
+  return launch_status("gather_rows");
+}
+
+extern "C" int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int B, int H, int W, int Cin, int kh, int kw, int ph,
+                                 int pw, int Kpad, void *stream) {
+  MUMPY_REQUIRE(in && out && Kpad >= kh * kw * Cin, "im2col_nhwc: bad arguments");
+  const long total = (long)B * H * W * Kpad;
+  im2col_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(in, ld_in, static_cast<__nv_bfloat16 *>(out), total, H, W, Cin, kh, kw, ph, pw, Kpad);
+  return launch_status("im2col_nhwc");
+}
+
+extern "C" int mumpy_resample_nhwc(const float *in, const float *mul, const float *add, float *out, long ld_out, int out_col,
+                                   int B, int H, int W, int C, int mode, int scale, void *stream) {
+  MUMPY_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0, "resample_nhwc: bad arguments");
+  int Ho = H, Wo = W, Co = C;
+  switch (mode) {
+    case MUMPY_RS_IDENTITY: break;
+    case MUMPY_RS_UP_ALIGNED:
+    case MUMPY_RS_UP_HALFPIX:
+      MUMPY_REQUIRE(scale >= 1, "resample_nhwc: bad scale");
+      Ho = H * scale; Wo = W * scale; break;
+    case MUMPY_RS_AVGPOOL2:
+      MUMPY_REQUIRE(H % 2 == 0 && W % 2 == 0, "resample_nhwc: odd map for avgpool2");
+      Ho = H / 2; Wo = W / 2; break;
+    case MUMPY_RS_PIXEL_SHUFFLE2:
+      MUMPY_REQUIRE(C % 4 == 0, "resample_nhwc: pixel_shuffle needs C %% 4 == 0");
+      Ho = 2 * H; Wo = 2 * W; Co = C / 4; break;
+    default: set_error("resample_nhwc: unknown mode %d", mode); return MUMPY_ERR_ARG;
+  }
+  const long total = (long)B * Ho * Wo * Co;
+  resample_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(in, mul, add, out, ld_out, out_col, total, H, W, C, Ho, Wo, Co, mode, scale);
+  return launch_status("resample_nhwc");
+}
+
+extern "C" int mumpy_mul_add(const float *a, const float *b, const float *c, float *out, long n, void *stream) {
+  MUMPY_REQUIRE(a && b && out && n > 0, "mul_add: bad arguments");
+  mul_add_kernel<<<flat_blocks(n), 256, 0, as_stream(stream)>>>(a, b, c, out, n);
+  return launch_status("mul_add");
+}
+
+extern "C" int mumpy_add(const float *a, const float *b, float *out, long n, void *stream) {
+  MUMPY_REQUIRE(a && b && out && n > 0, "add: bad arguments");
+  add_kernel<<<flat_blocks(n), 256, 0, as_stream(stream)>>>(a, b, out, n);
+  return launch_status("add");
+}
+
+extern "C" int mumpy_nchw_to_nhwc(const float *in, float *out, long ld_out, int out_col, int B, int C, int H, int W, int pool2,
+                                  void *stream) {
+  MUMPY_REQUIRE(in && out && B > 0, "nchw_to_nhwc: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (pool2) {
+    MUMPY_REQUIRE(H % 2 == 0 && W % 2 == 0, "nchw_to_nhwc: odd map for pool2");
+    const long total = (long)B * C * (H / 2) * (W / 2);
+    nchw_pool2_to_nhwc_kernel<<<flat_blocks(total), 256, 0, st>>>(in, out, ld_out, out_col, total, C, H, W);
+    return launch_status("nchw_pool2_to_nhwc");
+  }
+  const int P = H * W;
+  dim3 grid((unsigned)cdiv(P, 32), (unsigned)cdiv(C, 32), (unsigned)B);   // in: (B, R=C, Cc=P)
+  transpose_kernel<<<grid, 256, 0, st>>>(in, P, (long)C * P, out, ld_out, (long)P * ld_out, out_col, C, P);
+  return launch_status("nchw_to_nhwc");
+}
+
+extern "C" int mumpy_nhwc_to_nchw(const float *in, long ld_in, float *out, int B, int C, int H, int W, void *stream) {
+  MUMPY_REQUIRE(in && out && B > 0, "nhwc_to_nchw: bad arguments");
+  const int P = H * W;
+  dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(P, 32), (unsigned)B);   // in: (B, R=P, Cc=C)
+  transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, ld_in, (long)P * ld_in, out, P, (long)C * P, 0, P, C);
+  return launch_status("nhwc_to_nchw");
+}
+
+extern "C" int mumpy_channel_group_mean(const float *in, float *out, long pixels, int C, int k, void *stream) {
+  MUMPY_REQUIRE(in && out && pixels > 0 && k > 0 && C % k == 0, "channel_group_mean: bad arguments");
+  const long total = pixels * (C / k);
+  channel_group_mean_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(in, out, total, C, k);
+  return launch_status("channel_group_mean");
+}
+
+extern "C" int mumpy_mask_counts(const float *logits, const unsigned char *gt, unsigned char *mask, long long *counts, int B, int HW,
+                                 void *stream) {
+  MUMPY_REQUIRE(logits && B > 0 && HW > 0 && (mask || counts), "mask_counts: bad arguments");
+  dim3 grid((unsigned)(cdiv(HW, 256) < 64 ? cdiv(HW, 256) : 64), (unsigned)B);
+  mask_counts_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits, gt, mask, reinterpret_cast<unsigned long long *>(counts), HW);
+  return launch_status("mask_counts");
+}

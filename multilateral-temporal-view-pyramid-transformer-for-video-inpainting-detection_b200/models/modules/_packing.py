@@ -1,0 +1,44 @@
+"""Weight packing helpers shared by the mirror modules.
+
+Parameters stay ordinary fp32 nn.Parameters under the reference's state_dict keys; the kernel-side layouts
+(bf16 copies, gathered relative-position bias, fused k/v weights, NHWC conv filters, ...) are derived lazily
+and cached per module, keyed on the parameters' storage, version counter and the precision mode, so a
+load_state_dict / .cuda() / in-place update invalidates them automatically.
+"""
+import torch
+
+from ... import ops
+
+
+class PackedModule(torch.nn.Module):
+    def _packed(self, name, params, fn):
+        key = tuple((p.data_ptr(), p._version, p.device) for p in params) + (ops.precision(),)
+        cache = self.__dict__.setdefault("_pack_cache", {})
+        hit = cache.get(name)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, fn())
+            cache[name] = hit
+        return hit[1]
+
+    def _gemm_weight(self, name, param, reshape=None):
+        """(N,K) GEMM operand of `param` in the current precision (fp32 as is, or a cached bf16 copy)."""
+        def make():
+            w = param.detach()
+            if reshape is not None:
+                w = w.reshape(reshape)
+            w = w.contiguous()
+            return ops.cast_bf16(w) if ops.precision() == "bf16" else w
+        return self._packed("w:" + name, [param], make)
+
+
+def as_operand(x):
+    """fp32 activation -> GEMM A operand of the current precision."""
+    if ops.precision() == "bf16" and x.dtype == torch.float32:
+        return ops.cast_bf16(x)
+    return x
+
+
+def require_inference(module):
+    if module.training:
+        raise RuntimeError("%s: libmumpy_b200 implements the inference forward only; call .eval()" % type(module).__name__)

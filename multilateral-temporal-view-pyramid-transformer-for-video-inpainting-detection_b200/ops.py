@@ -1,0 +1,290 @@
+"""Tensor-level wrappers over the C ABI (include/mumpy_b200.h).
+
+PyTorch is used here for device memory and the current stream only; every computation is a libmumpy_b200
+kernel.  All tensors must live on a CUDA device and be contiguous -- anything else raises (no fallback).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
+RS_IDENTITY, RS_UP_ALIGNED, RS_UP_HALFPIX, RS_AVGPOOL2, RS_PIXEL_SHUFFLE2 = 0, 1, 2, 3, 4
+
+_precision = "bf16"
+_bound_device = None
+launch_count = 0            # kernels-launching C-ABI calls made (bench.py reports it as gpu_launches)
+
+
+def set_precision(mode: str):
+    """'bf16': tcgen05 GEMMs on bf16 operands with fp32 accumulation; 'fp32': exact fp32 FMA kernels."""
+    global _precision
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _precision = mode
+
+
+def precision() -> str:
+    return _precision
+
+
+def act_dtype():
+    """torch dtype of GEMM operands in the current precision mode."""
+    return torch.bfloat16 if _precision == "bf16" else torch.float32
+
+
+def code(dtype) -> int:
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise _lib.MumpyError("unsupported dtype %s" % dtype)
+
+
+def _prep(*tensors):
+    """Validates tensors, binds the library to their device, returns (lib, stream)."""
+    global _bound_device, launch_count
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.MumpyError("libmumpy_b200 needs CUDA tensors (got %s); there is no CPU fallback" % t.device)
+        if not t.is_contiguous():
+            raise _lib.MumpyError("non-contiguous tensor passed to a libmumpy_b200 op")
+        dev = t.device.index if dev is None else dev
+        if t.device.index != dev:
+            raise _lib.MumpyError("tensors on different devices")
+    lib = _lib.load()
+    if dev != _bound_device:
+        _lib.check(lib.mumpy_init(dev), "mumpy_init")
+        _bound_device = dev
+    launch_count += 1
+    return lib, torch.cuda.current_stream(dev).cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM / norms
+def linear(a, w, bias=None, residual=None, act=ACT_NONE, out_dtype=torch.float32, out=None):
+    """out = act(a @ w.T + bias) (+ residual).  a (..., K), w (N, K) same dtype; residual/out (..., N)."""
+    K = a.shape[-1]
+    N = w.shape[0]
+    M = a.numel() // K
+    if w.shape[1] != K or a.dtype != w.dtype:
+        raise _lib.MumpyError("linear: operand mismatch a%s %s w%s %s" % (tuple(a.shape), a.dtype, tuple(w.shape), w.dtype))
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (N,), dtype=out_dtype, device=a.device)
+    lib, st = _prep(a, w, bias, residual, out)
+    _lib.check(lib.mumpy_linear(_p(a), K, _p(w), _p(bias), _p(residual), _p(out), N, M, N, K, code(a.dtype),
+                                code(out.dtype), act, st), "mumpy_linear")
+    return out
+
+
+def linear_into(a, lda, w, bias, out, ldo, M, N, K, act=ACT_NONE, residual=None):
+    """Strided form: a/out are base tensors (possibly wider matrices) with explicit row strides."""
+    lib, st = _prep(a, w, bias, out)
+    _lib.check(lib.mumpy_linear(_p(a), lda, _p(w), _p(bias), _p(residual), _p(out), ldo, M, N, K, code(a.dtype),
+                                code(out.dtype), act, st), "mumpy_linear")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out_dtype=None):
+    C = x.shape[-1]
+    out = torch.empty(x.shape, dtype=out_dtype or act_dtype(), device=x.device)
+    lib, st = _prep(x, gamma, beta, out)
+    _lib.check(lib.mumpy_layernorm(_p(x), _p(gamma), _p(beta), _p(out), code(out.dtype), x.numel() // C, C, eps, st),
+               "mumpy_layernorm")
+    return out
+
+
+def patch_merge_norm(x, gamma, beta, B, TH, W, C, eps=1e-5, out_dtype=None):
+    out = torch.empty((B, (TH // 2) * (W // 2), 4 * C), dtype=out_dtype or act_dtype(), device=x.device)
+    lib, st = _prep(x, gamma, beta, out)
+    _lib.check(lib.mumpy_patch_merge_norm(_p(x), _p(gamma), _p(beta), _p(out), code(out.dtype), B, TH, W, C, eps, st),
+               "mumpy_patch_merge_norm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def window_attention(qkv, bias, mask, B, TH, W, C, heads, ws, shift):
+    out = torch.empty((B, TH * W, C), dtype=qkv.dtype, device=qkv.device)
+    lib, st = _prep(qkv, bias, mask, out)
+    _lib.check(lib.mumpy_window_attention(_p(qkv), _p(bias), _p(mask), _p(out), code(qkv.dtype), B, TH, W, C, heads, ws,
+                                          shift, st), "mumpy_window_attention")
+    return out
+
+
+def mha_short(qkv, Bn, N, C, heads):
+    out = torch.empty((Bn, N, C), dtype=qkv.dtype, device=qkv.device)
+    lib, st = _prep(qkv, out)
+    _lib.check(lib.mumpy_mha_short(_p(qkv), _p(out), code(qkv.dtype), Bn, N, C, heads, st), "mumpy_mha_short")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ front end
+def tokenize(x, w_kc, bias, gamma, beta, kt, eps=1e-5):
+    B, T, _, S, _ = x.shape
+    C = w_kc.shape[1]
+    To = T // kt
+    out = torch.empty((B, To * (S // 4) ** 2, C), dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, w_kc, bias, gamma, beta, out)
+    _lib.check(lib.mumpy_tokenize(_p(x), _p(w_kc), _p(bias), _p(gamma), _p(beta), _p(out), B, T, S, kt, C, eps, st),
+               "mumpy_tokenize")
+    return out
+
+
+def faf(x, dct, bands, frame=1):
+    B, T, _, S, _ = x.shape
+    ws = torch.empty((5 * B * 3 * S * S,), dtype=torch.float32, device=x.device)
+    out = torch.empty((B, 9, S, S), dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, dct, ws, out)
+    arr = (ctypes.c_int * 6)(*[int(v) for lohi in bands for v in lohi])
+    _lib.check(lib.mumpy_faf(_p(x), _p(dct), _p(ws), _p(out), B, T, frame, S, arr, st), "mumpy_faf")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ deformable cross-view attention
+def cva_offsets(q, dw_w, dw_b, ln_g, ln_b, pw, B, TH1, W, C, groups, ws):
+    N1 = B * (TH1 // ws) * (W // ws)
+    pix = torch.empty((N1, groups, ws * ws, 2), dtype=torch.float32, device=q.device)
+    lib, st = _prep(q, dw_w, dw_b, ln_g, ln_b, pw, pix)
+    _lib.check(lib.mumpy_cva_offsets(_p(q), _p(dw_w), _p(dw_b), _p(ln_g), _p(ln_b), _p(pw), _p(pix), B, TH1, W, C, groups,
+                                     ws, st), "mumpy_cva_offsets")
+    return pix
+
+
+def cva_sample(x2, pix, B, TH1, TH2, W, C, groups, ws, per_clip, out_dtype):
+    N2 = B * (TH2 // ws) * (W // ws)
+    out = torch.empty((N2 * ws * ws, C), dtype=out_dtype, device=x2.device)
+    lib, st = _prep(x2, pix, out)
+    _lib.check(lib.mumpy_cva_sample(_p(x2), _p(pix), _p(out), code(out_dtype), B, TH1, TH2, W, C, groups, ws,
+                                    int(per_clip), st), "mumpy_cva_sample")
+    return out
+
+
+def cva_attention(q, kv, B, TH1, TH2, W, C, heads, ws, per_clip):
+    N1 = B * (TH1 // ws) * (W // ws)
+    out = torch.empty((N1 * ws * ws, C), dtype=kv.dtype, device=q.device)
+    lib, st = _prep(q, kv, out)
+    _lib.check(lib.mumpy_cva_attention(_p(q), _p(kv), code(kv.dtype), _p(out), code(out.dtype), B, TH1, TH2, W, C, heads,
+                                       ws, int(per_clip), st), "mumpy_cva_attention")
+    return out
+
+
+def cva_residual(h, y, B, TH1, W, C, ws):
+    out = torch.empty_like(h)
+    lib, st = _prep(h, y, out)
+    _lib.check(lib.mumpy_cva_residual(_p(h), _p(y), _p(out), B, TH1, W, C, ws, st), "mumpy_cva_residual")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ data movement / decoder
+def gather_rows(src, C, dst, dst_ld, dst_col, B, rows_out, rows_src, div=1, mul_hi=1, mul_lo=0, add=0):
+    lib, st = _prep(src, dst)
+    _lib.check(lib.mumpy_gather_rows(_p(src), C, _p(dst), code(dst.dtype), dst_ld, dst_col, B, rows_out, rows_src, div,
+                                     mul_hi, mul_lo, add, st), "mumpy_gather_rows")
+    return dst
+
+
+def conv2d_nhwc(x, w_ohwi, bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in=None, out=None, ld_out=None):
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, w_ohwi, bias, out)
+    _lib.check(lib.mumpy_conv2d_nhwc(_p(x), ld_in or Cin, _p(w_ohwi), _p(bias), _p(out), ld_out or Cout, B, H, W, Cin,
+                                     Cout, kh, kw, ph, pw, st), "mumpy_conv2d_nhwc")
+    return out
+
+
+def im2col_nhwc(x, B, H, W, Cin, kh, kw, ph, pw, Kpad, ld_in=None):
+    out = torch.empty((B * H * W, Kpad), dtype=torch.bfloat16, device=x.device)
+    lib, st = _prep(x, out)
+    _lib.check(lib.mumpy_im2col_nhwc(_p(x), ld_in or Cin, _p(out), B, H, W, Cin, kh, kw, ph, pw, Kpad, st),
+               "mumpy_im2col_nhwc")
+    return out
+
+
+def groupnorm_nhwc(x, gamma, beta, B, HW, C, groups, act, eps=1e-5, out=None, ld_out=None, out_col=0):
+    if out is None:
+        out = torch.empty_like(x)
+    stats = torch.empty((2 * B * groups,), dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, gamma, beta, stats, out)
+    _lib.check(lib.mumpy_groupnorm_nhwc(_p(x), _p(gamma), _p(beta), _p(stats), _p(out), ld_out or C, out_col, B, HW, C,
+                                        groups, eps, act, st), "mumpy_groupnorm_nhwc")
+    return out
+
+
+def resample_nhwc(x, B, H, W, C, mode, scale=2, mul=None, add=None, out=None, ld_out=None, out_col=0):
+    Ho, Wo, Co = H, W, C
+    if mode in (RS_UP_ALIGNED, RS_UP_HALFPIX):
+        Ho, Wo = H * scale, W * scale
+    elif mode == RS_AVGPOOL2:
+        Ho, Wo = H // 2, W // 2
+    elif mode == RS_PIXEL_SHUFFLE2:
+        Ho, Wo, Co = 2 * H, 2 * W, C // 4
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Co), dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, mul, add, out)
+    _lib.check(lib.mumpy_resample_nhwc(_p(x), _p(mul), _p(add), _p(out), ld_out or Co, out_col, B, H, W, C, mode, scale, st),
+               "mumpy_resample_nhwc")
+    return out
+
+
+def mul_add(a, b, c=None):
+    out = torch.empty_like(a)
+    lib, st = _prep(a, b, c, out)
+    _lib.check(lib.mumpy_mul_add(_p(a), _p(b), _p(c), _p(out), a.numel(), st), "mumpy_mul_add")
+    return out
+
+
+def add(a, b):
+    out = torch.empty_like(a)
+    lib, st = _prep(a, b, out)
+    _lib.check(lib.mumpy_add(_p(a), _p(b), _p(out), a.numel(), st), "mumpy_add")
+    return out
+
+
+def nchw_to_nhwc(x, pool2=False, out=None, ld_out=None, out_col=0):
+    B, C, H, W = x.shape
+    Ho, Wo = (H // 2, W // 2) if pool2 else (H, W)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, C), dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, out)
+    _lib.check(lib.mumpy_nchw_to_nhwc(_p(x), _p(out), ld_out or C, out_col, B, C, H, W, int(pool2), st), "mumpy_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x, B, H, W, C, ld_in=None):
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, out)
+    _lib.check(lib.mumpy_nhwc_to_nchw(_p(x), ld_in or C, _p(out), B, C, H, W, st), "mumpy_nhwc_to_nchw")
+    return out
+
+
+def channel_group_mean(x, pixels, C, k):
+    out = torch.empty((pixels, C // k), dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, out)
+    _lib.check(lib.mumpy_channel_group_mean(_p(x), _p(out), pixels, C, k, st), "mumpy_channel_group_mean")
+    return out
+
+
+def mask_counts(logits, gt=None, want_mask=True):
+    """logits (B,1,H,W) fp32 -> (mask uint8 (B,H,W) in {0,255}, counts int64 (B,4) = [TP, n_pred, n_gt, n_union])."""
+    B = logits.shape[0]
+    HW = logits.numel() // B
+    mask = torch.empty((B,) + tuple(logits.shape[-2:]), dtype=torch.uint8, device=logits.device) if want_mask else None
+    counts = torch.zeros((B, 4), dtype=torch.int64, device=logits.device)
+    lib, st = _prep(logits, gt, mask, counts)
+    _lib.check(lib.mumpy_mask_counts(_p(logits), _p(gt), _p(mask), _p(counts), B, HW, st), "mumpy_mask_counts")
+    return mask, counts
+
+
+def cast_bf16(x):
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lib, st = _prep(x, out)
+    _lib.check(lib.mumpy_cast_bf16(_p(x), _p(out), x.numel(), st), "mumpy_cast_bf16")
+    return out

@@ -1,0 +1,127 @@
+"""GPU: each mirror module through the C ABI (fp32 mode) against the fixtures captured from the reference,
+and against the oracle on the same seeded inputs.  Bar: max-abs <= 1e-4 (fp32 parity mode, BASELINE north_star)."""
+import pytest
+import torch
+
+from oracle import mumpy_oracle as orc
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def mods():
+    return util.golden("modules.pt")
+
+
+@pytest.fixture(autouse=True)
+def fp32_mode():
+    import mumpy_b200
+    mumpy_b200.set_precision("fp32")
+    yield
+    mumpy_b200.set_precision("bf16")
+
+
+def _build(cls, ctor):
+    m = cls(**ctor).eval()
+    util.load_seeded(m)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("size", [56, 224])
+def test_faf(mods, size):
+    from mumpy_b200.models.modules.dct import FAF
+    f = mods["faf_%d" % size]
+    x = util.seeded_input(f["input_shape"], f["input_seed"])
+    y = FAF(size).eval().frame(x.cuda(), 1)
+    if size == 224:
+        assert util.maxabs(y[:, :, ::4, ::4], f["outputs"]["y_sub"]) < TOL
+    else:
+        assert util.maxabs(y, f["outputs"]["y"]) < TOL
+    assert util.maxabs(y, orc.faf_middle(x)) < TOL
+
+
+@pytest.mark.parametrize("name", ["swin_s0", "swin_s3", "swin_t1_s3", "swin_res7"])
+def test_swin_block(mods, name):
+    from mumpy_b200.models.modules.swinTransformer import SwinTransformerBlock
+    f = mods[name]
+    m = _build(SwinTransformerBlock, f["ctor"])
+    x = util.seeded_input(f["input_shape"], f["input_seed"])
+    assert util.maxabs(m(x.cuda()), f["outputs"]["y"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["sda_r3", "sda_r1"])
+def test_swin_dattention(mods, name):
+    from mumpy_b200.models.modules.deformableAttention import SwinDAttention
+    f = mods[name]
+    m = _build(SwinDAttention, f["ctor"])
+    x1 = util.seeded_input(f["x1_shape"], f["input_seed"])
+    x2 = util.seeded_input(f["x2_shape"], f["input_seed"] + 100)
+    y, _ = m(x1.cuda(), x2.cuda())
+    assert util.maxabs(y, f["outputs"]["y"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["cross_r3", "cross_r1", "cross_last"])
+def test_cross_swin_block(mods, name):
+    from mumpy_b200.models.encoder.multiTemporalViewEncoder import CrossSwinBlock
+    f = mods[name]
+    m = _build(CrossSwinBlock, f["ctor"])
+    x1 = util.seeded_input(f["x1_shape"], f["input_seed"])
+    x2 = x1 if f["ctor"]["last_view"] else util.seeded_input(f["x2_shape"], f["input_seed"] + 100)
+    y, out = m(x1.cuda(), x2.cuda())
+    assert util.maxabs(y, f["outputs"]["y"]) < TOL
+    assert util.maxabs(out, f["outputs"]["out"]) < TOL
+
+
+def test_patch_merging(mods):
+    from mumpy_b200.models.modules.swinTransformer import PatchMerging
+    f = mods["merge"]
+    m = _build(PatchMerging, f["ctor"])
+    x = util.seeded_input(f["input_shape"], f["input_seed"])
+    assert util.maxabs(m(x.cuda()), f["outputs"]["y"]) < TOL
+
+
+def test_vit_block(mods):
+    from mumpy_b200.models.modules.blocks import Block
+    f = mods["vit_block"]
+    m = _build(Block, f["ctor"])
+    x = util.seeded_input(f["input_shape"], f["input_seed"])
+    assert util.maxabs(m(x.cuda()), f["outputs"]["y"]) < TOL
+
+
+def test_tokenize(mods):
+    from mumpy_b200.models.encoder.multiTemporalViewEncoder import CrossThreeViewTokenize
+    from mumpy_b200.models.factory.modelFactory import default_view_configs
+    f = mods["tokenize"]
+    m = CrossThreeViewTokenize(default_view_configs()).eval()
+    util.load_seeded(m)
+    m = m.cuda()
+    x = util.seeded_input(f["input_shape"], f["input_seed"])
+    out = m(x.cuda())
+    for i in range(3):
+        assert util.maxabs(out[i].reshape(2, -1, out[i].shape[-1]), f["outputs"]["v%d" % i]) < TOL
+
+
+def test_window_attention_with_mask_api():
+    """WindowAttention.forward(x_windows, mask) keeps the reference call form (swinTransformer.py:134-166)."""
+    from mumpy_b200.models.modules.swinTransformer import WindowAttention
+    m = WindowAttention(64, (7, 7), 2).eval()
+    sd = util.load_seeded(m)
+    m = m.cuda()
+    x = util.seeded_input((8, 49, 64), 5)
+    mask = orc.shifted_window_mask(14, 14, 7, 3)
+    ref = orc.window_attention(sd, "", x, 2, 7, mask)
+    assert util.maxabs(m(x.cuda(), mask.cuda()), ref) < TOL
+
+
+def test_decoder(mods):
+    from mumpy_b200 import Decoder
+    f = mods["decoder"]
+    m = Decoder().eval()
+    util.load_seeded(m)
+    m = m.cuda()
+    final_x, view_x, ff = util.decoder_inputs(1)
+    lg, xf = m(final_x.cuda(), [[t.cuda() for t in st] for st in view_x], ff.cuda())
+    assert util.maxabs(lg, f["outputs"]["logits"]) < TOL
+    assert util.maxabs(xf[:, :, ::4, ::4], f["outputs"]["x_feats_sub"]) < TOL
