@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- clips/s (== frames/s, test.py slides the 3-frame clip by one frame) of the Mumpy inference forward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference] [--no-kernels]
+
+One "step" = Encoder -> Decoder -> thresholded mask + per-clip counts on one batch of B synthetic DVI-shaped clips
+(B,3,3,224,224), bf16 mode (tcgen05 GEMMs, fp32 accumulation), key-seeded random-init weights (oracle/weights.py).
+N > 1 is launched by torch.distributed.run, one rank per GPU; clips are sharded by rank (weak scaling, no data-path
+collective) and the per-clip F1/IoU sums are reduced with one NCCL all-reduce at the end of the timed region.
+Prints ONE JSON line on rank 0 (contract in the task statement; see DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GFLOP_PER_CLIP = 168.1            # algorithmic (minimal-work) matmul+conv GFLOP per clip @224^2, SURVEY section 8(d)
+METRIC = "frames/sec Mumpy fwd @224^2 clips"
+WORKLOAD = "configs[2]: full Mumpy forward bf16, synthetic DVI-shaped 224x224 3-frame clips, random-init (key-seeded) weights"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-kernels", action="store_true", help="skip the isolated-kernel (configs[1]) section")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
+    ap.add_argument("--cpu-clips", type=int, default=6, help="clips timed for cpu_baseline")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference forward on the host cores (the reference is Python
+# and cannot travel to the GPU box; oracle/mumpy_oracle.py is pinned to it by tests/golden)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_forward_clips_per_s(n_clips, warm=1):
+    import torch
+    from oracle import mumpy_oracle as orc
+    from oracle import weights as wts
+    from tests import util
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = util.manifest()
+    enc_sd, dec_sd = wts.from_manifest(m["encoder"]), wts.from_manifest(m["decoder"])
+    x = util.seeded_input((1, 3, 3, 224, 224), 1234)
+    with torch.no_grad():
+        for _ in range(warm):
+            orc.forward(enc_sd, dec_sd, x)
+        t0 = time.perf_counter()
+        for _ in range(n_clips):
+            orc.forward(enc_sd, dec_sd, x)
+        dt = time.perf_counter() - t0
+    return n_clips / dt, dt, torch.get_num_threads()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    cps, dt, threads = cpu_forward_clips_per_s(steps, warm=max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD + " -- CPU arm: one clip (batch 1, the reference's own setting) per step, fp32"},
+        "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
+                         "sample": "%d single-clip fp32 forwards of oracle/mumpy_oracle.py (restatement pinned to the reference)" % steps},
+        "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(device):
+    import torch
+    import mumpy_b200
+    from tests import util
+    mumpy_b200.set_precision("bf16")
+    enc, dec = mumpy_b200.Encoder().eval(), mumpy_b200.Decoder().eval()
+    util.load_seeded(enc)
+    util.load_seeded(dec)
+    return enc.to(device), dec.to(device)
+
+
+def kernel_section(peaks, device):
+    """configs[1]: isolated kernels at batch 64 (deformable sampling, DCT branch, one Swin stage-0 block's GEMMs),
+    each timed alone with CUDA events, L2 flushed between launches."""
+    import torch
+    from mumpy_b200 import ops
+    from mumpy_b200.models.modules.dct import FAF
+    out = []
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return sum(ts) / len(ts)
+
+    B = 64
+    with torch.no_grad():
+        # (i) deformable sampling, stage-0 v2<-v3: q windows 4096x49x96, kv windows 12288x49x96
+        pix = torch.rand((B * 64, 3, 49, 2), device=device) * 6.0
+        x2 = torch.randn((B, 3 * 56 * 56, 96), device=device)
+        t = timed(lambda: ops.cva_sample(x2, pix, B, 56, 168, 56, 96, 3, 7, False, torch.bfloat16))
+        byts = 4 * x2.numel() + 2 * x2.numel() + 4 * pix.numel()
+        out.append({"kernel": "cva_sample_kernel (stage-0 v2<-v3, B=64)", "bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3})
+        del x2, pix
+        # (ii) DCT branch (64,3,3,224,224) -> (64,9,224,224), dense fp32: 8 matmuls of 224^3 per image-channel
+        x = torch.randn((B, 3, 3, 224, 224), device=device)
+        faf = FAF(224).eval()
+        t = timed(lambda: faf.frame(x, 1), reps=3)
+        flops = B * 3 * 8 * 2 * 224 ** 3
+        byts = B * 224 * 224 * (3 * 4 + 9 * 4)
+        out.append({"kernel": "mumpy_faf (4 fp32 GEMM passes, B=64)", "bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3, "dense_tflops_fp32": flops / t / 1e12})
+        del x
+        # (iii) Swin stage-0 (view 3) GEMMs at B=64: M = 64*9408, C = 128
+        M = B * 9408
+        a = torch.randn((M, 128), device=device).bfloat16()
+        for name, N, K in (("qkv", 384, 128), ("fc1+GELU", 512, 128), ("fc2", 128, 512)):
+            aa = a if K == 128 else torch.randn((M, K), device=device).bfloat16()
+            w = (torch.randn((N, K), device=device) / K ** 0.5).bfloat16()
+            bias = torch.zeros(N, device=device)
+            act = ops.ACT_GELU if "GELU" in name else ops.ACT_NONE
+            odt = torch.float32 if name == "fc2" else torch.bfloat16
+            t = timed(lambda: ops.linear(aa, w, bias, act=act, out_dtype=odt))
+            flops = 2.0 * M * N * K
+            byts = 2 * M * K + 2 * N * K + (4 if odt == torch.float32 else 2) * M * N
+            out.append({"kernel": "gemm_tc_kernel %s M=%d N=%d K=%d" % (name, M, N, K), "bound": "hbm" if flops / byts < 250 else "tensor",
+                        "tflops": flops / t / 1e12, "tensor_frac": flops / t / 1e12 / peaks["bf16_tflops"], "gbs": byts / t / 1e9,
+                        "hbm_frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3})
+        # stage-2 shape (the 40%-of-FLOPs shape): M = 64*588, C = 512
+        M = B * 588
+        for name, N, K in (("qkv", 1536, 512), ("fc1+GELU", 2048, 512), ("fc2", 512, 2048)):
+            aa = torch.randn((M, K), device=device).bfloat16()
+            w = (torch.randn((N, K), device=device) / K ** 0.5).bfloat16()
+            bias = torch.zeros(N, device=device)
+            act = ops.ACT_GELU if "GELU" in name else ops.ACT_NONE
+            odt = torch.float32 if name == "fc2" else torch.bfloat16
+            t = timed(lambda: ops.linear(aa, w, bias, act=act, out_dtype=odt))
+            flops = 2.0 * M * N * K
+            byts = 2 * M * K + 2 * N * K + (4 if odt == torch.float32 else 2) * M * N
+            out.append({"kernel": "gemm_tc_kernel %s M=%d N=%d K=%d" % (name, M, N, K), "bound": "tensor", "tflops": flops / t / 1e12,
+                        "tensor_frac": flops / t / 1e12 / peaks["bf16_tflops"], "gbs": byts / t / 1e9, "hbm_frac": byts / t / 1e9 / peaks["hbm_gbs"],
+                        "ms": t * 1e3})
+    return out
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from mumpy_b200 import evaluate as ev
+    from mumpy_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmumpy_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    peaks = load_peaks()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    enc, dec = build_model(device)
+    n_in = 4                                            # rotate 4 distinct input batches (4 x 57.8 MB > 126 MB L2)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host_in = [torch.randn((B, 3, 3, 224, 224), generator=g).pin_memory() for _ in range(n_in)]
+    dev_in = [h.to(device) for h in host_in]
+    gt = (torch.rand((B, 224, 224), generator=g) > 0.7).to(torch.uint8).to(device)
+    x_static = torch.empty_like(dev_in[0])
+    host_mask = torch.empty((B, 224, 224), dtype=torch.uint8).pin_memory()
+    host_counts = torch.empty((B, 4), dtype=torch.int64).pin_memory()
+
+    def step():
+        final_x, view_x, ff = enc(x_static)
+        logits, _ = dec(final_x, view_x, ff)
+        return ops.mask_counts(logits, gt)
+
+    with torch.no_grad():
+        x_static.copy_(dev_in[0])
+        n0 = ops.launch_count
+        mask, counts = step()                            # eager warm-up: packs weights, sets function attributes
+        launches_per_step = ops.launch_count - n0
+        torch.cuda.synchronize()
+        graph = None
+        if not args.no_graph:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                step()
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                mask, counts = step()
+
+        def run_step(i):
+            x_static.copy_(dev_in[i % n_in], non_blocking=True)
+            if graph is not None:
+                graph.replay()
+                return mask, counts
+            return step()
+
+        for i in range(W):
+            run_step(i)
+        torch.cuda.synchronize()
+
+        # ---- timed region: K steps, inputs resident in HBM --------------------------------------------------
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sums = torch.zeros(3, dtype=torch.float64)
+        e0.record()
+        all_counts = []
+        for i in range(K):
+            m, c = run_step(i)
+            all_counts.append(c.clone())
+        if world > 1:                                    # the path's only exchange: 3 x fp64 metric sums
+            sums_dev = ev.local_sums(torch.cat(all_counts, 0), 224 * 224).to(device)
+            dist.all_reduce(sums_dev)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_dev = e0.elapsed_time(e1) * 1e-3
+        t = torch.tensor([t_dev], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_max = float(t)
+
+        # ---- end-to-end region: pinned host clips -> H2D -> forward -> D2H masks + counts, every step ---------
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(K):
+            x_static.copy_(host_in[i % n_in], non_blocking=True)
+            if graph is not None:
+                graph.replay()
+                m, c = mask, counts
+            else:
+                m, c = step()
+            host_mask.copy_(m, non_blocking=True)
+            host_counts.copy_(c, non_blocking=True)
+        f1.record()
+        torch.cuda.synchronize()
+        te = torch.tensor([f0.elapsed_time(f1) * 1e-3], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        t_e2e = float(te)
+        clocks = sampler.stop() if rank == 0 else None
+
+    clips = B * K * world
+    value = clips / t_max
+    line = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "global_batch": B * world, "parallelism": "clip-sharded dp%d" % world,
+                   "launch": "CUDA graph" if graph is not None else "eager",
+                   "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); per-step activation working set is several GB" % (n_in, n_in * B * 9 * 224 * 224 * 4 / 1e6),
+                   "residual_stream": "fp32", "gemm": "bf16 operands, fp32 accumulate (tcgen05)"},
+        "e2e": {"value": clips / t_e2e, "unit": "clips/s", "h2d_bytes_per_step": B * 9 * 224 * 224 * 4,
+                "d2h_bytes_per_step": B * 224 * 224 + B * 4 * 8, "ms_per_step": t_e2e / K * 1e3,
+                "api": "mumpy_b200.Encoder/Decoder forward + ops.mask_counts on host-pinned clips"},
+        "gpu_launches": launches_per_step * K,
+        "roofline": {"bound": "tensor", "achieved": GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12 if world == 1 else GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12,
+                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12 / peaks["bf16_tflops_sustained"],
+                     "traffic": None, "per": "GPU", "kernel": "whole step (gemm_tc_kernel dominates; per-kernel rooflines under `kernels`)",
+                     "flops_per_clip": GFLOP_PER_CLIP * 1e9, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)"},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if world == 1:
+            cps, dt, threads = cpu_forward_clips_per_s(args.cpu_clips)
+            line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
+                                    "sample": "%d single-clip fp32 forwards (batch 1) of the oracle port of the reference, %.1f s" % (args.cpu_clips, dt)}
+            if not args.no_kernels:
+                try:
+                    line["kernels"] = kernel_section(peaks, device)
+                except Exception as ex:       # the isolated section must never take the headline down
+                    line["kernels"] = {"error": repr(ex)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

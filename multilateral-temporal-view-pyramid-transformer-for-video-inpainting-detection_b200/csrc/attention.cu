@@ -188,11 +188,14 @@ __global__ void __launch_bounds__(128) cva_attention_kernel(const float *__restr
 template <typename K>
 static int ensure_smem(K kernel, size_t bytes) {
   if (bytes <= 48 * 1024) return MUMPY_OK;
+  static size_t granted = 0;          // per template instantiation: skip the driver call once it is large enough
+  if (bytes <= granted) return MUMPY_OK;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
     return MUMPY_ERR_CUDA;
   }
+  granted = bytes;
   return MUMPY_OK;
 }
 

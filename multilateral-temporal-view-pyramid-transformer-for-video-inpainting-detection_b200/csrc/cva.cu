@@ -164,12 +164,14 @@ extern "C" int mumpy_cva_offsets(const float *q, const float *dw_w, const float 
   MUMPY_REQUIRE(Cg <= 256, "cva_offsets: group width %d > 256 unsupported", Cg);
   const int N1 = B * (TH1 / ws) * (W / ws);
   const size_t smem = (size_t)ws * ws * Cg * sizeof(float);
-  if (smem > 48 * 1024) {
+  static size_t granted = 0;
+  if (smem > 48 * 1024 && smem > granted) {
     cudaError_t e = cudaFuncSetAttribute(cva_offsets_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("cva_offsets: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MUMPY_ERR_CUDA;
     }
+    granted = smem;
   }
   dim3 grid((unsigned)N1, (unsigned)groups);
   cva_offsets_kernel<8><<<grid, 128, smem, as_stream(stream)>>>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, TH1, W, C, groups, ws);

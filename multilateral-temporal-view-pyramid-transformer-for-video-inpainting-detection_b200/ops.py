@@ -15,7 +15,7 @@ RS_IDENTITY, RS_UP_ALIGNED, RS_UP_HALFPIX, RS_AVGPOOL2, RS_PIXEL_SHUFFLE2 = 0, 1
 
 _precision = "bf16"
 _bound_device = None
-launch_count = 0            # kernels-launching C-ABI calls made (bench.py reports it as gpu_launches)
+launch_count = 0            # libmumpy_b200 kernels launched so far (bench.py reports the per-step delta as gpu_launches)
 
 
 def set_precision(mode: str):
@@ -144,6 +144,8 @@ def faf(x, dct, bands, frame=1):
     out = torch.empty((B, 9, S, S), dtype=torch.float32, device=x.device)
     lib, st = _prep(x, dct, ws, out)
     arr = (ctypes.c_int * 6)(*[int(v) for lohi in bands for v in lohi])
+    global launch_count
+    launch_count += 3            # four GEMM passes per call
     _lib.check(lib.mumpy_faf(_p(x), _p(dct), _p(ws), _p(out), B, T, frame, S, arr, st), "mumpy_faf")
     return out
 
@@ -213,6 +215,8 @@ def groupnorm_nhwc(x, gamma, beta, B, HW, C, groups, act, eps=1e-5, out=None, ld
         out = torch.empty_like(x)
     stats = torch.empty((2 * B * groups,), dtype=torch.float32, device=x.device)
     lib, st = _prep(x, gamma, beta, stats, out)
+    global launch_count
+    launch_count += 1            # statistics + apply
     _lib.check(lib.mumpy_groupnorm_nhwc(_p(x), _p(gamma), _p(beta), _p(stats), _p(out), ld_out or C, out_col, B, HW, C,
                                         groups, eps, act, st), "mumpy_groupnorm_nhwc")
     return out
