@@ -119,6 +119,16 @@ int mumpy_gather_rows(const float *src, int C, void *dst, int dst_dtype, long ds
 /* conv (stride 1): in (B,H,W,Cin) row stride ld_in, w (Cout, kh, kw, Cin) fp32, out (B,H,W,Cout) fp32. */
 int mumpy_conv2d_nhwc(const float *in, long ld_in, const float *w, const float *bias, float *out, long ld_out, int B,
                       int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, void *stream);
+/* tensor-core implicit-GEMM convolution ('same', stride 1): in (B,H,W,Cin) bf16 NHWC with pixel stride ld_in (a channel
+ * slice of a wider map is allowed); w_packed (Cout, kh*kw*ceil(Cin/64)*64) bf16, K order (ky,kx,c), each tap's channels
+ * zero padded to a multiple of 64; out (B*H*W, Cout) fp32|bf16 = act(conv + bias) (+ residual).  The A tiles are
+ * fetched by an im2col-mode TMA tensor map (padding = zero fill), no im2col buffer is materialised. */
+int mumpy_conv2d_nhwc_bf16(const void *in, long ld_in, const void *w_packed, const float *bias, const float *residual,
+                           void *out, long ld_out, int B, int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw,
+                           int out_dtype, int act, void *stream);
+/* Cout == 1 convolution (final_out 3x3, decoder.py:95): in (B,H,W,Cin) fp32 contiguous, w (kh,kw,Cin), out (B,H,W). */
+int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const float *bias, float *out, int B, int H, int W, int Cin,
+                            int kh, int kw, int ph, int pw, void *stream);
 /* im2col for the tensor-core path: out (B*H*W, Kpad) bf16, K order (ky,kx,c), zero padded to Kpad. */
 int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int B, int H, int W, int Cin, int kh, int kw, int ph,
                       int pw, int Kpad, void *stream);

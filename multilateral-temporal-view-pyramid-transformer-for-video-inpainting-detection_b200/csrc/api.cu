@@ -30,6 +30,9 @@ int linear_f32(const float *A, long lda, const float *W, const float *bias, cons
 int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, long ldo,
                 long M, int N, int K, int out_dtype, int act, cudaStream_t st);
 
+int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, const float *residual, void *out, long ldo, int B,
+              int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int out_dtype, int act, cudaStream_t st);
+
 __global__ void cast_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, long n) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -74,6 +77,14 @@ extern "C" int mumpy_linear(const void *A, long lda, const void *W, const float 
   if (ab_dtype == MUMPY_BF16) return linear_bf16(A, lda, W, bias, residual, out, ldo, M, N, K, out_dtype, act, as_stream(stream));
   set_error("linear: unknown dtype %d", ab_dtype);
   return MUMPY_ERR_ARG;
+}
+
+extern "C" int mumpy_conv2d_nhwc_bf16(const void *in, long ld_in, const void *w_packed, const float *bias, const float *residual,
+                                      void *out, long ld_out, int B, int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw,
+                                      int out_dtype, int act, void *stream) {
+  MUMPY_REQUIRE(in && w_packed && out && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv2d_nhwc_bf16: bad arguments");
+  return conv_bf16(in, ld_in, w_packed, bias, residual, out, ld_out, B, H, W, Cin, Cout, kh, kw, ph, pw, out_dtype, act,
+                   as_stream(stream));
 }
 
 extern "C" int mumpy_cast_bf16(const float *in, void *out, long n, void *stream) {

@@ -199,6 +199,11 @@ static int ensure_smem(K kernel, size_t bytes) {
   return MUMPY_OK;
 }
 
+int window_attention_mma(const void *qkv, const float *bias, const float *mask, void *out, int B, int TH, int W, int C, int heads,
+                         int ws, int shift, cudaStream_t st);
+int cva_attention_mma(const float *q, const void *kv, void *o, int B, int TH1, int TH2, int W, int C, int heads, int ws, int per_clip,
+                      cudaStream_t st);
+
 }  // namespace mumpy
 
 using namespace mumpy;
@@ -212,6 +217,8 @@ extern "C" int mumpy_window_attention(const void *qkv, const float *bias, const 
   const int N = ws * ws;
   dim3 grid((unsigned)(B * (TH / ws) * (W / ws)), (unsigned)heads);
   cudaStream_t st = as_stream(stream);
+  if (dtype == MUMPY_BF16 && D == 32 && C % 8 == 0)      // tensor-pipe path (attention_mma.cu)
+    return window_attention_mma(qkv, bias, mask, out, B, TH, W, C, heads, ws, shift, st);
   int rc = MUMPY_OK;
 #define LAUNCH(T, DD)                                                                                                     \
   {                                                                                                                       \
@@ -250,6 +257,7 @@ extern "C" int mumpy_cva_attention(const float *q, const void *kv, int kv_dtype,
   dim3 grid((unsigned)N1, (unsigned)heads);
   const size_t smem = attn_smem_floats<32>(N) * sizeof(float);
   cudaStream_t st = as_stream(stream);
+  if (kv_dtype == MUMPY_BF16 && C % 8 == 0) return cva_attention_mma(q, kv, o, B, TH1, TH2, W, C, heads, ws, per_clip_pairing, st);
   if (kv_dtype == MUMPY_BF16)
     cva_attention_kernel<__nv_bfloat16, __nv_bfloat16, 32><<<grid, 128, smem, st>>>(q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1, TH1, W, C, ws, r, per_clip_pairing);
   else

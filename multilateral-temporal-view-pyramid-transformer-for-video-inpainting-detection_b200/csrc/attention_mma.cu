@@ -1,0 +1,292 @@
+// Window attention on the tensor pipe for the bf16 mode: one warp per (window, head), q/k/v staged in swizzled shared
+// memory with 16-byte gathers straight from the canvas-ordered qkv matrix (window partition / cyclic shift folded into
+// the row index), S = QK^T and O = PV as mma.sync m16n8k16 bf16 with fp32 accumulators, probabilities kept in
+// registers (S accumulator fragments are re-used as the A fragments of PV), fp32 softmax with the relative-position
+// bias and shift mask added in fp32.  49 (or 64) tokens x d=32 per head: ~1.7% of the forward's FLOPs, so the kernel is
+// HBM/L2-bound (reads 3C, writes C bf16 per token) -- the tiles are far too small for a 128-row tcgen05 atom.
+// The same core serves the deformable cross-view attention (q from the query view's fp32 canvas, k/v from the sampled
+// windows, outputs summed over the temporal ratio).
+#include "common.cuh"
+
+namespace mumpy {
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// [64 tokens][32 dims] bf16 tile, 64 B rows, 16-byte chunks XOR-swizzled by (row>>1)&3 (conflict-free ldmatrix)
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
+
+constexpr int ATT_TILE_BYTES = 64 * 64;     // one 64x32 bf16 tile
+constexpr int ATT_WARPS = 4;
+
+// scores for 16 query rows (m-tile mt) against NT n-tiles of keys, then softmax -> un-normalised probabilities in s,
+// returns the two row sums (rows g and g+8 of the m-tile) through sum_lo / sum_hi.
+template <int NT>
+__device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt, int lane, int N, float scale, const float *__restrict__ bias_h,
+                                               const float *__restrict__ mask_w, float (&s)[8][4], float &sum_lo, float &sum_hi) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[nt][i] = 0.0f;
+  uint32_t a[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    ldsm_x4(sQ + tile_off(row, ks * 2 + (lane >> 4)), a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    uint32_t b0, b1, b2, b3;
+    ldsm_x4(sK + tile_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
+    mma_bf16(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+    mma_bf16(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], b2, b3);
+  }
+  const int i_lo = mt * 16 + g, i_hi = i_lo + 8;
+  float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = (e < 2) ? i_lo : i_hi;
+      const int j = nt * 8 + 2 * t + (e & 1);
+      float v = -INFINITY;
+      if (j < N) {
+        v = s[nt][e] * scale;
+        if (i < N) {
+          if (bias_h) v += bias_h[i * N + j];
+          if (mask_w) v += mask_w[i * N + j];
+        }
+      }
+      s[nt][e] = v;
+      if (e < 2) m_lo = fmaxf(m_lo, v); else m_hi = fmaxf(m_hi, v);
+    }
+  }
+  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+  sum_lo = 0.0f;
+  sum_hi = 0.0f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float p = __expf(s[nt][e] - ((e < 2) ? m_lo : m_hi));      // exp(-inf) = 0 for the padded key columns
+      s[nt][e] = p;
+      if (e < 2) sum_lo += p; else sum_hi += p;
+    }
+  }
+  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+}
+
+// o[dn][4] += P(16 x 64) . V(64 x 32) for one m-tile; probabilities come straight from the score fragments
+__device__ __forceinline__ void pv_accumulate(uint32_t sV, int lane, const float (&s)[8][4], float inv_lo, float inv_hi, float (&o)[4][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint32_t a0 = pack_bf16(s[2 * kk][0] * inv_lo, s[2 * kk][1] * inv_lo);
+    const uint32_t a1 = pack_bf16(s[2 * kk][2] * inv_hi, s[2 * kk][3] * inv_hi);
+    const uint32_t a2 = pack_bf16(s[2 * kk + 1][0] * inv_lo, s[2 * kk + 1][1] * inv_lo);
+    const uint32_t a3 = pack_bf16(s[2 * kk + 1][2] * inv_hi, s[2 * kk + 1][3] * inv_hi);
+    const int tok = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(sV + tile_off(tok, dp * 2 + (lane >> 4)), b0, b1, b2, b3);
+      mma_bf16(o[dp * 2], a0, a1, a2, a3, b0, b1);
+      mma_bf16(o[dp * 2 + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+}
+
+// gathers `N` rows of 32 bf16 (64 B) into a swizzled tile; rows >= N are zero
+template <typename RowPtr>
+__device__ __forceinline__ void load_tile_bf16(uint8_t *tile, int lane, int N, RowPtr row_ptr) {
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    const int p = pass * 8 + (lane >> 2);
+    const int chunk = lane & 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (p < N) v = *reinterpret_cast<const uint4 *>(row_ptr(p) + chunk * 8);
+    *reinterpret_cast<uint4 *>(tile + tile_off(p, chunk)) = v;
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_mma_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ bias,
+                                                                              const float *__restrict__ mask, __nv_bfloat16 *__restrict__ out,
+                                                                              int TH, int W, int C, int heads, int ws, int shift, long n_tasks) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long task = (long)blockIdx.x * ATT_WARPS + warp;
+  if (task >= n_tasks) return;
+  const int N = ws * ws;
+  const int nW = (TH / ws) * (W / ws);
+  const long win = task / heads;
+  const int h = (int)(task % heads);
+  const long b = win / nW;
+  const int n = (int)(win % nW);
+  const long L = (long)TH * W;
+  uint8_t *tq = att_smem + warp * 3 * ATT_TILE_BYTES, *tk = tq + ATT_TILE_BYTES, *tv = tk + ATT_TILE_BYTES;
+  const __nv_bfloat16 *base = qkv + (b * L) * 3 * C + h * 32;
+  load_tile_bf16(tq, lane, N, [&](int p) { return base + (long)window_token_row(n, p, TH, W, ws, shift) * 3 * C; });
+  load_tile_bf16(tk, lane, N, [&](int p) { return base + (long)window_token_row(n, p, TH, W, ws, shift) * 3 * C + C; });
+  load_tile_bf16(tv, lane, N, [&](int p) { return base + (long)window_token_row(n, p, TH, W, ws, shift) * 3 * C + 2 * C; });
+  __syncwarp();
+  const uint32_t sQ = smem_addr(tq), sK = smem_addr(tk), sV = smem_addr(tv);
+  const float *bias_h = bias + (long)h * N * N;
+  const float *mask_w = mask ? mask + (long)n * N * N : nullptr;
+  const int g = lane >> 2, t = lane & 3;
+  for (int mt = 0; mt * 16 < N; ++mt) {
+    float s[8][4], sum_lo, sum_hi;
+    scores_softmax<NT>(sQ, sK, mt, lane, N, 0.17677669529663687f, bias_h, mask_w, s, sum_lo, sum_hi);
+    float o[4][4];
+#pragma unroll
+    for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[dn][e] = 0.0f;
+    pv_accumulate(sV, lane, s, 1.0f / sum_lo, 1.0f / sum_hi, o);
+    const int i_lo = mt * 16 + g, i_hi = i_lo + 8;
+    if (i_lo < N) {
+      __nv_bfloat16 *dst = out + (b * L + window_token_row(n, i_lo, TH, W, ws, shift)) * C + h * 32 + 2 * t;
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][0], o[dn][1]);
+    }
+    if (i_hi < N) {
+      __nv_bfloat16 *dst = out + (b * L + window_token_row(n, i_hi, TH, W, ws, shift)) * C + h * 32 + 2 * t;
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][2], o[dn][3]);
+    }
+  }
+}
+
+__device__ __forceinline__ int cva_query_window_m(int j, int r, int N1, int nW1, int per_clip) {
+  if (!per_clip) return j % N1;
+  const int i = j / r;
+  const int clip = i / nW1;
+  return clip * nW1 + ((i % nW1) * r + j % r) % nW1;
+}
+
+// deformable cross-view attention core: o[i] = sum_t softmax(q[qidx(r i + t)] k[r i + t]^T * d^-1/2) v[r i + t]
+template <int NT>
+__global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const float *__restrict__ q, const __nv_bfloat16 *__restrict__ kv,
+                                                                           __nv_bfloat16 *__restrict__ o_out, int N1, int TH1, int W, int C,
+                                                                           int heads, int ws, int r, int per_clip, long n_tasks) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long task = (long)blockIdx.x * ATT_WARPS + warp;
+  if (task >= n_tasks) return;
+  const int N = ws * ws;
+  const int nW1 = (TH1 / ws) * (W / ws);
+  const int i = (int)(task / heads);
+  const int h = (int)(task % heads);
+  const long L1 = (long)TH1 * W;
+  uint8_t *tq = att_smem + warp * 3 * ATT_TILE_BYTES, *tk = tq + ATT_TILE_BYTES, *tv = tk + ATT_TILE_BYTES;
+  const uint32_t sQ = smem_addr(tq), sK = smem_addr(tk), sV = smem_addr(tv);
+  const int g = lane >> 2, t4 = lane & 3;
+  float o[4][4][4];                       // [m-tile][d n-tile][frag]
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][dn][e] = 0.0f;
+  for (int t = 0; t < r; ++t) {
+    const int j = r * i + t;
+    const int qw = cva_query_window_m(j, r, N1, nW1, per_clip);
+    const long qb = qw / nW1;
+    const int qn = qw % nW1;
+    __syncwarp();
+    // q: fp32 canvas rows -> bf16 tile
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int p = pass * 8 + (lane >> 2);
+      const int chunk = lane & 3;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (p < N) {
+        const float *src = q + (qb * L1 + window_token_row(qn, p, TH1, W, ws, 0)) * C + h * 32 + chunk * 8;
+        const float4 f0 = *reinterpret_cast<const float4 *>(src), f1 = *reinterpret_cast<const float4 *>(src + 4);
+        v.x = pack_bf16(f0.x, f0.y); v.y = pack_bf16(f0.z, f0.w); v.z = pack_bf16(f1.x, f1.y); v.w = pack_bf16(f1.z, f1.w);
+      }
+      *reinterpret_cast<uint4 *>(tq + tile_off(p, chunk)) = v;
+    }
+    const __nv_bfloat16 *kvb = kv + ((long)j * N) * 2 * C + h * 32;
+    load_tile_bf16(tk, lane, N, [&](int p) { return kvb + (long)p * 2 * C; });
+    load_tile_bf16(tv, lane, N, [&](int p) { return kvb + (long)p * 2 * C + C; });
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      if (mt * 16 < N) {
+        float s[8][4], sum_lo, sum_hi;
+        scores_softmax<NT>(sQ, sK, mt, lane, N, 0.17677669529663687f, nullptr, nullptr, s, sum_lo, sum_hi);
+        pv_accumulate(sV, lane, s, 1.0f / sum_lo, 1.0f / sum_hi, o[mt]);
+      }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const int i_lo = mt * 16 + g, i_hi = i_lo + 8;
+    if (i_lo < N) {
+      __nv_bfloat16 *dst = o_out + ((long)i * N + i_lo) * C + h * 32 + 2 * t4;
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[mt][dn][0], o[mt][dn][1]);
+    }
+    if (i_hi < N) {
+      __nv_bfloat16 *dst = o_out + ((long)i * N + i_hi) * C + h * 32 + 2 * t4;
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[mt][dn][2], o[mt][dn][3]);
+    }
+  }
+}
+
+int window_attention_mma(const void *qkv, const float *bias, const float *mask, void *out, int B, int TH, int W, int C, int heads,
+                         int ws, int shift, cudaStream_t st) {
+  const long n_tasks = (long)B * (TH / ws) * (W / ws) * heads;
+  const unsigned grid = (unsigned)cdiv(n_tasks, ATT_WARPS);
+  const size_t smem = ATT_WARPS * 3 * ATT_TILE_BYTES;
+  const int N = ws * ws;
+  if (N <= 56)
+    window_attention_mma_kernel<7><<<grid, ATT_WARPS * 32, smem, st>>>(static_cast<const __nv_bfloat16 *>(qkv), bias, mask,
+                                                                      static_cast<__nv_bfloat16 *>(out), TH, W, C, heads, ws, shift, n_tasks);
+  else
+    window_attention_mma_kernel<8><<<grid, ATT_WARPS * 32, smem, st>>>(static_cast<const __nv_bfloat16 *>(qkv), bias, mask,
+                                                                      static_cast<__nv_bfloat16 *>(out), TH, W, C, heads, ws, shift, n_tasks);
+  return launch_status("window_attention_mma");
+}
+
+int cva_attention_mma(const float *q, const void *kv, void *o, int B, int TH1, int TH2, int W, int C, int heads, int ws, int per_clip,
+                      cudaStream_t st) {
+  const int N1 = B * (TH1 / ws) * (W / ws);
+  const long n_tasks = (long)N1 * heads;
+  const unsigned grid = (unsigned)cdiv(n_tasks, ATT_WARPS);
+  const size_t smem = ATT_WARPS * 3 * ATT_TILE_BYTES;
+  const int N = ws * ws;
+  const int r = TH2 / TH1;
+  if (N <= 56)
+    cva_attention_mma_kernel<7><<<grid, ATT_WARPS * 32, smem, st>>>(q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1,
+                                                                   TH1, W, C, heads, ws, r, per_clip, n_tasks);
+  else
+    cva_attention_mma_kernel<8><<<grid, ATT_WARPS * 32, smem, st>>>(q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1,
+                                                                   TH1, W, C, heads, ws, r, per_clip, n_tasks);
+  return launch_status("cva_attention_mma");
+}
+
+}  // namespace mumpy

@@ -173,6 +173,40 @@ __global__ void __launch_bounds__(256) channel_group_mean_kernel(const float *__
   }
 }
 
+// Cout == 1 convolution (final_out, decoder.py:95): one thread per output pixel, float4 channel loads, weights in smem.
+__global__ void __launch_bounds__(256) conv_cout1_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
+                                                         float *__restrict__ out, long pixels, int H, int W, int Cin, int kh, int kw, int ph,
+                                                         int pw) {
+  extern __shared__ float ws[];     // [kh*kw*Cin]
+  for (int i = threadIdx.x; i < kh * kw * Cin; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= pixels) return;
+  const int x = (int)(m % W);
+  const long r = m / W;
+  const int y = (int)(r % H);
+  const long b = r / H;
+  float acc = bias ? bias[0] : 0.0f;
+  for (int ky = 0; ky < kh; ++ky) {
+    const int yy = y + ky - ph;
+    if (yy < 0 || yy >= H) continue;
+    for (int kx = 0; kx < kw; ++kx) {
+      const int xx = x + kx - pw;
+      if (xx < 0 || xx >= W) continue;
+      const float4 *src = reinterpret_cast<const float4 *>(in + ((b * H + yy) * W + xx) * Cin);
+      const float *wt = ws + (ky * kw + kx) * Cin;
+      for (int c = 0; c < Cin / 4; ++c) {
+        const float4 v = src[c];
+        acc = fmaf(v.x, wt[4 * c], acc);
+        acc = fmaf(v.y, wt[4 * c + 1], acc);
+        acc = fmaf(v.z, wt[4 * c + 2], acc);
+        acc = fmaf(v.w, wt[4 * c + 3], acc);
+      }
+    }
+  }
+  out[m] = acc;
+}
+
 __global__ void __launch_bounds__(256) mask_counts_kernel(const float *__restrict__ logits, const unsigned char *__restrict__ gt,
                                                           unsigned char *__restrict__ mask, unsigned long long *__restrict__ counts, int HW) {
   __shared__ unsigned int red[4][8];
@@ -294,6 +328,15 @@ extern "C" int mumpy_channel_group_mean(const float *in, float *out, long pixels
   const long total = pixels * (C / k);
   channel_group_mean_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(in, out, total, C, k);
   return launch_status("channel_group_mean");
+}
+
+extern "C" int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const float *bias, float *out, int B, int H, int W, int Cin,
+                                       int kh, int kw, int ph, int pw, void *stream) {
+  MUMPY_REQUIRE(in && w && out && B > 0 && Cin % 4 == 0 && kh * kw * Cin * 4 <= 48 * 1024, "conv2d_nhwc_cout1: bad arguments");
+  const long pixels = (long)B * H * W;
+  conv_cout1_kernel<<<(unsigned)cdiv(pixels, 256), 256, kh * kw * Cin * sizeof(float), as_stream(stream)>>>(in, w, bias, out, pixels, H, W,
+                                                                                                           Cin, kh, kw, ph, pw);
+  return launch_status("conv2d_nhwc_cout1");
 }
 
 extern "C" int mumpy_mask_counts(const float *logits, const unsigned char *gt, unsigned char *mask, long long *counts, int B, int HW,

@@ -1,40 +1,62 @@
-// bf16 GEMM on the 5th-gen tensor cores: TMA (128B-swizzled tiles) -> smem ring -> tcgen05.mma (one elected
-// thread, fp32 accumulators in TMEM) -> tcgen05.ld epilogue with fused bias / GELU / fp32 residual.
+// bf16 GEMM / implicit-GEMM convolution on the 5th-gen tensor cores.
 //   D[m,n] = act( sum_k A[m,k] * W[n,k] + bias[n] ) + residual[m,n]      A (M,K), W (N,K) bf16, K-major both.
-// This is the workhorse of the "bf16 mode": qkv / proj / fc1 / fc2 / pre / proj_{q,k,v,out} / reduction /
-// globalembedding / global blocks / rgb_decoder linears (94% of the forward's FLOPs, SURVEY finding 3).
-//
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quadrant = warp id), warp 4 TMA producer,
-// warp 5 TMEM allocator + MMA issuer.  One 128 x BN output tile per CTA; BN and the ring depth are chosen
-// per problem so that two CTAs are co-resident per SM (one's epilogue overlaps the other's main loop).
-#include <cuda.h>
-
-#include "common.cuh"
+// Persistent, warp-specialised kernel, one CTA per SM, static round-robin tile scheduler (N-tile fastest so CTAs
+// running together share the A tile through L2):
+//   warp 8      TMA producer: 128B-swizzled A/B tiles into a 4-8 stage mbarrier ring.  In conv mode the A tile
+//               comes from an im2col-mode tensor map over the NHWC activation (128 consecutive output pixels x 64
+//               channels of one filter tap per k-block, zero-filled padding) -- no im2col buffer exists.
+//   warp 9      TMEM allocator + MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN<=256, K=16, fp32
+//               accumulators in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps the main
+//               loop of tile i+1; tcgen05.commit releases smem slots and publishes accumulators.
+//   warps 0-7   epilogue: tcgen05.ld (32 lanes x 32 columns per load; warp w reads lane quadrant w%4, column half
+//               w/4), fused bias / GELU / ReLU / fp32 residual, 16-byte stores, fp32 or bf16 output.
+// Workhorse of the bf16 mode: qkv / proj / fc1 / fc2 / pre / proj_{q,k,v,out} / reduction / globalembedding /
+// global blocks / rgb_decoder linears and every decoder convolution (94% + 11% of the forward's FLOPs).
+#include "tc_common.cuh"
 
 namespace mumpy {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t, const cuuint32_t *,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_num_sms = 0;
+static int g_driver_version = 0;
 
-int resolve_driver_entry_points() {
-  if (g_encode_tiled) return MUMPY_OK;
+static void *driver_symbol(const char *name) {
   void *fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
-    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+  cudaError_t e = cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+  return fn;
+}
+
+int resolve_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col && g_num_sms) return MUMPY_OK;
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(driver_symbol("cuTensorMapEncodeTiled"));
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(driver_symbol("cuTensorMapEncodeIm2col"));
+  if (!g_encode_tiled || !g_encode_im2col) {
+    set_error("cudaGetDriverEntryPoint(cuTensorMapEncode{Tiled,Im2col}) failed");
     return MUMPY_ERR_CUDA;
   }
-  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDriverGetVersion(&g_driver_version);
+  if (g_num_sms <= 0) g_num_sms = 148;
   return MUMPY_OK;
 }
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;       // 64 bf16 = 128 B = one swizzle span
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_SMEM_BUDGET = 196 * 1024;
 
 struct TcParams {
   const float *bias;
@@ -47,92 +69,20 @@ struct TcParams {
   int stages;
   int act;
   int out_bf16;
-  uint32_t tmem_cols;
+  int tiles_n;
+  long num_tiles;
+  uint32_t acc_cols;      // TMEM columns per accumulator slot (power of two >= BN)
   uint32_t idesc;
+  // conv mode (A through the im2col tensor map)
+  int conv;
+  int Wout, Hout, lower_w, lower_h, kw, cblocks;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ uint64_t global_timer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Parity wait with a watchdog: a pipeline bug becomes a trapped launch (reported through the C ABI) instead
-// of a hung GPU.  The timer is only read every 4096 failed probes, so the fast path is untouched.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && (++spins & 4095u) == 0) {
-      const uint64_t now = global_timer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) __trap();     // 4 s without progress
-    }
-  } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart): UMMA::SmemDescriptor with
-// start>>4 [0,14), LBO [16,30) (unused for swizzled K-major, 1), SBO=1024>>4 [32,46), version=1 [46,48),
-// layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                            const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+template <bool kConv>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[2 * TC_MAX_STAGES + 1];
+  __shared__ uint64_t bars[2 * TC_MAX_STAGES + 4];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -144,121 +94,164 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t full0 = smem_u32(&bars[0]);
   const uint32_t empty0 = smem_u32(&bars[TC_MAX_STAGES]);
-  const uint32_t accum_bar = smem_u32(&bars[2 * TC_MAX_STAGES]);
-  const int nkb = (p.K + TC_BK - 1) / TC_BK;
-  const int n0 = blockIdx.x * p.BN;
-  const long m0 = static_cast<long>(blockIdx.y) * TC_BM;
+  const uint32_t acc_full0 = smem_u32(&bars[2 * TC_MAX_STAGES]);
+  const uint32_t acc_empty0 = smem_u32(&bars[2 * TC_MAX_STAGES + 2]);
+  const int nkb = kConv ? p.K : (p.K + TC_BK - 1) / TC_BK;      // conv: p.K already counts k-blocks (taps x cblocks)
 
-  if (warp == 4 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  if (warp == TC_EPI_WARPS && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(accum_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full0 + 8 * s, 1);
+      mbar_init(acc_empty0 + 8 * s, TC_EPI_WARPS);
+    }
+    fence_barrier_init();
   }
-  if (warp == 5) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(p.tmem_cols)
+  if (warp == TC_EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2 * p.acc_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp == 4) {
+  if (warp == TC_EPI_WARPS) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        mbar_arrive_expect_tx(full0 + 8 * s, stage_bytes);
-        const uint32_t sa = tiles + s * stage_bytes;
-        tma_load_2d(sa, &tmA, full0 + 8 * s, kb * TC_BK, static_cast<int>(m0));
-        tma_load_2d(sa + a_bytes, &tmB, full0 + 8 * s, kb * TC_BK, n0);
+      uint32_t it = 0;
+      for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n0 = static_cast<int>(tile % p.tiles_n) * p.BN;
+        const long m0 = (tile / p.tiles_n) * TC_BM;
+        int cw = 0, ch = 0, cn = 0;
+        if (kConv) {
+          cw = static_cast<int>(m0 % p.Wout) + p.lower_w;
+          const long r = m0 / p.Wout;
+          ch = static_cast<int>(r % p.Hout) + p.lower_h;
+          cn = static_cast<int>(r / p.Hout);
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(full0 + 8 * s, stage_bytes);
+          const uint32_t sa = tiles + s * stage_bytes;
+          if (kConv) {
+            const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+            tma_load_im2col_4d(sa, &tmA, full0 + 8 * s, cb * TC_BK, cw, ch, cn, static_cast<uint16_t>(tap % p.kw),
+                               static_cast<uint16_t>(tap / p.kw));
+          } else {
+            tma_load_2d(sa, &tmA, full0 + 8 * s, kb * TC_BK, static_cast<int>(m0));
+          }
+          tma_load_2d(sa + a_bytes, &tmB, full0 + 8 * s, kb * TC_BK, n0);
+        }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------------
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(full0 + 8 * s, ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = tiles + s * stage_bytes;
-        const uint64_t adesc = make_kmajor_sw128_desc(sa);
-        const uint64_t bdesc = make_kmajor_sw128_desc(sa + a_bytes);
+      uint32_t it = 0, t = 0;
+      for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+        const uint32_t slot = t & 1, aph = (t >> 1) & 1;
+        mbar_wait(acc_empty0 + 8 * slot, aph ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + slot * p.acc_cols;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = tiles + s * stage_bytes;
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + a_bytes);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr>>4) field
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);      // frees the smem slot once these MMAs have read it
         }
-        umma_commit(empty0 + 8 * s);      // frees the smem slot once these MMAs have read it
+        umma_commit(acc_full0 + 8 * slot);  // accumulator complete
       }
-      umma_commit(accum_bar);             // accumulator complete
     }
   } else {
     // ---------------- epilogue: thread <-> accumulator row, 32 columns per tcgen05.ld ----------------
-    mbar_wait(accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const long gm = m0 + warp * 32 + lane;
-    const bool row_ok = gm < p.M;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(lane_addr + c0, v);
-      if (!row_ok) continue;
+    const int quad = warp & 3, half = warp >> 2;
+    uint32_t t = 0;
+    for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+      const uint32_t slot = t & 1, aph = (t >> 1) & 1;
+      const int n0 = static_cast<int>(tile % p.tiles_n) * p.BN;
+      const long m0 = (tile / p.tiles_n) * TC_BM;
+      mbar_wait(acc_full0 + 8 * slot, aph);
+      tc_fence_after();
+      const long gm = m0 + quad * 32 + lane;
+      const bool row_ok = gm < p.M;
+      const uint32_t lane_addr = tmem_base + slot * p.acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + c0, v);
+        if (!row_ok) continue;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int cl = c0 + g * 8;
-        const int n = n0 + cl;
-        if (cl >= p.BN || n >= p.N) break;           // N % 8 == 0 is required by the host wrapper
-        float f[8];
+        for (int g = 0; g < 4; ++g) {
+          const int cl = c0 + g * 8;
+          const int n = n0 + cl;
+          if (cl >= p.BN || n >= p.N) break;           // N % 8 == 0 is required by the host wrapper
+          float f[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
-        if (p.bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
-          const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + 4));
-          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-        }
-        if (p.act != MUMPY_ACT_NONE) {
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+          if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          if (p.act == MUMPY_ACT_GELU) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
-        }
-        if (p.residual) {
-          const float4 r0 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n);
-          const float4 r1 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n + 4);
-          f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-          f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-        }
-        if (p.out_bf16) {
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(f[2], f[3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]);
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(f[6], f[7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t *>(&h0);
-          u.y = *reinterpret_cast<uint32_t *>(&h1);
-          u.z = *reinterpret_cast<uint32_t *>(&h2);
-          u.w = *reinterpret_cast<uint32_t *>(&h3);
-          *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + gm * p.ldo + n) = u;
-        } else {
-          float *o = reinterpret_cast<float *>(p.out) + gm * p.ldo + n;
-          *reinterpret_cast<float4 *>(o) = make_float4(f[0], f[1], f[2], f[3]);
-          *reinterpret_cast<float4 *>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            for (int i = 0; i < 8; ++i) f[i] = gelu_fast(f[i]);
+          } else if (p.act != MUMPY_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
+          }
+          if (p.residual) {
+            const float4 r0 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n);
+            const float4 r1 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n + 4);
+            f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+            f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+          }
+          if (p.out_bf16) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(f[6], f[7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t *>(&h0);
+            u.y = *reinterpret_cast<uint32_t *>(&h1);
+            u.z = *reinterpret_cast<uint32_t *>(&h2);
+            u.w = *reinterpret_cast<uint32_t *>(&h3);
+            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + gm * p.ldo + n) = u;
+          } else {
+            float *o = reinterpret_cast<float *>(p.out) + gm * p.ldo + n;
+            *reinterpret_cast<float4 *>(o) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4 *>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          }
         }
       }
+      // this warp is done reading the accumulator: hand the TMEM slot back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty0 + 8 * slot);
     }
   }
 
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  if (warp == TC_EPI_WARPS + 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * p.acc_cols) : "memory");
   }
 }
 
@@ -286,7 +279,7 @@ static int pick_bn(long M, int N) {
   for (int c : cands) {                            // descending
     if (N % c != 0) continue;
     if (!largest) largest = c;
-    if (mt * (N / c) >= 2 * 148) return c;         // widest tile that still gives two CTAs per SM
+    if (mt * (N / c) >= g_num_sms) return c;       // widest tile that still gives every SM a tile
     if (c >= 64) smallest64 = c;
   }
   if (smallest64) return smallest64;               // small problem: favour parallelism, keep N >= 64
@@ -296,21 +289,53 @@ static int pick_bn(long M, int N) {
   return 16;
 }
 
-static bool g_attr_set = false;
+static bool g_attr_set[2] = {false, false};
+
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p, cudaStream_t st) {
+  uint32_t cols = 32;
+  while (cols < (uint32_t)p.BN) cols <<= 1;
+  p.acc_cols = cols;
+  p.idesc = make_idesc_bf16_f32(TC_BM, p.BN);
+  p.tiles_n = (int)cdiv(p.N, p.BN);
+  p.num_tiles = cdiv(p.M, TC_BM) * p.tiles_n;
+  const int stage_bytes = TC_BM * 128 + p.BN * 128;
+  const int nkb = p.conv ? p.K : (p.K + TC_BK - 1) / TC_BK;
+  int stages = TC_SMEM_BUDGET / stage_bytes;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  const long kb_per_cta = nkb * cdiv(p.num_tiles, g_num_sms);
+  if (stages > kb_per_cta) stages = (int)kb_per_cta;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const int smem = stages * stage_bytes + 1024;
+  const int which = p.conv ? 1 : 0;
+  if (!g_attr_set[which]) {
+    cudaError_t e = p.conv ? cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048)
+                           : cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+    g_attr_set[which] = true;
+  }
+  const unsigned grid = (unsigned)(p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms);
+  if (p.conv)
+    gemm_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+  else
+    gemm_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+  return launch_status("gemm_tc_kernel");
+}
 
 int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, long ldo,
                 long M, int N, int K, int out_dtype, int act, cudaStream_t st) {
-  if (!g_encode_tiled) {
-    int rc = resolve_driver_entry_points();
-    if (rc) return rc;
-  }
+  int rc = resolve_driver_entry_points();
+  if (rc) return rc;
   MUMPY_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0, "linear(bf16): N, K, lda must be multiples of 8 (N=%d K=%d lda=%ld)", N, K, lda);
   MUMPY_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "linear(bf16): A, W, out must be 16-byte aligned");
   MUMPY_REQUIRE(out_dtype == MUMPY_BF16 ? (ldo % 8 == 0) : (ldo % 4 == 0), "linear(bf16): ldo alignment");
   MUMPY_REQUIRE(M < (1l << 31), "linear(bf16): M too large");
-  TcParams p;
+  TcParams p = {};
   p.bias = bias;
   p.residual = residual;
   p.out = out;
@@ -321,34 +346,63 @@ int linear_bf16(const void *A, long lda, const void *W, const float *bias, const
   p.BN = pick_bn(M, N);
   p.act = act;
   p.out_bf16 = (out_dtype == MUMPY_BF16);
-  uint32_t cols = 32;
-  while (cols < (uint32_t)p.BN) cols <<= 1;
-  p.tmem_cols = cols;
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.BN >> 3) << 17) | (static_cast<uint32_t>(TC_BM >> 4) << 24);
-  const int stage_bytes = TC_BM * 128 + p.BN * 128;
-  const int nkb = (K + TC_BK - 1) / TC_BK;
-  int stages = (100 * 1024) / stage_bytes;           // ~100 KB of tiles -> two CTAs per SM
-  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  if (stages > nkb) stages = nkb;
-  if (stages < 1) stages = 1;
-  p.stages = stages;
-  const int smem = stages * stage_bytes + 1024;
-  if (!g_attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
-      return MUMPY_ERR_CUDA;
-    }
-    g_attr_set = true;
-  }
+  p.conv = 0;
   CUtensorMap tmA, tmB;
-  int rc = encode_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TC_BK, TC_BM);
+  rc = encode_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TC_BK, TC_BM);
   if (rc) return rc;
   rc = encode_2d_bf16(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K, TC_BK, (uint32_t)p.BN);
   if (rc) return rc;
-  dim3 grid((unsigned)cdiv(N, p.BN), (unsigned)cdiv(M, TC_BM));
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
-  return launch_status("gemm_tc_kernel");
+  return launch_tc(tmA, tmB, p, st);
+}
+
+// Implicit-GEMM convolution (stride 1): in (B,H,W,Cin) bf16 NHWC with pixel stride ld_in elements; wpk (Cout, taps*cblocks*64)
+// bf16 with K order (ky,kx,c) and every tap's channels zero padded to a multiple of 64; out (B*H*W, Cout).
+int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, const float *residual, void *out, long ldo, int B,
+              int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int out_dtype, int act, cudaStream_t st) {
+  int rc = resolve_driver_entry_points();
+  if (rc) return rc;
+  MUMPY_REQUIRE(Cout % 8 == 0 && ld_in % 8 == 0, "conv(bf16): Cout and ld_in must be multiples of 8");
+  MUMPY_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpk) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "conv(bf16): in, w, out must be 16-byte aligned");
+  MUMPY_REQUIRE(2 * ph == kh - 1 && 2 * pw == kw - 1, "conv(bf16): only 'same' stride-1 convolutions");
+  const int cblocks = (Cin + TC_BK - 1) / TC_BK;
+  TcParams p = {};
+  p.bias = bias;
+  p.residual = residual;
+  p.out = out;
+  p.ldo = ldo;
+  p.M = (long)B * H * W;
+  p.N = Cout;
+  p.K = kh * kw * cblocks;          // k-blocks
+  p.BN = pick_bn(p.M, Cout);
+  p.act = act;
+  p.out_bf16 = (out_dtype == MUMPY_BF16);
+  p.conv = 1;
+  p.Wout = W;
+  p.Hout = H;
+  p.lower_w = -pw;
+  p.lower_h = -ph;
+  p.kw = kw;
+  p.cblocks = cblocks;
+  CUtensorMap tmA, tmB;
+  cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld_in * 2, (cuuint64_t)ld_in * 2 * W, (cuuint64_t)ld_in * 2 * W * H};
+  int lower[2] = {-pw, -ph};
+  int upper[2] = {pw - (kw - 1), ph - (kh - 1)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(in), gdim, gstr, lower, upper, TC_BK, TC_BM,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed (%d): B=%d H=%d W=%d Cin=%d ld=%ld k=%dx%d", (int)r, B, H, W, Cin, ld_in, kh, kw);
+    return MUMPY_ERR_CUDA;
+  }
+  // same workaround CUTLASS applies (copy_traits_sm90_im2col.hpp) for small tensors on drivers <= 13.1
+  if (g_driver_version <= 13010 && (size_t)B * H * W * ld_in * 2 < 131072) reinterpret_cast<uint64_t *>(&tmA)[1] &= ~(1ull << 21);
+  rc = encode_2d_bf16(&tmB, wpk, (uint64_t)p.K * TC_BK, (uint64_t)Cout, (uint64_t)p.K * TC_BK, TC_BK, (uint32_t)p.BN);
+  if (rc) return rc;
+  return launch_tc(tmA, tmB, p, st);
 }
 
 }  // namespace mumpy

@@ -17,6 +17,21 @@ def _conv(owner, name, conv, x, B, H, W, ld_in=None):
     Cout, Cin, kh, kw = conv.weight.shape
     ph, pw = conv.padding
     K = kh * kw * Cin
+    if Cout == 1 and Cin % 4 == 0 and ld_in in (None, Cin):
+        w = owner._packed("hwi:" + name, [conv.weight], lambda: conv.weight.detach().permute(0, 2, 3, 1).contiguous())
+        return ops.conv2d_nhwc_cout1(x, w, conv.bias, B, H, W, Cin, kh, kw, ph, pw)
+    if ops.precision() == "bf16" and Cout % 8 == 0 and Cin % 8 == 0 and (ld_in or Cin) % 8 == 0:
+        # implicit GEMM on the tensor cores: im2col-mode TMA feeds tcgen05 directly (no im2col buffer)
+        cb = (Cin + 63) // 64
+
+        def make_tc():
+            w = conv.weight.detach().permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin)
+            wp = w.new_zeros(Cout, kh * kw, cb * 64)
+            wp[:, :, :Cin] = w
+            return ops.cast_bf16(wp.reshape(Cout, -1).contiguous())
+        wq = owner._packed("tcconv:" + name, [conv.weight], make_tc)
+        xb = x if x.dtype == torch.bfloat16 else ops.cast_bf16(x)
+        return ops.conv2d_nhwc_bf16(xb, wq, conv.bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in)
     if ops.precision() == "bf16" and Cout % 8 == 0:
         Kpad = (K + 7) // 8 * 8
 

@@ -202,6 +202,24 @@ def conv2d_nhwc(x, w_ohwi, bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in=None,
     return out
 
 
+def conv2d_nhwc_bf16(x, w_packed, bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in=None, act=ACT_NONE, out_dtype=torch.float32,
+                     residual=None):
+    """Tensor-core implicit GEMM: x (B,H,W,Cin[ld_in]) bf16 NHWC, w_packed (Cout, kh*kw*ceil(Cin/64)*64) bf16."""
+    out = torch.empty((B, H, W, Cout), dtype=out_dtype, device=x.device)
+    lib, st = _prep(x, w_packed, bias, residual, out)
+    _lib.check(lib.mumpy_conv2d_nhwc_bf16(_p(x), ld_in or Cin, _p(w_packed), _p(bias), _p(residual), _p(out), Cout, B, H, W, Cin,
+                                          Cout, kh, kw, ph, pw, code(out_dtype), act, st), "mumpy_conv2d_nhwc_bf16")
+    return out
+
+
+def conv2d_nhwc_cout1(x, w_hwi, bias, B, H, W, Cin, kh, kw, ph, pw):
+    out = torch.empty((B, H, W, 1), dtype=torch.float32, device=x.device)
+    lib, st = _prep(x, w_hwi, bias, out)
+    _lib.check(lib.mumpy_conv2d_nhwc_cout1(_p(x), _p(w_hwi), _p(bias), _p(out), B, H, W, Cin, kh, kw, ph, pw, st),
+               "mumpy_conv2d_nhwc_cout1")
+    return out
+
+
 def im2col_nhwc(x, B, H, W, Cin, kh, kw, ph, pw, Kpad, ld_in=None):
     out = torch.empty((B * H * W, Kpad), dtype=torch.bfloat16, device=x.device)
     lib, st = _prep(x, out)

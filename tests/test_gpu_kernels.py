@@ -1,0 +1,104 @@
+"""GPU: individual bf16-mode kernels through the C ABI against the oracle on bf16-rounded operands."""
+import pytest
+import torch
+
+from oracle import mumpy_oracle as orc
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import mumpy_b200
+    return mumpy_b200.ops
+
+
+def _pack_conv(w, Cin):
+    Cout, _, kh, kw = w.shape
+    cb = (Cin + 63) // 64
+    wp = torch.zeros(Cout, kh * kw, cb * 64)
+    wp[:, :, :Cin] = w.permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin)
+    return wp.reshape(Cout, -1).bfloat16().contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kh,kw", [
+    (1, 7, 7, 256, 128, 3, 3),        # < 128 KB tensor (driver work-around path)
+    (2, 14, 14, 32, 128, 3, 3),       # Cin < 64: channel block zero-filled by TMA
+    (2, 28, 28, 768, 256, 3, 3),      # seb3
+    (2, 56, 56, 256, 128, 7, 1),      # gcm4 conv_l1
+    (2, 56, 56, 128, 128, 1, 7),      # gcm4 conv_l2
+    (1, 7, 7, 2560, 128, 7, 1),       # gcm1
+    (3, 112, 112, 128, 128, 3, 3),    # decoder_5, M tail across image borders
+    (5, 7, 7, 128, 64, 3, 3),         # 245 pixels: tiles straddle images
+])
+def test_conv_implicit_gemm_tcgen05(B, H, W, Cin, Cout, kh, kw):
+    ops = _ops()
+    x = util.seeded_input((B, Cin, H, W), 1).bfloat16()
+    w = (util.seeded_input((Cout, Cin, kh, kw), 2) / (Cin * kh * kw) ** 0.5).bfloat16()
+    bias = util.seeded_input((Cout,), 3)
+    ref = orc.conv2d(x.float(), w.float(), bias, ((kh - 1) // 2, (kw - 1) // 2)).permute(0, 2, 3, 1)
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+    out = ops.conv2d_nhwc_bf16(xn, _pack_conv(w.float(), Cin).cuda(), bias.cuda(), B, H, W, Cin, Cout, kh, kw, (kh - 1) // 2, (kw - 1) // 2)
+    assert util.maxabs(out, ref) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_conv_reads_channel_slice_of_wider_map():
+    ops = _ops()
+    B, H, W, Cin, ld, Cout = 2, 14, 14, 64, 192, 32
+    x = util.seeded_input((B, H, W, ld), 1).bfloat16()
+    w = (util.seeded_input((Cout, Cin, 3, 3), 2) / (Cin * 9) ** 0.5).bfloat16()
+    ref = orc.conv2d(x[..., :Cin].float().permute(0, 3, 1, 2), w.float(), None, (1, 1)).permute(0, 2, 3, 1)
+    out = ops.conv2d_nhwc_bf16(x.cuda(), _pack_conv(w.float(), Cin).cuda(), None, B, H, W, Cin, Cout, 3, 3, 1, 1, ld_in=ld)
+    assert util.maxabs(out, ref) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_conv_cout1():
+    ops = _ops()
+    x = util.seeded_input((2, 32, 24, 20), 1)
+    w = util.seeded_input((1, 32, 3, 3), 2) / 17.0
+    b = util.seeded_input((1,), 3)
+    ref = orc.conv2d(x, w, b, (1, 1))
+    out = ops.conv2d_nhwc_cout1(x.permute(0, 2, 3, 1).contiguous().cuda(), w.permute(0, 2, 3, 1).contiguous().cuda(), b.cuda(), 2, 24, 20, 32, 3, 3, 1, 1)
+    assert util.maxabs(out.view(2, 1, 24, 20), ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,H,C,heads,shift", [(2, 3, 14, 64, 2, 3), (2, 1, 14, 96, 3, 0), (1, 3, 7, 128, 4, 0), (3, 3, 28, 128, 4, 3)])
+def test_window_attention_tensor_pipe(B, T, H, C, heads, shift):
+    """bf16 qkv -> mma.sync kernel vs the oracle's attention on the same bf16-rounded qkv (P is rounded to bf16
+    before PV inside the kernel: tolerance 1e-2 on O(1) outputs)."""
+    ops = _ops()
+    TH, W, ws, N = T * H, H, 7, 49
+    qkv = util.seeded_input((B, TH * W, 3 * C), 1).bfloat16()
+    table = 0.5 * util.seeded_input((169, heads), 2)
+    bias = orc.relative_position_bias(table, ws)
+    mask = orc.shifted_window_mask(TH, W, ws, shift) if shift else None
+    x = qkv.float().view(B, TH, W, 3 * C)
+    if shift:
+        x = torch.roll(x, (-shift, -shift), (1, 2))
+    xw = orc.window_partition(x, ws)
+    Bn = xw.shape[0]
+    q, k, v = xw.reshape(Bn, N, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    attn = (q * 32 ** -0.5) @ k.transpose(-2, -1) + bias.unsqueeze(0)
+    if mask is not None:
+        nW = mask.shape[0]
+        attn = (attn.view(Bn // nW, nW, heads, N, N) + mask.view(1, nW, 1, N, N)).view(Bn, heads, N, N)
+    o = (torch.softmax(attn, -1) @ v).transpose(1, 2).reshape(Bn, N, C)
+    o = orc.window_reverse(o, ws, TH, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    out = ops.window_attention(qkv.cuda(), bias.cuda(), None if mask is None else mask.cuda(), B, TH, W, C, heads, ws, shift)
+    assert out.dtype == torch.bfloat16
+    assert util.maxabs(out.float(), o.reshape(B, TH * W, C)) < 2e-2
+
+
+def test_fast_gelu_epilogue_accuracy():
+    """bf16-mode GEMM epilogue GELU (log2-erfc polynomial) vs exact erf GELU, fp32 output."""
+    ops = _ops()
+    M, N, K = 256, 128, 64
+    a = torch.zeros(M, K)
+    a[:, 0] = torch.linspace(-8, 8, M)
+    w = torch.zeros(N, K)
+    w[:, 0] = torch.linspace(0.5, 1.0, N)
+    ref = orc.gelu(a.bfloat16().float() @ w.bfloat16().float().t())
+    out = ops.linear(a.bfloat16().cuda(), w.bfloat16().cuda(), act=ops.ACT_GELU)
+    assert util.maxabs(out, ref) < 2e-6
