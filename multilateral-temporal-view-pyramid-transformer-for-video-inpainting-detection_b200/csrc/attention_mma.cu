@@ -36,14 +36,29 @@ constexpr int ATT_WARPS = 4;
 
 // scores for 16 query rows (m-tile mt) against NT n-tiles of keys, then softmax -> un-normalised probabilities in s,
 // returns the two row sums (rows g and g+8 of the m-tile) through sum_lo / sum_hi.
-template <int NT>
-__device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt, int lane, int N, float scale, const float *__restrict__ bias_h,
+// The relative-position bias and the shift mask are loaded (branch-free, clamped indices, all loads in flight before
+// the MMAs) straight into the accumulators as (bias + mask) / scale, so that scale * acc = scale * q.k + bias + mask.
+template <int N>
+__device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt, int lane, float scale, const float *__restrict__ bias_h,
                                                const float *__restrict__ mask_w, float (&s)[8][4], float &sum_lo, float &sum_hi) {
+  constexpr int NT = (N + 7) / 8;
   const int g = lane >> 2, t = lane & 3;
+  const int i_lo = min(mt * 16 + g, N - 1), i_hi = min(mt * 16 + g + 8, N - 1);
+  const float inv_scale = 1.0f / scale;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s[nt][i] = 0.0f;
+    for (int e = 0; e < 4; ++e) {
+      float v = 0.0f;
+      if (nt < NT && bias_h) {
+        const int j = min(nt * 8 + 2 * t + (e & 1), N - 1);
+        const int idx = ((e < 2) ? i_lo : i_hi) * N + j;
+        v = __ldg(bias_h + idx);
+        if (mask_w) v += __ldg(mask_w + idx);
+        v *= inv_scale;
+      }
+      s[nt][e] = v;
+    }
   uint32_t a[2][4];
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
@@ -57,22 +72,13 @@ __device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt,
     mma_bf16(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
     mma_bf16(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], b2, b3);
   }
-  const int i_lo = mt * 16 + g, i_hi = i_lo + 8;
   float m_lo = -INFINITY, m_hi = -INFINITY;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int i = (e < 2) ? i_lo : i_hi;
       const int j = nt * 8 + 2 * t + (e & 1);
-      float v = -INFINITY;
-      if (j < N) {
-        v = s[nt][e] * scale;
-        if (i < N) {
-          if (bias_h) v += bias_h[i * N + j];
-          if (mask_w) v += mask_w[i * N + j];
-        }
-      }
+      const float v = (j < N) ? s[nt][e] * scale : -INFINITY;       // only the last n-tile can be out of range
       s[nt][e] = v;
       if (e < 2) m_lo = fmaxf(m_lo, v); else m_hi = fmaxf(m_hi, v);
     }
@@ -117,47 +123,68 @@ __device__ __forceinline__ void pv_accumulate(uint32_t sV, int lane, const float
   }
 }
 
-// gathers `N` rows of 32 bf16 (64 B) into a swizzled tile; rows >= N are zero
-template <typename RowPtr>
-__device__ __forceinline__ void load_tile_bf16(uint8_t *tile, int lane, int N, RowPtr row_ptr) {
-#pragma unroll
-  for (int pass = 0; pass < 8; ++pass) {
-    const int p = pass * 8 + (lane >> 2);
-    const int chunk = lane & 3;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (p < N) v = *reinterpret_cast<const uint4 *>(row_ptr(p) + chunk * 8);
-    *reinterpret_cast<uint4 *>(tile + tile_off(p, chunk)) = v;
-  }
+// canvas row of token p of window n for a compile-time window size (divisions by constants)
+template <int WS>
+__device__ __forceinline__ int token_row(int wr, int wc, int p, int TH, int W, int shift) {
+  int r = wr * WS + p / WS + shift;
+  int c = wc * WS + p % WS + shift;
+  if (r >= TH) r -= TH;
+  if (c >= W) c -= W;
+  return r * W + c;
 }
 
-template <int NT>
+constexpr int ATT_WARP_SMEM = 3 * ATT_TILE_BYTES + 64 * sizeof(long);
+
+template <int WS>
 __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_mma_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ bias,
                                                                               const float *__restrict__ mask, __nv_bfloat16 *__restrict__ out,
-                                                                              int TH, int W, int C, int heads, int ws, int shift, long n_tasks) {
+                                                                              int TH, int W, int C, int heads, int shift, long n_tasks) {
+  constexpr int N = WS * WS;
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long task = (long)blockIdx.x * ATT_WARPS + warp;
   if (task >= n_tasks) return;
-  const int N = ws * ws;
-  const int nW = (TH / ws) * (W / ws);
+  const int wpr = W / WS;
+  const int nW = (TH / WS) * wpr;
   const long win = task / heads;
-  const int h = (int)(task % heads);
+  const int h = (int)(task - win * heads);
   const long b = win / nW;
-  const int n = (int)(win % nW);
+  const int n = (int)(win - b * nW);
+  const int wr = n / wpr, wc = n - wr * wpr;
   const long L = (long)TH * W;
-  uint8_t *tq = att_smem + warp * 3 * ATT_TILE_BYTES, *tk = tq + ATT_TILE_BYTES, *tv = tk + ATT_TILE_BYTES;
-  const __nv_bfloat16 *base = qkv + (b * L) * 3 * C + h * 32;
-  load_tile_bf16(tq, lane, N, [&](int p) { return base + (long)window_token_row(n, p, TH, W, ws, shift) * 3 * C; });
-  load_tile_bf16(tk, lane, N, [&](int p) { return base + (long)window_token_row(n, p, TH, W, ws, shift) * 3 * C + C; });
-  load_tile_bf16(tv, lane, N, [&](int p) { return base + (long)window_token_row(n, p, TH, W, ws, shift) * 3 * C + 2 * C; });
+  uint8_t *tq = att_smem + warp * ATT_WARP_SMEM, *tk = tq + ATT_TILE_BYTES, *tv = tk + ATT_TILE_BYTES;
+  long *rows = reinterpret_cast<long *>(tv + ATT_TILE_BYTES);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int p = lane + 32 * u;
+    if (p < N) rows[p] = b * L + token_row<WS>(wr, wc, p, TH, W, shift);
+  }
+  __syncwarp();
+  // rows[] holds canvas token indices; qkv rows are 3C wide, out rows C wide
+  {
+    const __nv_bfloat16 *base = qkv + h * 32;
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+      uint8_t *tile = which == 0 ? tq : (which == 1 ? tk : tv);
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int p = pass * 8 + (lane >> 2);
+        const int chunk = lane & 3;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (p < N) v = __ldg(reinterpret_cast<const uint4 *>(base + rows[p] * 3 * C + which * C + chunk * 8));
+        *reinterpret_cast<uint4 *>(tile + tile_off(p, chunk)) = v;
+      }
+    }
+  }
   __syncwarp();
   const uint32_t sQ = smem_addr(tq), sK = smem_addr(tk), sV = smem_addr(tv);
   const float *bias_h = bias + (long)h * N * N;
   const float *mask_w = mask ? mask + (long)n * N * N : nullptr;
   const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
   for (int mt = 0; mt * 16 < N; ++mt) {
     float s[8][4], sum_lo, sum_hi;
-    scores_softmax<NT>(sQ, sK, mt, lane, N, 0.17677669529663687f, bias_h, mask_w, s, sum_lo, sum_hi);
+    scores_softmax<N>(sQ, sK, mt, lane, 0.17677669529663687f, bias_h, mask_w, s, sum_lo, sum_hi);
     float o[4][4];
 #pragma unroll
     for (int dn = 0; dn < 4; ++dn)
@@ -166,12 +193,12 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_mma_kernel(co
     pv_accumulate(sV, lane, s, 1.0f / sum_lo, 1.0f / sum_hi, o);
     const int i_lo = mt * 16 + g, i_hi = i_lo + 8;
     if (i_lo < N) {
-      __nv_bfloat16 *dst = out + (b * L + window_token_row(n, i_lo, TH, W, ws, shift)) * C + h * 32 + 2 * t;
+      __nv_bfloat16 *dst = out + rows[i_lo] * C + h * 32 + 2 * t;
 #pragma unroll
       for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][0], o[dn][1]);
     }
     if (i_hi < N) {
-      __nv_bfloat16 *dst = out + (b * L + window_token_row(n, i_hi, TH, W, ws, shift)) * C + h * 32 + 2 * t;
+      __nv_bfloat16 *dst = out + rows[i_hi] * C + h * 32 + 2 * t;
 #pragma unroll
       for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][2], o[dn][3]);
     }
@@ -186,20 +213,22 @@ __device__ __forceinline__ int cva_query_window_m(int j, int r, int N1, int nW1,
 }
 
 // deformable cross-view attention core: o[i] = sum_t softmax(q[qidx(r i + t)] k[r i + t]^T * d^-1/2) v[r i + t]
-template <int NT>
+template <int WS>
 __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const float *__restrict__ q, const __nv_bfloat16 *__restrict__ kv,
                                                                            __nv_bfloat16 *__restrict__ o_out, int N1, int TH1, int W, int C,
-                                                                           int heads, int ws, int r, int per_clip, long n_tasks) {
+                                                                           int heads, int r, int per_clip, long n_tasks) {
+  constexpr int N = WS * WS;
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long task = (long)blockIdx.x * ATT_WARPS + warp;
   if (task >= n_tasks) return;
-  const int N = ws * ws;
-  const int nW1 = (TH1 / ws) * (W / ws);
+  const int wpr = W / WS;
+  const int nW1 = (TH1 / WS) * wpr;
   const int i = (int)(task / heads);
-  const int h = (int)(task % heads);
+  const int h = (int)(task - (long)i * heads);
   const long L1 = (long)TH1 * W;
-  uint8_t *tq = att_smem + warp * 3 * ATT_TILE_BYTES, *tk = tq + ATT_TILE_BYTES, *tv = tk + ATT_TILE_BYTES;
+  uint8_t *tq = att_smem + warp * ATT_WARP_SMEM, *tk = tq + ATT_TILE_BYTES, *tv = tk + ATT_TILE_BYTES;
+  long *rows = reinterpret_cast<long *>(tv + ATT_TILE_BYTES);
   const uint32_t sQ = smem_addr(tq), sK = smem_addr(tk), sV = smem_addr(tv);
   const int g = lane >> 2, t4 = lane & 3;
   float o[4][4][4];                       // [m-tile][d n-tile][frag]
@@ -213,7 +242,14 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const
     const int j = r * i + t;
     const int qw = cva_query_window_m(j, r, N1, nW1, per_clip);
     const long qb = qw / nW1;
-    const int qn = qw % nW1;
+    const int qn = qw - (int)qb * nW1;
+    const int wr = qn / wpr, wc = qn - wr * wpr;
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int p = lane + 32 * u;
+      if (p < N) rows[p] = qb * L1 + token_row<WS>(wr, wc, p, TH1, W, 0);
+    }
     __syncwarp();
     // q: fp32 canvas rows -> bf16 tile
 #pragma unroll
@@ -222,21 +258,31 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const
       const int chunk = lane & 3;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (p < N) {
-        const float *src = q + (qb * L1 + window_token_row(qn, p, TH1, W, ws, 0)) * C + h * 32 + chunk * 8;
-        const float4 f0 = *reinterpret_cast<const float4 *>(src), f1 = *reinterpret_cast<const float4 *>(src + 4);
+        const float *src = q + rows[p] * C + h * 32 + chunk * 8;
+        const float4 f0 = __ldg(reinterpret_cast<const float4 *>(src)), f1 = __ldg(reinterpret_cast<const float4 *>(src + 4));
         v.x = pack_bf16(f0.x, f0.y); v.y = pack_bf16(f0.z, f0.w); v.z = pack_bf16(f1.x, f1.y); v.w = pack_bf16(f1.z, f1.w);
       }
       *reinterpret_cast<uint4 *>(tq + tile_off(p, chunk)) = v;
     }
     const __nv_bfloat16 *kvb = kv + ((long)j * N) * 2 * C + h * 32;
-    load_tile_bf16(tk, lane, N, [&](int p) { return kvb + (long)p * 2 * C; });
-    load_tile_bf16(tv, lane, N, [&](int p) { return kvb + (long)p * 2 * C + C; });
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint8_t *tile = which == 0 ? tk : tv;
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int p = pass * 8 + (lane >> 2);
+        const int chunk = lane & 3;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (p < N) v = __ldg(reinterpret_cast<const uint4 *>(kvb + (long)p * 2 * C + which * C + chunk * 8));
+        *reinterpret_cast<uint4 *>(tile + tile_off(p, chunk)) = v;
+      }
+    }
     __syncwarp();
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
       if (mt * 16 < N) {
         float s[8][4], sum_lo, sum_hi;
-        scores_softmax<NT>(sQ, sK, mt, lane, N, 0.17677669529663687f, nullptr, nullptr, s, sum_lo, sum_hi);
+        scores_softmax<N>(sQ, sK, mt, lane, 0.17677669529663687f, nullptr, nullptr, s, sum_lo, sum_hi);
         pv_accumulate(sV, lane, s, 1.0f / sum_lo, 1.0f / sum_hi, o[mt]);
       }
     }
@@ -257,18 +303,37 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const
   }
 }
 
+template <typename K>
+static int att_smem_attr(K kernel) {
+  static bool done = false;
+  if (done) return MUMPY_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_WARPS * ATT_WARP_SMEM);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
+    return MUMPY_ERR_CUDA;
+  }
+  done = true;
+  return MUMPY_OK;
+}
+
 int window_attention_mma(const void *qkv, const float *bias, const float *mask, void *out, int B, int TH, int W, int C, int heads,
                          int ws, int shift, cudaStream_t st) {
   const long n_tasks = (long)B * (TH / ws) * (W / ws) * heads;
   const unsigned grid = (unsigned)cdiv(n_tasks, ATT_WARPS);
-  const size_t smem = ATT_WARPS * 3 * ATT_TILE_BYTES;
-  const int N = ws * ws;
-  if (N <= 56)
+  const size_t smem = ATT_WARPS * ATT_WARP_SMEM;
+  int rc;
+  if (ws == 7) {
+    if ((rc = att_smem_attr(window_attention_mma_kernel<7>))) return rc;
     window_attention_mma_kernel<7><<<grid, ATT_WARPS * 32, smem, st>>>(static_cast<const __nv_bfloat16 *>(qkv), bias, mask,
-                                                                      static_cast<__nv_bfloat16 *>(out), TH, W, C, heads, ws, shift, n_tasks);
-  else
+                                                                      static_cast<__nv_bfloat16 *>(out), TH, W, C, heads, shift, n_tasks);
+  } else if (ws == 8) {
+    if ((rc = att_smem_attr(window_attention_mma_kernel<8>))) return rc;
     window_attention_mma_kernel<8><<<grid, ATT_WARPS * 32, smem, st>>>(static_cast<const __nv_bfloat16 *>(qkv), bias, mask,
-                                                                      static_cast<__nv_bfloat16 *>(out), TH, W, C, heads, ws, shift, n_tasks);
+                                                                      static_cast<__nv_bfloat16 *>(out), TH, W, C, heads, shift, n_tasks);
+  } else {
+    set_error("window_attention(bf16): window size %d unsupported (7 or 8)", ws);
+    return MUMPY_ERR_UNSUPPORTED;
+  }
   return launch_status("window_attention_mma");
 }
 
@@ -277,15 +342,21 @@ int cva_attention_mma(const float *q, const void *kv, void *o, int B, int TH1, i
   const int N1 = B * (TH1 / ws) * (W / ws);
   const long n_tasks = (long)N1 * heads;
   const unsigned grid = (unsigned)cdiv(n_tasks, ATT_WARPS);
-  const size_t smem = ATT_WARPS * 3 * ATT_TILE_BYTES;
-  const int N = ws * ws;
+  const size_t smem = ATT_WARPS * ATT_WARP_SMEM;
   const int r = TH2 / TH1;
-  if (N <= 56)
+  int rc;
+  if (ws == 7) {
+    if ((rc = att_smem_attr(cva_attention_mma_kernel<7>))) return rc;
     cva_attention_mma_kernel<7><<<grid, ATT_WARPS * 32, smem, st>>>(q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1,
-                                                                   TH1, W, C, heads, ws, r, per_clip, n_tasks);
-  else
+                                                                   TH1, W, C, heads, r, per_clip, n_tasks);
+  } else if (ws == 8) {
+    if ((rc = att_smem_attr(cva_attention_mma_kernel<8>))) return rc;
     cva_attention_mma_kernel<8><<<grid, ATT_WARPS * 32, smem, st>>>(q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1,
-                                                                   TH1, W, C, heads, ws, r, per_clip, n_tasks);
+                                                                   TH1, W, C, heads, r, per_clip, n_tasks);
+  } else {
+    set_error("cva_attention(bf16): window size %d unsupported (7 or 8)", ws);
+    return MUMPY_ERR_UNSUPPORTED;
+  }
   return launch_status("cva_attention_mma");
 }
 
