@@ -12,6 +12,8 @@
 //               w/4), fused bias / GELU / ReLU / fp32 residual, 16-byte stores, fp32 or bf16 output.
 // Workhorse of the bf16 mode: qkv / proj / fc1 / fc2 / pre / proj_{q,k,v,out} / reduction / globalembedding /
 // global blocks / rgb_decoder linears and every decoder convolution (94% + 11% of the forward's FLOPs).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace mumpy {
@@ -56,7 +58,7 @@ constexpr int TC_BK = 64;       // 64 bf16 = 128 B = one swizzle span
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
-constexpr int TC_SMEM_BUDGET = 196 * 1024;
+constexpr int TC_SMEM_BUDGET = 164 * 1024;      // operand ring; + 8 x 4 KB epilogue staging + 1 KB alignment slack
 
 struct TcParams {
   const float *bias;
@@ -74,9 +76,97 @@ struct TcParams {
   uint32_t acc_cols;      // TMEM columns per accumulator slot (power of two >= BN)
   uint32_t idesc;
   // conv mode (A through the im2col tensor map)
+  int debug;
   int conv;
   int Wout, Hout, lower_w, lower_h, kw, cblocks;
 };
+
+constexpr int EPI_STAGE_BYTES = 32 * 128;      // per-warp staging tile: 32 rows x 32 fp32, 16-byte chunks XOR-swizzled by row&7
+
+// Epilogue of one 128 x BN accumulator tile for one warp (lane quadrant warp&3, column half warp>>2).
+// Phase 1 (thread <-> accumulator row): tcgen05.ld of 32 columns, + bias, activation, into the swizzled staging tile.
+// Phase 2 (coalesced): the warp re-reads the tile row-wise so that every global access is a full 128 B (fp32) or 64 B
+// (bf16) row segment: residual loads, fp32->bf16 packing and the output stores are all coalesced.
+template <int ACT, bool OUT_BF16, bool HAS_RES>
+__device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage, uint32_t acc, int warp, int lane, long m0, int n0) {
+  const int quad = warp & 3, half = warp >> 2;
+  const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
+  const long row0 = m0 + quad * 32;
+  const uint32_t st_base = smem_u32(stage);
+  for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+    uint32_t v[32];
+    tmem_ld32(lane_addr + c0, v);
+    if (p.debug == 2) continue;
+    const int nb = n0 + c0;
+    // ---- phase 1 ----
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float4 f = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+      if (p.bias && nb + 4 * g < p.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + nb + 4 * g));
+        f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
+      }
+      if (ACT == 1) {
+        f.x = gelu_fast(f.x); f.y = gelu_fast(f.y); f.z = gelu_fast(f.z); f.w = gelu_fast(f.w);
+      } else if (ACT == 2) {
+        f.x = apply_act(f.x, p.act); f.y = apply_act(f.y, p.act); f.z = apply_act(f.z, p.act); f.w = apply_act(f.w, p.act);
+      }
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + lane * 128 + ((g ^ (lane & 7)) << 4)), "f"(f.x), "f"(f.y),
+                   "f"(f.z), "f"(f.w)
+                   : "memory");
+    }
+    __syncwarp();
+    // ---- phase 2 ----
+    if (p.debug != 1) {
+      if (OUT_BF16) {
+        const int c8 = lane & 3;                 // 8 columns (16 B of bf16) per lane, 4 lanes per row, 8 rows per pass
+        const int col = c0 + c8 * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + (lane >> 2);
+          const long gm = row0 + r;
+          float4 x, y;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st_base + r * 128 + (((2 * c8) ^ (r & 7)) << 4)));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(st_base + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4)));
+          if (gm < p.M && col < p.BN && n0 + col < p.N) {
+            if (HAS_RES) {
+              const float4 r0 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n0 + col);
+              const float4 r1 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n0 + col + 4);
+              x.x += r0.x; x.y += r0.y; x.z += r0.z; x.w += r0.w;
+              y.x += r1.x; y.y += r1.y; y.z += r1.z; y.w += r1.w;
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(y.x, y.y), h3 = __floats2bfloat162_rn(y.z, y.w);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t *>(&h0);
+            u.y = *reinterpret_cast<uint32_t *>(&h1);
+            u.z = *reinterpret_cast<uint32_t *>(&h2);
+            u.w = *reinterpret_cast<uint32_t *>(&h3);
+            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + gm * p.ldo + n0 + col) = u;
+          }
+        }
+      } else {
+        const int c4 = lane & 7;                 // 4 columns (16 B of fp32) per lane, 8 lanes per row, 4 rows per pass
+        const int col = c0 + c4 * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          const long gm = row0 + r;
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st_base + r * 128 + ((c4 ^ (r & 7)) << 4)));
+          if (gm < p.M && col < p.BN && n0 + col < p.N) {
+            if (HAS_RES) {
+              const float4 r0 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n0 + col);
+              x.x += r0.x; x.y += r0.y; x.z += r0.z; x.w += r0.w;
+            }
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + gm * p.ldo + n0 + col) = x;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
 
 template <bool kConv>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -180,8 +270,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
     }
   } else {
-    // ---------------- epilogue: thread <-> accumulator row, 32 columns per tcgen05.ld ----------------
-    const int quad = warp & 3, half = warp >> 2;
+    // ---------------- epilogue ----------------
+    uint8_t *stage = smem_raw + (tiles - raw) + p.stages * stage_bytes + warp * EPI_STAGE_BYTES;
+    const int mode = (p.act == MUMPY_ACT_GELU ? 1 : (p.act == MUMPY_ACT_NONE ? 0 : 2)) | (p.out_bf16 ? 4 : 0) | (p.residual ? 8 : 0);
     uint32_t t = 0;
     for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
       const uint32_t slot = t & 1, aph = (t >> 1) & 1;
@@ -189,57 +280,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const long m0 = (tile / p.tiles_n) * TC_BM;
       mbar_wait(acc_full0 + 8 * slot, aph);
       tc_fence_after();
-      const long gm = m0 + quad * 32 + lane;
-      const bool row_ok = gm < p.M;
-      const uint32_t lane_addr = tmem_base + slot * p.acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
-      for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + c0, v);
-        if (!row_ok) continue;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int cl = c0 + g * 8;
-          const int n = n0 + cl;
-          if (cl >= p.BN || n >= p.N) break;           // N % 8 == 0 is required by the host wrapper
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
-          if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + 4));
-            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-          }
-          if (p.act == MUMPY_ACT_GELU) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = gelu_fast(f[i]);
-          } else if (p.act != MUMPY_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
-          }
-          if (p.residual) {
-            const float4 r0 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n);
-            const float4 r1 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n + 4);
-            f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-            f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-          }
-          if (p.out_bf16) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[2], f[3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(f[6], f[7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t *>(&h0);
-            u.y = *reinterpret_cast<uint32_t *>(&h1);
-            u.z = *reinterpret_cast<uint32_t *>(&h2);
-            u.w = *reinterpret_cast<uint32_t *>(&h3);
-            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + gm * p.ldo + n) = u;
-          } else {
-            float *o = reinterpret_cast<float *>(p.out) + gm * p.ldo + n;
-            *reinterpret_cast<float4 *>(o) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4 *>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-          }
-        }
+      const uint32_t acc = tmem_base + slot * p.acc_cols;
+      switch (mode) {
+        case 0: epilogue_tile<0, false, false>(p, stage, acc, warp, lane, m0, n0); break;
+        case 1: epilogue_tile<1, false, false>(p, stage, acc, warp, lane, m0, n0); break;
+        case 2: epilogue_tile<2, false, false>(p, stage, acc, warp, lane, m0, n0); break;
+        case 4: epilogue_tile<0, true, false>(p, stage, acc, warp, lane, m0, n0); break;
+        case 5: epilogue_tile<1, true, false>(p, stage, acc, warp, lane, m0, n0); break;
+        case 6: epilogue_tile<2, true, false>(p, stage, acc, warp, lane, m0, n0); break;
+        case 8: epilogue_tile<0, false, true>(p, stage, acc, warp, lane, m0, n0); break;
+        case 9: epilogue_tile<1, false, true>(p, stage, acc, warp, lane, m0, n0); break;
+        case 10: epilogue_tile<2, false, true>(p, stage, acc, warp, lane, m0, n0); break;
+        case 12: epilogue_tile<0, true, true>(p, stage, acc, warp, lane, m0, n0); break;
+        case 13: epilogue_tile<1, true, true>(p, stage, acc, warp, lane, m0, n0); break;
+        default: epilogue_tile<2, true, true>(p, stage, acc, warp, lane, m0, n0); break;
       }
       // this warp is done reading the accumulator: hand the TMEM slot back to the MMA issuer
       tc_fence_before();
@@ -272,7 +326,17 @@ static int encode_2d_bf16(CUtensorMap *map, const void *ptr, uint64_t inner, uin
   return MUMPY_OK;
 }
 
+// development knobs (environment, read once): MUMPY_TC_BN / MUMPY_TC_STAGES override the tile heuristics,
+// MUMPY_TC_DEBUG=1 skips the epilogue's global stores, =2 also skips its math (timing attribution only).
+static int env_int(const char *name) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+static int g_dbg_bn = -1, g_dbg_stages = -1, g_dbg_mode = -1;
+
 static int pick_bn(long M, int N) {
+  if (g_dbg_bn < 0) g_dbg_bn = env_int("MUMPY_TC_BN");
+  if (g_dbg_bn > 0 && N % g_dbg_bn == 0) return g_dbg_bn;
   static const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
   const long mt = cdiv(M, TC_BM);
   int largest = 0, smallest64 = 0;
@@ -291,6 +355,7 @@ static int pick_bn(long M, int N) {
 
 static bool g_attr_set[2] = {false, false};
 
+
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p, cudaStream_t st) {
   uint32_t cols = 32;
   while (cols < (uint32_t)p.BN) cols <<= 1;
@@ -298,19 +363,25 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   p.idesc = make_idesc_bf16_f32(TC_BM, p.BN);
   p.tiles_n = (int)cdiv(p.N, p.BN);
   p.num_tiles = cdiv(p.M, TC_BM) * p.tiles_n;
+  if (g_dbg_stages < 0) {
+    g_dbg_stages = env_int("MUMPY_TC_STAGES");
+    g_dbg_mode = env_int("MUMPY_TC_DEBUG");
+  }
+  p.debug = g_dbg_mode;
   const int stage_bytes = TC_BM * 128 + p.BN * 128;
   const int nkb = p.conv ? p.K : (p.K + TC_BK - 1) / TC_BK;
   int stages = TC_SMEM_BUDGET / stage_bytes;
+  if (g_dbg_stages > 0 && g_dbg_stages < stages) stages = g_dbg_stages;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   const long kb_per_cta = nkb * cdiv(p.num_tiles, g_num_sms);
   if (stages > kb_per_cta) stages = (int)kb_per_cta;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  const int smem = stages * stage_bytes + 1024;
+  const int smem = stages * stage_bytes + 1024 + TC_EPI_WARPS * 32 * 128;
   const int which = p.conv ? 1 : 0;
   if (!g_attr_set[which]) {
-    cudaError_t e = p.conv ? cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048)
-                           : cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048);
+    cudaError_t e = p.conv ? cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * 32 * 128)
+                           : cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * 32 * 128);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
       return MUMPY_ERR_CUDA;
