@@ -132,7 +132,8 @@ int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const float *bias, 
 /* im2col for the tensor-core path: out (B*H*W, Kpad) bf16, K order (ky,kx,c), zero padded to Kpad. */
 int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int B, int H, int W, int Cin, int kh, int kw, int ph,
                       int pw, int Kpad, void *stream);
-/* GroupNorm + activation; stats over (H*W, C/groups) per (b, group); stats_ws: 2*B*groups floats. */
+/* GroupNorm + activation; stats over (H*W, C/groups) per (b, group), exact two-pass per pixel chunk + Chan combine.
+ * stats_ws: 2*B*groups*(1 + nchunks) floats, nchunks = ceil(HW / min(64, 12288 / C, HW)). */
 int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *stats_ws, float *out,
                          long ld_out, int out_col, int B, int HW, int C, int groups, float eps, int act, void *stream);
 /* out[..., col:col+Cout] = resample(in) (* mul) (+ add); mul/add are (B,Ho,Wo,Cout) contiguous or NULL. */

@@ -59,6 +59,58 @@ __global__ void __launch_bounds__(256) layernorm_kernel(Rows rows, const float *
   }
 }
 
+// Plain rows, C % 4 == 0, C <= 1024: the row lives in registers (<= 8 float4 per lane): one coalesced global read,
+// exact two-pass statistics, one coalesced write (8-byte bf16x4 or 16-byte fp32x4 per lane).
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                                                            const float *__restrict__ beta, OutT *__restrict__ out, long n_rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int nv = C >> 2;
+  const float4 *xr = reinterpret_cast<const float4 *>(x + row * C);
+  float4 v[8];
+  float s = 0.0f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int i = lane + 32 * u;
+    if (i < nv) {
+      v[u] = xr[i];
+      s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.0f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int i = lane + 32 * u;
+    if (i < nv) {
+      const float a = v[u].x - mean, b = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+  const float4 *g4 = reinterpret_cast<const float4 *>(gamma), *b4 = reinterpret_cast<const float4 *>(beta);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int i = lane + 32 * u;
+    if (i < nv) {
+      const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+      const float o0 = (v[u].x - mean) * rstd * g.x + b.x, o1 = (v[u].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[u].z - mean) * rstd * g.z + b.z, o3 = (v[u].w - mean) * rstd * g.w + b.w;
+      if (sizeof(OutT) == 2) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t *>(&h0);
+        pk.y = *reinterpret_cast<uint32_t *>(&h1);
+        reinterpret_cast<uint2 *>(out + row * C)[i] = pk;
+      } else {
+        reinterpret_cast<float4 *>(out + row * C)[i] = make_float4(o0, o1, o2, o3);
+      }
+    }
+  }
+}
+
 template <typename Rows>
 static int launch_ln(Rows rows, const float *gamma, const float *beta, void *out, int out_dtype, long n_rows, int C, float eps,
                      cudaStream_t st) {
@@ -71,60 +123,85 @@ static int launch_ln(Rows rows, const float *gamma, const float *beta, void *out
   return launch_status("layernorm");
 }
 
-// ---- GroupNorm on NHWC: one CTA per (b, group) for the statistics, then a flat apply pass ----
-__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float *__restrict__ x, float *__restrict__ stats, int HW, int C,
-                                                              int groups, float eps) {
-  __shared__ float red[8];
-  __shared__ float bcast;
-  const int bg = blockIdx.x;
-  const int b = bg / groups, g = bg % groups;
+// ---- GroupNorm on NHWC ----
+// (1) gn_partial_kernel: one CTA per (image, pixel chunk) stages its chunk in shared memory and writes, per group, the
+//     chunk's exact two-pass (mean, M2);  (2) gn_finalize_kernel combines the chunks with Chan's parallel-variance formula in
+//     a fixed order (deterministic);  (3) groupnorm_apply_kernel normalises + activates with float4 accesses.
+constexpr int GN_SMEM_FLOATS = 12 * 1024;      // 48 KB staging
+
+__global__ void __launch_bounds__(256) gn_partial_kernel(const float *__restrict__ x, float *__restrict__ partial, int HW, int C, int groups, int pix,
+                                                         int nchunks) {
+  extern __shared__ float tile[];   // [pix][C]
+  const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
+  const int p0 = chunk * pix;
+  const int np = min(pix, HW - p0);
+  const float4 *src = reinterpret_cast<const float4 *>(x + ((long)b * HW + p0) * C);
+  float4 *dst = reinterpret_cast<float4 *>(tile);
+  const int nvec = np * C / 4;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
   const int cg = C / groups;
-  const float *base = x + (long)b * HW * C + g * cg;
-  const long n = (long)HW * cg;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float s = 0.0f;
-  for (long e = threadIdx.x; e < n; e += blockDim.x) s += base[(e / cg) * C + (e % cg)];
-  s = warp_sum(s);
-  if (lane == 0) red[warp] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.0f;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    bcast = t / (float)n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int n = np * cg;
+  for (int g = warp; g < groups; g += nwarps) {
+    float s = 0.0f;
+    for (int e = lane; e < n; e += 32) s += tile[(e / cg) * C + g * cg + (e % cg)];
+    const float mean = warp_sum(s) / n;
+    float q = 0.0f;
+    for (int e = lane; e < n; e += 32) {
+      const float d = tile[(e / cg) * C + g * cg + (e % cg)] - mean;
+      q = fmaf(d, d, q);
+    }
+    q = warp_sum(q);
+    if (lane == 0) {
+      float *o = partial + (((long)b * groups + g) * nchunks + chunk) * 2;
+      o[0] = mean;
+      o[1] = q;
+    }
   }
-  __syncthreads();
-  const float mean = bcast;
-  float v = 0.0f;
-  for (long e = threadIdx.x; e < n; e += blockDim.x) {
-    const float d = base[(e / cg) * C + (e % cg)] - mean;
-    v = fmaf(d, d, v);
+}
+
+__global__ void gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ stats, int total_bg, int HW, int cg, int pix, int nchunks,
+                                   float eps) {
+  const int bg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bg >= total_bg) return;
+  const float *p = partial + (long)bg * nchunks * 2;
+  float n_a = 0.0f, mean_a = 0.0f, m2_a = 0.0f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float n_b = (float)(min(pix, HW - c * pix) * cg);
+    const float mean_b = p[2 * c], m2_b = p[2 * c + 1];
+    const float n_ab = n_a + n_b;
+    const float delta = mean_b - mean_a;
+    mean_a += delta * (n_b / n_ab);
+    m2_a += m2_b + delta * delta * (n_a * n_b / n_ab);
+    n_a = n_ab;
   }
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.0f;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    stats[2 * bg] = mean;
-    stats[2 * bg + 1] = 1.0f / sqrtf(t / (float)n + eps);
-  }
+  stats[2 * bg] = mean_a;
+  stats[2 * bg + 1] = 1.0f / sqrtf(m2_a / n_a + eps);
 }
 
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float *__restrict__ x, const float *__restrict__ stats,
                                                               const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                              float *__restrict__ out, long ld_out, int out_col, long total, int HW,
+                                                              float *__restrict__ out, long ld_out, int out_col, long total4, int HW,
                                                               int C, int groups, int act) {
   const int cg = C / groups;
+  const int C4 = C / 4;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    const int c = (int)(i % C);
-    const long pix = i / C;
+  for (; i < total4; i += stride) {
+    const int c = (int)(i % C4) * 4;
+    const long pix = i / C4;
     const long b = pix / HW;
-    const float *st = stats + 2 * (b * groups + c / cg);
-    const float v = (x[i] - st[0]) * st[1] * gamma[c] + beta[c];
-    out[pix * ld_out + out_col + c] = apply_act(v, act);
+    const float4 v = reinterpret_cast<const float4 *>(x)[i];
+    const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + c)), bt = __ldg(reinterpret_cast<const float4 *>(beta + c));
+    const float *st = stats + 2 * (b * groups + c / cg);          // cg % 4 == 0: the four channels share a group
+    const float mean = st[0], rstd = st[1];
+    float4 o;
+    o.x = apply_act((v.x - mean) * rstd * g.x + bt.x, act);
+    o.y = apply_act((v.y - mean) * rstd * g.y + bt.y, act);
+    o.z = apply_act((v.z - mean) * rstd * g.z + bt.z, act);
+    o.w = apply_act((v.w - mean) * rstd * g.w + bt.w, act);
+    *reinterpret_cast<float4 *>(out + pix * ld_out + out_col + c) = o;
   }
 }
 
@@ -135,6 +212,15 @@ using namespace mumpy;
 extern "C" int mumpy_layernorm(const float *x, const float *gamma, const float *beta, void *out, int out_dtype, long rows, int C,
                                float eps, void *stream) {
   MUMPY_REQUIRE(x && gamma && beta && out && rows > 0 && C > 0, "layernorm: bad arguments");
+  if (C % 4 == 0 && C <= 1024 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
+                                   reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
+    dim3 grid((unsigned)cdiv(rows, 8));
+    if (out_dtype == MUMPY_BF16)
+      layernorm_vec_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(x, gamma, beta, static_cast<__nv_bfloat16 *>(out), rows, C, eps);
+    else
+      layernorm_vec_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(x, gamma, beta, static_cast<float *>(out), rows, C, eps);
+    return launch_status("layernorm_vec");
+  }
   return launch_ln(PlainRows{x, C}, gamma, beta, out, out_dtype, rows, C, eps, as_stream(stream));
 }
 
@@ -149,11 +235,23 @@ extern "C" int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const fl
                                     long ld_out, int out_col, int B, int HW, int C, int groups, float eps, int act,
                                     void *stream) {
   MUMPY_REQUIRE(x && gamma && beta && stats_ws && out && C % groups == 0, "groupnorm_nhwc: bad arguments");
-  groupnorm_stats_kernel<<<B * groups, 256, 0, as_stream(stream)>>>(x, stats_ws, HW, C, groups, eps);
-  int rc = launch_status("groupnorm_stats");
+  MUMPY_REQUIRE((C / groups) % 4 == 0 && ld_out % 4 == 0 && out_col % 4 == 0, "groupnorm_nhwc: channels per group, ld_out, out_col must be multiples of 4");
+  MUMPY_REQUIRE(C <= GN_SMEM_FLOATS, "groupnorm_nhwc: C too large");
+  cudaStream_t st = as_stream(stream);
+  int pix = GN_SMEM_FLOATS / C;
+  if (pix > 64) pix = 64;
+  if (pix > HW) pix = HW;
+  const int nchunks = (int)cdiv(HW, pix);
+  float *stats = stats_ws;                                  // 2 * B * groups
+  float *partial = stats_ws + 2 * (long)B * groups;         // 2 * B * groups * nchunks
+  gn_partial_kernel<<<B * nchunks, 256, (size_t)pix * C * sizeof(float), st>>>(x, partial, HW, C, groups, pix, nchunks);
+  int rc = launch_status("gn_partial");
   if (rc) return rc;
-  const long total = (long)B * HW * C;
-  const int blocks = (int)(cdiv(total, 256) < 148 * 16 ? cdiv(total, 256) : 148 * 16);
-  groupnorm_apply_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, stats_ws, gamma, beta, out, ld_out, out_col, total, HW, C, groups, act);
+  gn_finalize_kernel<<<(unsigned)cdiv(B * groups, 128), 128, 0, st>>>(partial, stats, B * groups, HW, C / groups, pix, nchunks, eps);
+  rc = launch_status("gn_finalize");
+  if (rc) return rc;
+  const long total4 = (long)B * HW * C / 4;
+  const int blocks = (int)(cdiv(total4, 256) < 148 * 16 ? cdiv(total4, 256) : 148 * 16);
+  groupnorm_apply_kernel<<<blocks, 256, 0, st>>>(x, stats, gamma, beta, out, ld_out, out_col, total4, HW, C, groups, act);
   return launch_status("groupnorm_apply");
 }
