@@ -71,9 +71,12 @@ int mumpy_patch_merge_norm(const float *x, const float *gamma, const float *beta
  * window partition/reverse of SwinTransformerBlock.forward (:270-301) folded into the addressing.
  * qkv (B*TH*W, 3C) canvas order, channel o -> (which=o/C, head=(o%C)/d, o%d); bias (heads,N,N) fp32 =
  * relative_position_bias_table gathered by relative_position_index; mask (nW,N,N) fp32 or NULL;
- * out (B*TH*W, C) canvas order; N = ws*ws (<=64), d = C/heads in {32,64}. */
-int mumpy_window_attention(const void *qkv, const float *bias, const float *mask, void *out, int dtype, int B, int TH,
-                           int W, int C, int heads, int ws, int shift, void *stream);
+ * out (B*TH*W, C) canvas order; N = ws*ws (<=64), d = C/heads in {32,64}.
+ * Optional fast path (bf16, d = 32): rel_table = the raw relative_position_bias_table ((2ws-1)^2, heads) fp32 and
+ * standard_mask = 1 when `mask` is exactly the Swin shift mask of swinTransformer.py:233-252 for (TH, W, ws, shift): the
+ * kernel then looks the bias up in a shared-memory copy of the table and recomputes the mask from region ids. */
+int mumpy_window_attention(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask,
+                           void *out, int dtype, int B, int TH, int W, int C, int heads, int ws, int shift, void *stream);
 
 /* Attention.forward core for short sequences (blocks.py:64-70): qkv (Bn*N, 3C) -> out (Bn*N, C), N <= 8. */
 int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, int N, int C, int heads, void *stream);

@@ -199,8 +199,8 @@ static int ensure_smem(K kernel, size_t bytes) {
   return MUMPY_OK;
 }
 
-int window_attention_mma(const void *qkv, const float *bias, const float *mask, void *out, int B, int TH, int W, int C, int heads,
-                         int ws, int shift, cudaStream_t st);
+int window_attention_mma(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask, void *out, int B,
+                         int TH, int W, int C, int heads, int ws, int shift, cudaStream_t st);
 int cva_attention_mma(const float *q, const void *kv, void *o, int B, int TH1, int TH2, int W, int C, int heads, int ws, int per_clip,
                       cudaStream_t st);
 
@@ -208,8 +208,8 @@ int cva_attention_mma(const float *q, const void *kv, void *o, int B, int TH1, i
 
 using namespace mumpy;
 
-extern "C" int mumpy_window_attention(const void *qkv, const float *bias, const float *mask, void *out, int dtype, int B, int TH,
-                                      int W, int C, int heads, int ws, int shift, void *stream) {
+extern "C" int mumpy_window_attention(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask,
+                                      void *out, int dtype, int B, int TH, int W, int C, int heads, int ws, int shift, void *stream) {
   MUMPY_REQUIRE(qkv && bias && out && B > 0 && heads > 0 && C % heads == 0, "window_attention: bad arguments");
   MUMPY_REQUIRE(TH % ws == 0 && W % ws == 0 && ws * ws <= 64 && shift >= 0 && shift < ws, "window_attention: bad window geometry");
   const int D = C / heads;
@@ -218,7 +218,7 @@ extern "C" int mumpy_window_attention(const void *qkv, const float *bias, const 
   dim3 grid((unsigned)(B * (TH / ws) * (W / ws)), (unsigned)heads);
   cudaStream_t st = as_stream(stream);
   if (dtype == MUMPY_BF16 && D == 32 && C % 8 == 0)      // tensor-pipe path (attention_mma.cu)
-    return window_attention_mma(qkv, bias, mask, out, B, TH, W, C, heads, ws, shift, st);
+    return window_attention_mma(qkv, bias, mask, rel_table, standard_mask, out, B, TH, W, C, heads, ws, shift, st);
   int rc = MUMPY_OK;
 #define LAUNCH(T, DD)                                                                                                     \
   {                                                                                                                       \

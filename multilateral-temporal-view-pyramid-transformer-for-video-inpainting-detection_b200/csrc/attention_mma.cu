@@ -34,31 +34,53 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return row * 
 constexpr int ATT_TILE_BYTES = 64 * 64;     // one 64x32 bf16 tile
 constexpr int ATT_WARPS = 4;
 
-// scores for 16 query rows (m-tile mt) against NT n-tiles of keys, then softmax -> un-normalised probabilities in s,
-// returns the two row sums (rows g and g+8 of the m-tile) through sum_lo / sum_hi.
-// The relative-position bias and the shift mask are loaded (branch-free, clamped indices, all loads in flight before
-// the MMAs) straight into the accumulators as (bias + mask) / scale, so that scale * acc = scale * q.k + bias + mask.
+// Additive score terms (relative-position bias + shift mask), returned pre-divided by the qk scale so that they can be
+// used as the initial value of the score accumulators: scale * (q.k + init) = scale * q.k + bias + mask.
+struct NoBias {
+  __device__ __forceinline__ float operator()(int, int, int) const { return 0.0f; }
+};
+// gathered bias (nH,N,N) and optional mask tensor (nW,N,N): clamped, branch-free loads issued before the MMAs
 template <int N>
-__device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt, int lane, float scale, const float *__restrict__ bias_h,
-                                               const float *__restrict__ mask_w, float (&s)[8][4], float &sum_lo, float &sum_hi) {
+struct LoadedBias {
+  const float *bias_h, *mask_w;
+  int i_lo, i_hi, t;
+  float inv_scale;
+  __device__ __forceinline__ float operator()(int hi, int nt, int e) const {
+    const int j = min(nt * 8 + 2 * t + (e & 1), N - 1);
+    const int idx = (hi ? i_hi : i_lo) * N + j;
+    float v = __ldg(bias_h + idx);
+    if (mask_w) v += __ldg(mask_w + idx);
+    return v * inv_scale;
+  }
+};
+// bias from the (2ws-1)^2-entry relative-position table of this head (shared memory, pre-divided by the scale):
+// index a(i) - a(j) + OFF with a(p) = (p/ws)(2ws-1) + p%ws; standard Swin shift mask from region ids (no loads at all).
+template <int WS>
+struct TableBias {
+  const float *tbl;          // smem, pre-divided by scale
+  const int *aj;             // per-lane packed (a(j) | region(j) << 16) for its 16 key columns [nt*2 + e]
+  int a_lo, a_hi, reg_lo, reg_hi;
+  float mask_val;            // -100 / scale, or 0 when the block is not shifted
+  __device__ __forceinline__ float operator()(int hi, int nt, int e) const {
+    const int pj = aj[nt * 2 + (e & 1)];
+    const int a_i = hi ? a_hi : a_lo, r_i = hi ? reg_hi : reg_lo;
+    float v = tbl[a_i - (pj & 0xffff)];
+    if ((pj >> 16) != r_i) v += mask_val;
+    return v;
+  }
+};
+
+// scores for 16 query rows (m-tile mt) against the key n-tiles, then softmax -> un-normalised probabilities in s (base-2
+// exponentials of scale*log2e*(q.k + init) minus the row maximum); the row sums of rows g / g+8 come back in sum_lo / sum_hi.
+template <int N, typename Init>
+__device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt, int lane, float scale, const Init &init, float (&s)[8][4],
+                                               float &sum_lo, float &sum_hi) {
   constexpr int NT = (N + 7) / 8;
-  const int g = lane >> 2, t = lane & 3;
-  const int i_lo = min(mt * 16 + g, N - 1), i_hi = min(mt * 16 + g + 8, N - 1);
-  const float inv_scale = 1.0f / scale;
+  const int t = lane & 3;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float v = 0.0f;
-      if (nt < NT && bias_h) {
-        const int j = min(nt * 8 + 2 * t + (e & 1), N - 1);
-        const int idx = ((e < 2) ? i_lo : i_hi) * N + j;
-        v = __ldg(bias_h + idx);
-        if (mask_w) v += __ldg(mask_w + idx);
-        v *= inv_scale;
-      }
-      s[nt][e] = v;
-    }
+    for (int e = 0; e < 4; ++e) s[nt][e] = (nt < NT) ? init(e >> 1, nt, e) : 0.0f;
   uint32_t a[2][4];
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
@@ -72,28 +94,32 @@ __device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt,
     mma_bf16(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
     mma_bf16(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], b2, b3);
   }
+  const float c = scale * 1.4426950408889634f;     // exp(x) = 2^(x log2 e)
   float m_lo = -INFINITY, m_hi = -INFINITY;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int j = nt * 8 + 2 * t + (e & 1);
-      const float v = (j < N) ? s[nt][e] * scale : -INFINITY;       // only the last n-tile can be out of range
-      s[nt][e] = v;
-      if (e < 2) m_lo = fmaxf(m_lo, v); else m_hi = fmaxf(m_hi, v);
+      if (nt * 8 + 7 >= N) {                        // only the last n-tile can hold padded key columns
+        const int j = nt * 8 + 2 * t + (e & 1);
+        if (j >= N) s[nt][e] = -INFINITY;
+      }
+      if (e < 2) m_lo = fmaxf(m_lo, s[nt][e]); else m_hi = fmaxf(m_hi, s[nt][e]);
     }
   }
   m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
   m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
   m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
   m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+  const float mc_lo = m_lo * c, mc_hi = m_hi * c;
   sum_lo = 0.0f;
   sum_hi = 0.0f;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float p = __expf(s[nt][e] - ((e < 2) ? m_lo : m_hi));      // exp(-inf) = 0 for the padded key columns
+      float p;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[nt][e], c, -((e < 2) ? mc_lo : mc_hi))));   // 2^-inf = 0 for padding
       s[nt][e] = p;
       if (e < 2) sum_lo += p; else sum_hi += p;
     }
@@ -104,14 +130,14 @@ __device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt,
   sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
 }
 
-// o[dn][4] += P(16 x 64) . V(64 x 32) for one m-tile; probabilities come straight from the score fragments
-__device__ __forceinline__ void pv_accumulate(uint32_t sV, int lane, const float (&s)[8][4], float inv_lo, float inv_hi, float (&o)[4][4]) {
+// o[dn][4] += P(16 x 64) . V(64 x 32) for one m-tile; un-normalised probabilities come straight from the score fragments
+__device__ __forceinline__ void pv_accumulate(uint32_t sV, int lane, const float (&s)[8][4], float (&o)[4][4]) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    const uint32_t a0 = pack_bf16(s[2 * kk][0] * inv_lo, s[2 * kk][1] * inv_lo);
-    const uint32_t a1 = pack_bf16(s[2 * kk][2] * inv_hi, s[2 * kk][3] * inv_hi);
-    const uint32_t a2 = pack_bf16(s[2 * kk + 1][0] * inv_lo, s[2 * kk + 1][1] * inv_lo);
-    const uint32_t a3 = pack_bf16(s[2 * kk + 1][2] * inv_hi, s[2 * kk + 1][3] * inv_hi);
+    const uint32_t a0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    const uint32_t a1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    const uint32_t a2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    const uint32_t a3 = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
     const int tok = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
     for (int dp = 0; dp < 2; ++dp) {
@@ -133,13 +159,19 @@ __device__ __forceinline__ int token_row(int wr, int wc, int p, int TH, int W, i
   return r * W + c;
 }
 
-constexpr int ATT_WARP_SMEM = 3 * ATT_TILE_BYTES + 64 * sizeof(long);
+constexpr int ATT_TABLE_FLOATS = 232;       // (2*8-1)^2 = 225 entries for ws 8, 169 for ws 7
+constexpr int ATT_WARP_SMEM = 3 * ATT_TILE_BYTES + 64 * sizeof(long) + ATT_TABLE_FLOATS * sizeof(float);
 
-template <int WS>
+// MODE 0: gathered bias (nH,N,N) + optional mask tensor (nW,N,N) through global loads.
+// MODE 1: bias from the raw relative_position_bias_table (T,nH) staged in shared memory; the mask is the standard Swin
+//         shift mask, recomputed from region ids on the stacked canvas (swinTransformer.py:233-252) -- no bias/mask loads.
+template <int WS, int MODE>
 __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_mma_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ bias,
-                                                                              const float *__restrict__ mask, __nv_bfloat16 *__restrict__ out,
-                                                                              int TH, int W, int C, int heads, int shift, long n_tasks) {
+                                                                              const float *__restrict__ mask, const float *__restrict__ rel_table,
+                                                                              __nv_bfloat16 *__restrict__ out, int TH, int W, int C, int heads,
+                                                                              int shift, int mshift, long n_tasks) {
   constexpr int N = WS * WS;
+  constexpr float kScale = 0.17677669529663687f;    // 32^-0.5
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long task = (long)blockIdx.x * ATT_WARPS + warp;
@@ -154,13 +186,17 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_mma_kernel(co
   const long L = (long)TH * W;
   uint8_t *tq = att_smem + warp * ATT_WARP_SMEM, *tk = tq + ATT_TILE_BYTES, *tv = tk + ATT_TILE_BYTES;
   long *rows = reinterpret_cast<long *>(tv + ATT_TILE_BYTES);
+  float *tbl = reinterpret_cast<float *>(rows + 64);
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int p = lane + 32 * u;
     if (p < N) rows[p] = b * L + token_row<WS>(wr, wc, p, TH, W, shift);
   }
+  if (MODE == 1) {
+    constexpr int T = (2 * WS - 1) * (2 * WS - 1);
+    for (int i = lane; i < T; i += 32) tbl[i] = __ldg(rel_table + (long)i * heads + h) * (1.0f / kScale);
+  }
   __syncwarp();
-  // rows[] holds canvas token indices; qkv rows are 3C wide, out rows C wide
   {
     const __nv_bfloat16 *base = qkv + h * 32;
 #pragma unroll
@@ -176,31 +212,57 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_mma_kernel(co
       }
     }
   }
-  __syncwarp();
   const uint32_t sQ = smem_addr(tq), sK = smem_addr(tk), sV = smem_addr(tv);
-  const float *bias_h = bias + (long)h * N * N;
-  const float *mask_w = mask ? mask + (long)n * N * N : nullptr;
   const int g = lane >> 2, t = lane & 3;
+  // per-lane key-column descriptors for MODE 1: a(j) | region(j) << 16 for j = nt*8 + 2t + e
+  auto a_of = [](int p) { return (p / WS) * (2 * WS - 1) + p % WS; };
+  auto region_of = [&](int p) {
+    const int rr = wr * WS + p / WS, cc = wc * WS + p % WS;       // coordinates on the shifted canvas
+    const int hr = rr < TH - WS ? 0 : (rr < TH - mshift ? 1 : 2);
+    const int wreg = cc < W - WS ? 0 : (cc < W - mshift ? 1 : 2);
+    return hr * 3 + wreg;
+  };
+  int aj[16];
+  if (MODE == 1) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = min(nt * 8 + 2 * t + e, N - 1);
+        aj[nt * 2 + e] = a_of(j) | ((mshift > 0 ? region_of(j) : 0) << 16);
+      }
+  }
+  __syncwarp();
 #pragma unroll 1
   for (int mt = 0; mt * 16 < N; ++mt) {
     float s[8][4], sum_lo, sum_hi;
-    scores_softmax<N>(sQ, sK, mt, lane, 0.17677669529663687f, bias_h, mask_w, s, sum_lo, sum_hi);
+    const int i_lo = mt * 16 + g, i_hi = i_lo + 8;
+    const int ic_lo = min(i_lo, N - 1), ic_hi = min(i_hi, N - 1);
+    if (MODE == 1) {
+      constexpr int OFF = (WS - 1) * 2 * WS;
+      TableBias<WS> init{tbl, aj, a_of(ic_lo) + OFF, a_of(ic_hi) + OFF, mshift > 0 ? region_of(ic_lo) : 0, mshift > 0 ? region_of(ic_hi) : 0,
+                         mshift > 0 ? -100.0f / kScale : 0.0f};
+      scores_softmax<N>(sQ, sK, mt, lane, kScale, init, s, sum_lo, sum_hi);
+    } else {
+      LoadedBias<N> init{bias + (long)h * N * N, mask ? mask + (long)n * N * N : nullptr, ic_lo, ic_hi, t, 1.0f / kScale};
+      scores_softmax<N>(sQ, sK, mt, lane, kScale, init, s, sum_lo, sum_hi);
+    }
     float o[4][4];
 #pragma unroll
     for (int dn = 0; dn < 4; ++dn)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[dn][e] = 0.0f;
-    pv_accumulate(sV, lane, s, 1.0f / sum_lo, 1.0f / sum_hi, o);
-    const int i_lo = mt * 16 + g, i_hi = i_lo + 8;
+    pv_accumulate(sV, lane, s, o);
+    const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
     if (i_lo < N) {
       __nv_bfloat16 *dst = out + rows[i_lo] * C + h * 32 + 2 * t;
 #pragma unroll
-      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][0], o[dn][1]);
+      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][0] * inv_lo, o[dn][1] * inv_lo);
     }
     if (i_hi < N) {
       __nv_bfloat16 *dst = out + rows[i_hi] * C + h * 32 + 2 * t;
 #pragma unroll
-      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][2], o[dn][3]);
+      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][2] * inv_hi, o[dn][3] * inv_hi);
     }
   }
 }
@@ -282,8 +344,21 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const
     for (int mt = 0; mt < 4; ++mt) {
       if (mt * 16 < N) {
         float s[8][4], sum_lo, sum_hi;
-        scores_softmax<N>(sQ, sK, mt, lane, 0.17677669529663687f, nullptr, nullptr, s, sum_lo, sum_hi);
-        pv_accumulate(sV, lane, s, 1.0f / sum_lo, 1.0f / sum_hi, o[mt]);
+        scores_softmax<N>(sQ, sK, mt, lane, 0.17677669529663687f, NoBias{}, s, sum_lo, sum_hi);
+        float ot[4][4];
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ot[dn][e] = 0.0f;
+        pv_accumulate(sV, lane, s, ot);
+        const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+          o[mt][dn][0] = fmaf(ot[dn][0], inv_lo, o[mt][dn][0]);
+          o[mt][dn][1] = fmaf(ot[dn][1], inv_lo, o[mt][dn][1]);
+          o[mt][dn][2] = fmaf(ot[dn][2], inv_hi, o[mt][dn][2]);
+          o[mt][dn][3] = fmaf(ot[dn][3], inv_hi, o[mt][dn][3]);
+        }
       }
     }
   }
@@ -316,20 +391,32 @@ static int att_smem_attr(K kernel) {
   return MUMPY_OK;
 }
 
-int window_attention_mma(const void *qkv, const float *bias, const float *mask, void *out, int B, int TH, int W, int C, int heads,
-                         int ws, int shift, cudaStream_t st) {
+int window_attention_mma(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask, void *out, int B,
+                         int TH, int W, int C, int heads, int ws, int shift, cudaStream_t st) {
   const long n_tasks = (long)B * (TH / ws) * (W / ws) * heads;
   const unsigned grid = (unsigned)cdiv(n_tasks, ATT_WARPS);
   const size_t smem = ATT_WARPS * ATT_WARP_SMEM;
+  const bool table_mode = rel_table != nullptr && (mask == nullptr || standard_mask);
+  const __nv_bfloat16 *q = static_cast<const __nv_bfloat16 *>(qkv);
+  __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out);
   int rc;
+  const int mshift = (mask != nullptr) ? shift : 0;      // region-id mask only when the caller passed the (standard) mask
   if (ws == 7) {
-    if ((rc = att_smem_attr(window_attention_mma_kernel<7>))) return rc;
-    window_attention_mma_kernel<7><<<grid, ATT_WARPS * 32, smem, st>>>(static_cast<const __nv_bfloat16 *>(qkv), bias, mask,
-                                                                      static_cast<__nv_bfloat16 *>(out), TH, W, C, heads, shift, n_tasks);
+    if (table_mode) {
+      if ((rc = att_smem_attr(window_attention_mma_kernel<7, 1>))) return rc;
+      window_attention_mma_kernel<7, 1><<<grid, ATT_WARPS * 32, smem, st>>>(q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks);
+    } else {
+      if ((rc = att_smem_attr(window_attention_mma_kernel<7, 0>))) return rc;
+      window_attention_mma_kernel<7, 0><<<grid, ATT_WARPS * 32, smem, st>>>(q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks);
+    }
   } else if (ws == 8) {
-    if ((rc = att_smem_attr(window_attention_mma_kernel<8>))) return rc;
-    window_attention_mma_kernel<8><<<grid, ATT_WARPS * 32, smem, st>>>(static_cast<const __nv_bfloat16 *>(qkv), bias, mask,
-                                                                      static_cast<__nv_bfloat16 *>(out), TH, W, C, heads, shift, n_tasks);
+    if (table_mode) {
+      if ((rc = att_smem_attr(window_attention_mma_kernel<8, 1>))) return rc;
+      window_attention_mma_kernel<8, 1><<<grid, ATT_WARPS * 32, smem, st>>>(q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks);
+    } else {
+      if ((rc = att_smem_attr(window_attention_mma_kernel<8, 0>))) return rc;
+      window_attention_mma_kernel<8, 0><<<grid, ATT_WARPS * 32, smem, st>>>(q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks);
+    }
   } else {
     set_error("window_attention(bf16): window size %d unsupported (7 or 8)", ws);
     return MUMPY_ERR_UNSUPPORTED;

@@ -84,11 +84,17 @@ class WindowAttention(PackedModule):
             return t.view(n, n, -1).permute(2, 0, 1).contiguous().float()
         return self._packed("bias", [self.relative_position_bias_table, self.relative_position_index], make)
 
-    def canvas_attention(self, xn, B, TH, W, shift, mask):
-        """xn (B, TH*W, C) normalised canvas in operand precision -> attention output before `proj`."""
+    def _table(self):
+        return self._packed("table", [self.relative_position_bias_table],
+                            lambda: self.relative_position_bias_table.detach().float().contiguous())
+
+    def canvas_attention(self, xn, B, TH, W, shift, mask, standard_mask=False):
+        """xn (B, TH*W, C) normalised canvas in operand precision -> attention output before `proj`.
+        standard_mask: `mask` is exactly the Swin shift mask for (TH, W, ws, shift) (lets the kernel recompute it)."""
         C = self.dim
         qkv = ops.linear(xn, self._gemm_weight("qkv", self.qkv.weight), self.qkv.bias, out_dtype=ops.act_dtype())
-        return ops.window_attention(qkv, self._bias(), mask, B, TH, W, C, self.num_heads, self.window_size[0], shift)
+        return ops.window_attention(qkv, self._bias(), mask, B, TH, W, C, self.num_heads, self.window_size[0], shift,
+                                    rel_table=self._table(), standard_mask=standard_mask)
 
     def project(self, ao, residual=None):
         return ops.linear(ao, self._gemm_weight("proj", self.proj.weight), self.proj.bias, residual=residual)
@@ -148,6 +154,16 @@ class SwinTransformerBlock(PackedModule):
         self.register_buffer("attn_mask", attn_mask)
         self.fused_window_process = fused_window_process
 
+    def _mask_is_standard(self, TH, W):
+        """True when the attn_mask buffer equals the mask the constructor builds for this canvas (checked once per load)."""
+        if self.attn_mask is None:
+            return False
+
+        def check():
+            ref = _shift_mask(TH, W, 1, self.window_size, self.shift_size).to(self.attn_mask.device)
+            return bool(ref.shape == self.attn_mask.shape and torch.equal(ref, self.attn_mask))
+        return self._packed("std_mask:%d:%d" % (TH, W), [self.attn_mask], check)
+
     def forward(self, x):
         require_inference(self)
         H, W = self.input_resolution
@@ -156,7 +172,7 @@ class SwinTransformerBlock(PackedModule):
         TH = L // W
         x = x.contiguous()
         xn = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        ao = self.attn.canvas_attention(xn, B, TH, W, self.shift_size, self.attn_mask)
+        ao = self.attn.canvas_attention(xn, B, TH, W, self.shift_size, self.attn_mask, self._mask_is_standard(TH, W))
         x = self.attn.project(ao, residual=x)                    # shortcut + W-MSA  (:302)
         xn = ops.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         return self.mlp.fused(xn, residual=x)                    # x + Mlp(LN2(x))   (:305)

@@ -111,11 +111,11 @@ def patch_merge_norm(x, gamma, beta, B, TH, W, C, eps=1e-5, out_dtype=None):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def window_attention(qkv, bias, mask, B, TH, W, C, heads, ws, shift):
+def window_attention(qkv, bias, mask, B, TH, W, C, heads, ws, shift, rel_table=None, standard_mask=False):
     out = torch.empty((B, TH * W, C), dtype=qkv.dtype, device=qkv.device)
-    lib, st = _prep(qkv, bias, mask, out)
-    _lib.check(lib.mumpy_window_attention(_p(qkv), _p(bias), _p(mask), _p(out), code(qkv.dtype), B, TH, W, C, heads, ws,
-                                          shift, st), "mumpy_window_attention")
+    lib, st = _prep(qkv, bias, mask, rel_table, out)
+    _lib.check(lib.mumpy_window_attention(_p(qkv), _p(bias), _p(mask), _p(rel_table), int(standard_mask), _p(out), code(qkv.dtype),
+                                          B, TH, W, C, heads, ws, shift, st), "mumpy_window_attention")
     return out
 
 

@@ -89,6 +89,11 @@ def test_window_attention_tensor_pipe(B, T, H, C, heads, shift):
     out = ops.window_attention(qkv.cuda(), bias.cuda(), None if mask is None else mask.cuda(), B, TH, W, C, heads, ws, shift)
     assert out.dtype == torch.bfloat16
     assert util.maxabs(out.float(), o.reshape(B, TH * W, C)) < 2e-2
+    # fast path: bias looked up in the raw table, standard shift mask recomputed from region ids
+    out2 = ops.window_attention(qkv.cuda(), bias.cuda(), None if mask is None else mask.cuda(), B, TH, W, C, heads, ws, shift,
+                                rel_table=table.cuda().contiguous(), standard_mask=mask is not None)
+    assert util.maxabs(out2.float(), o.reshape(B, TH * W, C)) < 2e-2
+    assert util.maxabs(out2.float(), out.float()) < 1e-2
 
 
 def test_fast_gelu_epilogue_accuracy():

@@ -20,8 +20,9 @@ if what == "attn":
     qkv = torch.randn((B, TH * W, 3 * C), device=dev).bfloat16()
     bias = torch.randn((heads, 49, 49), device=dev)
     mask = orc.shifted_window_mask(TH, W, 7, 3).to(dev)
+    table = torch.randn((169, heads), device=dev)
     for _ in range(reps):
-        ops.window_attention(qkv, bias, mask, B, TH, W, C, heads, 7, 3)
+        ops.window_attention(qkv, bias, mask, B, TH, W, C, heads, 7, 3, rel_table=table, standard_mask=True)
 elif what.startswith("gemm"):
     shapes = {"gemm_fc1": (B * 588, 2048, 512, ops.ACT_GELU, torch.bfloat16), "gemm_fc2": (B * 588, 512, 2048, ops.ACT_NONE, torch.float32),
               "gemm_s0": (B * 9408, 512, 128, ops.ACT_GELU, torch.bfloat16), "gemm_qkv": (B * 588, 1536, 512, ops.ACT_NONE, torch.bfloat16)}
