@@ -188,14 +188,24 @@ __global__ void __launch_bounds__(128) cva_attention_kernel(const float *__restr
 template <typename K>
 static int ensure_smem(K kernel, size_t bytes) {
   if (bytes <= 48 * 1024) return MUMPY_OK;
-  static size_t granted = 0;          // per template instantiation: skip the driver call once it is large enough
-  if (bytes <= granted) return MUMPY_OK;
+  static const void *seen[16];          // keyed by entry address: instantiations may share one function-pointer type
+  static size_t granted[16];
+  static int n_seen = 0;
+  const void *key = reinterpret_cast<const void *>(kernel);
+  int slot = -1;
+  for (int i = 0; i < n_seen; ++i)
+    if (seen[i] == key) slot = i;
+  if (slot >= 0 && bytes <= granted[slot]) return MUMPY_OK;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
     return MUMPY_ERR_CUDA;
   }
-  granted = bytes;
+  if (slot < 0 && n_seen < 16) slot = n_seen++;
+  if (slot >= 0) {
+    seen[slot] = key;
+    granted[slot] = bytes;
+  }
   return MUMPY_OK;
 }
 

@@ -378,16 +378,21 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const
   }
 }
 
+// opt the kernel into > 48 KB of dynamic shared memory, once per kernel (keyed by entry address: several template
+// instantiations share one function-pointer type)
 template <typename K>
 static int att_smem_attr(K kernel) {
-  static bool done = false;
-  if (done) return MUMPY_OK;
+  static const void *seen[16];
+  static int n_seen = 0;
+  const void *key = reinterpret_cast<const void *>(kernel);
+  for (int i = 0; i < n_seen; ++i)
+    if (seen[i] == key) return MUMPY_OK;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_WARPS * ATT_WARP_SMEM);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
     return MUMPY_ERR_CUDA;
   }
-  done = true;
+  if (n_seen < 16) seen[n_seen++] = key;
   return MUMPY_OK;
 }
 
