@@ -94,6 +94,29 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
   const long row0 = m0 + quad * 32;
   const uint32_t st_base = smem_u32(stage);
   for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+    // residual tile of this chunk, fetched in the coalesced phase-2 layout before anything else so that the global-load
+    // latency overlaps the TMEM load and the phase-1 math
+    float4 res[8];
+    if (HAS_RES) {
+      if (OUT_BF16) {
+        const int col = c0 + (lane & 3) * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long gm = row0 + i * 8 + (lane >> 2);
+          const bool ok = gm < p.M && col < p.BN && n0 + col < p.N;
+          res[2 * i] = ok ? *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n0 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          res[2 * i + 1] = ok ? *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n0 + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        const int col = c0 + (lane & 7) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long gm = row0 + i * 4 + (lane >> 3);
+          const bool ok = gm < p.M && col < p.BN && n0 + col < p.N;
+          res[i] = ok ? *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n0 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
     uint32_t v[32];
     tmem_ld32(lane_addr + c0, v);
     if (p.debug == 2) continue;
@@ -130,8 +153,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(st_base + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4)));
           if (gm < p.M && col < p.BN && n0 + col < p.N) {
             if (HAS_RES) {
-              const float4 r0 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n0 + col);
-              const float4 r1 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n0 + col + 4);
+              const float4 r0 = res[2 * i], r1 = res[2 * i + 1];
               x.x += r0.x; x.y += r0.y; x.z += r0.z; x.w += r0.w;
               y.x += r1.x; y.y += r1.y; y.z += r1.z; y.w += r1.w;
             }
@@ -156,7 +178,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st_base + r * 128 + ((c4 ^ (r & 7)) << 4)));
           if (gm < p.M && col < p.BN && n0 + col < p.N) {
             if (HAS_RES) {
-              const float4 r0 = *reinterpret_cast<const float4 *>(p.residual + gm * p.ldo + n0 + col);
+              const float4 r0 = res[i];
               x.x += r0.x; x.y += r0.y; x.z += r0.z; x.w += r0.w;
             }
             *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + gm * p.ldo + n0 + col) = x;

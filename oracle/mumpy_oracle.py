@@ -43,8 +43,12 @@ def layer_norm(x, w, b, eps=LN_EPS):
     return (x - mu) / torch.sqrt(var + eps) * w + b
 
 
-def gelu(x):  # nn.GELU() default = exact erf form
-    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+def gelu(x):
+    """nn.GELU() default = exact erf form.  erf is evaluated in float64 and rounded once: the result is then independent
+    of the host's single-precision erf implementation (a B200 box whose CPU path differed by 3e-4 on a 49x96 tensor was
+    observed), and still within 1 ulp of what the reference's ATen kernel returns."""
+    xd = x.double()
+    return (0.5 * xd * (1.0 + torch.erf(xd / math.sqrt(2.0)))).to(x.dtype)
 
 
 def linear(x, w, b=None):
