@@ -57,6 +57,11 @@ const char *mumpy_last_error(void);
  * residual (M,N) fp32 with row stride ldo or NULL (may alias out); out (M,N) of `out_dtype`, row stride ldo. */
 int mumpy_linear(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out,
                  long ldo, long M, int N, int K, int ab_dtype, int out_dtype, int act, void *stream);
+/* Same GEMM on bf16 operands with two results: out = act(A . W^T + bias) + residual (fp32) and
+ * aux_bf16 = bf16(act(A . W^T + bias)) -- the un-summed W-MSA branch that CrossSwinBlock returns as the next view's
+ * key/value source (multiTemporalViewEncoder.py:275-276) together with the shortcut sum, in one pass. */
+int mumpy_linear_dual(const void *A, long lda, const void *W, const float *bias, const float *residual, float *out,
+                      void *aux_bf16, long ldo, long M, int N, int K, int act, void *stream);
 
 /* nn.LayerNorm over the last dim (eps inside the sqrt).  swinTransformer.py:266,305; blocks.py:88,92. */
 int mumpy_layernorm(const float *x, const float *gamma, const float *beta, void *out, int out_dtype, long rows,
@@ -98,10 +103,10 @@ int mumpy_faf(const float *x, const float *dct, float *ws, float *out, int B, in
  *          units (y,x) of an aligned-corners ws x ws grid (:334-356).  dw_w (Cg,25), dw_b, ln_g, ln_b (Cg), pw (2,Cg). */
 int mumpy_cva_offsets(const float *q, const float *dw_w, const float *dw_b, const float *ln_g, const float *ln_b,
                       const float *pw, float *pix, int B, int TH1, int W, int C, int groups, int ws, void *stream);
-/* sample: x2 (B*L2, C) fp32 canvas (after `pre`) -> sampled (N2*P, C) window-major rows of `out_dtype`;
- *         kv window j uses the offsets of query window qidx(j) (see mumpy_cva_attention). */
-int mumpy_cva_sample(const float *x2, const float *pix, void *sampled, int out_dtype, int B, int TH1, int TH2, int W,
-                     int C, int groups, int ws, int per_clip_pairing, void *stream);
+/* sample: x2 (B*L2, C) canvas of `x2_dtype` (after `pre`) -> sampled (N2*P, C) window-major rows of `out_dtype`
+ *         (bf16 input needs bf16 output); kv window j uses the offsets of query window qidx(j) (see mumpy_cva_attention). */
+int mumpy_cva_sample(const void *x2, int x2_dtype, const float *pix, void *sampled, int out_dtype, int B, int TH1, int TH2,
+                     int W, int C, int groups, int ws, int per_clip_pairing, void *stream);
 /* attention: q (B*L1,C) fp32 canvas, kv (N2*P, 2C) window-major of `kv_dtype` -> o (N1*P, C) of `out_dtype`
  *         o[i] = sum_t softmax(q[qidx(r*i+t)] k[r*i+t]^T * d^-1/2) v[r*i+t], r = N2/N1 (:329-330,364,390-395);
  *         qidx(j) = j mod N1 (reference, batch-global) or the same map applied inside each clip. */

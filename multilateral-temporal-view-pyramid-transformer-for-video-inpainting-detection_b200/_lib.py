@@ -18,6 +18,7 @@ SIGNATURES = {
     "mumpy_abi_version": [],
     "mumpy_init": [ci],
     "mumpy_linear": [vp, cl, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, ci, vp],
+    "mumpy_linear_dual": [vp, cl, vp, vp, vp, vp, vp, cl, cl, ci, ci, ci, vp],
     "mumpy_layernorm": [vp, vp, vp, vp, ci, cl, ci, cf, vp],
     "mumpy_patch_merge_norm": [vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
     "mumpy_window_attention": [vp, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],
@@ -25,7 +26,7 @@ SIGNATURES = {
     "mumpy_tokenize": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
     "mumpy_faf": [vp, vp, vp, vp, ci, ci, ci, ci, ctypes.POINTER(ci), vp],
     "mumpy_cva_offsets": [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
-    "mumpy_cva_sample": [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_cva_sample": [vp, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_cva_attention": [vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_cva_residual": [vp, vp, vp, ci, ci, ci, ci, ci, vp],
     "mumpy_gather_rows": [vp, ci, vp, ci, cl, ci, ci, ci, ci, ci, ci, ci, ci, vp],

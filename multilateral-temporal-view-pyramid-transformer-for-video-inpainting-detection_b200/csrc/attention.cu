@@ -116,6 +116,80 @@ __global__ void __launch_bounds__(128) mha_short_kernel(const T *__restrict__ qk
   }
 }
 
+// N == 3 tokens (the temporal "global" encoder): LP = d*sizeof(T)/16 lanes per (sequence, head); each lane owns one
+// 16-byte chunk of the head dimension of all nine q/k/v slices (nine independent 16-byte loads), partial dot products are
+// combined with log2(LP) shuffles, and the lane writes its chunk of the three output rows.
+template <typename T, int LP>
+__global__ void __launch_bounds__(256) mha3_kernel(const T *__restrict__ qkv, T *__restrict__ out, long n_pairs, int C, int heads, float scale) {
+  constexpr int E = 16 / sizeof(T);                 // elements per 16-byte chunk
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long pair = gid / LP;
+  const int sub = (int)(gid % LP);
+  const bool live = pair < n_pairs;
+  const long bn = live ? pair / heads : 0;
+  const int h = live ? (int)(pair - bn * heads) : 0;
+  const int d = C / heads;
+  const T *base = qkv + bn * 3 * 3 * C + h * d + sub * E;
+  float x[9][E];                                    // [token*3 + which][e]
+#pragma unroll
+  for (int s = 0; s < 9; ++s) {
+    const uint4 u = live ? __ldg(reinterpret_cast<const uint4 *>(base + (long)(s / 3) * 3 * C + (s % 3) * C)) : make_uint4(0, 0, 0, 0);
+    if (sizeof(T) == 4) {
+      x[s][0] = __uint_as_float(u.x); x[s][1] = __uint_as_float(u.y); x[s][2 % E] = __uint_as_float(u.z); x[s][3 % E] = __uint_as_float(u.w);
+    } else {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162 *>(&w[e]);
+        x[s][(2 * e) % E] = __low2float(hh);
+        x[s][(2 * e + 1) % E] = __high2float(hh);
+      }
+    }
+  }
+  float sc[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float a = 0.0f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) a = fmaf(x[i * 3][e], x[j * 3 + 1][e], a);
+      sc[i][j] = a;
+    }
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) sc[i][j] += __shfl_xor_sync(0xffffffffu, sc[i][j], o);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float s0 = sc[i][0] * scale, s1 = sc[i][1] * scale, s2 = sc[i][2] * scale;
+    const float m = fmaxf(s0, fmaxf(s1, s2));
+    const float p0 = expf(s0 - m), p1 = expf(s1 - m), p2 = expf(s2 - m);
+    const float inv = 1.0f / (p0 + p1 + p2);
+    float o[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) o[e] = fmaf(p0 * inv, x[2][e], fmaf(p1 * inv, x[5][e], (p2 * inv) * x[8][e]));
+    if (live) {
+      T *dst = out + (bn * 3 + i) * C + h * d + sub * E;
+      uint4 u;
+      if (sizeof(T) == 4) {
+        u = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2 % E]), __float_as_uint(o[3 % E]));
+      } else {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 hh = __floats2bfloat162_rn(o[(2 * e) % E], o[(2 * e + 1) % E]);
+          w[e] = *reinterpret_cast<uint32_t *>(&hh);
+        }
+        u = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      *reinterpret_cast<uint4 *>(dst) = u;
+    }
+  }
+}
+
 // query window paired with kv window j (deformableAttention.py:329-330 + :394)
 __device__ __forceinline__ int cva_query_window(int j, int r, int N1, int nW1, int per_clip) {
   if (!per_clip) return j % N1;
@@ -249,6 +323,22 @@ extern "C" int mumpy_window_attention(const void *qkv, const float *bias, const 
 extern "C" int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, int N, int C, int heads, void *stream) {
   MUMPY_REQUIRE(qkv && out && Bn > 0 && N > 0 && N <= 8 && C % heads == 0, "mha_short: bad arguments (N=%d)", N);
   cudaStream_t st = as_stream(stream);
+  const int d = C / heads;
+  const int lp = d * (dtype == MUMPY_BF16 ? 2 : 4) / 16;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && (d * (dtype == MUMPY_BF16 ? 2 : 4)) % 16 == 0;
+  if (N == 3 && aligned && (lp == 4 || lp == 8 || lp == 16)) {
+    const long n_pairs = Bn * heads;
+    const float scale = 1.0f / sqrtf((float)d);
+    const unsigned grid = (unsigned)cdiv(n_pairs * lp, 256);
+#define MHA3(T, LP) mha3_kernel<T, LP><<<grid, 256, 0, st>>>(static_cast<const T *>(qkv), static_cast<T *>(out), n_pairs, C, heads, scale)
+    if (dtype == MUMPY_BF16) {
+      if (lp == 4) MHA3(__nv_bfloat16, 4); else if (lp == 8) MHA3(__nv_bfloat16, 8); else MHA3(__nv_bfloat16, 16);
+    } else {
+      if (lp == 4) MHA3(float, 4); else if (lp == 8) MHA3(float, 8); else MHA3(float, 16);
+    }
+#undef MHA3
+    return launch_status("mha3");
+  }
   if (dtype == MUMPY_BF16)
     mha_short_kernel<__nv_bfloat16><<<(unsigned)Bn, 128, 0, st>>>(static_cast<const __nv_bfloat16 *>(qkv), static_cast<__nv_bfloat16 *>(out), N, C, heads);
   else

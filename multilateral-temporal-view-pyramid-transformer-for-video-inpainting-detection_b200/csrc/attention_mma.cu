@@ -160,111 +160,244 @@ __device__ __forceinline__ int token_row(int wr, int wc, int p, int TH, int W, i
 }
 
 constexpr int ATT_TABLE_FLOATS = 232;       // (2*8-1)^2 = 225 entries for ws 8, 169 for ws 7
-constexpr int ATT_WARP_SMEM = 3 * ATT_TILE_BYTES + 64 * sizeof(long) + ATT_TABLE_FLOATS * sizeof(float);
+constexpr int ATT_WARP_SMEM = 3 * ATT_TILE_BYTES + 64 * sizeof(long) + ATT_TABLE_FLOATS * sizeof(float);   // cva kernel
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent window attention: 8 warps per CTA, one CTA per SM; every warp walks its own strided list of (window, head)
+// tasks with a two-stage cp.async ring, so the q/k/v gather of task i+1 (49 x 64 B row segments each, straight from
+// the canvas-ordered qkv matrix) is in flight while task i runs on the tensor pipe.  K and V fragments are loaded
+// once per task into registers and reused by the four 16-row query tiles.
+constexpr int WATT_WARPS = 8;
+constexpr int WATT_STAGE_BYTES = 3 * ATT_TILE_BYTES;
+constexpr int WATT_WARP_BYTES = 2 * WATT_STAGE_BYTES + 2 * 64 * (int)sizeof(int);
 
 // MODE 0: gathered bias (nH,N,N) + optional mask tensor (nW,N,N) through global loads.
-// MODE 1: bias from the raw relative_position_bias_table (T,nH) staged in shared memory; the mask is the standard Swin
-//         shift mask, recomputed from region ids on the stacked canvas (swinTransformer.py:233-252) -- no bias/mask loads.
+// MODE 1: bias from the raw relative_position_bias_table (T,nH), staged for all heads in shared memory; the mask is the
+//         standard Swin shift mask recomputed from region ids on the stacked canvas (swinTransformer.py:233-252) and is
+//         only evaluated for the windows of the last window row / column (the only ones that hold masked pairs).
 template <int WS, int MODE>
-__global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_mma_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ bias,
-                                                                              const float *__restrict__ mask, const float *__restrict__ rel_table,
-                                                                              __nv_bfloat16 *__restrict__ out, int TH, int W, int C, int heads,
-                                                                              int shift, int mshift, long n_tasks) {
+__global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ bias,
+                                                                                  const float *__restrict__ mask, const float *__restrict__ rel_table,
+                                                                                  __nv_bfloat16 *__restrict__ out, int TH, int W, int C, int heads,
+                                                                                  int shift, int mshift, long n_tasks) {
   constexpr int N = WS * WS;
+  constexpr int NT = (N + 7) / 8;
+  constexpr int T = (2 * WS - 1) * (2 * WS - 1);
   constexpr float kScale = 0.17677669529663687f;    // 32^-0.5
+  constexpr float kC = kScale * 1.4426950408889634f;
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long task = (long)blockIdx.x * ATT_WARPS + warp;
-  if (task >= n_tasks) return;
-  const int wpr = W / WS;
-  const int nW = (TH / WS) * wpr;
-  const long win = task / heads;
-  const int h = (int)(task - win * heads);
-  const long b = win / nW;
-  const int n = (int)(win - b * nW);
-  const int wr = n / wpr, wc = n - wr * wpr;
+  uint8_t *wbase = att_smem + warp * WATT_WARP_BYTES;
+  int *rows_base = reinterpret_cast<int *>(wbase + 2 * WATT_STAGE_BYTES);
+  float *tbl_all = reinterpret_cast<float *>(att_smem + WATT_WARPS * WATT_WARP_BYTES);      // [heads][T], pre-divided by the scale
+  if (MODE == 1) {
+    for (int i = threadIdx.x; i < T * heads; i += blockDim.x) {
+      const int hh = i / T, e = i - hh * T;
+      tbl_all[i] = __ldg(rel_table + (long)e * heads + hh) * (1.0f / kScale);
+    }
+  }
+  // rows >= N of every tile stay zero for the whole kernel (only rows < N are ever copied)
+  for (int i = lane; i < 2 * WATT_STAGE_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(wbase)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
+  const int wpr = W / WS, wrows = TH / WS;
+  const int nW = wrows * wpr;
   const long L = (long)TH * W;
-  uint8_t *tq = att_smem + warp * ATT_WARP_SMEM, *tk = tq + ATT_TILE_BYTES, *tv = tk + ATT_TILE_BYTES;
-  long *rows = reinterpret_cast<long *>(tv + ATT_TILE_BYTES);
-  float *tbl = reinterpret_cast<float *>(rows + 64);
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int p = lane + 32 * u;
-    if (p < N) rows[p] = b * L + token_row<WS>(wr, wc, p, TH, W, shift);
-  }
-  if (MODE == 1) {
-    constexpr int T = (2 * WS - 1) * (2 * WS - 1);
-    for (int i = lane; i < T; i += 32) tbl[i] = __ldg(rel_table + (long)i * heads + h) * (1.0f / kScale);
-  }
-  __syncwarp();
-  {
-    const __nv_bfloat16 *base = qkv + h * 32;
-#pragma unroll
-    for (int which = 0; which < 3; ++which) {
-      uint8_t *tile = which == 0 ? tq : (which == 1 ? tk : tv);
-#pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        const int p = pass * 8 + (lane >> 2);
-        const int chunk = lane & 3;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (p < N) v = __ldg(reinterpret_cast<const uint4 *>(base + rows[p] * 3 * C + which * C + chunk * 8));
-        *reinterpret_cast<uint4 *>(tile + tile_off(p, chunk)) = v;
-      }
-    }
-  }
-  const uint32_t sQ = smem_addr(tq), sK = smem_addr(tk), sV = smem_addr(tv);
   const int g = lane >> 2, t = lane & 3;
-  // per-lane key-column descriptors for MODE 1: a(j) | region(j) << 16 for j = nt*8 + 2t + e
+  // per-lane constants: key columns j = nt*8 + 2t + e  ->  a(j) | (j / WS) << 8 | (j % WS) << 12
   auto a_of = [](int p) { return (p / WS) * (2 * WS - 1) + p % WS; };
-  auto region_of = [&](int p) {
-    const int rr = wr * WS + p / WS, cc = wc * WS + p % WS;       // coordinates on the shifted canvas
-    const int hr = rr < TH - WS ? 0 : (rr < TH - mshift ? 1 : 2);
-    const int wreg = cc < W - WS ? 0 : (cc < W - mshift ? 1 : 2);
-    return hr * 3 + wreg;
-  };
-  int aj[16];
-  if (MODE == 1) {
+  int jpack[16];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+  for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = min(nt * 8 + 2 * t + e, N - 1);
-        aj[nt * 2 + e] = a_of(j) | ((mshift > 0 ? region_of(j) : 0) << 16);
+    for (int e = 0; e < 2; ++e) {
+      const int j = min(nt * 8 + 2 * t + e, N - 1);
+      jpack[nt * 2 + e] = a_of(j) | ((j / WS) << 8) | ((j % WS) << 12);
+    }
+  const long total_warps = (long)gridDim.x * WATT_WARPS;
+  const long first = (long)blockIdx.x * WATT_WARPS + warp;
+
+  auto issue = [&](long task, int stage) {
+    const long win = task / heads;
+    const int h = (int)(task - win * heads);
+    const long b = win / nW;
+    const int n = (int)(win - b * nW);
+    const int wr = n / wpr, wc = n - wr * wpr;
+    int *rows = rows_base + stage * 64;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int p = lane + 32 * u;
+      if (p < N) rows[p] = (int)(b * L) + token_row<WS>(wr, wc, p, TH, W, shift);
+    }
+    __syncwarp();
+    const __nv_bfloat16 *base = qkv + h * 32 + (lane & 3) * 8;
+    const uint32_t sbase = smem_addr(wbase + stage * WATT_STAGE_BYTES);
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int p = pass * 8 + (lane >> 2);
+      if (pass * 8 < N && p < N) {
+        const __nv_bfloat16 *src = base + (long)rows[p] * 3 * C;
+        const uint32_t dst = sbase + tile_off(p, lane & 3);
+        cp_async_16(dst, src);
+        cp_async_16(dst + ATT_TILE_BYTES, src + C);
+        cp_async_16(dst + 2 * ATT_TILE_BYTES, src + 2 * C);
       }
-  }
-  __syncwarp();
+    }
+  };
+
+  if (first < n_tasks) issue(first, 0);
+  cp_async_commit();
+  int stage = 0;
+  for (long task = first; task < n_tasks; task += total_warps, stage ^= 1) {
+    const long next = task + total_warps;
+    if (next < n_tasks) issue(next, stage ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+
+    const long win = task / heads;
+    const int h = (int)(task - win * heads);
+    const int n = (int)(win % nW);
+    const int wr = n / wpr, wc = n - wr * wpr;
+    const int *rows = rows_base + stage * 64;
+    const uint32_t sQ = smem_addr(wbase + stage * WATT_STAGE_BYTES), sK = sQ + ATT_TILE_BYTES, sV = sK + ATT_TILE_BYTES;
+    const bool last_r = wr == wrows - 1, last_c = wc == wpr - 1;
+    const bool masked = MODE == 1 && mshift > 0 && (last_r || last_c);
+    const float *tbl = tbl_all + h * T;
+
+    uint32_t kf[NT][4], vf[4][2][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) ldsm_x4(sK + tile_off(nt * 8 + (lane & 7), lane >> 3), kf[nt][0], kf[nt][1], kf[nt][2], kf[nt][3]);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int tok = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int dp = 0; dp < 2; ++dp) ldsm_x4_t(sV + tile_off(tok, dp * 2 + (lane >> 4)), vf[kk][dp][0], vf[kk][dp][1], vf[kk][dp][2], vf[kk][dp][3]);
+    }
+    // region ids of this lane's key columns (standard shift mask), only for windows that hold masked pairs
+    int regj[16];
+    if (masked) {
+#pragma unroll
+      for (int s = 0; s < 16; ++s) {
+        const int jr = (jpack[s] >> 8) & 15, jc = (jpack[s] >> 12) & 15;
+        const int hr = last_r ? (jr < WS - mshift ? 1 : 2) : 0;
+        const int wreg = last_c ? (jc < WS - mshift ? 1 : 2) : 0;
+        regj[s] = hr * 3 + wreg;
+      }
+    }
+    const float mask_val = -100.0f / kScale;
+
 #pragma unroll 1
-  for (int mt = 0; mt * 16 < N; ++mt) {
-    float s[8][4], sum_lo, sum_hi;
-    const int i_lo = mt * 16 + g, i_hi = i_lo + 8;
-    const int ic_lo = min(i_lo, N - 1), ic_hi = min(i_hi, N - 1);
-    if (MODE == 1) {
-      constexpr int OFF = (WS - 1) * 2 * WS;
-      TableBias<WS> init{tbl, aj, a_of(ic_lo) + OFF, a_of(ic_hi) + OFF, mshift > 0 ? region_of(ic_lo) : 0, mshift > 0 ? region_of(ic_hi) : 0,
-                         mshift > 0 ? -100.0f / kScale : 0.0f};
-      scores_softmax<N>(sQ, sK, mt, lane, kScale, init, s, sum_lo, sum_hi);
-    } else {
-      LoadedBias<N> init{bias + (long)h * N * N, mask ? mask + (long)n * N * N : nullptr, ic_lo, ic_hi, t, 1.0f / kScale};
-      scores_softmax<N>(sQ, sK, mt, lane, kScale, init, s, sum_lo, sum_hi);
+    for (int mt = 0; mt * 16 < N; ++mt) {
+      float s[8][4];
+      const int i_lo = mt * 16 + g, i_hi = i_lo + 8;
+      const int ic_lo = min(i_lo, N - 1), ic_hi = min(i_hi, N - 1);
+      if (MODE == 1) {
+        constexpr int OFF = (WS - 1) * 2 * WS;
+        const float *t_lo = tbl + a_of(ic_lo) + OFF, *t_hi = tbl + a_of(ic_hi) + OFF;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[nt][e] = ((e >> 1) ? t_hi : t_lo)[-(jpack[nt * 2 + (e & 1)] & 0xff)];
+        if (masked) {
+          const int r_lo = (last_r ? (ic_lo / WS < WS - mshift ? 1 : 2) : 0) * 3 + (last_c ? (ic_lo % WS < WS - mshift ? 1 : 2) : 0);
+          const int r_hi = (last_r ? (ic_hi / WS < WS - mshift ? 1 : 2) : 0) * 3 + (last_c ? (ic_hi % WS < WS - mshift ? 1 : 2) : 0);
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (regj[nt * 2 + (e & 1)] != ((e >> 1) ? r_hi : r_lo)) s[nt][e] += mask_val;
+        }
+      } else {
+        LoadedBias<N> init{bias + (long)h * N * N, mask ? mask + (long)n * N * N : nullptr, ic_lo, ic_hi, t, 1.0f / kScale};
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[nt][e] = init(e >> 1, nt, e);
+      }
+      uint32_t a[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldsm_x4(sQ + tile_off(row, ks * 2 + (lane >> 4)), a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        mma_bf16(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], kf[nt][0], kf[nt][1]);
+        mma_bf16(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], kf[nt][2], kf[nt][3]);
+      }
+      float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (nt * 8 + 7 >= N) {                        // only the last n-tile can hold padded key columns
+            const int j = nt * 8 + 2 * t + (e & 1);
+            if (j >= N) s[nt][e] = -INFINITY;
+          }
+          if (e < 2) m_lo = fmaxf(m_lo, s[nt][e]); else m_hi = fmaxf(m_hi, s[nt][e]);
+        }
+      }
+      m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+      m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+      m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+      m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+      const float mc_lo = m_lo * kC, mc_hi = m_hi * kC;
+      float sum_lo = 0.0f, sum_hi = 0.0f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float p;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[nt][e], kC, -((e < 2) ? mc_lo : mc_hi))));   // 2^-inf = 0 for padding
+          s[nt][e] = p;
+          if (e < 2) sum_lo += p; else sum_hi += p;
+        }
+      }
+      sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+      sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+      sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+      sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+      float o[4][4];
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[dn][e] = 0.0f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (kk * 16 < N) {
+          const bool two = 2 * kk + 1 < NT;             // second key n-tile of this k-step exists
+          const uint32_t a0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+          const uint32_t a1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+          const uint32_t a2 = two ? pack_bf16(s[(2 * kk + 1) & 7][0], s[(2 * kk + 1) & 7][1]) : 0u;
+          const uint32_t a3 = two ? pack_bf16(s[(2 * kk + 1) & 7][2], s[(2 * kk + 1) & 7][3]) : 0u;
+#pragma unroll
+          for (int dp = 0; dp < 2; ++dp) {
+            mma_bf16(o[dp * 2], a0, a1, a2, a3, vf[kk][dp][0], vf[kk][dp][1]);
+            mma_bf16(o[dp * 2 + 1], a0, a1, a2, a3, vf[kk][dp][2], vf[kk][dp][3]);
+          }
+        }
+      }
+      const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
+      if (i_lo < N) {
+        __nv_bfloat16 *dst = out + (long)rows[i_lo] * C + h * 32 + 2 * t;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][0] * inv_lo, o[dn][1] * inv_lo);
+      }
+      if (i_hi < N) {
+        __nv_bfloat16 *dst = out + (long)rows[i_hi] * C + h * 32 + 2 * t;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][2] * inv_hi, o[dn][3] * inv_hi);
+      }
     }
-    float o[4][4];
-#pragma unroll
-    for (int dn = 0; dn < 4; ++dn)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[dn][e] = 0.0f;
-    pv_accumulate(sV, lane, s, o);
-    const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
-    if (i_lo < N) {
-      __nv_bfloat16 *dst = out + rows[i_lo] * C + h * 32 + 2 * t;
-#pragma unroll
-      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][0] * inv_lo, o[dn][1] * inv_lo);
-    }
-    if (i_hi < N) {
-      __nv_bfloat16 *dst = out + rows[i_hi] * C + h * 32 + 2 * t;
-#pragma unroll
-      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][2] * inv_hi, o[dn][3] * inv_hi);
-    }
+    __syncwarp();      // every lane is done with this stage's tiles and rows before the next iteration refills them
   }
+  cp_async_wait<0>();
 }
 
 __device__ __forceinline__ int cva_query_window_m(int j, int r, int N1, int nW1, int per_clip) {
@@ -396,36 +529,64 @@ static int att_smem_attr(K kernel) {
   return MUMPY_OK;
 }
 
+template <typename K>
+static int watt_smem_attr(K kernel, size_t bytes) {
+  static const void *seen[8];
+  static size_t granted[8];
+  static int n_seen = 0;
+  const void *key = reinterpret_cast<const void *>(kernel);
+  int slot = -1;
+  for (int i = 0; i < n_seen; ++i)
+    if (seen[i] == key) slot = i;
+  if (slot >= 0 && bytes <= granted[slot]) return MUMPY_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(window attention, %zu B): %s", bytes, cudaGetErrorString(e));
+    return MUMPY_ERR_CUDA;
+  }
+  if (slot < 0 && n_seen < 8) slot = n_seen++;
+  if (slot >= 0) {
+    seen[slot] = key;
+    granted[slot] = bytes;
+  }
+  return MUMPY_OK;
+}
+
 int window_attention_mma(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask, void *out, int B,
                          int TH, int W, int C, int heads, int ws, int shift, cudaStream_t st) {
   const long n_tasks = (long)B * (TH / ws) * (W / ws) * heads;
-  const unsigned grid = (unsigned)cdiv(n_tasks, ATT_WARPS);
-  const size_t smem = ATT_WARPS * ATT_WARP_SMEM;
+  MUMPY_REQUIRE((long)B * TH * W < (1l << 31), "window_attention(bf16): too many tokens");
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const long want = cdiv(n_tasks, WATT_WARPS);
+  const unsigned grid = (unsigned)(want < num_sms ? want : num_sms);
   const bool table_mode = rel_table != nullptr && (mask == nullptr || standard_mask);
+  const int T = (2 * ws - 1) * (2 * ws - 1);
+  const size_t smem = (size_t)WATT_WARPS * WATT_WARP_BYTES + (table_mode ? (size_t)T * heads * sizeof(float) : 0);
+  MUMPY_REQUIRE(smem <= 227 * 1024, "window_attention(bf16): %d heads need %zu B of shared memory", heads, smem);
   const __nv_bfloat16 *q = static_cast<const __nv_bfloat16 *>(qkv);
   __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out);
   int rc;
   const int mshift = (mask != nullptr) ? shift : 0;      // region-id mask only when the caller passed the (standard) mask
+#define WATT_LAUNCH(WS_, MODE_)                                                                                               \
+  {                                                                                                                           \
+    if ((rc = watt_smem_attr(window_attention_mma_kernel<WS_, MODE_>, smem))) return rc;                                      \
+    window_attention_mma_kernel<WS_, MODE_><<<grid, WATT_WARPS * 32, smem, st>>>(q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks); \
+  }
   if (ws == 7) {
-    if (table_mode) {
-      if ((rc = att_smem_attr(window_attention_mma_kernel<7, 1>))) return rc;
-      window_attention_mma_kernel<7, 1><<<grid, ATT_WARPS * 32, smem, st>>>(q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks);
-    } else {
-      if ((rc = att_smem_attr(window_attention_mma_kernel<7, 0>))) return rc;
-      window_attention_mma_kernel<7, 0><<<grid, ATT_WARPS * 32, smem, st>>>(q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks);
-    }
+    if (table_mode) WATT_LAUNCH(7, 1) else WATT_LAUNCH(7, 0)
   } else if (ws == 8) {
-    if (table_mode) {
-      if ((rc = att_smem_attr(window_attention_mma_kernel<8, 1>))) return rc;
-      window_attention_mma_kernel<8, 1><<<grid, ATT_WARPS * 32, smem, st>>>(q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks);
-    } else {
-      if ((rc = att_smem_attr(window_attention_mma_kernel<8, 0>))) return rc;
-      window_attention_mma_kernel<8, 0><<<grid, ATT_WARPS * 32, smem, st>>>(q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks);
-    }
+    if (table_mode) WATT_LAUNCH(8, 1) else WATT_LAUNCH(8, 0)
   } else {
     set_error("window_attention(bf16): window size %d unsupported (7 or 8)", ws);
     return MUMPY_ERR_UNSUPPORTED;
   }
+#undef WATT_LAUNCH
   return launch_status("window_attention_mma");
 }
 

@@ -16,26 +16,34 @@ __device__ __forceinline__ int cva_query_window_s(int j, int r, int N1, int nW1,
 // conv_offset = dw5x5(pad 2, within the window) -> LayerNorm(Cg) -> GELU -> 1x1 (Cg->2)   (:253-258)
 // pix = ((tanh(o) * (1/ws) * 2 + ref) + 1) / 2 * (ws-1)                                    (:338-356)
 template <int MAXC>   // channels per lane = Cg/32 <= MAXC
-__global__ void __launch_bounds__(128) cva_offsets_kernel(const float *__restrict__ q, const float *__restrict__ dw_w,
+__global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restrict__ q, const float *__restrict__ dw_w,
                                                           const float *__restrict__ dw_b, const float *__restrict__ ln_g,
                                                           const float *__restrict__ ln_b, const float *__restrict__ pw,
                                                           float *__restrict__ pix, int TH1, int W, int C, int groups, int ws) {
-  extern __shared__ float tile[];   // [P][Cg]
+  extern __shared__ float tile[];   // [P][Cg] query window, then [25][Cg] depthwise taps (tap-major: conflict-free per lane)
   const int P = ws * ws;
   const int Cg = C / groups;
+  float *wsm = tile + P * Cg;
   const int win = blockIdx.x, g = blockIdx.y;
   const int nW1 = (TH1 / ws) * (W / ws);
   const int b = win / nW1, n = win % nW1;
   const long L1 = (long)TH1 * W;
-  for (int e = threadIdx.x; e < P * Cg; e += blockDim.x) {
-    const int p = e / Cg, c = e % Cg;
+  const int cg4 = Cg >> 2;
+  for (int e = threadIdx.x; e < P * cg4; e += blockDim.x) {
+    const int p = e / cg4, c4 = e - p * cg4;
     const long row = b * L1 + window_token_row(n, p, TH1, W, ws, 0);
-    tile[e] = q[row * C + g * Cg + c];
+    reinterpret_cast<float4 *>(tile)[e] = __ldg(reinterpret_cast<const float4 *>(q + row * C + g * Cg) + c4);
+  }
+  for (int e = threadIdx.x; e < 25 * Cg; e += blockDim.x) {
+    const int c = e / 25, tap = e - c * 25;
+    wsm[tap * Cg + c] = __ldg(dw_w + e);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int p = warp; p < P; p += nwarps) {
     const int pi = p / ws, pj = p % ws;
+    const int a0 = max(0, 2 - pi), a1 = min(5, ws + 2 - pi);
+    const int b0 = max(0, 2 - pj), b1 = min(5, ws + 2 - pj);
     float val[MAXC];
     float s = 0.0f;
 #pragma unroll
@@ -43,16 +51,12 @@ __global__ void __launch_bounds__(128) cva_offsets_kernel(const float *__restric
       const int c = lane + 32 * u;
       float acc = 0.0f;
       if (c < Cg) {
-        for (int a = 0; a < 5; ++a) {
-          const int yy = pi + a - 2;
-          if (yy < 0 || yy >= ws) continue;
-          for (int bb = 0; bb < 5; ++bb) {
-            const int xx = pj + bb - 2;
-            if (xx < 0 || xx >= ws) continue;
-            acc = fmaf(tile[(yy * ws + xx) * Cg + c], dw_w[c * 25 + a * 5 + bb], acc);
-          }
+        for (int a = a0; a < a1; ++a) {
+          const float *trow = tile + ((pi + a - 2) * ws + pj - 2) * Cg + c;
+          const float *wrow = wsm + a * 5 * Cg + c;
+          for (int bb = b0; bb < b1; ++bb) acc = fmaf(trow[bb * Cg], wrow[bb * Cg], acc);
         }
-        acc += dw_b[c];
+        acc += __ldg(dw_b + c);
         s += acc;
       }
       val[u] = acc;
@@ -73,9 +77,9 @@ __global__ void __launch_bounds__(128) cva_offsets_kernel(const float *__restric
     for (int u = 0; u < MAXC; ++u) {
       const int c = lane + 32 * u;
       if (c < Cg) {
-        const float a = gelu_erf((val[u] - mean) * rstd * ln_g[c] + ln_b[c]);
-        oy = fmaf(a, pw[c], oy);
-        ox = fmaf(a, pw[Cg + c], ox);
+        const float a = gelu_erf((val[u] - mean) * rstd * __ldg(ln_g + c) + __ldg(ln_b + c));
+        oy = fmaf(a, __ldg(pw + c), oy);
+        ox = fmaf(a, __ldg(pw + Cg + c), ox);
       }
     }
     oy = warp_sum(oy);
@@ -94,8 +98,8 @@ __global__ void __launch_bounds__(128) cva_offsets_kernel(const float *__restric
 }
 
 // F.grid_sample(bilinear, zeros padding, align_corners=True) of kv window j with the offsets of its query window.
-template <typename OutT>
-__global__ void __launch_bounds__(256) cva_sample_kernel(const float *__restrict__ x2, const float *__restrict__ pix,
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__ x2, const float *__restrict__ pix,
                                                          OutT *__restrict__ sampled, int N1, int TH1, int TH2, int W, int C,
                                                          int groups, int ws, int per_clip) {
   const int P = ws * ws;
@@ -107,27 +111,48 @@ __global__ void __launch_bounds__(256) cva_sample_kernel(const float *__restrict
   const int qw = cva_query_window_s(j, r, N1, nW1, per_clip);
   const int b2 = j / nW2, n2 = j % nW2;
   const long L2 = (long)TH2 * W;
-  for (int e = threadIdx.x; e < P * C; e += blockDim.x) {
-    const int p = e / C, c = e % C;
-    const int g = c / Cg;
-    const float *pp = pix + (((long)qw * groups + g) * P + p) * 2;
-    const float py = pp[0], px = pp[1];
+  const int wpr = W / ws;
+  const long base_row = b2 * L2 + (long)(n2 / wpr) * ws * W + (n2 % wpr) * ws;      // canvas row of the window's pixel (0,0)
+  const int C4 = C >> 2;
+  for (int e = threadIdx.x; e < P * C4; e += blockDim.x) {
+    const int p = e / C4, c = (e - p * C4) * 4;
+    const int g = c / Cg;                                  // Cg % 4 == 0: the four channels share a group
+    const float2 pp = __ldg(reinterpret_cast<const float2 *>(pix + (((long)qw * groups + g) * P + p) * 2));
+    const float py = pp.x, px = pp.y;
     const float fy = floorf(py), fx = floorf(px);
     const int y0 = (int)fy, x0 = (int)fx;
     const float wy1 = py - fy, wx1 = px - fx;
     const float wy0 = 1.0f - wy1, wx0 = 1.0f - wx1;
-    float acc = 0.0f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
         const int yy = y0 + dy, xx = x0 + dx;
         if (yy < 0 || yy >= ws || xx < 0 || xx >= ws) continue;
-        const long row = b2 * L2 + window_token_row(n2, yy * ws + xx, TH2, W, ws, 0);
-        acc = fmaf(x2[row * C + c], (dy ? wy1 : wy0) * (dx ? wx1 : wx0), acc);
+        const float wgt = (dy ? wy1 : wy0) * (dx ? wx1 : wx0);
+        const InT *src = x2 + (base_row + (long)yy * W + xx) * C + c;
+        float4 v;
+        if (sizeof(InT) == 4) {
+          v = __ldg(reinterpret_cast<const float4 *>(src));
+        } else {
+          const uint2 u = __ldg(reinterpret_cast<const uint2 *>(src));
+          const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162 *>(&u.x), h1 = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
+          v = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
+        }
+        acc.x = fmaf(v.x, wgt, acc.x); acc.y = fmaf(v.y, wgt, acc.y); acc.z = fmaf(v.z, wgt, acc.z); acc.w = fmaf(v.w, wgt, acc.w);
       }
     }
-    sampled[((long)j * P + p) * C + c] = from_f32<OutT>(acc);
+    OutT *dst = sampled + ((long)j * P + p) * C + c;
+    if (sizeof(OutT) == 2) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t *>(&h0);
+      pk.y = *reinterpret_cast<uint32_t *>(&h1);
+      *reinterpret_cast<uint2 *>(dst) = pk;
+    } else {
+      *reinterpret_cast<float4 *>(dst) = acc;
+    }
   }
 }
 
@@ -156,17 +181,12 @@ __global__ void __launch_bounds__(256) cva_residual_kernel(const float *__restri
 
 using namespace mumpy;
 
-extern "C" int mumpy_cva_offsets(const float *q, const float *dw_w, const float *dw_b, const float *ln_g, const float *ln_b,
-                                 const float *pw, float *pix, int B, int TH1, int W, int C, int groups, int ws, void *stream) {
-  MUMPY_REQUIRE(q && dw_w && dw_b && ln_g && ln_b && pw && pix && B > 0 && C % groups == 0, "cva_offsets: bad arguments");
-  MUMPY_REQUIRE(TH1 % ws == 0 && W % ws == 0 && ws <= 8, "cva_offsets: bad window geometry");
-  const int Cg = C / groups;
-  MUMPY_REQUIRE(Cg <= 256, "cva_offsets: group width %d > 256 unsupported", Cg);
-  const int N1 = B * (TH1 / ws) * (W / ws);
-  const size_t smem = (size_t)ws * ws * Cg * sizeof(float);
+template <int MAXC>
+static int launch_cva_offsets(const float *q, const float *dw_w, const float *dw_b, const float *ln_g, const float *ln_b, const float *pw,
+                              float *pix, int N1, int TH1, int W, int C, int groups, int ws, size_t smem, cudaStream_t st) {
   static size_t granted = 0;
   if (smem > 48 * 1024 && smem > granted) {
-    cudaError_t e = cudaFuncSetAttribute(cva_offsets_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(cva_offsets_kernel<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("cva_offsets: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MUMPY_ERR_CUDA;
@@ -174,20 +194,41 @@ extern "C" int mumpy_cva_offsets(const float *q, const float *dw_w, const float 
     granted = smem;
   }
   dim3 grid((unsigned)N1, (unsigned)groups);
-  cva_offsets_kernel<8><<<grid, 128, smem, as_stream(stream)>>>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, TH1, W, C, groups, ws);
+  cva_offsets_kernel<MAXC><<<grid, 256, smem, st>>>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, TH1, W, C, groups, ws);
   return launch_status("cva_offsets");
 }
 
-extern "C" int mumpy_cva_sample(const float *x2, const float *pix, void *sampled, int out_dtype, int B, int TH1, int TH2, int W,
-                                int C, int groups, int ws, int per_clip_pairing, void *stream) {
+extern "C" int mumpy_cva_offsets(const float *q, const float *dw_w, const float *dw_b, const float *ln_g, const float *ln_b,
+                                 const float *pw, float *pix, int B, int TH1, int W, int C, int groups, int ws, void *stream) {
+  MUMPY_REQUIRE(q && dw_w && dw_b && ln_g && ln_b && pw && pix && B > 0 && C % groups == 0, "cva_offsets: bad arguments");
+  MUMPY_REQUIRE(TH1 % ws == 0 && W % ws == 0 && ws <= 8, "cva_offsets: bad window geometry");
+  const int Cg = C / groups;
+  MUMPY_REQUIRE(Cg <= 256 && Cg % 4 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0, "cva_offsets: group width %d unsupported (<= 256, multiple of 4)", Cg);
+  const int N1 = B * (TH1 / ws) * (W / ws);
+  const size_t smem = (size_t)(ws * ws + 25) * Cg * sizeof(float);
+  cudaStream_t st = as_stream(stream);
+  if (Cg <= 32) return launch_cva_offsets<1>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups, ws, smem, st);
+  if (Cg <= 64) return launch_cva_offsets<2>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups, ws, smem, st);
+  if (Cg <= 128) return launch_cva_offsets<4>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups, ws, smem, st);
+  return launch_cva_offsets<8>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups, ws, smem, st);
+}
+
+extern "C" int mumpy_cva_sample(const void *x2, int x2_dtype, const float *pix, void *sampled, int out_dtype, int B, int TH1, int TH2,
+                                int W, int C, int groups, int ws, int per_clip_pairing, void *stream) {
   MUMPY_REQUIRE(x2 && pix && sampled && B > 0 && TH2 % TH1 == 0, "cva_sample: bad arguments");
+  MUMPY_REQUIRE(C % groups == 0 && (C / groups) % 4 == 0, "cva_sample: channels per group must be a multiple of 4");
+  MUMPY_REQUIRE(((reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(sampled) | reinterpret_cast<uintptr_t>(pix)) & 15) == 0,
+                "cva_sample: buffers must be 16-byte aligned");
+  MUMPY_REQUIRE(x2_dtype == MUMPY_F32 || out_dtype == MUMPY_BF16, "cva_sample: bf16 input needs bf16 output");
   const int N1 = B * (TH1 / ws) * (W / ws);
   const int N2 = B * (TH2 / ws) * (W / ws);
   cudaStream_t st = as_stream(stream);
-  if (out_dtype == MUMPY_BF16)
-    cva_sample_kernel<__nv_bfloat16><<<N2, 256, 0, st>>>(x2, pix, static_cast<__nv_bfloat16 *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
+  if (x2_dtype == MUMPY_BF16)
+    cva_sample_kernel<__nv_bfloat16, __nv_bfloat16><<<N2, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(x2), pix, static_cast<__nv_bfloat16 *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
+  else if (out_dtype == MUMPY_BF16)
+    cva_sample_kernel<float, __nv_bfloat16><<<N2, 256, 0, st>>>(static_cast<const float *>(x2), pix, static_cast<__nv_bfloat16 *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
   else
-    cva_sample_kernel<float><<<N2, 256, 0, st>>>(x2, pix, static_cast<float *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
+    cva_sample_kernel<float, float><<<N2, 256, 0, st>>>(static_cast<const float *>(x2), pix, static_cast<float *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
   return launch_status("cva_sample");
 }
 

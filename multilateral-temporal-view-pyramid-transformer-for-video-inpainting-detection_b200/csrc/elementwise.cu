@@ -26,6 +26,33 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restric
   }
 }
 
+__device__ __forceinline__ void store4(float *dst, float4 v) { *reinterpret_cast<float4 *>(dst) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16 *dst, float4 v) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t *>(&h0);
+  pk.y = *reinterpret_cast<uint32_t *>(&h1);
+  *reinterpret_cast<uint2 *>(dst) = pk;
+}
+
+// 4 channels per thread (C, dst_ld, dst_col multiples of 4; 16-byte aligned bases)
+template <typename OutT>
+__global__ void __launch_bounds__(256) gather_rows_vec_kernel(const float *__restrict__ src, int C4, OutT *__restrict__ dst, long dst_ld,
+                                                              int dst_col, long total4, int rows_out, int rows_src, int div, int mul_hi,
+                                                              int mul_lo, int add) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < total4; i += stride) {
+    const int c4 = (int)(i % C4);
+    const long r = i / C4;
+    const long b = r / rows_out;
+    const int q = (int)(r - b * rows_out);
+    const long srow = b * rows_src + (q / div) * mul_hi + (q % div) * mul_lo + add;
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + srow * C4 + c4);
+    store4(dst + r * dst_ld + dst_col + 4 * c4, v);
+  }
+}
+
 __global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ in, long ld_in, __nv_bfloat16 *__restrict__ out, long total,
                                                      int H, int W, int Cin, int kh, int kw, int ph, int pw, int Kpad) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,6 +128,71 @@ __global__ void __launch_bounds__(256) resample_kernel(const float *__restrict__
     if (mul) v *= mul[i];
     if (add) v += add[i];
     out[(i / Co) * ld_out + out_col + c] = v;
+  }
+}
+
+// 4 channels per thread for every mode but pixel-shuffle (C, ld_out, out_col multiples of 4)
+__global__ void __launch_bounds__(256) resample_vec_kernel(const float *__restrict__ in, const float *__restrict__ mul,
+                                                           const float *__restrict__ add, float *__restrict__ out, long ld_out, int out_col,
+                                                           long total4, int H, int W, int C4, int Ho, int Wo, int mode, int scale) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const float4 *in4 = reinterpret_cast<const float4 *>(in);
+  for (; i < total4; i += stride) {
+    const int c4 = (int)(i % C4);
+    long t = i / C4;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const long b = t / Ho;
+    const float4 *img = in4 + b * H * W * C4 + c4;
+    float4 v;
+    if (mode == MUMPY_RS_IDENTITY) {
+      v = __ldg(img + ((long)ho * W + wo) * C4);
+    } else if (mode == MUMPY_RS_AVGPOOL2) {
+      const float4 *p = img + ((long)(2 * ho) * W + 2 * wo) * C4;
+      const float4 a = __ldg(p), bb = __ldg(p + C4), c = __ldg(p + (long)W * C4), d = __ldg(p + (long)W * C4 + C4);
+      v.x = (a.x + bb.x + c.x + d.x) * 0.25f; v.y = (a.y + bb.y + c.y + d.y) * 0.25f;
+      v.z = (a.z + bb.z + c.z + d.z) * 0.25f; v.w = (a.w + bb.w + c.w + d.w) * 0.25f;
+    } else {
+      int y0, y1, x0, x1;
+      float wy, wx;
+      const bool aligned = mode == MUMPY_RS_UP_ALIGNED;
+      bilinear_axis(ho, H, Ho, scale, aligned, y0, y1, wy);
+      bilinear_axis(wo, W, Wo, scale, aligned, x0, x1, wx);
+      const float4 v00 = __ldg(img + ((long)y0 * W + x0) * C4), v01 = __ldg(img + ((long)y0 * W + x1) * C4);
+      const float4 v10 = __ldg(img + ((long)y1 * W + x0) * C4), v11 = __ldg(img + ((long)y1 * W + x1) * C4);
+      // ATen upsample_bilinear2d: w0*(w0x*v00 + w1x*v01) + w1*(w0x*v10 + w1x*v11)
+      const float ux = 1.0f - wx, uy = 1.0f - wy;
+      v.x = uy * (ux * v00.x + wx * v01.x) + wy * (ux * v10.x + wx * v11.x);
+      v.y = uy * (ux * v00.y + wx * v01.y) + wy * (ux * v10.y + wx * v11.y);
+      v.z = uy * (ux * v00.z + wx * v01.z) + wy * (ux * v10.z + wx * v11.z);
+      v.w = uy * (ux * v00.w + wx * v01.w) + wy * (ux * v10.w + wx * v11.w);
+    }
+    if (mul) {
+      const float4 m = __ldg(reinterpret_cast<const float4 *>(mul) + i);
+      v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+    }
+    if (add) {
+      const float4 m = __ldg(reinterpret_cast<const float4 *>(add) + i);
+      v.x += m.x; v.y += m.y; v.z += m.z; v.w += m.w;
+    }
+    *reinterpret_cast<float4 *>(out + (i / C4) * ld_out + out_col + 4 * c4) = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) mul_add_vec_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, const float4 *__restrict__ c,
+                                                          float4 *__restrict__ out, long n4) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 x = __ldg(a + i), y = b ? __ldg(b + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 v = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
+    if (c) {
+      const float4 z = __ldg(c + i);
+      v.x += z.x; v.y += z.y; v.z += z.z; v.w += z.w;
+    }
+    out[i] = v;
   }
 }
 
@@ -207,6 +299,42 @@ __global__ void __launch_bounds__(256) conv_cout1_kernel(const float *__restrict
   out[m] = acc;
 }
 
+// Cout == 1, LPP = Cin/4 lanes per output pixel: every lane owns one float4 of channels over the kh*kw taps (coalesced
+// 16-byte loads, neighbouring pixels re-hit L1), the partial sums are combined with log2(LPP) shuffles.
+template <int LPP>
+__global__ void __launch_bounds__(256) conv_cout1_vec_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
+                                                             float *__restrict__ out, long pixels, int H, int W, int kh, int kw, int ph, int pw) {
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long m = gid / LPP;
+  const int sub = (int)(gid % LPP);
+  const bool live = m < pixels;
+  const long mm = live ? m : 0;
+  const int x = (int)(mm % W);
+  const long r = mm / W;
+  const int y = (int)(r % H);
+  const long b = r / H;
+  const float4 *in4 = reinterpret_cast<const float4 *>(in);
+  const float4 *w4 = reinterpret_cast<const float4 *>(w);
+  float acc = 0.0f;
+  for (int ky = 0; ky < kh; ++ky) {
+    const int yy = y + ky - ph;
+    if (yy < 0 || yy >= H) continue;
+    for (int kx = 0; kx < kw; ++kx) {
+      const int xx = x + kx - pw;
+      if (xx < 0 || xx >= W) continue;
+      const float4 v = __ldg(in4 + ((b * H + yy) * W + xx) * LPP + sub);
+      const float4 wt = __ldg(w4 + (ky * kw + kx) * LPP + sub);
+      acc = fmaf(v.x, wt.x, acc);
+      acc = fmaf(v.y, wt.y, acc);
+      acc = fmaf(v.z, wt.z, acc);
+      acc = fmaf(v.w, wt.w, acc);
+    }
+  }
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (live && sub == 0) out[m] = acc + (bias ? bias[0] : 0.0f);
+}
+
 __global__ void __launch_bounds__(256) mask_counts_kernel(const float *__restrict__ logits, const unsigned char *__restrict__ gt,
                                                           unsigned char *__restrict__ mask, unsigned long long *__restrict__ counts, int HW) {
   __shared__ unsigned int red[4][8];
@@ -249,6 +377,14 @@ extern "C" int mumpy_gather_rows(const float *src, int C, void *dst, int dst_dty
   MUMPY_REQUIRE(src && dst && C > 0 && B > 0 && rows_out > 0 && div > 0, "gather_rows: bad arguments");
   const long total = (long)B * rows_out * C;
   cudaStream_t st = as_stream(stream);
+  if (C % 4 == 0 && dst_ld % 4 == 0 && dst_col % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const long total4 = total / 4;
+    if (dst_dtype == MUMPY_BF16)
+      gather_rows_vec_kernel<__nv_bfloat16><<<flat_blocks(total4), 256, 0, st>>>(src, C / 4, static_cast<__nv_bfloat16 *>(dst), dst_ld, dst_col, total4, rows_out, rows_src, div, mul_hi, mul_lo, add);
+    else
+      gather_rows_vec_kernel<float><<<flat_blocks(total4), 256, 0, st>>>(src, C / 4, static_cast<float *>(dst), dst_ld, dst_col, total4, rows_out, rows_src, div, mul_hi, mul_lo, add);
+    return launch_status("gather_rows_vec");
+  }
   if (dst_dtype == MUMPY_BF16)
     gather_rows_kernel<__nv_bfloat16><<<flat_blocks(total), 256, 0, st>>>(src, C, static_cast<__nv_bfloat16 *>(dst), dst_ld, dst_col, total, rows_out, rows_src, div, mul_hi, mul_lo, add);
   else
@@ -283,18 +419,34 @@ extern "C" int mumpy_resample_nhwc(const float *in, const float *mul, const floa
     default: set_error("resample_nhwc: unknown mode %d", mode); return MUMPY_ERR_ARG;
   }
   const long total = (long)B * Ho * Wo * Co;
+  if (mode != MUMPY_RS_PIXEL_SHUFFLE2 && C % 4 == 0 && ld_out % 4 == 0 && out_col % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mul) | reinterpret_cast<uintptr_t>(add)) & 15) == 0) {
+    resample_vec_kernel<<<flat_blocks(total / 4), 256, 0, as_stream(stream)>>>(in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale);
+    return launch_status("resample_vec");
+  }
   resample_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(in, mul, add, out, ld_out, out_col, total, H, W, C, Ho, Wo, Co, mode, scale);
   return launch_status("resample_nhwc");
 }
 
 extern "C" int mumpy_mul_add(const float *a, const float *b, const float *c, float *out, long n, void *stream) {
   MUMPY_REQUIRE(a && b && out && n > 0, "mul_add: bad arguments");
+  if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    mul_add_vec_kernel<<<flat_blocks(n / 4), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(b),
+                                                                        reinterpret_cast<const float4 *>(c), reinterpret_cast<float4 *>(out), n / 4);
+    return launch_status("mul_add_vec");
+  }
   mul_add_kernel<<<flat_blocks(n), 256, 0, as_stream(stream)>>>(a, b, c, out, n);
   return launch_status("mul_add");
 }
 
 extern "C" int mumpy_add(const float *a, const float *b, float *out, long n, void *stream) {
   MUMPY_REQUIRE(a && b && out && n > 0, "add: bad arguments");
+  if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    // out = a * 1 + b through the fused kernel (b slot = nullptr means multiply by one)
+    mul_add_vec_kernel<<<flat_blocks(n / 4), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(a), nullptr, reinterpret_cast<const float4 *>(b),
+                                                                        reinterpret_cast<float4 *>(out), n / 4);
+    return launch_status("add_vec");
+  }
   add_kernel<<<flat_blocks(n), 256, 0, as_stream(stream)>>>(a, b, out, n);
   return launch_status("add");
 }
@@ -334,6 +486,16 @@ extern "C" int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const fl
                                        int kh, int kw, int ph, int pw, void *stream) {
   MUMPY_REQUIRE(in && w && out && B > 0 && Cin % 4 == 0 && kh * kw * Cin * 4 <= 48 * 1024, "conv2d_nhwc_cout1: bad arguments");
   const long pixels = (long)B * H * W;
+  if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w)) & 15) == 0 && (Cin == 32 || Cin == 64 || Cin == 128 || Cin == 16)) {
+    cudaStream_t st = as_stream(stream);
+    const int lpp = Cin / 4;
+    const unsigned grid = (unsigned)cdiv(pixels * lpp, 256);
+    if (lpp == 4) conv_cout1_vec_kernel<4><<<grid, 256, 0, st>>>(in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
+    else if (lpp == 8) conv_cout1_vec_kernel<8><<<grid, 256, 0, st>>>(in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
+    else if (lpp == 16) conv_cout1_vec_kernel<16><<<grid, 256, 0, st>>>(in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
+    else conv_cout1_vec_kernel<32><<<grid, 256, 0, st>>>(in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
+    return launch_status("conv2d_nhwc_cout1_vec");
+  }
   conv_cout1_kernel<<<(unsigned)cdiv(pixels, 256), 256, kh * kw * Cin * sizeof(float), as_stream(stream)>>>(in, w, bias, out, pixels, H, W,
                                                                                                            Cin, kh, kw, ph, pw);
   return launch_status("conv2d_nhwc_cout1");

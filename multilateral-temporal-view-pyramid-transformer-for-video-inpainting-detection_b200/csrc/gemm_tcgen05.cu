@@ -64,6 +64,7 @@ struct TcParams {
   const float *bias;
   const float *residual;
   void *out;
+  __nv_bfloat16 *aux;     // optional second output (fp32-out mode only): bf16 of act(acc + bias) BEFORE the residual add, row stride ldo
   long ldo;
   long M;
   int N, K;
@@ -177,6 +178,13 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
           float4 x;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st_base + r * 128 + ((c4 ^ (r & 7)) << 4)));
           if (gm < p.M && col < p.BN && n0 + col < p.N) {
+            if (p.aux) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t *>(&h0);
+              pk.y = *reinterpret_cast<uint32_t *>(&h1);
+              *reinterpret_cast<uint2 *>(p.aux + gm * p.ldo + n0 + col) = pk;
+            }
             if (HAS_RES) {
               const float4 r0 = res[i];
               x.x += r0.x; x.y += r0.y; x.z += r0.z; x.w += r0.w;
@@ -356,20 +364,31 @@ static int env_int(const char *name) {
 }
 static int g_dbg_bn = -1, g_dbg_stages = -1, g_dbg_mode = -1;
 
-static int pick_bn(long M, int N) {
+// Tile width: minimise  waves * max(mma, epilogue) + min(mma, epilogue)  (accumulators are double buffered, so the epilogue
+// of one tile overlaps the main loop of the next) over the divisors of N; times in ns from the measured rates of this
+// kernel: 128 x BN x 64 k-block = BN * 1.9 ns of tensor pipe (~1100 TFLOP/s), 32-column epilogue chunk per warp pair
+// ~450 ns (+250 ns with an fp32 residual to fetch, +150 ns for GELU).
+static int pick_bn(long M, int N, int nkb, bool has_res, bool gelu) {
   if (g_dbg_bn < 0) g_dbg_bn = env_int("MUMPY_TC_BN");
   if (g_dbg_bn > 0 && N % g_dbg_bn == 0) return g_dbg_bn;
   static const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
   const long mt = cdiv(M, TC_BM);
-  int largest = 0, smallest64 = 0;
-  for (int c : cands) {                            // descending
+  const double t_chunk = 450.0 + (has_res ? 250.0 : 0.0) + (gelu ? 150.0 : 0.0);
+  int best = 0;
+  double best_cost = 1e30;
+  for (int c : cands) {
     if (N % c != 0) continue;
-    if (!largest) largest = c;
-    if (mt * (N / c) >= g_num_sms) return c;       // widest tile that still gives every SM a tile
-    if (c >= 64) smallest64 = c;
+    const long tiles = mt * (N / c);
+    const double waves = (double)cdiv(tiles, g_num_sms);
+    const double mma = (double)nkb * c * 1.9 + 300.0;
+    const double epi = (double)((c + 63) / 64) * t_chunk;
+    const double cost = waves * (mma > epi ? mma : epi) + (mma > epi ? epi : mma);
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      best = c;
+    }
   }
-  if (smallest64) return smallest64;               // small problem: favour parallelism, keep N >= 64
-  if (largest) return largest;
+  if (best) return best;
   for (int c : cands)
     if (c <= N) return c;                          // no divisor: the tail tile is masked
   return 16;
@@ -418,7 +437,7 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   return launch_status("gemm_tc_kernel");
 }
 
-int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, long ldo,
+int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, void *aux, long ldo,
                 long M, int N, int K, int out_dtype, int act, cudaStream_t st) {
   int rc = resolve_driver_entry_points();
   if (rc) return rc;
@@ -428,15 +447,18 @@ int linear_bf16(const void *A, long lda, const void *W, const float *bias, const
                 "linear(bf16): A, W, out must be 16-byte aligned");
   MUMPY_REQUIRE(out_dtype == MUMPY_BF16 ? (ldo % 8 == 0) : (ldo % 4 == 0), "linear(bf16): ldo alignment");
   MUMPY_REQUIRE(M < (1l << 31), "linear(bf16): M too large");
+  MUMPY_REQUIRE(!aux || (out_dtype == MUMPY_F32 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ldo % 8 == 0),
+                "linear(bf16): the bf16 side output needs an fp32 main output, 16-byte alignment and ldo %% 8 == 0");
   TcParams p = {};
   p.bias = bias;
   p.residual = residual;
   p.out = out;
+  p.aux = static_cast<__nv_bfloat16 *>(aux);
   p.ldo = ldo;
   p.M = M;
   p.N = N;
   p.K = K;
-  p.BN = pick_bn(M, N);
+  p.BN = pick_bn(M, N, (K + TC_BK - 1) / TC_BK, residual != nullptr, act == MUMPY_ACT_GELU);
   p.act = act;
   p.out_bf16 = (out_dtype == MUMPY_BF16);
   p.conv = 0;
@@ -468,7 +490,7 @@ int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, co
   p.M = (long)B * H * W;
   p.N = Cout;
   p.K = kh * kw * cblocks;          // k-blocks
-  p.BN = pick_bn(p.M, Cout);
+  p.BN = pick_bn(p.M, Cout, p.K, residual != nullptr, act == MUMPY_ACT_GELU);
   p.act = act;
   p.out_bf16 = (out_dtype == MUMPY_BF16);
   p.conv = 1;

@@ -59,55 +59,99 @@ __global__ void __launch_bounds__(256) layernorm_kernel(Rows rows, const float *
   }
 }
 
-// Plain rows, C % 4 == 0, C <= 1024: the row lives in registers (<= 8 float4 per lane): one coalesced global read,
-// exact two-pass statistics, one coalesced write (8-byte bf16x4 or 16-byte fp32x4 per lane).
-template <typename OutT>
+// Plain rows, C % 4 == 0, C <= 1024: rows live in registers as float4 (NV vectors per lane per row); a warp normalises
+// R rows at once so that every lane keeps 8 independent 16-byte loads in flight whatever the row width (C = 96 .. 1024):
+// one coalesced global read, exact two-pass statistics, one coalesced write (8-byte bf16x4 or 16-byte fp32x4 per lane).
+template <typename OutT, int NV, int R>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
                                                             const float *__restrict__ beta, OutT *__restrict__ out, long n_rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
-  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
+  const long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= n_rows) return;
   const int nv = C >> 2;
-  const float4 *xr = reinterpret_cast<const float4 *>(x + row * C);
-  float4 v[8];
-  float s = 0.0f;
+  float4 v[R][NV];
+  float s[R];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int i = lane + 32 * u;
-    if (i < nv) {
-      v[u] = xr[i];
-      s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+  for (int r = 0; r < R; ++r) {
+    s[r] = 0.0f;
+    const bool live = row0 + r < n_rows;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (row0 + r) * C);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int i = lane + 32 * u;
+      v[r][u] = (live && i < nv) ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  const float mean = warp_sum(s) / C;
-  float q = 0.0f;
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int i = lane + 32 * u;
-    if (i < nv) {
-      const float a = v[u].x - mean, b = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int u = 0; u < NV; ++u) s[r] += (v[r][u].x + v[r][u].y) + (v[r][u].z + v[r][u].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  float mean[R], q[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    mean[r] = s[r] / C;
+    q[r] = 0.0f;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      if (lane + 32 * u < nv) {
+        const float a = v[r][u].x - mean[r], b = v[r][u].y - mean[r], c = v[r][u].z - mean[r], d = v[r][u].w - mean[r];
+        q[r] += (a * a + b * b) + (c * c + d * d);
+      }
     }
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
   const float4 *g4 = reinterpret_cast<const float4 *>(gamma), *b4 = reinterpret_cast<const float4 *>(beta);
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
+  for (int u = 0; u < NV; ++u) {
     const int i = lane + 32 * u;
     if (i < nv) {
       const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
-      const float o0 = (v[u].x - mean) * rstd * g.x + b.x, o1 = (v[u].y - mean) * rstd * g.y + b.y;
-      const float o2 = (v[u].z - mean) * rstd * g.z + b.z, o3 = (v[u].w - mean) * rstd * g.w + b.w;
-      if (sizeof(OutT) == 2) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t *>(&h0);
-        pk.y = *reinterpret_cast<uint32_t *>(&h1);
-        reinterpret_cast<uint2 *>(out + row * C)[i] = pk;
-      } else {
-        reinterpret_cast<float4 *>(out + row * C)[i] = make_float4(o0, o1, o2, o3);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (row0 + r < n_rows) {
+          const float rstd = 1.0f / sqrtf(q[r] / C + eps);
+          const float o0 = (v[r][u].x - mean[r]) * rstd * g.x + b.x, o1 = (v[r][u].y - mean[r]) * rstd * g.y + b.y;
+          const float o2 = (v[r][u].z - mean[r]) * rstd * g.z + b.z, o3 = (v[r][u].w - mean[r]) * rstd * g.w + b.w;
+          if (sizeof(OutT) == 2) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t *>(&h0);
+            pk.y = *reinterpret_cast<uint32_t *>(&h1);
+            reinterpret_cast<uint2 *>(out + (row0 + r) * C)[i] = pk;
+          } else {
+            reinterpret_cast<float4 *>(out + (row0 + r) * C)[i] = make_float4(o0, o1, o2, o3);
+          }
+        }
       }
     }
+  }
+}
+
+template <typename OutT, int NV, int R>
+static void launch_ln_vec(const float *x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
+  const long warps = cdiv(rows, R);
+  layernorm_vec_kernel<OutT, NV, R><<<(unsigned)cdiv(warps, 8), 256, 0, st>>>(x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
+}
+
+template <typename OutT>
+static void dispatch_ln_vec(const float *x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
+  const int nvl = (C / 4 + 31) / 32;      // float4 vectors per lane per row
+  switch (nvl) {
+    case 1: launch_ln_vec<OutT, 1, 8>(x, gamma, beta, out, rows, C, eps, st); break;
+    case 2: launch_ln_vec<OutT, 2, 4>(x, gamma, beta, out, rows, C, eps, st); break;
+    case 3: launch_ln_vec<OutT, 3, 2>(x, gamma, beta, out, rows, C, eps, st); break;
+    case 4: launch_ln_vec<OutT, 4, 2>(x, gamma, beta, out, rows, C, eps, st); break;
+    case 5:
+    case 6: launch_ln_vec<OutT, 6, 1>(x, gamma, beta, out, rows, C, eps, st); break;
+    default: launch_ln_vec<OutT, 8, 1>(x, gamma, beta, out, rows, C, eps, st); break;
   }
 }
 
@@ -214,11 +258,10 @@ extern "C" int mumpy_layernorm(const float *x, const float *gamma, const float *
   MUMPY_REQUIRE(x && gamma && beta && out && rows > 0 && C > 0, "layernorm: bad arguments");
   if (C % 4 == 0 && C <= 1024 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
                                    reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
-    dim3 grid((unsigned)cdiv(rows, 8));
     if (out_dtype == MUMPY_BF16)
-      layernorm_vec_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(x, gamma, beta, static_cast<__nv_bfloat16 *>(out), rows, C, eps);
+      dispatch_ln_vec<__nv_bfloat16>(x, gamma, beta, out, rows, C, eps, as_stream(stream));
     else
-      layernorm_vec_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(x, gamma, beta, static_cast<float *>(out), rows, C, eps);
+      dispatch_ln_vec<float>(x, gamma, beta, out, rows, C, eps, as_stream(stream));
     return launch_status("layernorm_vec");
   }
   return launch_ln(PlainRows{x, C}, gamma, beta, out, out_dtype, rows, C, eps, as_stream(stream));

@@ -84,27 +84,44 @@ class CrossSwinBlock(PackedModule):
         self.register_buffer("attn_mask", attn_mask)
         self.fused_window_process = fused_window_process
 
-    def forward(self, x1, x2):
-        """x1 (B,L1,C1), x2 (B,L2,C2) canvases -> (x1', out) with out = the un-summed W-MSA branch (:228-291)."""
-        require_inference(self)
+    def cross(self, x1, x2_op, need_out=True, need_out_fp32=False):
+        """x1 (B,L1,C1) fp32 canvas; x2_op (B,L2,C2) canvas of the other view already in GEMM-operand precision (or None
+        for the last view) -> (x1', out_fp32 or None, out_op) where out is the un-summed W-MSA branch (:275): `out_op` is
+        its GEMM-operand form, which is all the next view's `pre` needs.  In bf16 mode the projection writes the
+        shortcut sum (fp32) and `out_op` (bf16) from the same accumulators (mumpy_linear_dual)."""
         H, W = self.input_resolution
         B, L1, C1 = x1.shape
         TH1 = L1 // W
         x1 = x1.contiguous()
         xn = ops.layernorm(x1, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         ao = self.attn.canvas_attention(xn, B, TH1, W, self.shift_size, self.attn_mask)
-        out = self.attn.project(ao)                                   # `out` (:275)
-        h = ops.add(x1, out)                                          # shortcut + attn (:276)
+        out = None
+        if ops.precision() == "bf16" and not need_out_fp32:
+            if need_out:
+                h, out_op = ops.linear_dual(ao, self.attn._gemm_weight("proj", self.attn.proj.weight), self.attn.proj.bias, x1)
+            else:
+                h, out_op = self.attn.project(ao, residual=x1), None
+        else:
+            out = self.attn.project(ao)                               # `out` (:275)
+            h = ops.add(x1, out)                                      # shortcut + attn (:276)
+            out_op = as_operand(out) if need_out else None
         if not self.last_view:
-            L2, C2 = x2.shape[1], x2.shape[2]
-            TH2 = L2 // W
-            # `pre` is per token, so it commutes with window_partition: apply it on the canvas (:282-283)
-            x2p = ops.linear(as_operand(x2.contiguous()), self._gemm_weight("pre", self.pre.weight), self.pre.bias)
+            TH2 = x2_op.shape[1] // W
+            # `pre` is per token, so it commutes with window_partition: apply it on the canvas (:282-283); its result is
+            # only ever bilinearly sampled, so it is kept in operand precision
+            x2p = ops.linear(x2_op, self._gemm_weight("pre", self.pre.weight), self.pre.bias, out_dtype=ops.act_dtype())
             y = self.cva.crossattn.canvas_forward(h, x2p, B, TH1, TH2, W, PER_CLIP_PAIRING)
             # h + (window_partition(h) + raw_reshape(y)) added in window-major order, no window_reverse (:138,284-286)
             h = ops.cva_residual(h, y, B, TH1, W, C1, self.window_size)
         xn = ops.layernorm(h, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        return self.mlp.fused(xn, residual=h), out
+        return self.mlp.fused(xn, residual=h), out, out_op
+
+    def forward(self, x1, x2):
+        """x1 (B,L1,C1), x2 (B,L2,C2) canvases -> (x1', out) with out = the un-summed W-MSA branch (:228-291)."""
+        require_inference(self)
+        x2_op = None if self.last_view else as_operand(x2.contiguous())
+        y, out, _ = self.cross(x1, x2_op, need_out=True, need_out_fp32=True)
+        return y, out
 
 
 class CrossThreeViewSwinBlock(nn.Module):
@@ -126,9 +143,11 @@ class CrossThreeViewSwinBlock(nn.Module):
 
     def forward(self, x):
         # order view3 -> view2 (+CVA from view3) -> view1 (+CVA from view2)   (:345-350)
-        x[2], out2 = self.block3(x[2], x[2])
-        x[1], out1 = self.block2(x[1], out2)
-        x[0], _ = self.block1(x[0], out1)
+        for blk in (self.block1, self.block2, self.block3):
+            require_inference(blk)
+        x[2], _, op3 = self.block3.cross(x[2], None)
+        x[1], _, op2 = self.block2.cross(x[1], op3)
+        x[0], _, _ = self.block1.cross(x[0], op2, need_out=False)
         return x
 
 

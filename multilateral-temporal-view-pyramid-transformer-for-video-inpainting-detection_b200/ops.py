@@ -85,6 +85,21 @@ def linear(a, w, bias=None, residual=None, act=ACT_NONE, out_dtype=torch.float32
     return out
 
 
+def linear_dual(a, w, bias, residual):
+    """bf16 operands only: returns (act-free a @ w.T + bias + residual as fp32, bf16(a @ w.T + bias))."""
+    K = a.shape[-1]
+    N = w.shape[0]
+    M = a.numel() // K
+    if w.shape[1] != K or a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise _lib.MumpyError("linear_dual: bf16 operands required")
+    out = torch.empty(a.shape[:-1] + (N,), dtype=torch.float32, device=a.device)
+    aux = torch.empty(a.shape[:-1] + (N,), dtype=torch.bfloat16, device=a.device)
+    lib, st = _prep(a, w, bias, residual, out, aux)
+    _lib.check(lib.mumpy_linear_dual(_p(a), K, _p(w), _p(bias), _p(residual), _p(out), _p(aux), N, M, N, K, ACT_NONE, st),
+               "mumpy_linear_dual")
+    return out, aux
+
+
 def linear_into(a, lda, w, bias, out, ldo, M, N, K, act=ACT_NONE, residual=None):
     """Strided form: a/out are base tensors (possibly wider matrices) with explicit row strides."""
     lib, st = _prep(a, w, bias, out)
@@ -164,7 +179,7 @@ def cva_sample(x2, pix, B, TH1, TH2, W, C, groups, ws, per_clip, out_dtype):
     N2 = B * (TH2 // ws) * (W // ws)
     out = torch.empty((N2 * ws * ws, C), dtype=out_dtype, device=x2.device)
     lib, st = _prep(x2, pix, out)
-    _lib.check(lib.mumpy_cva_sample(_p(x2), _p(pix), _p(out), code(out_dtype), B, TH1, TH2, W, C, groups, ws,
+    _lib.check(lib.mumpy_cva_sample(_p(x2), code(x2.dtype), _p(pix), _p(out), code(out_dtype), B, TH1, TH2, W, C, groups, ws,
                                     int(per_clip), st), "mumpy_cva_sample")
     return out
 

@@ -25,7 +25,8 @@ if what == "attn":
         ops.window_attention(qkv, bias, mask, B, TH, W, C, heads, 7, 3, rel_table=table, standard_mask=True)
 elif what.startswith("gemm"):
     shapes = {"gemm_fc1": (B * 588, 2048, 512, ops.ACT_GELU, torch.bfloat16), "gemm_fc2": (B * 588, 512, 2048, ops.ACT_NONE, torch.float32),
-              "gemm_s0": (B * 9408, 512, 128, ops.ACT_GELU, torch.bfloat16), "gemm_qkv": (B * 588, 1536, 512, ops.ACT_NONE, torch.bfloat16)}
+              "gemm_s0": (B * 9408, 512, 128, ops.ACT_GELU, torch.bfloat16), "gemm_qkv": (B * 588, 1536, 512, ops.ACT_NONE, torch.bfloat16),
+              "gemm_small": (B * 196, 384, 384, ops.ACT_NONE, torch.float32), "gemm_small_fc1": (B * 196, 1536, 384, ops.ACT_GELU, torch.bfloat16)}
     M, N, K, act, odt = shapes[what]
     a = torch.randn((M, K), device=dev).bfloat16()
     w = (torch.randn((N, K), device=dev) / K ** 0.5).bfloat16()
