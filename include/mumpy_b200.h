@@ -49,6 +49,9 @@ int mumpy_abi_version(void);
 /* Binds the calling thread to `device` and resolves the driver entry point used to encode TMA maps. */
 int mumpy_init(int device);
 const char *mumpy_last_error(void);
+/* Programmatic dependent launch of the library's kernels (default on; environment MUMPY_PDL=0 disables): each kernel
+ * may be scheduled while its predecessor in the stream drains and synchronises on it in-kernel (griddepcontrol.wait). */
+int mumpy_set_pdl(int enabled);
 
 /* nn.Linear / 1x1 conv:  out = act(A . W^T + bias) (+ residual).   swinTransformer.py:45-51,142,164,365;
  * blocks.py:28-34,56,71; deformableAttention.py:333,361-362,402; multiTemporalViewEncoder.py:283,740;

@@ -17,6 +17,7 @@ vp, ci, cl, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
 SIGNATURES = {
     "mumpy_abi_version": [],
     "mumpy_init": [ci],
+    "mumpy_set_pdl": [ci],
     "mumpy_linear": [vp, cl, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, ci, vp],
     "mumpy_linear_dual": [vp, cl, vp, vp, vp, vp, vp, cl, cl, ci, ci, ci, vp],
     "mumpy_layernorm": [vp, vp, vp, vp, ci, cl, ci, cf, vp],

@@ -1,6 +1,7 @@
 // Error plumbing, init and the dtype dispatch of mumpy_linear.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,15 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+static int g_pdl = -1;      // -1: read MUMPY_PDL (default on) at first use
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char *v = getenv("MUMPY_PDL");
+    g_pdl = (v && v[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
 }
 
 int launch_status(const char *what) {
@@ -34,12 +44,14 @@ int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, co
               int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int out_dtype, int act, cudaStream_t st);
 
 __global__ void cast_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, long n) {
+  pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
 }
 
 __global__ void cast_bf16_vec_kernel(const float4 *__restrict__ in, uint2 *__restrict__ out, long n4) {
+  pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
@@ -59,6 +71,11 @@ using namespace mumpy;
 extern "C" int mumpy_abi_version(void) { return 1; }
 
 extern "C" const char *mumpy_last_error(void) { return g_err; }
+
+extern "C" int mumpy_set_pdl(int enabled) {
+  g_pdl = enabled ? 1 : 0;
+  return MUMPY_OK;
+}
 
 extern "C" int mumpy_init(int device) {
   cudaError_t e = cudaSetDevice(device);
@@ -111,10 +128,10 @@ extern "C" int mumpy_cast_bf16(const float *in, void *out, long n, void *stream)
   if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     const long n4 = n / 4;
     const int vb = (int)(cdiv(n4, 256) < 148 * 16 ? cdiv(n4, 256) : 148 * 16);
-    cast_bf16_vec_kernel<<<vb, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(in), reinterpret_cast<uint2 *>(out), n4);
+    launch_kernel(cast_bf16_vec_kernel, vb, 256, 0, as_stream(stream), reinterpret_cast<const float4 *>(in), reinterpret_cast<uint2 *>(out), n4);
     return launch_status("cast_bf16_vec");
   }
   int blocks = (int)(cdiv(n, 256) < 148 * 8 ? cdiv(n, 256) : 148 * 8);
-  cast_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(in, static_cast<__nv_bfloat16 *>(out), n);
+  launch_kernel(cast_bf16_kernel, blocks, 256, 0, as_stream(stream), in, static_cast<__nv_bfloat16 *>(out), n);
   return launch_status("cast_bf16");
 }

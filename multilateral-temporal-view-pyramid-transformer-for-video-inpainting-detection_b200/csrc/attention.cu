@@ -33,6 +33,7 @@ template <typename T, int D>
 __global__ void __launch_bounds__(128) window_attention_kernel(const T *__restrict__ qkv, const float *__restrict__ bias,
                                                                const float *__restrict__ mask, T *__restrict__ out, int TH, int W,
                                                                int C, int ws, int shift) {
+  pdl_grid_sync();
   extern __shared__ float sm[];
   const int N = ws * ws;
   float *q = sm, *k = q + N * (D + 1), *v = k + N * (D + 1), *S = v + N * (D + 1);
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const T *__restri
 // blocks.py:55-70 for N <= 8 tokens: one warp per (head, query); lanes span the head dim.
 template <typename T>
 __global__ void __launch_bounds__(128) mha_short_kernel(const T *__restrict__ qkv, T *__restrict__ out, int N, int C, int heads) {
+  pdl_grid_sync();
   const long bn = blockIdx.x;
   const int d = C / heads;
   const float scale = 1.0f / sqrtf((float)d);
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(128) mha_short_kernel(const T *__restrict__ qk
 // combined with log2(LP) shuffles, and the lane writes its chunk of the three output rows.
 template <typename T, int LP>
 __global__ void __launch_bounds__(256) mha3_kernel(const T *__restrict__ qkv, T *__restrict__ out, long n_pairs, int C, int heads, float scale) {
+  pdl_grid_sync();
   constexpr int E = 16 / sizeof(T);                 // elements per 16-byte chunk
   const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long pair = gid / LP;
@@ -201,6 +204,7 @@ __device__ __forceinline__ int cva_query_window(int j, int r, int N1, int nW1, i
 template <typename TKV, typename TO, int D>
 __global__ void __launch_bounds__(128) cva_attention_kernel(const float *__restrict__ q, const TKV *__restrict__ kv, TO *__restrict__ o,
                                                             int N1, int TH1, int W, int C, int ws, int r, int per_clip) {
+  pdl_grid_sync();
   extern __shared__ float sm[];
   const int N = ws * ws;
   float *qs = sm, *ks = qs + N * (D + 1), *vs = ks + N * (D + 1), *S = vs + N * (D + 1);
@@ -309,7 +313,7 @@ extern "C" int mumpy_window_attention(const void *qkv, const float *bias, const 
     const size_t smem = attn_smem_floats<DD>(N) * sizeof(float);                                                          \
     rc = ensure_smem(window_attention_kernel<T, DD>, smem);                                                               \
     if (rc) return rc;                                                                                                    \
-    window_attention_kernel<T, DD><<<grid, 128, smem, st>>>(static_cast<const T *>(qkv), bias, mask, static_cast<T *>(out), TH, W, C, ws, shift); \
+    launch_kernel(window_attention_kernel<T, DD>, grid, 128, smem, st, static_cast<const T *>(qkv), bias, mask, static_cast<T *>(out), TH, W, C, ws, shift); \
   }
   if (dtype == MUMPY_BF16) {
     if (D == 32) LAUNCH(__nv_bfloat16, 32) else LAUNCH(__nv_bfloat16, 64)
@@ -330,7 +334,7 @@ extern "C" int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, i
     const long n_pairs = Bn * heads;
     const float scale = 1.0f / sqrtf((float)d);
     const unsigned grid = (unsigned)cdiv(n_pairs * lp, 256);
-#define MHA3(T, LP) mha3_kernel<T, LP><<<grid, 256, 0, st>>>(static_cast<const T *>(qkv), static_cast<T *>(out), n_pairs, C, heads, scale)
+#define MHA3(T, LP) launch_kernel(mha3_kernel<T, LP>, grid, 256, 0, st, static_cast<const T *>(qkv), static_cast<T *>(out), n_pairs, C, heads, scale)
     if (dtype == MUMPY_BF16) {
       if (lp == 4) MHA3(__nv_bfloat16, 4); else if (lp == 8) MHA3(__nv_bfloat16, 8); else MHA3(__nv_bfloat16, 16);
     } else {
@@ -340,9 +344,9 @@ extern "C" int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, i
     return launch_status("mha3");
   }
   if (dtype == MUMPY_BF16)
-    mha_short_kernel<__nv_bfloat16><<<(unsigned)Bn, 128, 0, st>>>(static_cast<const __nv_bfloat16 *>(qkv), static_cast<__nv_bfloat16 *>(out), N, C, heads);
+    launch_kernel(mha_short_kernel<__nv_bfloat16>, (unsigned)Bn, 128, 0, st, static_cast<const __nv_bfloat16 *>(qkv), static_cast<__nv_bfloat16 *>(out), N, C, heads);
   else
-    mha_short_kernel<float><<<(unsigned)Bn, 128, 0, st>>>(static_cast<const float *>(qkv), static_cast<float *>(out), N, C, heads);
+    launch_kernel(mha_short_kernel<float>, (unsigned)Bn, 128, 0, st, static_cast<const float *>(qkv), static_cast<float *>(out), N, C, heads);
   return launch_status("mha_short");
 }
 
@@ -359,8 +363,8 @@ extern "C" int mumpy_cva_attention(const float *q, const void *kv, int kv_dtype,
   cudaStream_t st = as_stream(stream);
   if (kv_dtype == MUMPY_BF16 && C % 8 == 0) return cva_attention_mma(q, kv, o, B, TH1, TH2, W, C, heads, ws, per_clip_pairing, st);
   if (kv_dtype == MUMPY_BF16)
-    cva_attention_kernel<__nv_bfloat16, __nv_bfloat16, 32><<<grid, 128, smem, st>>>(q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1, TH1, W, C, ws, r, per_clip_pairing);
+    launch_kernel(cva_attention_kernel<__nv_bfloat16, __nv_bfloat16, 32>, grid, 128, smem, st, q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1, TH1, W, C, ws, r, per_clip_pairing);
   else
-    cva_attention_kernel<float, float, 32><<<grid, 128, smem, st>>>(q, static_cast<const float *>(kv), static_cast<float *>(o), N1, TH1, W, C, ws, r, per_clip_pairing);
+    launch_kernel(cva_attention_kernel<float, float, 32>, grid, 128, smem, st, q, static_cast<const float *>(kv), static_cast<float *>(o), N1, TH1, W, C, ws, r, per_clip_pairing);
   return launch_status("cva_attention");
 }

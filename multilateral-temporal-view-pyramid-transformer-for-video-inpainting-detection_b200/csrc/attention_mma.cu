@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
                                                                                   const float *__restrict__ mask, const float *__restrict__ rel_table,
                                                                                   __nv_bfloat16 *__restrict__ out, int TH, int W, int C, int heads,
                                                                                   int shift, int mshift, long n_tasks) {
+  pdl_grid_sync();
   constexpr int N = WS * WS;
   constexpr int NT = (N + 7) / 8;
   constexpr int T = (2 * WS - 1) * (2 * WS - 1);
@@ -412,6 +413,7 @@ template <int WS>
 __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const float *__restrict__ q, const __nv_bfloat16 *__restrict__ kv,
                                                                            __nv_bfloat16 *__restrict__ o_out, int N1, int TH1, int W, int C,
                                                                            int heads, int r, int per_clip, long n_tasks) {
+  pdl_grid_sync();
   constexpr int N = WS * WS;
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -576,7 +578,7 @@ int window_attention_mma(const void *qkv, const float *bias, const float *mask, 
 #define WATT_LAUNCH(WS_, MODE_)                                                                                               \
   {                                                                                                                           \
     if ((rc = watt_smem_attr(window_attention_mma_kernel<WS_, MODE_>, smem))) return rc;                                      \
-    window_attention_mma_kernel<WS_, MODE_><<<grid, WATT_WARPS * 32, smem, st>>>(q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks); \
+    launch_kernel(window_attention_mma_kernel<WS_, MODE_>, grid, WATT_WARPS * 32, smem, st, q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks); \
   }
   if (ws == 7) {
     if (table_mode) WATT_LAUNCH(7, 1) else WATT_LAUNCH(7, 0)
@@ -600,11 +602,11 @@ int cva_attention_mma(const float *q, const void *kv, void *o, int B, int TH1, i
   int rc;
   if (ws == 7) {
     if ((rc = att_smem_attr(cva_attention_mma_kernel<7>))) return rc;
-    cva_attention_mma_kernel<7><<<grid, ATT_WARPS * 32, smem, st>>>(q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1,
+    launch_kernel(cva_attention_mma_kernel<7>, grid, ATT_WARPS * 32, smem, st, q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1,
                                                                    TH1, W, C, heads, r, per_clip, n_tasks);
   } else if (ws == 8) {
     if ((rc = att_smem_attr(cva_attention_mma_kernel<8>))) return rc;
-    cva_attention_mma_kernel<8><<<grid, ATT_WARPS * 32, smem, st>>>(q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1,
+    launch_kernel(cva_attention_mma_kernel<8>, grid, ATT_WARPS * 32, smem, st, q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1,
                                                                    TH1, W, C, heads, r, per_clip, n_tasks);
   } else {
     set_error("cva_attention(bf16): window size %d unsupported (7 or 8)", ws);

@@ -20,6 +20,34 @@ int launch_status(const char *what);   // cudaGetLastError -> MUMPY_OK / MUMPY_E
   } while (0)
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch: every kernel of the library is launched with the programmatic-stream-serialisation
+// attribute and starts with pdl_grid_sync(): griddepcontrol.wait blocks until the preceding kernel of the stream has
+// completed and its writes are visible (a no-op without the attribute), launch_dependents lets the next kernel's CTAs be
+// scheduled -- and run their own prologue up to their wait -- while this one is still running.  Inside a CUDA graph
+// this removes the drain-then-launch bubble between the ~750 dependent kernels of one forward.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  if (pdl_enabled()) {
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float to_f32(float v) { return v; }

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restric
                                                           const float *__restrict__ dw_b, const float *__restrict__ ln_g,
                                                           const float *__restrict__ ln_b, const float *__restrict__ pw,
                                                           float *__restrict__ pix, int TH1, int W, int C, int groups, int ws) {
+  pdl_grid_sync();
   extern __shared__ float tile[];   // [P][Cg] query window, then [25][Cg] depthwise taps (tap-major: conflict-free per lane)
   const int P = ws * ws;
   const int Cg = C / groups;
@@ -102,6 +103,7 @@ template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__ x2, const float *__restrict__ pix,
                                                          OutT *__restrict__ sampled, int N1, int TH1, int TH2, int W, int C,
                                                          int groups, int ws, int per_clip) {
+  pdl_grid_sync();
   const int P = ws * ws;
   const int Cg = C / groups;
   const int j = blockIdx.x;
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__
 // x_new = h + window_partition(h) (window-major, added at flat position) + reinterpret_(C,P)->(P,C)(y)
 __global__ void __launch_bounds__(256) cva_residual_kernel(const float *__restrict__ h, const float *__restrict__ y,
                                                            float *__restrict__ x_new, long total, int TH1, int W, int C, int ws) {
+  pdl_grid_sync();
   const int P = ws * ws;
   const long L1 = (long)TH1 * W;
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,7 +197,7 @@ static int launch_cva_offsets(const float *q, const float *dw_w, const float *dw
     granted = smem;
   }
   dim3 grid((unsigned)N1, (unsigned)groups);
-  cva_offsets_kernel<MAXC><<<grid, 256, smem, st>>>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, TH1, W, C, groups, ws);
+  launch_kernel(cva_offsets_kernel<MAXC>, grid, 256, smem, st, q, dw_w, dw_b, ln_g, ln_b, pw, pix, TH1, W, C, groups, ws);
   return launch_status("cva_offsets");
 }
 
@@ -224,11 +227,11 @@ extern "C" int mumpy_cva_sample(const void *x2, int x2_dtype, const float *pix, 
   const int N2 = B * (TH2 / ws) * (W / ws);
   cudaStream_t st = as_stream(stream);
   if (x2_dtype == MUMPY_BF16)
-    cva_sample_kernel<__nv_bfloat16, __nv_bfloat16><<<N2, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(x2), pix, static_cast<__nv_bfloat16 *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
+    launch_kernel(cva_sample_kernel<__nv_bfloat16, __nv_bfloat16>, N2, 256, 0, st, static_cast<const __nv_bfloat16 *>(x2), pix, static_cast<__nv_bfloat16 *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
   else if (out_dtype == MUMPY_BF16)
-    cva_sample_kernel<float, __nv_bfloat16><<<N2, 256, 0, st>>>(static_cast<const float *>(x2), pix, static_cast<__nv_bfloat16 *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
+    launch_kernel(cva_sample_kernel<float, __nv_bfloat16>, N2, 256, 0, st, static_cast<const float *>(x2), pix, static_cast<__nv_bfloat16 *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
   else
-    cva_sample_kernel<float, float><<<N2, 256, 0, st>>>(static_cast<const float *>(x2), pix, static_cast<float *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
+    launch_kernel(cva_sample_kernel<float, float>, N2, 256, 0, st, static_cast<const float *>(x2), pix, static_cast<float *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
   return launch_status("cva_sample");
 }
 
@@ -237,6 +240,6 @@ extern "C" int mumpy_cva_residual(const float *h, const float *y, float *x_new, 
   MUMPY_REQUIRE(h && y && x_new && h != x_new && B > 0, "cva_residual: bad arguments (must be out of place)");
   const long total = (long)B * TH1 * W * C;
   const int blocks = (int)(cdiv(total, 256) < 148 * 16 ? cdiv(total, 256) : 148 * 16);
-  cva_residual_kernel<<<blocks, 256, 0, as_stream(stream)>>>(h, y, x_new, total, TH1, W, C, ws);
+  launch_kernel(cva_residual_kernel, blocks, 256, 0, as_stream(stream), h, y, x_new, total, TH1, W, C, ws);
   return launch_status("cva_residual");
 }

@@ -14,6 +14,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ src, int C, OutT *__restrict__ dst, long dst_ld,
                                                           int dst_col, long total, int rows_out, int rows_src, int div, int mul_hi,
                                                           int mul_lo, int add) {
+  pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
@@ -40,6 +41,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) gather_rows_vec_kernel(const float *__restrict__ src, int C4, OutT *__restrict__ dst, long dst_ld,
                                                               int dst_col, long total4, int rows_out, int rows_src, int div, int mul_hi,
                                                               int mul_lo, int add) {
+  pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < total4; i += stride) {
@@ -55,6 +57,7 @@ __global__ void __launch_bounds__(256) gather_rows_vec_kernel(const float *__res
 
 __global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ in, long ld_in, __nv_bfloat16 *__restrict__ out, long total,
                                                      int H, int W, int Cin, int kh, int kw, int ph, int pw, int Kpad) {
+  pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   const int K = kh * kw * Cin;
@@ -96,6 +99,7 @@ __device__ __forceinline__ void bilinear_axis(int o, int n_in, int n_out, int sc
 __global__ void __launch_bounds__(256) resample_kernel(const float *__restrict__ in, const float *__restrict__ mul,
                                                        const float *__restrict__ add, float *__restrict__ out, long ld_out, int out_col,
                                                        long total, int H, int W, int C, int Ho, int Wo, int Co, int mode, int scale) {
+  pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(256) resample_kernel(const float *__restrict__
 __global__ void __launch_bounds__(256) resample_vec_kernel(const float *__restrict__ in, const float *__restrict__ mul,
                                                            const float *__restrict__ add, float *__restrict__ out, long ld_out, int out_col,
                                                            long total4, int H, int W, int C4, int Ho, int Wo, int mode, int scale) {
+  pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   const float4 *in4 = reinterpret_cast<const float4 *>(in);
@@ -183,6 +188,7 @@ __global__ void __launch_bounds__(256) resample_vec_kernel(const float *__restri
 
 __global__ void __launch_bounds__(256) mul_add_vec_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, const float4 *__restrict__ c,
                                                           float4 *__restrict__ out, long n4) {
+  pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
@@ -198,6 +204,7 @@ __global__ void __launch_bounds__(256) mul_add_vec_kernel(const float4 *__restri
 
 __global__ void __launch_bounds__(256) mul_add_kernel(const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ c,
                                                       float *__restrict__ out, long n) {
+  pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -208,6 +215,7 @@ __global__ void __launch_bounds__(256) mul_add_kernel(const float *__restrict__ 
 }
 
 __global__ void __launch_bounds__(256) add_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long n) {
+  pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = a[i] + b[i];
@@ -216,6 +224,7 @@ __global__ void __launch_bounds__(256) add_kernel(const float *__restrict__ a, c
 // in (batch, R, Cc) with row stride ld_in -> out (batch, Cc, R) with row stride ld_out (+ column offset), tiled via smem
 __global__ void __launch_bounds__(256) transpose_kernel(const float *__restrict__ in, long ld_in, long in_batch, float *__restrict__ out,
                                                         long ld_out, long out_batch, int out_col, int R, int Cc) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -234,6 +243,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float *__restrict_
 // NCHW -> NHWC with a fused 2x2 average (ffinfo -> decoder_frequency_0 input)
 __global__ void __launch_bounds__(256) nchw_pool2_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, long ld_out,
                                                                  int out_col, long total, int C, int H, int W) {
+  pdl_grid_sync();
   const int Ho = H / 2, Wo = W / 2;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(256) nchw_pool2_to_nhwc_kernel(const float *__
 
 __global__ void __launch_bounds__(256) channel_group_mean_kernel(const float *__restrict__ in, float *__restrict__ out, long total, int C,
                                                                  int k) {
+  pdl_grid_sync();
   const int Co = C / k;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -269,6 +280,7 @@ __global__ void __launch_bounds__(256) channel_group_mean_kernel(const float *__
 __global__ void __launch_bounds__(256) conv_cout1_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
                                                          float *__restrict__ out, long pixels, int H, int W, int Cin, int kh, int kw, int ph,
                                                          int pw) {
+  pdl_grid_sync();
   extern __shared__ float ws[];     // [kh*kw*Cin]
   for (int i = threadIdx.x; i < kh * kw * Cin; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -304,6 +316,7 @@ __global__ void __launch_bounds__(256) conv_cout1_kernel(const float *__restrict
 template <int LPP>
 __global__ void __launch_bounds__(256) conv_cout1_vec_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
                                                              float *__restrict__ out, long pixels, int H, int W, int kh, int kw, int ph, int pw) {
+  pdl_grid_sync();
   const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long m = gid / LPP;
   const int sub = (int)(gid % LPP);
@@ -337,6 +350,7 @@ __global__ void __launch_bounds__(256) conv_cout1_vec_kernel(const float *__rest
 
 __global__ void __launch_bounds__(256) mask_counts_kernel(const float *__restrict__ logits, const unsigned char *__restrict__ gt,
                                                           unsigned char *__restrict__ mask, unsigned long long *__restrict__ counts, int HW) {
+  pdl_grid_sync();
   __shared__ unsigned int red[4][8];
   const int b = blockIdx.y;
   unsigned int tp = 0, np = 0, ng = 0, nu = 0;
@@ -380,15 +394,15 @@ extern "C" int mumpy_gather_rows(const float *src, int C, void *dst, int dst_dty
   if (C % 4 == 0 && dst_ld % 4 == 0 && dst_col % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
     const long total4 = total / 4;
     if (dst_dtype == MUMPY_BF16)
-      gather_rows_vec_kernel<__nv_bfloat16><<<flat_blocks(total4), 256, 0, st>>>(src, C / 4, static_cast<__nv_bfloat16 *>(dst), dst_ld, dst_col, total4, rows_out, rows_src, div, mul_hi, mul_lo, add);
+      launch_kernel(gather_rows_vec_kernel<__nv_bfloat16>, flat_blocks(total4), 256, 0, st, src, C / 4, static_cast<__nv_bfloat16 *>(dst), dst_ld, dst_col, total4, rows_out, rows_src, div, mul_hi, mul_lo, add);
     else
-      gather_rows_vec_kernel<float><<<flat_blocks(total4), 256, 0, st>>>(src, C / 4, static_cast<float *>(dst), dst_ld, dst_col, total4, rows_out, rows_src, div, mul_hi, mul_lo, add);
+      launch_kernel(gather_rows_vec_kernel<float>, flat_blocks(total4), 256, 0, st, src, C / 4, static_cast<float *>(dst), dst_ld, dst_col, total4, rows_out, rows_src, div, mul_hi, mul_lo, add);
     return launch_status("gather_rows_vec");
   }
   if (dst_dtype == MUMPY_BF16)
-    gather_rows_kernel<__nv_bfloat16><<<flat_blocks(total), 256, 0, st>>>(src, C, static_cast<__nv_bfloat16 *>(dst), dst_ld, dst_col, total, rows_out, rows_src, div, mul_hi, mul_lo, add);
+    launch_kernel(gather_rows_kernel<__nv_bfloat16>, flat_blocks(total), 256, 0, st, src, C, static_cast<__nv_bfloat16 *>(dst), dst_ld, dst_col, total, rows_out, rows_src, div, mul_hi, mul_lo, add);
   else
-    gather_rows_kernel<float><<<flat_blocks(total), 256, 0, st>>>(src, C, static_cast<float *>(dst), dst_ld, dst_col, total, rows_out, rows_src, div, mul_hi, mul_lo, add);
+    launch_kernel(gather_rows_kernel<float>, flat_blocks(total), 256, 0, st, src, C, static_cast<float *>(dst), dst_ld, dst_col, total, rows_out, rows_src, div, mul_hi, mul_lo, add);
   return launch_status("gather_rows");
 }
 
@@ -396,7 +410,7 @@ extern "C" int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int B, 
                                  int pw, int Kpad, void *stream) {
   MUMPY_REQUIRE(in && out && Kpad >= kh * kw * Cin, "im2col_nhwc: bad arguments");
   const long total = (long)B * H * W * Kpad;
-  im2col_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(in, ld_in, static_cast<__nv_bfloat16 *>(out), total, H, W, Cin, kh, kw, ph, pw, Kpad);
+  launch_kernel(im2col_kernel, flat_blocks(total), 256, 0, as_stream(stream), in, ld_in, static_cast<__nv_bfloat16 *>(out), total, H, W, Cin, kh, kw, ph, pw, Kpad);
   return launch_status("im2col_nhwc");
 }
 
@@ -421,21 +435,21 @@ extern "C" int mumpy_resample_nhwc(const float *in, const float *mul, const floa
   const long total = (long)B * Ho * Wo * Co;
   if (mode != MUMPY_RS_PIXEL_SHUFFLE2 && C % 4 == 0 && ld_out % 4 == 0 && out_col % 4 == 0 &&
       ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mul) | reinterpret_cast<uintptr_t>(add)) & 15) == 0) {
-    resample_vec_kernel<<<flat_blocks(total / 4), 256, 0, as_stream(stream)>>>(in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale);
+    launch_kernel(resample_vec_kernel, flat_blocks(total / 4), 256, 0, as_stream(stream), in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale);
     return launch_status("resample_vec");
   }
-  resample_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(in, mul, add, out, ld_out, out_col, total, H, W, C, Ho, Wo, Co, mode, scale);
+  launch_kernel(resample_kernel, flat_blocks(total), 256, 0, as_stream(stream), in, mul, add, out, ld_out, out_col, total, H, W, C, Ho, Wo, Co, mode, scale);
   return launch_status("resample_nhwc");
 }
 
 extern "C" int mumpy_mul_add(const float *a, const float *b, const float *c, float *out, long n, void *stream) {
   MUMPY_REQUIRE(a && b && out && n > 0, "mul_add: bad arguments");
   if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
-    mul_add_vec_kernel<<<flat_blocks(n / 4), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(b),
+    launch_kernel(mul_add_vec_kernel, flat_blocks(n / 4), 256, 0, as_stream(stream), reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(b),
                                                                         reinterpret_cast<const float4 *>(c), reinterpret_cast<float4 *>(out), n / 4);
     return launch_status("mul_add_vec");
   }
-  mul_add_kernel<<<flat_blocks(n), 256, 0, as_stream(stream)>>>(a, b, c, out, n);
+  launch_kernel(mul_add_kernel, flat_blocks(n), 256, 0, as_stream(stream), a, b, c, out, n);
   return launch_status("mul_add");
 }
 
@@ -443,11 +457,11 @@ extern "C" int mumpy_add(const float *a, const float *b, float *out, long n, voi
   MUMPY_REQUIRE(a && b && out && n > 0, "add: bad arguments");
   if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     // out = a * 1 + b through the fused kernel (b slot = nullptr means multiply by one)
-    mul_add_vec_kernel<<<flat_blocks(n / 4), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(a), nullptr, reinterpret_cast<const float4 *>(b),
+    launch_kernel(mul_add_vec_kernel, flat_blocks(n / 4), 256, 0, as_stream(stream), reinterpret_cast<const float4 *>(a), nullptr, reinterpret_cast<const float4 *>(b),
                                                                         reinterpret_cast<float4 *>(out), n / 4);
     return launch_status("add_vec");
   }
-  add_kernel<<<flat_blocks(n), 256, 0, as_stream(stream)>>>(a, b, out, n);
+  launch_kernel(add_kernel, flat_blocks(n), 256, 0, as_stream(stream), a, b, out, n);
   return launch_status("add");
 }
 
@@ -458,12 +472,12 @@ extern "C" int mumpy_nchw_to_nhwc(const float *in, float *out, long ld_out, int 
   if (pool2) {
     MUMPY_REQUIRE(H % 2 == 0 && W % 2 == 0, "nchw_to_nhwc: odd map for pool2");
     const long total = (long)B * C * (H / 2) * (W / 2);
-    nchw_pool2_to_nhwc_kernel<<<flat_blocks(total), 256, 0, st>>>(in, out, ld_out, out_col, total, C, H, W);
+    launch_kernel(nchw_pool2_to_nhwc_kernel, flat_blocks(total), 256, 0, st, in, out, ld_out, out_col, total, C, H, W);
     return launch_status("nchw_pool2_to_nhwc");
   }
   const int P = H * W;
   dim3 grid((unsigned)cdiv(P, 32), (unsigned)cdiv(C, 32), (unsigned)B);   // in: (B, R=C, Cc=P)
-  transpose_kernel<<<grid, 256, 0, st>>>(in, P, (long)C * P, out, ld_out, (long)P * ld_out, out_col, C, P);
+  launch_kernel(transpose_kernel, grid, 256, 0, st, in, P, (long)C * P, out, ld_out, (long)P * ld_out, out_col, C, P);
   return launch_status("nchw_to_nhwc");
 }
 
@@ -471,14 +485,14 @@ extern "C" int mumpy_nhwc_to_nchw(const float *in, long ld_in, float *out, int B
   MUMPY_REQUIRE(in && out && B > 0, "nhwc_to_nchw: bad arguments");
   const int P = H * W;
   dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(P, 32), (unsigned)B);   // in: (B, R=P, Cc=C)
-  transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, ld_in, (long)P * ld_in, out, P, (long)C * P, 0, P, C);
+  launch_kernel(transpose_kernel, grid, 256, 0, as_stream(stream), in, ld_in, (long)P * ld_in, out, P, (long)C * P, 0, P, C);
   return launch_status("nhwc_to_nchw");
 }
 
 extern "C" int mumpy_channel_group_mean(const float *in, float *out, long pixels, int C, int k, void *stream) {
   MUMPY_REQUIRE(in && out && pixels > 0 && k > 0 && C % k == 0, "channel_group_mean: bad arguments");
   const long total = pixels * (C / k);
-  channel_group_mean_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(in, out, total, C, k);
+  launch_kernel(channel_group_mean_kernel, flat_blocks(total), 256, 0, as_stream(stream), in, out, total, C, k);
   return launch_status("channel_group_mean");
 }
 
@@ -490,13 +504,13 @@ extern "C" int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const fl
     cudaStream_t st = as_stream(stream);
     const int lpp = Cin / 4;
     const unsigned grid = (unsigned)cdiv(pixels * lpp, 256);
-    if (lpp == 4) conv_cout1_vec_kernel<4><<<grid, 256, 0, st>>>(in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
-    else if (lpp == 8) conv_cout1_vec_kernel<8><<<grid, 256, 0, st>>>(in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
-    else if (lpp == 16) conv_cout1_vec_kernel<16><<<grid, 256, 0, st>>>(in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
-    else conv_cout1_vec_kernel<32><<<grid, 256, 0, st>>>(in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
+    if (lpp == 4) launch_kernel(conv_cout1_vec_kernel<4>, grid, 256, 0, st, in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
+    else if (lpp == 8) launch_kernel(conv_cout1_vec_kernel<8>, grid, 256, 0, st, in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
+    else if (lpp == 16) launch_kernel(conv_cout1_vec_kernel<16>, grid, 256, 0, st, in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
+    else launch_kernel(conv_cout1_vec_kernel<32>, grid, 256, 0, st, in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
     return launch_status("conv2d_nhwc_cout1_vec");
   }
-  conv_cout1_kernel<<<(unsigned)cdiv(pixels, 256), 256, kh * kw * Cin * sizeof(float), as_stream(stream)>>>(in, w, bias, out, pixels, H, W,
+  launch_kernel(conv_cout1_kernel, (unsigned)cdiv(pixels, 256), 256, kh * kw * Cin * sizeof(float), as_stream(stream), in, w, bias, out, pixels, H, W,
                                                                                                            Cin, kh, kw, ph, pw);
   return launch_status("conv2d_nhwc_cout1");
 }
@@ -505,6 +519,6 @@ extern "C" int mumpy_mask_counts(const float *logits, const unsigned char *gt, u
                                  void *stream) {
   MUMPY_REQUIRE(logits && B > 0 && HW > 0 && (mask || counts), "mask_counts: bad arguments");
   dim3 grid((unsigned)(cdiv(HW, 256) < 64 ? cdiv(HW, 256) : 64), (unsigned)B);
-  mask_counts_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits, gt, mask, reinterpret_cast<unsigned long long *>(counts), HW);
+  launch_kernel(mask_counts_kernel, grid, 256, 0, as_stream(stream), logits, gt, mask, reinterpret_cast<unsigned long long *>(counts), HW);
   return launch_status("mask_counts");
 }

@@ -11,6 +11,7 @@ constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_TM = 4, SG_TN = 4;
 
 template <typename ALoader, typename BLoader, typename Epilogue>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(ALoader A, BLoader Bm, Epilogue E, long M, int N, int K) {
+  pdl_grid_sync();
   __shared__ float As[SG_BK][SG_BM + 4];
   __shared__ float Bs[SG_BK][SG_BN + 4];
   const int tid = threadIdx.x;
@@ -72,7 +73,7 @@ template <typename ALoader, typename BLoader, typename Epilogue>
 static inline int launch_gemm_simt(ALoader A, BLoader Bm, Epilogue E, long M, int N, int K, int batch, cudaStream_t st,
                                    const char *what) {
   dim3 grid((unsigned)cdiv(M, SG_BM), (unsigned)cdiv(N, SG_BN), (unsigned)batch);
-  gemm_simt_kernel<ALoader, BLoader, Epilogue><<<grid, 256, 0, st>>>(A, Bm, E, M, N, K);
+  launch_kernel(gemm_simt_kernel<ALoader, BLoader, Epilogue>, grid, 256, 0, st, A, Bm, E, M, N, K);
   return launch_status(what);
 }
 

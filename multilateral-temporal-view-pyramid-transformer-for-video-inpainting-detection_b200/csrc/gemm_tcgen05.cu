@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the previous kernel in the
+  // stream; from here on global memory written by it is read
+  pdl_grid_sync();
 
   if (warp == TC_EPI_WARPS) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
@@ -364,26 +367,28 @@ static int env_int(const char *name) {
 }
 static int g_dbg_bn = -1, g_dbg_stages = -1, g_dbg_mode = -1;
 
-// Tile width: minimise  waves * max(mma, epilogue) + min(mma, epilogue)  (accumulators are double buffered, so the epilogue
-// of one tile overlaps the main loop of the next) over the divisors of N; times in ns from the measured rates of this
-// kernel: 128 x BN x 64 k-block = BN * 1.9 ns of tensor pipe (~1100 TFLOP/s), 32-column epilogue chunk per warp pair
-// ~450 ns (+250 ns with an fp32 residual to fetch, +150 ns for GELU).
+// Tile width: minimise  waves * max(mainloop, epilogue) + min(mainloop, epilogue)  over the divisors of N (accumulators are
+// double buffered, so the epilogue of one tile overlaps the main loop of the next).  Calibration (round-1 measurements,
+// gpurun_out/gemm_knobs*.txt): the main loop of a 1-CTA tile is bound by the L2->SM path, ~42.5 B/clk per SM, i.e.
+// (128 + BN) * 128 B per k-block = (128 + BN) * 1.6 ns, never faster than the tensor pipe (BN * 1.06 ns); an epilogue pass
+// over 32 columns costs a warp ~0.55 us (+0.25 us with an fp32 residual to fetch, +1.1 us for the GELU polynomial).
 static int pick_bn(long M, int N, int nkb, bool has_res, bool gelu) {
   if (g_dbg_bn < 0) g_dbg_bn = env_int("MUMPY_TC_BN");
   if (g_dbg_bn > 0 && N % g_dbg_bn == 0) return g_dbg_bn;
   static const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
   const long mt = cdiv(M, TC_BM);
-  const double t_chunk = 450.0 + (has_res ? 250.0 : 0.0) + (gelu ? 150.0 : 0.0);
+  const double t_chunk = 550.0 + (has_res ? 250.0 : 0.0) + (gelu ? 1100.0 : 0.0);
   int best = 0;
   double best_cost = 1e30;
-  for (int c : cands) {
+  for (int c : cands) {                            // descending: ties go to the wider tile
     if (N % c != 0) continue;
     const long tiles = mt * (N / c);
     const double waves = (double)cdiv(tiles, g_num_sms);
-    const double mma = (double)nkb * c * 1.9 + 300.0;
+    const double load = (128.0 + c) * 1.6, pipe = c * 1.06;
+    const double mma = (double)nkb * (load > pipe ? load : pipe) + 300.0;
     const double epi = (double)((c + 63) / 64) * t_chunk;
     const double cost = waves * (mma > epi ? mma : epi) + (mma > epi ? epi : mma);
-    if (cost < best_cost * 0.999) {
+    if (cost < best_cost * 0.98) {
       best_cost = cost;
       best = c;
     }
@@ -431,9 +436,9 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   }
   const unsigned grid = (unsigned)(p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms);
   if (p.conv)
-    gemm_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+    launch_kernel(gemm_tc_kernel<true>, grid, TC_THREADS, smem, st, tmA, tmB, p);
   else
-    gemm_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+    launch_kernel(gemm_tc_kernel<false>, grid, TC_THREADS, smem, st, tmA, tmB, p);
   return launch_status("gemm_tc_kernel");
 }
 

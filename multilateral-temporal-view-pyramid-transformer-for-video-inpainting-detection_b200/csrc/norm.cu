@@ -30,6 +30,7 @@ struct MergeRows {
 template <typename Rows, typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(Rows rows, const float *__restrict__ gamma, const float *__restrict__ beta,
                                                         OutT *__restrict__ out, long n_rows, int C, float eps) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(Rows rows, const float *
 template <typename OutT, int NV, int R>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
                                                             const float *__restrict__ beta, OutT *__restrict__ out, long n_rows, int C, float eps) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   if (row0 >= n_rows) return;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restr
 template <typename OutT, int NV, int R>
 static void launch_ln_vec(const float *x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
   const long warps = cdiv(rows, R);
-  layernorm_vec_kernel<OutT, NV, R><<<(unsigned)cdiv(warps, 8), 256, 0, st>>>(x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
+  launch_kernel(layernorm_vec_kernel<OutT, NV, R>, (unsigned)cdiv(warps, 8), 256, 0, st, x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
 }
 
 template <typename OutT>
@@ -161,9 +163,9 @@ static int launch_ln(Rows rows, const float *gamma, const float *beta, void *out
   const int warps = 8;
   dim3 grid((unsigned)cdiv(n_rows, warps));
   if (out_dtype == MUMPY_BF16)
-    layernorm_kernel<Rows, __nv_bfloat16><<<grid, warps * 32, 0, st>>>(rows, gamma, beta, static_cast<__nv_bfloat16 *>(out), n_rows, C, eps);
+    launch_kernel(layernorm_kernel<Rows, __nv_bfloat16>, grid, warps * 32, 0, st, rows, gamma, beta, static_cast<__nv_bfloat16 *>(out), n_rows, C, eps);
   else
-    layernorm_kernel<Rows, float><<<grid, warps * 32, 0, st>>>(rows, gamma, beta, static_cast<float *>(out), n_rows, C, eps);
+    launch_kernel(layernorm_kernel<Rows, float>, grid, warps * 32, 0, st, rows, gamma, beta, static_cast<float *>(out), n_rows, C, eps);
   return launch_status("layernorm");
 }
 
@@ -175,6 +177,7 @@ constexpr int GN_SMEM_FLOATS = 12 * 1024;      // 48 KB staging
 
 __global__ void __launch_bounds__(256) gn_partial_kernel(const float *__restrict__ x, float *__restrict__ partial, int HW, int C, int groups, int pix,
                                                          int nchunks) {
+  pdl_grid_sync();
   extern __shared__ float tile[];   // [pix][C]
   const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
   const int p0 = chunk * pix;
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float *__restrict
 
 __global__ void gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ stats, int total_bg, int HW, int cg, int pix, int nchunks,
                                    float eps) {
+  pdl_grid_sync();
   const int bg = blockIdx.x * blockDim.x + threadIdx.x;
   if (bg >= total_bg) return;
   const float *p = partial + (long)bg * nchunks * 2;
@@ -228,6 +232,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float *__res
                                                               const float *__restrict__ gamma, const float *__restrict__ beta,
                                                               float *__restrict__ out, long ld_out, int out_col, long total4, int HW,
                                                               int C, int groups, int act) {
+  pdl_grid_sync();
   const int cg = C / groups;
   const int C4 = C / 4;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -287,14 +292,14 @@ extern "C" int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const fl
   const int nchunks = (int)cdiv(HW, pix);
   float *stats = stats_ws;                                  // 2 * B * groups
   float *partial = stats_ws + 2 * (long)B * groups;         // 2 * B * groups * nchunks
-  gn_partial_kernel<<<B * nchunks, 256, (size_t)pix * C * sizeof(float), st>>>(x, partial, HW, C, groups, pix, nchunks);
+  launch_kernel(gn_partial_kernel, B * nchunks, 256, (size_t)pix * C * sizeof(float), st, x, partial, HW, C, groups, pix, nchunks);
   int rc = launch_status("gn_partial");
   if (rc) return rc;
-  gn_finalize_kernel<<<(unsigned)cdiv(B * groups, 128), 128, 0, st>>>(partial, stats, B * groups, HW, C / groups, pix, nchunks, eps);
+  launch_kernel(gn_finalize_kernel, (unsigned)cdiv(B * groups, 128), 128, 0, st, partial, stats, B * groups, HW, C / groups, pix, nchunks, eps);
   rc = launch_status("gn_finalize");
   if (rc) return rc;
   const long total4 = (long)B * HW * C / 4;
   const int blocks = (int)(cdiv(total4, 256) < 148 * 16 ? cdiv(total4, 256) : 148 * 16);
-  groupnorm_apply_kernel<<<blocks, 256, 0, st>>>(x, stats, gamma, beta, out, ld_out, out_col, total4, HW, C, groups, act);
+  launch_kernel(groupnorm_apply_kernel, blocks, 256, 0, st, x, stats, gamma, beta, out, ld_out, out_col, total4, HW, C, groups, act);
   return launch_status("groupnorm_apply");
 }

@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(128) tokenize_kernel(const float *__restrict__
                                                        const float *__restrict__ bias, const float *__restrict__ gamma,
                                                        const float *__restrict__ beta, float *__restrict__ out, int T, int S, int kt,
                                                        int C, float eps) {
+  pdl_grid_sync();
   extern __shared__ float sm[];
   const int K = 3 * kt * 16;
   float *patch = sm;                       // [TOK][K]
@@ -84,6 +85,6 @@ extern "C" int mumpy_tokenize(const float *x, const float *w_kc, const float *bi
   const int groups_per_row = (Hp + TOK_PER_CTA - 1) / TOK_PER_CTA;
   const long ctas = (long)B * To * Hp * groups_per_row;
   const size_t smem = (size_t)TOK_PER_CTA * (K + C) * sizeof(float);
-  tokenize_kernel<<<(unsigned)ctas, 128, smem, as_stream(stream)>>>(x, w_kc, bias, gamma, beta, out, T, S, kt, C, eps);
+  launch_kernel(tokenize_kernel, (unsigned)ctas, 128, smem, as_stream(stream), x, w_kc, bias, gamma, beta, out, T, S, kt, C, eps);
   return launch_status("tokenize");
 }

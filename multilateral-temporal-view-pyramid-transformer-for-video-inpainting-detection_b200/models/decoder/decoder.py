@@ -8,7 +8,7 @@ All maps are NHWC inside; convolutions are implicit GEMMs (exact fp32 in 'fp32' 
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import ops, streams
 from ..modules._packing import PackedModule, require_inference
 
 
@@ -215,47 +215,78 @@ class Decoder(PackedModule):
         s0, s1, s2, s3 = self.shape
         xh = x.permute(0, 2, 3, 1)
         xh = xh if xh.is_contiguous() else ops.nchw_to_nhwc(x.contiguous())            # (B,n,n,2304)
-        rgb1, rgb2, rgb3, rgb4 = [self._rgb_stage(i, view_x[i], B, self.shape[i]) for i in range(4)]
-
         S = ffinfo.shape[-1]
-        f_in = ops.nchw_to_nhwc(ffinfo.contiguous().float(), pool2=True)                # AvgPool2 of decoder_frequency_0
-        freq0 = self._freq_stage("decoder_frequency_0", f_in, B, S // 2, S // 2, pooled=True)
-        freq1 = self._freq_stage("decoder_frequency_1", freq0, B, S // 2, S // 2)
-        freq2 = self._freq_stage("decoder_frequency_2", freq1, B, S // 4, S // 4)
-        freq3 = self._freq_stage("decoder_frequency_3", freq2, B, S // 8, S // 8)
-        freq4 = self._freq_stage("decoder_frequency_4", freq3, B, S // 16, S // 16)
+        # Independent branches run on lanes (streams.py): lane 3 the frequency pyramid, lanes 0-2 the rgb pyramid levels
+        # with their SEB / global-conv modules; the decoder_2..5 chain follows on lane 0.  Hand-overs are events.
+        with streams.region(x.device) as reg:
+            with reg.lane(3):
+                f_in = ops.nchw_to_nhwc(ffinfo.contiguous().float(), pool2=True)            # AvgPool2 of decoder_frequency_0
+                freq0 = self._freq_stage("decoder_frequency_0", f_in, B, S // 2, S // 2, pooled=True)
+                reg.publish("freq0", freq0)
+                freq1 = self._freq_stage("decoder_frequency_1", freq0, B, S // 2, S // 2)
+                reg.publish("freq1", freq1)
+                freq2 = self._freq_stage("decoder_frequency_2", freq1, B, S // 4, S // 4)
+                reg.publish("freq2", freq2)
+                freq3 = self._freq_stage("decoder_frequency_3", freq2, B, S // 8, S // 8)
+                reg.publish("freq3", freq3)
+                freq4 = self._freq_stage("decoder_frequency_4", freq3, B, S // 16, S // 16)
+                reg.publish("freq4", freq4)
+            with reg.lane(0):
+                rgb4 = self._rgb_stage(3, view_x[3], B, s3)
+                reg.publish("rgb4", rgb4)
+            with reg.lane(1):
+                rgb3 = self._rgb_stage(2, view_x[2], B, s2)
+                reg.publish("rgb3", rgb3)
+            with reg.lane(2):
+                rgb2 = self._rgb_stage(1, view_x[1], B, s1)
+                reg.publish("rgb2", rgb2)
+            c2, c3, c4 = rgb2.shape[-1], rgb3.shape[-1], rgb4.shape[-1]
 
-        cin = rgb4.shape[-1] + xh.shape[-1]
-        cat0 = torch.empty((B, s3, s3, cin), dtype=torch.float32, device=x.device)        # cat[rgb4, x] (:204)
-        ops.resample_nhwc(rgb4, B, s3, s3, rgb4.shape[-1], ops.RS_IDENTITY, out=cat0, ld_out=cin, out_col=0)
-        ops.resample_nhwc(xh, B, s3, s3, xh.shape[-1], ops.RS_IDENTITY, out=cat0, ld_out=cin, out_col=rgb4.shape[-1])
-        gcn0 = self.gcm1.nhwc(cat0, B, s3, s3)
-        g0 = ops.mul_add(gcn0, freq4)
-        out1 = ops.resample_nhwc(g0, B, s3, s3, g0.shape[-1], ops.RS_PIXEL_SHUFFLE2)      # ecre (:205)
+            with reg.lane(0):
+                cin = c4 + xh.shape[-1]
+                cat0 = torch.empty((B, s3, s3, cin), dtype=torch.float32, device=x.device)    # cat[rgb4, x] (:204)
+                ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_IDENTITY, out=cat0, ld_out=cin, out_col=0)
+                ops.resample_nhwc(xh, B, s3, s3, xh.shape[-1], ops.RS_IDENTITY, out=cat0, ld_out=cin, out_col=c4)
+                gcn0 = self.gcm1.nhwc(cat0, B, s3, s3)
+                reg.need("freq4")
+                g0 = ops.mul_add(gcn0, freq4)
+                out1 = ops.resample_nhwc(g0, B, s3, s3, g0.shape[-1], ops.RS_PIXEL_SHUFFLE2)  # ecre (:205)
+            with reg.lane(1):
+                reg.need("rgb4")
+                seb1 = self.seb1.nhwc(rgb3, rgb4, B, s3, s3)
+                gcn1 = self.gcm2.nhwc(seb1, B, s2, s2)
+                reg.publish("gcn1", gcn1)
+            with reg.lane(2):
+                reg.need("rgb3")
+                reg.need("rgb4")
+                cat2 = torch.empty((B, s2, s2, c3 + c4), dtype=torch.float32, device=x.device)  # cat[rgb3, up2(rgb4)] (:210)
+                ops.resample_nhwc(rgb3, B, s2, s2, c3, ops.RS_IDENTITY, out=cat2, ld_out=c3 + c4, out_col=0)
+                ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_UP_HALFPIX, 2, out=cat2, ld_out=c3 + c4, out_col=c3)
+                seb2 = self.seb2.nhwc(rgb2, cat2, B, s2, s2)
+                gcn2 = self.gcm3.nhwc(seb2, B, s1, s1)
+                reg.publish("gcn2", gcn2)
+            with reg.lane(0):
+                rgb1 = self._rgb_stage(0, view_x[0], B, s0)
+                reg.need("rgb2")
+                reg.need("rgb3")
+                ct = c2 + c3 + c4
+                cat3 = torch.empty((B, s1, s1, ct), dtype=torch.float32, device=x.device)     # cat[rgb2, up2(rgb3), up4(rgb4)] (:213)
+                ops.resample_nhwc(rgb2, B, s1, s1, c2, ops.RS_IDENTITY, out=cat3, ld_out=ct, out_col=0)
+                ops.resample_nhwc(rgb3, B, s2, s2, c3, ops.RS_UP_HALFPIX, 2, out=cat3, ld_out=ct, out_col=c2)
+                ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_UP_HALFPIX, 4, out=cat3, ld_out=ct, out_col=c2 + c3)
+                seb3 = self.seb3.nhwc(rgb1, cat3, B, s1, s1)
+                gcn3 = self.gcm4.nhwc(seb3, B, s0, s0)
 
-        seb1 = self.seb1.nhwc(rgb3, rgb4, B, s3, s3)
-        gcn1 = self.gcm2.nhwc(seb1, B, s2, s2)
-
-        c3, c4 = rgb3.shape[-1], rgb4.shape[-1]
-        cat2 = torch.empty((B, s2, s2, c3 + c4), dtype=torch.float32, device=x.device)    # cat[rgb3, up2(rgb4)] (:210)
-        ops.resample_nhwc(rgb3, B, s2, s2, c3, ops.RS_IDENTITY, out=cat2, ld_out=c3 + c4, out_col=0)
-        ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_UP_HALFPIX, 2, out=cat2, ld_out=c3 + c4, out_col=c3)
-        seb2 = self.seb2.nhwc(rgb2, cat2, B, s2, s2)
-        gcn2 = self.gcm3.nhwc(seb2, B, s1, s1)
-
-        c2 = rgb2.shape[-1]
-        ct = c2 + c3 + c4
-        cat3 = torch.empty((B, s1, s1, ct), dtype=torch.float32, device=x.device)         # cat[rgb2, up2(rgb3), up4(rgb4)] (:213)
-        ops.resample_nhwc(rgb2, B, s1, s1, c2, ops.RS_IDENTITY, out=cat3, ld_out=ct, out_col=0)
-        ops.resample_nhwc(rgb3, B, s2, s2, c3, ops.RS_UP_HALFPIX, 2, out=cat3, ld_out=ct, out_col=c2)
-        ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_UP_HALFPIX, 4, out=cat3, ld_out=ct, out_col=c2 + c3)
-        seb3 = self.seb3.nhwc(rgb1, cat3, B, s1, s1)
-        gcn3 = self.gcm4.nhwc(seb3, B, s0, s0)
-
-        d = self._dec_stage("decoder_2", ops.mul_add(gcn1, freq3, out1), B, s2, s2)        # (:218)
-        d = self._dec_stage("decoder_3", ops.mul_add(gcn2, freq2, d), B, s1, s1)           # (:219)
-        d = self._dec_stage("decoder_4", ops.mul_add(gcn3, freq1, d), B, s0, s0)           # (:220)
-        feats = self._dec_stage("decoder_5", ops.mul_add(d, freq0), B, 2 * s0, 2 * s0, dap=True)   # (:221-222) (B,S,S,32)
+                reg.need("gcn1")
+                reg.need("freq3")
+                d = self._dec_stage("decoder_2", ops.mul_add(gcn1, freq3, out1), B, s2, s2)        # (:218)
+                reg.need("gcn2")
+                reg.need("freq2")
+                d = self._dec_stage("decoder_3", ops.mul_add(gcn2, freq2, d), B, s1, s1)           # (:219)
+                reg.need("freq1")
+                d = self._dec_stage("decoder_4", ops.mul_add(gcn3, freq1, d), B, s0, s0)           # (:220)
+                reg.need("freq0")
+                feats = self._dec_stage("decoder_5", ops.mul_add(d, freq0), B, 2 * s0, 2 * s0, dap=True)   # (:221-222) (B,S,S,32)
         Sf = 4 * s0
         mask = _conv(self, "final_out", self.final_out, feats, B, Sf, Sf)                  # (B,S,S,1) == (B,1,S,S)
         x_feats = ops.nhwc_to_nchw(feats, B, Sf, Sf, feats.shape[-1])

@@ -12,7 +12,7 @@ and the temporal-view regrouping are index maps inside the kernels, so no permut
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import ops, streams
 from ..modules._packing import PackedModule, as_operand, require_inference
 from ..modules.blocks import Block
 from ..modules.dct import FAF
@@ -84,27 +84,32 @@ class CrossSwinBlock(PackedModule):
         self.register_buffer("attn_mask", attn_mask)
         self.fused_window_process = fused_window_process
 
-    def cross(self, x1, x2_op, need_out=True, need_out_fp32=False):
-        """x1 (B,L1,C1) fp32 canvas; x2_op (B,L2,C2) canvas of the other view already in GEMM-operand precision (or None
-        for the last view) -> (x1', out_fp32 or None, out_op) where out is the un-summed W-MSA branch (:275): `out_op` is
-        its GEMM-operand form, which is all the next view's `pre` needs.  In bf16 mode the projection writes the
-        shortcut sum (fp32) and `out_op` (bf16) from the same accumulators (mumpy_linear_dual)."""
+    def attn_phase(self, x1, need_out=True, need_out_fp32=False):
+        """LN1 -> W-MSA -> proj on the canvas x1 (B,L1,C1) fp32 -> (h, out_fp32 or None, out_op): h = x1 + out is the
+        shortcut sum (:276), out the un-summed W-MSA branch (:275) and out_op its GEMM-operand form, which is all the
+        next view's `pre` needs.  In bf16 mode the projection writes h (fp32) and out_op (bf16) from the same
+        accumulators (mumpy_linear_dual)."""
         H, W = self.input_resolution
         B, L1, C1 = x1.shape
         TH1 = L1 // W
         x1 = x1.contiguous()
         xn = ops.layernorm(x1, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         ao = self.attn.canvas_attention(xn, B, TH1, W, self.shift_size, self.attn_mask)
-        out = None
         if ops.precision() == "bf16" and not need_out_fp32:
             if need_out:
                 h, out_op = ops.linear_dual(ao, self.attn._gemm_weight("proj", self.attn.proj.weight), self.attn.proj.bias, x1)
             else:
                 h, out_op = self.attn.project(ao, residual=x1), None
-        else:
-            out = self.attn.project(ao)                               # `out` (:275)
-            h = ops.add(x1, out)                                      # shortcut + attn (:276)
-            out_op = as_operand(out) if need_out else None
+            return h, None, out_op
+        out = self.attn.project(ao)                                   # `out` (:275)
+        h = ops.add(x1, out)                                          # shortcut + attn (:276)
+        return h, out, (as_operand(out) if need_out else None)
+
+    def tail_phase(self, h, x2_op):
+        """Deformable cross-view attention against the other view's branch output (skipped for the last view), then the MLP."""
+        H, W = self.input_resolution
+        B, L1, C1 = h.shape
+        TH1 = L1 // W
         if not self.last_view:
             TH2 = x2_op.shape[1] // W
             # `pre` is per token, so it commutes with window_partition: apply it on the canvas (:282-283); its result is
@@ -114,14 +119,14 @@ class CrossSwinBlock(PackedModule):
             # h + (window_partition(h) + raw_reshape(y)) added in window-major order, no window_reverse (:138,284-286)
             h = ops.cva_residual(h, y, B, TH1, W, C1, self.window_size)
         xn = ops.layernorm(h, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        return self.mlp.fused(xn, residual=h), out, out_op
+        return self.mlp.fused(xn, residual=h)
 
     def forward(self, x1, x2):
         """x1 (B,L1,C1), x2 (B,L2,C2) canvases -> (x1', out) with out = the un-summed W-MSA branch (:228-291)."""
         require_inference(self)
         x2_op = None if self.last_view else as_operand(x2.contiguous())
-        y, out, _ = self.cross(x1, x2_op, need_out=True, need_out_fp32=True)
-        return y, out
+        h, out, _ = self.attn_phase(x1, need_out=False, need_out_fp32=True)
+        return self.tail_phase(h, x2_op), out
 
 
 class CrossThreeViewSwinBlock(nn.Module):
@@ -145,9 +150,22 @@ class CrossThreeViewSwinBlock(nn.Module):
         # order view3 -> view2 (+CVA from view3) -> view1 (+CVA from view2)   (:345-350)
         for blk in (self.block1, self.block2, self.block3):
             require_inference(blk)
-        x[2], _, op3 = self.block3.cross(x[2], None)
-        x[1], _, op2 = self.block2.cross(x[1], op3)
-        x[0], _, _ = self.block1.cross(x[0], op2, need_out=False)
+        # the three attention phases are independent; only the deformable cross-view step of view v waits for the
+        # attention branch of view v+1, so each view runs on its own lane with two event hand-overs
+        with streams.region(x[0].device) as reg:
+            with reg.lane(2):
+                h3, _, op3 = self.block3.attn_phase(x[2])
+                reg.publish((id(self), 3), op3)
+                x[2] = self.block3.tail_phase(h3, None)
+            with reg.lane(1):
+                h2, _, op2 = self.block2.attn_phase(x[1])
+                reg.publish((id(self), 2), op2)
+                reg.need((id(self), 3))
+                x[1] = self.block2.tail_phase(h2, op3)
+            with reg.lane(0):
+                h1, _, _ = self.block1.attn_phase(x[0], need_out=False)
+                reg.need((id(self), 2))
+                x[0] = self.block1.tail_phase(h1, op2)
         return x
 
 
@@ -170,9 +188,13 @@ class OriginalThreeViewSwinBlock(nn.Module):
             setattr(self, "block%d" % (i + 1), blk)
 
     def forward(self, x):
-        x[0] = self.block1(x[0])
-        x[1] = self.block2(x[1])
-        x[2] = self.block3(x[2])
+        with streams.region(x[2].device) as reg:          # the three views are independent: one lane each
+            with reg.lane(2):
+                x[2] = self.block3(x[2])
+            with reg.lane(1):
+                x[1] = self.block2(x[1])
+            with reg.lane(0):
+                x[0] = self.block1(x[0])
         return x
 
 
@@ -193,11 +215,12 @@ class MultiViewBasicLayer(nn.Module):
 
     def forward(self, x):
         out = []
-        for blk in self.blocks:
-            x = blk(x)
-            out = x.copy()
-        if self.downsample is not None:
-            x = self.downsample(x)
+        with streams.region(x[0].device):
+            for blk in self.blocks:
+                x = blk(x)
+                out = x.copy()
+            if self.downsample is not None:
+                x = self.downsample(x)
         return x, out
 
 
@@ -217,9 +240,10 @@ class CreateStages(nn.Module):
 
     def forward(self, x):
         out = []
-        for lyr in self.layers:
-            x, out_stage = lyr(x)
-            out.append(out_stage)
+        with streams.region(x[0].device):
+            for lyr in self.layers:
+                x, out_stage = lyr(x)
+                out.append(out_stage)
         return x, out
 
 
@@ -239,16 +263,18 @@ class CrossThreeViewTokenize(PackedModule):
         x = x.contiguous().float()
         B, T, _, S, _ = x.shape
         out = []
-        for i in range(3):
-            proj = getattr(self, "project%d" % (i + 1))
-            norm = getattr(self, "norm%d" % (i + 1))
-            kt = proj.kernel_size[0]
-            if proj.kernel_size[1:] != (4, 4):
-                raise NotImplementedError("tokenizer kernel supports 4x4 spatial patches")
-            C = proj.out_channels
-            w_kc = self._packed("w%d" % i, [proj.weight], lambda p=proj, c=C: p.weight.detach().reshape(c, -1).t().contiguous())
-            tok = ops.tokenize(x, w_kc, proj.bias, norm.weight, norm.bias, kt, norm.eps)
-            out.append(tok.view(B, T // kt, (S // 4) ** 2, C))
+        with streams.region(x.device) as reg:
+            for i in range(3):
+                proj = getattr(self, "project%d" % (i + 1))
+                norm = getattr(self, "norm%d" % (i + 1))
+                kt = proj.kernel_size[0]
+                if proj.kernel_size[1:] != (4, 4):
+                    raise NotImplementedError("tokenizer kernel supports 4x4 spatial patches")
+                C = proj.out_channels
+                w_kc = self._packed("w%d" % i, [proj.weight], lambda p=proj, c=C: p.weight.detach().reshape(c, -1).t().contiguous())
+                with reg.lane(i):
+                    tok = ops.tokenize(x, w_kc, proj.bias, norm.weight, norm.bias, kt, norm.eps)
+                out.append(tok.view(B, T // kt, (S // 4) ** 2, C))
         return out
 
 
@@ -289,11 +315,13 @@ class ThreeViewSwinTransformer(PackedModule):
         require_inference(self)
         x = x.contiguous().float()
         B = x.shape[0]
-        ffinfo = self.faf.frame(x, 1)                                  # == faf(x)[:, 1]  
-        toks = self.tokenize(x)
-        # align_temporal_dimension_across_views + vmap over the size-1 dim == flatten (t, n) (:701-708,737)
-        xs = [t.reshape(B, -1, t.shape[-1]) for t in toks]
-        xs, outs = self.layers(xs)
+        with streams.region(x.device) as reg:
+            with reg.lane(3):
+                ffinfo = self.faf.frame(x, 1)                              # == faf(x)[:, 1]  
+            toks = self.tokenize(x)
+            # align_temporal_dimension_across_views + vmap over the size-1 dim == flatten (t, n) (:701-708,737)
+            xs = [t.reshape(B, -1, t.shape[-1]) for t in toks]
+            xs, outs = self.layers(xs)
         out_x = [[t.unsqueeze(1) for t in stage] for stage in outs]
         # merge_views_along_channel_axis + globalembedding (:710-718,740); rows ordered (b, n, t)
         T = max(self.input_token_temporal_dims)

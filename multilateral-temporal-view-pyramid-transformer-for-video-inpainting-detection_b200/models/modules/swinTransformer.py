@@ -8,7 +8,7 @@ Inference only (DropPath / dropout are identities in eval()); arithmetic is done
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import ops, streams
 from ._packing import PackedModule, as_operand, require_inference
 
 
@@ -205,7 +205,11 @@ class ThreeViewPatchMerging(nn.Module):
                     PatchMerging((view_configs[i]["temporal_dim"] * r, r), view_configs[i]["hidden_size"][cur_stage]))
 
     def forward(self, x):
-        x[0] = self.downsample1(x[0])
-        x[1] = self.downsample2(x[1])
-        x[2] = self.downsample3(x[2])
+        with streams.region(x[0].device) as reg:
+            with reg.lane(0):
+                x[0] = self.downsample1(x[0])
+            with reg.lane(1):
+                x[1] = self.downsample2(x[1])
+            with reg.lane(2):
+                x[2] = self.downsample3(x[2])
         return x

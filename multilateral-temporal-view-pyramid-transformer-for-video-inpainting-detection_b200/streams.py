@@ -1,0 +1,96 @@
+"""Branch-level concurrency for the forward: independent branches of the model (the three temporal views inside a
+stage, the frequency branch, the decoder's pyramid inputs) are enqueued on side streams that fork from and re-join
+the caller's stream.  Under `torch.cuda.graph` capture the fork/join pattern becomes parallel branches of the graph,
+so the ~750 small dependent kernels of one forward no longer form a single serial chain (at batch 1 that chain alone
+costs ~6 ms of launch + drain latency on a B200).
+
+Rules that keep this safe with PyTorch's caching allocator (which reuses a freed block on its *allocation* stream
+without waiting for other streams):
+  * a tensor produced on one lane and consumed on another is handed over with `Region.publish()` / `Region.need()`
+    (CUDA event) and kept alive by the region until the join, so its block cannot be recycled while a consumer on a
+    different stream is still pending;
+  * everything produced inside a region is only used by the caller after the region's join.
+Regions nest: only the outermost one forks and joins, inner ones (e.g. a three-view block called from the encoder)
+just pick lanes.  No torch computation happens here; streams and events only.
+"""
+import contextlib
+import os
+
+import torch
+
+N_LANES = 4
+_lanes = {}            # device index -> [torch.cuda.Stream]
+_active = {}           # device index -> Region
+enabled = os.environ.get("MUMPY_STREAMS", "1") != "0"      # MUMPY_STREAMS=0: one serial chain (A/B measurements)
+
+
+def set_enabled(flag: bool):
+    """False runs every branch on the caller's stream (single serial chain)."""
+    global enabled
+    enabled = bool(flag)
+
+
+class Region:
+    def __init__(self, device):
+        self.device = device
+        self.keep = []
+        self.events = {}
+        self.parallel = enabled
+        if self.parallel:
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+            if idx not in _lanes:
+                _lanes[idx] = [torch.cuda.Stream(device=idx) for _ in range(N_LANES)]
+            self.lanes = _lanes[idx]
+            self.main = torch.cuda.current_stream(idx)
+            for s in self.lanes:
+                s.wait_stream(self.main)
+
+    @contextlib.contextmanager
+    def lane(self, i):
+        """Work issued inside runs on side stream i (or on the caller's stream when concurrency is off)."""
+        if not self.parallel:
+            yield
+            return
+        with torch.cuda.stream(self.lanes[i % N_LANES]):
+            yield
+
+    def publish(self, key, *tensors):
+        """Called on the producing lane right after `tensors` were enqueued: marks them ready and keeps them alive."""
+        self.keep.extend(t for t in tensors if t is not None)
+        if self.parallel:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.events[key] = ev
+
+    def need(self, key):
+        """Called on the consuming lane before the first use of what `key` published."""
+        if self.parallel:
+            torch.cuda.current_stream().wait_event(self.events[key])
+
+    def hold(self, *tensors):
+        """Keeps tensors alive until the join (inputs of work that is still pending on a lane)."""
+        self.keep.extend(t for t in tensors if t is not None)
+
+    def join(self):
+        if self.parallel:
+            for s in self.lanes:
+                self.main.wait_stream(s)
+        self.keep.clear()
+        self.events.clear()
+
+
+@contextlib.contextmanager
+def region(device):
+    """Outermost use forks the lanes from the current stream and joins them on exit; nested uses share the region."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    cur = _active.get(idx)
+    if cur is not None:
+        yield cur
+        return
+    reg = Region(torch.device("cuda", idx))
+    _active[idx] = reg
+    try:
+        yield reg
+    finally:
+        del _active[idx]
+        reg.join()
