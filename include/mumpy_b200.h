@@ -14,8 +14,10 @@
  *   - return 0 on success, a negative MUMPY_ERR_* otherwise; mumpy_last_error() gives the text;
  *   - token tensors are "canvases": row-major (B, T*H, W, C), frame t in rows [t*H,(t+1)*H)
  *     (multiTemporalViewEncoder.py:614,707; swinTransformer.py:267); decoder maps are NHWC;
- *   - dtype codes: MUMPY_F32 / MUMPY_BF16.  MUMPY_F32 GEMMs run exact fp32 FMA kernels (the <=1e-4
- *     parity mode); MUMPY_BF16 GEMMs run the TMA + tcgen05 + TMEM kernel with fp32 accumulation.
+ *   - dtype codes: MUMPY_F32 / MUMPY_BF16 / MUMPY_F16.  MUMPY_F32 GEMMs run exact fp32 FMA kernels (the <=1e-4
+ *     parity mode); MUMPY_BF16 and MUMPY_F16 GEMMs run the TMA + tcgen05 + TMEM kernel on 16-bit operands with fp32
+ *     accumulation.  Wherever a prototype below says "bf16" for an operand buffer, MUMPY_F16 buffers are accepted too
+ *     (same kernels instantiated for IEEE half); a call never mixes the two 16-bit types.
  *   - no CPU fallback exists anywhere in this library.
  */
 #ifndef MUMPY_B200_H
@@ -27,6 +29,7 @@ extern "C" {
 
 #define MUMPY_F32 0
 #define MUMPY_BF16 1
+#define MUMPY_F16 2      /* IEEE half operands: same tensor-core rate as bf16, 3 more mantissa bits (the "fp16" precision mode) */
 
 #define MUMPY_ACT_NONE 0
 #define MUMPY_ACT_GELU 1      /* exact erf GELU (nn.GELU default) */
@@ -52,6 +55,9 @@ const char *mumpy_last_error(void);
 /* Programmatic dependent launch of the library's kernels (default on; environment MUMPY_PDL=0 disables): each kernel
  * may be scheduled while its predecessor in the stream drains and synchronises on it in-kernel (griddepcontrol.wait). */
 int mumpy_set_pdl(int enabled);
+/* CTA-pair (tcgen05 cta_group::2, 256 x BN tiles on a (2,1,1) cluster) policy of the bf16 GEMM / implicit-GEMM convolution:
+ * 0 never (default), 1 the tile cost model decides, 2 whenever the shape allows.  Environment: MUMPY_TC_PAIR. */
+int mumpy_set_gemm_pair_mode(int mode);
 
 /* nn.Linear / 1x1 conv:  out = act(A . W^T + bias) (+ residual).   swinTransformer.py:45-51,142,164,365;
  * blocks.py:28-34,56,71; deformableAttention.py:333,361-362,402; multiTemporalViewEncoder.py:283,740;
@@ -61,10 +67,10 @@ int mumpy_set_pdl(int enabled);
 int mumpy_linear(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out,
                  long ldo, long M, int N, int K, int ab_dtype, int out_dtype, int act, void *stream);
 /* Same GEMM on bf16 operands with two results: out = act(A . W^T + bias) + residual (fp32) and
- * aux_bf16 = bf16(act(A . W^T + bias)) -- the un-summed W-MSA branch that CrossSwinBlock returns as the next view's
+ * aux16 = (operand type)(act(A . W^T + bias)) -- the un-summed W-MSA branch that CrossSwinBlock returns as the next view's
  * key/value source (multiTemporalViewEncoder.py:275-276) together with the shortcut sum, in one pass. */
 int mumpy_linear_dual(const void *A, long lda, const void *W, const float *bias, const float *residual, float *out,
-                      void *aux_bf16, long ldo, long M, int N, int K, int act, void *stream);
+                      void *aux16, long ldo, long M, int N, int K, int ab_dtype, int act, void *stream);
 
 /* nn.LayerNorm over the last dim (eps inside the sqrt).  swinTransformer.py:266,305; blocks.py:88,92. */
 int mumpy_layernorm(const float *x, const float *gamma, const float *beta, void *out, int out_dtype, long rows,
@@ -136,13 +142,13 @@ int mumpy_conv2d_nhwc(const float *in, long ld_in, const float *w, const float *
  * fetched by an im2col-mode TMA tensor map (padding = zero fill), no im2col buffer is materialised. */
 int mumpy_conv2d_nhwc_bf16(const void *in, long ld_in, const void *w_packed, const float *bias, const float *residual,
                            void *out, long ld_out, int B, int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw,
-                           int out_dtype, int act, void *stream);
+                           int in_dtype, int out_dtype, int act, void *stream);
 /* Cout == 1 convolution (final_out 3x3, decoder.py:95): in (B,H,W,Cin) fp32 contiguous, w (kh,kw,Cin), out (B,H,W). */
 int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const float *bias, float *out, int B, int H, int W, int Cin,
                             int kh, int kw, int ph, int pw, void *stream);
 /* im2col for the tensor-core path: out (B*H*W, Kpad) bf16, K order (ky,kx,c), zero padded to Kpad. */
-int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int B, int H, int W, int Cin, int kh, int kw, int ph,
-                      int pw, int Kpad, void *stream);
+int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int out_dtype, int B, int H, int W, int Cin, int kh, int kw,
+                      int ph, int pw, int Kpad, void *stream);
 /* GroupNorm + activation; stats over (H*W, C/groups) per (b, group), exact two-pass per pixel chunk + Chan combine.
  * stats_ws: 2*B*groups*(1 + nchunks) floats, nchunks = ceil(HW / min(64, 12288 / C, HW)). */
 int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *stats_ws, float *out,
@@ -168,8 +174,8 @@ int mumpy_channel_group_mean(const float *in, float *out, long pixels, int C, in
 int mumpy_mask_counts(const float *logits, const unsigned char *gt, unsigned char *mask, long long *counts, int B,
                       int HW, void *stream);
 
-/* fp32 -> bf16 cast (weight packing). */
-int mumpy_cast_bf16(const float *in, void *out, long n, void *stream);
+/* fp32 -> bf16 / f16 cast (weight packing, operand hand-over). */
+int mumpy_cast16(const float *in, void *out, int out_dtype, long n, void *stream);
 
 #ifdef __cplusplus
 }

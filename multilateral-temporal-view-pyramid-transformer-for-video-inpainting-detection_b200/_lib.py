@@ -18,8 +18,9 @@ SIGNATURES = {
     "mumpy_abi_version": [],
     "mumpy_init": [ci],
     "mumpy_set_pdl": [ci],
+    "mumpy_set_gemm_pair_mode": [ci],
     "mumpy_linear": [vp, cl, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, ci, vp],
-    "mumpy_linear_dual": [vp, cl, vp, vp, vp, vp, vp, cl, cl, ci, ci, ci, vp],
+    "mumpy_linear_dual": [vp, cl, vp, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, vp],
     "mumpy_layernorm": [vp, vp, vp, vp, ci, cl, ci, cf, vp],
     "mumpy_patch_merge_norm": [vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
     "mumpy_window_attention": [vp, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],
@@ -32,9 +33,9 @@ SIGNATURES = {
     "mumpy_cva_residual": [vp, vp, vp, ci, ci, ci, ci, ci, vp],
     "mumpy_gather_rows": [vp, ci, vp, ci, cl, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_conv2d_nhwc": [vp, cl, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
-    "mumpy_conv2d_nhwc_bf16": [vp, cl, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_conv2d_nhwc_bf16": [vp, cl, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_conv2d_nhwc_cout1": [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],
-    "mumpy_im2col_nhwc": [vp, cl, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_im2col_nhwc": [vp, cl, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_groupnorm_nhwc": [vp, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, cf, ci, vp],
     "mumpy_resample_nhwc": [vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_mul_add": [vp, vp, vp, vp, cl, vp],
@@ -43,7 +44,7 @@ SIGNATURES = {
     "mumpy_nhwc_to_nchw": [vp, cl, vp, ci, ci, ci, ci, vp],
     "mumpy_channel_group_mean": [vp, vp, cl, ci, ci, vp],
     "mumpy_mask_counts": [vp, vp, vp, vp, ci, ci, vp],
-    "mumpy_cast_bf16": [vp, vp, cl, vp],
+    "mumpy_cast16": [vp, vp, ci, cl, vp],
 }
 
 

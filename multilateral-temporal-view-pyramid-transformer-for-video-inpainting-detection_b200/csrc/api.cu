@@ -35,31 +35,33 @@ int launch_status(const char *what) {
 }
 
 int resolve_driver_entry_points();
+void set_gemm_pair_mode(int mode);
 int linear_f32(const float *A, long lda, const float *W, const float *bias, const float *residual, float *out, long ldo,
                long M, int N, int K, int act, cudaStream_t st);
 int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, void *aux, long ldo,
-                long M, int N, int K, int out_dtype, int act, cudaStream_t st);
+                long M, int N, int K, int ab_dtype, int out_dtype, int act, cudaStream_t st);
 
 int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, const float *residual, void *out, long ldo, int B,
-              int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int out_dtype, int act, cudaStream_t st);
+              int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int in_dtype, int out_dtype, int act, cudaStream_t st);
 
-__global__ void cast_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, long n) {
+template <typename T>
+__global__ void cast16_kernel(const float *__restrict__ in, T *__restrict__ out, long n) {
   pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+  for (; i < n; i += stride) out[i] = from_f32<T>(in[i]);
 }
 
-__global__ void cast_bf16_vec_kernel(const float4 *__restrict__ in, uint2 *__restrict__ out, long n4) {
+template <typename T>
+__global__ void cast16_vec_kernel(const float4 *__restrict__ in, uint2 *__restrict__ out, long n4) {
   pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
     const float4 v = __ldg(in + i);
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
     uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t *>(&h0);
-    pk.y = *reinterpret_cast<uint32_t *>(&h1);
+    pk.x = pack2<T>(v.x, v.y);
+    pk.y = pack2<T>(v.z, v.w);
     out[i] = pk;
   }
 }
@@ -71,6 +73,11 @@ using namespace mumpy;
 extern "C" int mumpy_abi_version(void) { return 1; }
 
 extern "C" const char *mumpy_last_error(void) { return g_err; }
+
+extern "C" int mumpy_set_gemm_pair_mode(int mode) {
+  set_gemm_pair_mode(mode);
+  return MUMPY_OK;
+}
 
 extern "C" int mumpy_set_pdl(int enabled) {
   g_pdl = enabled ? 1 : 0;
@@ -104,34 +111,34 @@ extern "C" int mumpy_linear(const void *A, long lda, const void *W, const float 
     return linear_f32(static_cast<const float *>(A), lda, static_cast<const float *>(W), bias, residual,
                       static_cast<float *>(out), ldo, M, N, K, act, as_stream(stream));
   }
-  if (ab_dtype == MUMPY_BF16) return linear_bf16(A, lda, W, bias, residual, out, nullptr, ldo, M, N, K, out_dtype, act, as_stream(stream));
+  if (is_16bit(ab_dtype)) return linear_bf16(A, lda, W, bias, residual, out, nullptr, ldo, M, N, K, ab_dtype, out_dtype, act, as_stream(stream));
   set_error("linear: unknown dtype %d", ab_dtype);
   return MUMPY_ERR_ARG;
 }
 
 extern "C" int mumpy_linear_dual(const void *A, long lda, const void *W, const float *bias, const float *residual, float *out,
-                                 void *aux_bf16, long ldo, long M, int N, int K, int act, void *stream) {
-  MUMPY_REQUIRE(A && W && out && aux_bf16 && M > 0 && N > 0 && K > 0, "linear_dual: bad arguments (M=%ld N=%d K=%d)", M, N, K);
-  return linear_bf16(A, lda, W, bias, residual, out, aux_bf16, ldo, M, N, K, MUMPY_F32, act, as_stream(stream));
+                                 void *aux16, long ldo, long M, int N, int K, int ab_dtype, int act, void *stream) {
+  MUMPY_REQUIRE(A && W && out && aux16 && M > 0 && N > 0 && K > 0 && is_16bit(ab_dtype), "linear_dual: bad arguments (M=%ld N=%d K=%d)", M, N, K);
+  return linear_bf16(A, lda, W, bias, residual, out, aux16, ldo, M, N, K, ab_dtype, MUMPY_F32, act, as_stream(stream));
 }
 
 extern "C" int mumpy_conv2d_nhwc_bf16(const void *in, long ld_in, const void *w_packed, const float *bias, const float *residual,
                                       void *out, long ld_out, int B, int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw,
-                                      int out_dtype, int act, void *stream) {
-  MUMPY_REQUIRE(in && w_packed && out && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv2d_nhwc_bf16: bad arguments");
-  return conv_bf16(in, ld_in, w_packed, bias, residual, out, ld_out, B, H, W, Cin, Cout, kh, kw, ph, pw, out_dtype, act,
+                                      int in_dtype, int out_dtype, int act, void *stream) {
+  MUMPY_REQUIRE(in && w_packed && out && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && is_16bit(in_dtype), "conv2d_nhwc_bf16: bad arguments");
+  return conv_bf16(in, ld_in, w_packed, bias, residual, out, ld_out, B, H, W, Cin, Cout, kh, kw, ph, pw, in_dtype, out_dtype, act,
                    as_stream(stream));
 }
 
-extern "C" int mumpy_cast_bf16(const float *in, void *out, long n, void *stream) {
-  MUMPY_REQUIRE(in && out && n > 0, "cast_bf16: bad arguments");
+extern "C" int mumpy_cast16(const float *in, void *out, int out_dtype, long n, void *stream) {
+  MUMPY_REQUIRE(in && out && n > 0 && is_16bit(out_dtype), "cast16: bad arguments");
   if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     const long n4 = n / 4;
     const int vb = (int)(cdiv(n4, 256) < 148 * 16 ? cdiv(n4, 256) : 148 * 16);
-    launch_kernel(cast_bf16_vec_kernel, vb, 256, 0, as_stream(stream), reinterpret_cast<const float4 *>(in), reinterpret_cast<uint2 *>(out), n4);
-    return launch_status("cast_bf16_vec");
+    MUMPY_WITH_16(out_dtype, T, launch_kernel(cast16_vec_kernel<T>, vb, 256, 0, as_stream(stream), reinterpret_cast<const float4 *>(in), reinterpret_cast<uint2 *>(out), n4));
+    return launch_status("cast16_vec");
   }
   int blocks = (int)(cdiv(n, 256) < 148 * 8 ? cdiv(n, 256) : 148 * 8);
-  launch_kernel(cast_bf16_kernel, blocks, 256, 0, as_stream(stream), in, static_cast<__nv_bfloat16 *>(out), n);
-  return launch_status("cast_bf16");
+  MUMPY_WITH_16(out_dtype, T, launch_kernel(cast16_kernel<T>, blocks, 256, 0, as_stream(stream), in, static_cast<T *>(out), n));
+  return launch_status("cast16");
 }

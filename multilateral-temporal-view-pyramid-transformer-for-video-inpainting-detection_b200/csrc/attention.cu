@@ -143,9 +143,11 @@ __global__ void __launch_bounds__(256) mha3_kernel(const T *__restrict__ qkv, T 
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162 *>(&w[e]);
-        x[s][(2 * e) % E] = __low2float(hh);
-        x[s][(2 * e + 1) % E] = __high2float(hh);
+        if constexpr (sizeof(T) == 2) {
+          const float2 f = unpack2<T>(w[e]);
+          x[s][(2 * e) % E] = f.x;
+          x[s][(2 * e + 1) % E] = f.y;
+        }
       }
     }
   }
@@ -183,8 +185,8 @@ __global__ void __launch_bounds__(256) mha3_kernel(const T *__restrict__ qkv, T 
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          __nv_bfloat162 hh = __floats2bfloat162_rn(o[(2 * e) % E], o[(2 * e + 1) % E]);
-          w[e] = *reinterpret_cast<uint32_t *>(&hh);
+          if constexpr (sizeof(T) == 2) w[e] = pack2<T>(o[(2 * e) % E], o[(2 * e + 1) % E]);
+          else w[e] = 0;
         }
         u = make_uint4(w[0], w[1], w[2], w[3]);
       }
@@ -287,9 +289,9 @@ static int ensure_smem(K kernel, size_t bytes) {
   return MUMPY_OK;
 }
 
-int window_attention_mma(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask, void *out, int B,
-                         int TH, int W, int C, int heads, int ws, int shift, cudaStream_t st);
-int cva_attention_mma(const float *q, const void *kv, void *o, int B, int TH1, int TH2, int W, int C, int heads, int ws, int per_clip,
+int window_attention_mma(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask, void *out, int dtype,
+                         int B, int TH, int W, int C, int heads, int ws, int shift, cudaStream_t st);
+int cva_attention_mma(const float *q, const void *kv, void *o, int dtype, int B, int TH1, int TH2, int W, int C, int heads, int ws, int per_clip,
                       cudaStream_t st);
 
 }  // namespace mumpy
@@ -305,8 +307,8 @@ extern "C" int mumpy_window_attention(const void *qkv, const float *bias, const 
   const int N = ws * ws;
   dim3 grid((unsigned)(B * (TH / ws) * (W / ws)), (unsigned)heads);
   cudaStream_t st = as_stream(stream);
-  if (dtype == MUMPY_BF16 && D == 32 && C % 8 == 0)      // tensor-pipe path (attention_mma.cu)
-    return window_attention_mma(qkv, bias, mask, rel_table, standard_mask, out, B, TH, W, C, heads, ws, shift, st);
+  if (is_16bit(dtype) && D == 32 && C % 8 == 0)      // tensor-pipe path (attention_mma.cu)
+    return window_attention_mma(qkv, bias, mask, rel_table, standard_mask, out, dtype, B, TH, W, C, heads, ws, shift, st);
   int rc = MUMPY_OK;
 #define LAUNCH(T, DD)                                                                                                     \
   {                                                                                                                       \
@@ -317,6 +319,8 @@ extern "C" int mumpy_window_attention(const void *qkv, const float *bias, const 
   }
   if (dtype == MUMPY_BF16) {
     if (D == 32) LAUNCH(__nv_bfloat16, 32) else LAUNCH(__nv_bfloat16, 64)
+  } else if (dtype == MUMPY_F16) {
+    if (D == 32) LAUNCH(__half, 32) else LAUNCH(__half, 64)
   } else {
     if (D == 32) LAUNCH(float, 32) else LAUNCH(float, 64)
   }
@@ -328,8 +332,9 @@ extern "C" int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, i
   MUMPY_REQUIRE(qkv && out && Bn > 0 && N > 0 && N <= 8 && C % heads == 0, "mha_short: bad arguments (N=%d)", N);
   cudaStream_t st = as_stream(stream);
   const int d = C / heads;
-  const int lp = d * (dtype == MUMPY_BF16 ? 2 : 4) / 16;
-  const bool aligned = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && (d * (dtype == MUMPY_BF16 ? 2 : 4)) % 16 == 0;
+  const int esz = is_16bit(dtype) ? 2 : 4;
+  const int lp = d * esz / 16;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && (d * esz) % 16 == 0;
   if (N == 3 && aligned && (lp == 4 || lp == 8 || lp == 16)) {
     const long n_pairs = Bn * heads;
     const float scale = 1.0f / sqrtf((float)d);
@@ -337,13 +342,17 @@ extern "C" int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, i
 #define MHA3(T, LP) launch_kernel(mha3_kernel<T, LP>, grid, 256, 0, st, static_cast<const T *>(qkv), static_cast<T *>(out), n_pairs, C, heads, scale)
     if (dtype == MUMPY_BF16) {
       if (lp == 4) MHA3(__nv_bfloat16, 4); else if (lp == 8) MHA3(__nv_bfloat16, 8); else MHA3(__nv_bfloat16, 16);
+    } else if (dtype == MUMPY_F16) {
+      if (lp == 4) MHA3(__half, 4); else if (lp == 8) MHA3(__half, 8); else MHA3(__half, 16);
     } else {
       if (lp == 4) MHA3(float, 4); else if (lp == 8) MHA3(float, 8); else MHA3(float, 16);
     }
 #undef MHA3
     return launch_status("mha3");
   }
-  if (dtype == MUMPY_BF16)
+  if (dtype == MUMPY_F16)
+    launch_kernel(mha_short_kernel<__half>, (unsigned)Bn, 128, 0, st, static_cast<const __half *>(qkv), static_cast<__half *>(out), N, C, heads);
+  else if (dtype == MUMPY_BF16)
     launch_kernel(mha_short_kernel<__nv_bfloat16>, (unsigned)Bn, 128, 0, st, static_cast<const __nv_bfloat16 *>(qkv), static_cast<__nv_bfloat16 *>(out), N, C, heads);
   else
     launch_kernel(mha_short_kernel<float>, (unsigned)Bn, 128, 0, st, static_cast<const float *>(qkv), static_cast<float *>(out), N, C, heads);
@@ -361,8 +370,10 @@ extern "C" int mumpy_cva_attention(const float *q, const void *kv, int kv_dtype,
   dim3 grid((unsigned)N1, (unsigned)heads);
   const size_t smem = attn_smem_floats<32>(N) * sizeof(float);
   cudaStream_t st = as_stream(stream);
-  if (kv_dtype == MUMPY_BF16 && C % 8 == 0) return cva_attention_mma(q, kv, o, B, TH1, TH2, W, C, heads, ws, per_clip_pairing, st);
-  if (kv_dtype == MUMPY_BF16)
+  if (is_16bit(kv_dtype) && C % 8 == 0) return cva_attention_mma(q, kv, o, kv_dtype, B, TH1, TH2, W, C, heads, ws, per_clip_pairing, st);
+  if (kv_dtype == MUMPY_F16)
+    launch_kernel(cva_attention_kernel<__half, __half, 32>, grid, 128, smem, st, q, static_cast<const __half *>(kv), static_cast<__half *>(o), N1, TH1, W, C, ws, r, per_clip_pairing);
+  else if (kv_dtype == MUMPY_BF16)
     launch_kernel(cva_attention_kernel<__nv_bfloat16, __nv_bfloat16, 32>, grid, 128, smem, st, q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1, TH1, W, C, ws, r, per_clip_pairing);
   else
     launch_kernel(cva_attention_kernel<float, float, 32>, grid, 128, smem, st, q, static_cast<const float *>(kv), static_cast<float *>(o), N1, TH1, W, C, ws, r, per_clip_pairing);

@@ -6,6 +6,8 @@
 // HBM/L2-bound (reads 3C, writes C bf16 per token) -- the tiles are far too small for a 128-row tcgen05 atom.
 // The same core serves the deformable cross-view attention (q from the query view's fp32 canvas, k/v from the sampled
 // windows, outputs summed over the temporal ratio).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mumpy {
@@ -18,14 +20,18 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t &r0, uint32_t &r
 __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t *>(&h);
+// T = __nv_bfloat16 or __half: the 16-bit operand type of q/k/v (and of the probabilities fed to P.V)
+template <typename T>
+__device__ __forceinline__ void mma_16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
 }
 
 // [64 tokens][32 dims] bf16 tile, 64 B rows, 16-byte chunks XOR-swizzled by (row>>1)&3 (conflict-free ldmatrix)
@@ -72,7 +78,7 @@ struct TableBias {
 
 // scores for 16 query rows (m-tile mt) against the key n-tiles, then softmax -> un-normalised probabilities in s (base-2
 // exponentials of scale*log2e*(q.k + init) minus the row maximum); the row sums of rows g / g+8 come back in sum_lo / sum_hi.
-template <int N, typename Init>
+template <typename T, int N, typename Init>
 __device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt, int lane, float scale, const Init &init, float (&s)[8][4],
                                                float &sum_lo, float &sum_hi) {
   constexpr int NT = (N + 7) / 8;
@@ -91,8 +97,8 @@ __device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt,
   for (int nt = 0; nt < NT; ++nt) {
     uint32_t b0, b1, b2, b3;
     ldsm_x4(sK + tile_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
-    mma_bf16(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-    mma_bf16(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], b2, b3);
+    mma_16<T>(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+    mma_16<T>(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], b2, b3);
   }
   const float c = scale * 1.4426950408889634f;     // exp(x) = 2^(x log2 e)
   float m_lo = -INFINITY, m_hi = -INFINITY;
@@ -131,20 +137,21 @@ __device__ __forceinline__ void scores_softmax(uint32_t sQ, uint32_t sK, int mt,
 }
 
 // o[dn][4] += P(16 x 64) . V(64 x 32) for one m-tile; un-normalised probabilities come straight from the score fragments
+template <typename T>
 __device__ __forceinline__ void pv_accumulate(uint32_t sV, int lane, const float (&s)[8][4], float (&o)[4][4]) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    const uint32_t a0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-    const uint32_t a1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-    const uint32_t a2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    const uint32_t a3 = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    const uint32_t a0 = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
+    const uint32_t a1 = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
+    const uint32_t a2 = pack2<T>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    const uint32_t a3 = pack2<T>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
     const int tok = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
     for (int dp = 0; dp < 2; ++dp) {
       uint32_t b0, b1, b2, b3;
       ldsm_x4_t(sV + tile_off(tok, dp * 2 + (lane >> 4)), b0, b1, b2, b3);
-      mma_bf16(o[dp * 2], a0, a1, a2, a3, b0, b1);
-      mma_bf16(o[dp * 2 + 1], a0, a1, a2, a3, b2, b3);
+      mma_16<T>(o[dp * 2], a0, a1, a2, a3, b0, b1);
+      mma_16<T>(o[dp * 2 + 1], a0, a1, a2, a3, b2, b3);
     }
   }
 }
@@ -180,15 +187,15 @@ constexpr int WATT_WARP_BYTES = 2 * WATT_STAGE_BYTES + 2 * 64 * (int)sizeof(int)
 // MODE 1: bias from the raw relative_position_bias_table (T,nH), staged for all heads in shared memory; the mask is the
 //         standard Swin shift mask recomputed from region ids on the stacked canvas (swinTransformer.py:233-252) and is
 //         only evaluated for the windows of the last window row / column (the only ones that hold masked pairs).
-template <int WS, int MODE>
-__global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ bias,
+template <typename T, int WS, int MODE>
+__global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kernel(const T *__restrict__ qkv, const float *__restrict__ bias,
                                                                                   const float *__restrict__ mask, const float *__restrict__ rel_table,
-                                                                                  __nv_bfloat16 *__restrict__ out, int TH, int W, int C, int heads,
+                                                                                  T *__restrict__ out, int TH, int W, int C, int heads,
                                                                                   int shift, int mshift, long n_tasks) {
   pdl_grid_sync();
   constexpr int N = WS * WS;
   constexpr int NT = (N + 7) / 8;
-  constexpr int T = (2 * WS - 1) * (2 * WS - 1);
+  constexpr int TBL = (2 * WS - 1) * (2 * WS - 1);
   constexpr float kScale = 0.17677669529663687f;    // 32^-0.5
   constexpr float kC = kScale * 1.4426950408889634f;
   extern __shared__ __align__(128) uint8_t att_smem[];
@@ -197,8 +204,8 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
   int *rows_base = reinterpret_cast<int *>(wbase + 2 * WATT_STAGE_BYTES);
   float *tbl_all = reinterpret_cast<float *>(att_smem + WATT_WARPS * WATT_WARP_BYTES);      // [heads][T], pre-divided by the scale
   if (MODE == 1) {
-    for (int i = threadIdx.x; i < T * heads; i += blockDim.x) {
-      const int hh = i / T, e = i - hh * T;
+    for (int i = threadIdx.x; i < TBL * heads; i += blockDim.x) {
+      const int hh = i / TBL, e = i - hh * TBL;
       tbl_all[i] = __ldg(rel_table + (long)e * heads + hh) * (1.0f / kScale);
     }
   }
@@ -236,13 +243,13 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
       if (p < N) rows[p] = (int)(b * L) + token_row<WS>(wr, wc, p, TH, W, shift);
     }
     __syncwarp();
-    const __nv_bfloat16 *base = qkv + h * 32 + (lane & 3) * 8;
+    const T *base = qkv + h * 32 + (lane & 3) * 8;
     const uint32_t sbase = smem_addr(wbase + stage * WATT_STAGE_BYTES);
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
       const int p = pass * 8 + (lane >> 2);
       if (pass * 8 < N && p < N) {
-        const __nv_bfloat16 *src = base + (long)rows[p] * 3 * C;
+        const T *src = base + (long)rows[p] * 3 * C;
         const uint32_t dst = sbase + tile_off(p, lane & 3);
         cp_async_16(dst, src);
         cp_async_16(dst + ATT_TILE_BYTES, src + C);
@@ -269,7 +276,7 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
     const uint32_t sQ = smem_addr(wbase + stage * WATT_STAGE_BYTES), sK = sQ + ATT_TILE_BYTES, sV = sK + ATT_TILE_BYTES;
     const bool last_r = wr == wrows - 1, last_c = wc == wpr - 1;
     const bool masked = MODE == 1 && mshift > 0 && (last_r || last_c);
-    const float *tbl = tbl_all + h * T;
+    const float *tbl = tbl_all + h * TBL;
 
     uint32_t kf[NT][4], vf[4][2][4];
 #pragma unroll
@@ -329,8 +336,8 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        mma_bf16(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], kf[nt][0], kf[nt][1]);
-        mma_bf16(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], kf[nt][2], kf[nt][3]);
+        mma_16<T>(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], kf[nt][0], kf[nt][1]);
+        mma_16<T>(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], kf[nt][2], kf[nt][3]);
       }
       float m_lo = -INFINITY, m_hi = -INFINITY;
 #pragma unroll
@@ -373,27 +380,27 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
       for (int kk = 0; kk < 4; ++kk) {
         if (kk * 16 < N) {
           const bool two = 2 * kk + 1 < NT;             // second key n-tile of this k-step exists
-          const uint32_t a0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-          const uint32_t a1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-          const uint32_t a2 = two ? pack_bf16(s[(2 * kk + 1) & 7][0], s[(2 * kk + 1) & 7][1]) : 0u;
-          const uint32_t a3 = two ? pack_bf16(s[(2 * kk + 1) & 7][2], s[(2 * kk + 1) & 7][3]) : 0u;
+          const uint32_t a0 = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
+          const uint32_t a1 = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
+          const uint32_t a2 = two ? pack2<T>(s[(2 * kk + 1) & 7][0], s[(2 * kk + 1) & 7][1]) : 0u;
+          const uint32_t a3 = two ? pack2<T>(s[(2 * kk + 1) & 7][2], s[(2 * kk + 1) & 7][3]) : 0u;
 #pragma unroll
           for (int dp = 0; dp < 2; ++dp) {
-            mma_bf16(o[dp * 2], a0, a1, a2, a3, vf[kk][dp][0], vf[kk][dp][1]);
-            mma_bf16(o[dp * 2 + 1], a0, a1, a2, a3, vf[kk][dp][2], vf[kk][dp][3]);
+            mma_16<T>(o[dp * 2], a0, a1, a2, a3, vf[kk][dp][0], vf[kk][dp][1]);
+            mma_16<T>(o[dp * 2 + 1], a0, a1, a2, a3, vf[kk][dp][2], vf[kk][dp][3]);
           }
         }
       }
       const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
       if (i_lo < N) {
-        __nv_bfloat16 *dst = out + (long)rows[i_lo] * C + h * 32 + 2 * t;
+        T *dst = out + (long)rows[i_lo] * C + h * 32 + 2 * t;
 #pragma unroll
-        for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][0] * inv_lo, o[dn][1] * inv_lo);
+        for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack2<T>(o[dn][0] * inv_lo, o[dn][1] * inv_lo);
       }
       if (i_hi < N) {
-        __nv_bfloat16 *dst = out + (long)rows[i_hi] * C + h * 32 + 2 * t;
+        T *dst = out + (long)rows[i_hi] * C + h * 32 + 2 * t;
 #pragma unroll
-        for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[dn][2] * inv_hi, o[dn][3] * inv_hi);
+        for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack2<T>(o[dn][2] * inv_hi, o[dn][3] * inv_hi);
       }
     }
     __syncwarp();      // every lane is done with this stage's tiles and rows before the next iteration refills them
@@ -409,9 +416,9 @@ __device__ __forceinline__ int cva_query_window_m(int j, int r, int N1, int nW1,
 }
 
 // deformable cross-view attention core: o[i] = sum_t softmax(q[qidx(r i + t)] k[r i + t]^T * d^-1/2) v[r i + t]
-template <int WS>
-__global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const float *__restrict__ q, const __nv_bfloat16 *__restrict__ kv,
-                                                                           __nv_bfloat16 *__restrict__ o_out, int N1, int TH1, int W, int C,
+template <typename T, int WS>
+__global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const float *__restrict__ q, const T *__restrict__ kv,
+                                                                           T *__restrict__ o_out, int N1, int TH1, int W, int C,
                                                                            int heads, int r, int per_clip, long n_tasks) {
   pdl_grid_sync();
   constexpr int N = WS * WS;
@@ -457,11 +464,11 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const
       if (p < N) {
         const float *src = q + rows[p] * C + h * 32 + chunk * 8;
         const float4 f0 = __ldg(reinterpret_cast<const float4 *>(src)), f1 = __ldg(reinterpret_cast<const float4 *>(src + 4));
-        v.x = pack_bf16(f0.x, f0.y); v.y = pack_bf16(f0.z, f0.w); v.z = pack_bf16(f1.x, f1.y); v.w = pack_bf16(f1.z, f1.w);
+        v.x = pack2<T>(f0.x, f0.y); v.y = pack2<T>(f0.z, f0.w); v.z = pack2<T>(f1.x, f1.y); v.w = pack2<T>(f1.z, f1.w);
       }
       *reinterpret_cast<uint4 *>(tq + tile_off(p, chunk)) = v;
     }
-    const __nv_bfloat16 *kvb = kv + ((long)j * N) * 2 * C + h * 32;
+    const T *kvb = kv + ((long)j * N) * 2 * C + h * 32;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       uint8_t *tile = which == 0 ? tk : tv;
@@ -479,13 +486,13 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const
     for (int mt = 0; mt < 4; ++mt) {
       if (mt * 16 < N) {
         float s[8][4], sum_lo, sum_hi;
-        scores_softmax<N>(sQ, sK, mt, lane, 0.17677669529663687f, NoBias{}, s, sum_lo, sum_hi);
+        scores_softmax<T, N>(sQ, sK, mt, lane, 0.17677669529663687f, NoBias{}, s, sum_lo, sum_hi);
         float ot[4][4];
 #pragma unroll
         for (int dn = 0; dn < 4; ++dn)
 #pragma unroll
           for (int e = 0; e < 4; ++e) ot[dn][e] = 0.0f;
-        pv_accumulate(sV, lane, s, ot);
+        pv_accumulate<T>(sV, lane, s, ot);
         const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
 #pragma unroll
         for (int dn = 0; dn < 4; ++dn) {
@@ -501,14 +508,14 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const
   for (int mt = 0; mt < 4; ++mt) {
     const int i_lo = mt * 16 + g, i_hi = i_lo + 8;
     if (i_lo < N) {
-      __nv_bfloat16 *dst = o_out + ((long)i * N + i_lo) * C + h * 32 + 2 * t4;
+      T *dst = o_out + ((long)i * N + i_lo) * C + h * 32 + 2 * t4;
 #pragma unroll
-      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[mt][dn][0], o[mt][dn][1]);
+      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack2<T>(o[mt][dn][0], o[mt][dn][1]);
     }
     if (i_hi < N) {
-      __nv_bfloat16 *dst = o_out + ((long)i * N + i_hi) * C + h * 32 + 2 * t4;
+      T *dst = o_out + ((long)i * N + i_hi) * C + h * 32 + 2 * t4;
 #pragma unroll
-      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack_bf16(o[mt][dn][2], o[mt][dn][3]);
+      for (int dn = 0; dn < 4; ++dn) *reinterpret_cast<uint32_t *>(dst + dn * 8) = pack2<T>(o[mt][dn][2], o[mt][dn][3]);
     }
   }
 }
@@ -554,10 +561,11 @@ static int watt_smem_attr(K kernel, size_t bytes) {
   return MUMPY_OK;
 }
 
-int window_attention_mma(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask, void *out, int B,
-                         int TH, int W, int C, int heads, int ws, int shift, cudaStream_t st) {
+template <typename T>
+static int window_attention_mma_t(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask, void *out, int B,
+                                  int TH, int W, int C, int heads, int ws, int shift, cudaStream_t st) {
   const long n_tasks = (long)B * (TH / ws) * (W / ws) * heads;
-  MUMPY_REQUIRE((long)B * TH * W < (1l << 31), "window_attention(bf16): too many tokens");
+  MUMPY_REQUIRE((long)B * TH * W < (1l << 31), "window_attention(16-bit): too many tokens");
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -568,32 +576,39 @@ int window_attention_mma(const void *qkv, const float *bias, const float *mask, 
   const long want = cdiv(n_tasks, WATT_WARPS);
   const unsigned grid = (unsigned)(want < num_sms ? want : num_sms);
   const bool table_mode = rel_table != nullptr && (mask == nullptr || standard_mask);
-  const int T = (2 * ws - 1) * (2 * ws - 1);
-  const size_t smem = (size_t)WATT_WARPS * WATT_WARP_BYTES + (table_mode ? (size_t)T * heads * sizeof(float) : 0);
-  MUMPY_REQUIRE(smem <= 227 * 1024, "window_attention(bf16): %d heads need %zu B of shared memory", heads, smem);
-  const __nv_bfloat16 *q = static_cast<const __nv_bfloat16 *>(qkv);
-  __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out);
+  const int Tn = (2 * ws - 1) * (2 * ws - 1);
+  const size_t smem = (size_t)WATT_WARPS * WATT_WARP_BYTES + (table_mode ? (size_t)Tn * heads * sizeof(float) : 0);
+  MUMPY_REQUIRE(smem <= 227 * 1024, "window_attention(16-bit): %d heads need %zu B of shared memory", heads, smem);
+  const T *q = static_cast<const T *>(qkv);
+  T *o = static_cast<T *>(out);
   int rc;
   const int mshift = (mask != nullptr) ? shift : 0;      // region-id mask only when the caller passed the (standard) mask
 #define WATT_LAUNCH(WS_, MODE_)                                                                                               \
   {                                                                                                                           \
-    if ((rc = watt_smem_attr(window_attention_mma_kernel<WS_, MODE_>, smem))) return rc;                                      \
-    launch_kernel(window_attention_mma_kernel<WS_, MODE_>, grid, WATT_WARPS * 32, smem, st, q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks); \
+    if ((rc = watt_smem_attr(window_attention_mma_kernel<T, WS_, MODE_>, smem))) return rc;                                   \
+    launch_kernel(window_attention_mma_kernel<T, WS_, MODE_>, grid, WATT_WARPS * 32, smem, st, q, bias, mask, rel_table, o, TH, W, C, heads, shift, mshift, n_tasks); \
   }
   if (ws == 7) {
     if (table_mode) WATT_LAUNCH(7, 1) else WATT_LAUNCH(7, 0)
   } else if (ws == 8) {
     if (table_mode) WATT_LAUNCH(8, 1) else WATT_LAUNCH(8, 0)
   } else {
-    set_error("window_attention(bf16): window size %d unsupported (7 or 8)", ws);
+    set_error("window_attention(16-bit): window size %d unsupported (7 or 8)", ws);
     return MUMPY_ERR_UNSUPPORTED;
   }
 #undef WATT_LAUNCH
   return launch_status("window_attention_mma");
 }
 
-int cva_attention_mma(const float *q, const void *kv, void *o, int B, int TH1, int TH2, int W, int C, int heads, int ws, int per_clip,
-                      cudaStream_t st) {
+int window_attention_mma(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask, void *out, int dtype,
+                         int B, int TH, int W, int C, int heads, int ws, int shift, cudaStream_t st) {
+  if (dtype == MUMPY_F16) return window_attention_mma_t<__half>(qkv, bias, mask, rel_table, standard_mask, out, B, TH, W, C, heads, ws, shift, st);
+  return window_attention_mma_t<__nv_bfloat16>(qkv, bias, mask, rel_table, standard_mask, out, B, TH, W, C, heads, ws, shift, st);
+}
+
+template <typename T>
+static int cva_attention_mma_t(const float *q, const void *kv, void *o, int B, int TH1, int TH2, int W, int C, int heads, int ws, int per_clip,
+                               cudaStream_t st) {
   const int N1 = B * (TH1 / ws) * (W / ws);
   const long n_tasks = (long)N1 * heads;
   const unsigned grid = (unsigned)cdiv(n_tasks, ATT_WARPS);
@@ -601,18 +616,24 @@ int cva_attention_mma(const float *q, const void *kv, void *o, int B, int TH1, i
   const int r = TH2 / TH1;
   int rc;
   if (ws == 7) {
-    if ((rc = att_smem_attr(cva_attention_mma_kernel<7>))) return rc;
-    launch_kernel(cva_attention_mma_kernel<7>, grid, ATT_WARPS * 32, smem, st, q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1,
-                                                                   TH1, W, C, heads, r, per_clip, n_tasks);
+    if ((rc = att_smem_attr(cva_attention_mma_kernel<T, 7>))) return rc;
+    launch_kernel(cva_attention_mma_kernel<T, 7>, grid, ATT_WARPS * 32, smem, st, q, static_cast<const T *>(kv), static_cast<T *>(o), N1, TH1, W, C, heads, r,
+                  per_clip, n_tasks);
   } else if (ws == 8) {
-    if ((rc = att_smem_attr(cva_attention_mma_kernel<8>))) return rc;
-    launch_kernel(cva_attention_mma_kernel<8>, grid, ATT_WARPS * 32, smem, st, q, static_cast<const __nv_bfloat16 *>(kv), static_cast<__nv_bfloat16 *>(o), N1,
-                                                                   TH1, W, C, heads, r, per_clip, n_tasks);
+    if ((rc = att_smem_attr(cva_attention_mma_kernel<T, 8>))) return rc;
+    launch_kernel(cva_attention_mma_kernel<T, 8>, grid, ATT_WARPS * 32, smem, st, q, static_cast<const T *>(kv), static_cast<T *>(o), N1, TH1, W, C, heads, r,
+                  per_clip, n_tasks);
   } else {
-    set_error("cva_attention(bf16): window size %d unsupported (7 or 8)", ws);
+    set_error("cva_attention(16-bit): window size %d unsupported (7 or 8)", ws);
     return MUMPY_ERR_UNSUPPORTED;
   }
   return launch_status("cva_attention_mma");
+}
+
+int cva_attention_mma(const float *q, const void *kv, void *o, int dtype, int B, int TH1, int TH2, int W, int C, int heads, int ws, int per_clip,
+                      cudaStream_t st) {
+  if (dtype == MUMPY_F16) return cva_attention_mma_t<__half>(q, kv, o, B, TH1, TH2, W, C, heads, ws, per_clip, st);
+  return cva_attention_mma_t<__nv_bfloat16>(q, kv, o, B, TH1, TH2, W, C, heads, ws, per_clip, st);
 }
 
 }  // namespace mumpy

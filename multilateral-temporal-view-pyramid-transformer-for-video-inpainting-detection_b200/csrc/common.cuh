@@ -1,6 +1,7 @@
 // Shared helpers for libmumpy_b200 (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -55,6 +56,41 @@ __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162flo
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// two fp32 -> one 32-bit word of two 16-bit operands (round to nearest even) and back, for either operand type
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t u);
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) {
+  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&u);
+  return make_float2(__low2float(h), __high2float(h));
+}
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
+  const __half2 h = *reinterpret_cast<const __half2 *>(&u);
+  return __half22float2(h);
+}
+static inline bool is_16bit(int dtype) { return dtype == MUMPY_BF16 || dtype == MUMPY_F16; }
+// runs `...` with T bound to the 16-bit operand type that `dtype` (MUMPY_BF16 / MUMPY_F16) names
+#define MUMPY_WITH_16(dtype, T, ...)       \
+  do {                                      \
+    if ((dtype) == MUMPY_F16) {             \
+      using T = __half;                     \
+      __VA_ARGS__;                          \
+    } else {                                \
+      using T = __nv_bfloat16;              \
+      __VA_ARGS__;                          \
+    }                                       \
+  } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -139,18 +139,19 @@ __global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__
           v = __ldg(reinterpret_cast<const float4 *>(src));
         } else {
           const uint2 u = __ldg(reinterpret_cast<const uint2 *>(src));
-          const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162 *>(&u.x), h1 = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
-          v = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
+          if constexpr (sizeof(InT) == 2) {
+            const float2 a = unpack2<InT>(u.x), b = unpack2<InT>(u.y);
+            v = make_float4(a.x, a.y, b.x, b.y);
+          }
         }
         acc.x = fmaf(v.x, wgt, acc.x); acc.y = fmaf(v.y, wgt, acc.y); acc.z = fmaf(v.z, wgt, acc.z); acc.w = fmaf(v.w, wgt, acc.w);
       }
     }
     OutT *dst = sampled + ((long)j * P + p) * C + c;
-    if (sizeof(OutT) == 2) {
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
+    if constexpr (sizeof(OutT) == 2) {
       uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t *>(&h0);
-      pk.y = *reinterpret_cast<uint32_t *>(&h1);
+      pk.x = pack2<OutT>(acc.x, acc.y);
+      pk.y = pack2<OutT>(acc.z, acc.w);
       *reinterpret_cast<uint2 *>(dst) = pk;
     } else {
       *reinterpret_cast<float4 *>(dst) = acc;
@@ -222,14 +223,14 @@ extern "C" int mumpy_cva_sample(const void *x2, int x2_dtype, const float *pix, 
   MUMPY_REQUIRE(C % groups == 0 && (C / groups) % 4 == 0, "cva_sample: channels per group must be a multiple of 4");
   MUMPY_REQUIRE(((reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(sampled) | reinterpret_cast<uintptr_t>(pix)) & 15) == 0,
                 "cva_sample: buffers must be 16-byte aligned");
-  MUMPY_REQUIRE(x2_dtype == MUMPY_F32 || out_dtype == MUMPY_BF16, "cva_sample: bf16 input needs bf16 output");
+  MUMPY_REQUIRE(x2_dtype == MUMPY_F32 || x2_dtype == out_dtype, "cva_sample: a 16-bit input needs the same 16-bit output type");
   const int N1 = B * (TH1 / ws) * (W / ws);
   const int N2 = B * (TH2 / ws) * (W / ws);
   cudaStream_t st = as_stream(stream);
-  if (x2_dtype == MUMPY_BF16)
-    launch_kernel(cva_sample_kernel<__nv_bfloat16, __nv_bfloat16>, N2, 256, 0, st, static_cast<const __nv_bfloat16 *>(x2), pix, static_cast<__nv_bfloat16 *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
-  else if (out_dtype == MUMPY_BF16)
-    launch_kernel(cva_sample_kernel<float, __nv_bfloat16>, N2, 256, 0, st, static_cast<const float *>(x2), pix, static_cast<__nv_bfloat16 *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
+  if (is_16bit(x2_dtype))
+    MUMPY_WITH_16(x2_dtype, T, launch_kernel(cva_sample_kernel<T, T>, N2, 256, 0, st, static_cast<const T *>(x2), pix, static_cast<T *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing));
+  else if (is_16bit(out_dtype))
+    MUMPY_WITH_16(out_dtype, T, launch_kernel(cva_sample_kernel<float, T>, N2, 256, 0, st, static_cast<const float *>(x2), pix, static_cast<T *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing));
   else
     launch_kernel(cva_sample_kernel<float, float>, N2, 256, 0, st, static_cast<const float *>(x2), pix, static_cast<float *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
   return launch_status("cva_sample");

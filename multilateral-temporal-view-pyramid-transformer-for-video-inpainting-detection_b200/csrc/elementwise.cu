@@ -28,11 +28,11 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restric
 }
 
 __device__ __forceinline__ void store4(float *dst, float4 v) { *reinterpret_cast<float4 *>(dst) = v; }
-__device__ __forceinline__ void store4(__nv_bfloat16 *dst, float4 v) {
-  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+template <typename T>
+__device__ __forceinline__ void store4(T *dst, float4 v) {
   uint2 pk;
-  pk.x = *reinterpret_cast<uint32_t *>(&h0);
-  pk.y = *reinterpret_cast<uint32_t *>(&h1);
+  pk.x = pack2<T>(v.x, v.y);
+  pk.y = pack2<T>(v.z, v.w);
   *reinterpret_cast<uint2 *>(dst) = pk;
 }
 
@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(256) gather_rows_vec_kernel(const float *__res
   }
 }
 
-__global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ in, long ld_in, __nv_bfloat16 *__restrict__ out, long total,
+template <typename OutT>
+__global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ in, long ld_in, OutT *__restrict__ out, long total,
                                                      int H, int W, int Cin, int kh, int kw, int ph, int pw, int Kpad) {
   pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ i
       const int yy = y + ky - ph, xx = x + kx - pw;
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = in[((b * H + yy) * W + xx) * ld_in + c];
     }
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = from_f32<OutT>(v);
   }
 }
 
@@ -393,24 +394,24 @@ extern "C" int mumpy_gather_rows(const float *src, int C, void *dst, int dst_dty
   cudaStream_t st = as_stream(stream);
   if (C % 4 == 0 && dst_ld % 4 == 0 && dst_col % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
     const long total4 = total / 4;
-    if (dst_dtype == MUMPY_BF16)
-      launch_kernel(gather_rows_vec_kernel<__nv_bfloat16>, flat_blocks(total4), 256, 0, st, src, C / 4, static_cast<__nv_bfloat16 *>(dst), dst_ld, dst_col, total4, rows_out, rows_src, div, mul_hi, mul_lo, add);
+    if (is_16bit(dst_dtype))
+      MUMPY_WITH_16(dst_dtype, T, launch_kernel(gather_rows_vec_kernel<T>, flat_blocks(total4), 256, 0, st, src, C / 4, static_cast<T *>(dst), dst_ld, dst_col, total4, rows_out, rows_src, div, mul_hi, mul_lo, add));
     else
       launch_kernel(gather_rows_vec_kernel<float>, flat_blocks(total4), 256, 0, st, src, C / 4, static_cast<float *>(dst), dst_ld, dst_col, total4, rows_out, rows_src, div, mul_hi, mul_lo, add);
     return launch_status("gather_rows_vec");
   }
-  if (dst_dtype == MUMPY_BF16)
-    launch_kernel(gather_rows_kernel<__nv_bfloat16>, flat_blocks(total), 256, 0, st, src, C, static_cast<__nv_bfloat16 *>(dst), dst_ld, dst_col, total, rows_out, rows_src, div, mul_hi, mul_lo, add);
+  if (is_16bit(dst_dtype))
+    MUMPY_WITH_16(dst_dtype, T, launch_kernel(gather_rows_kernel<T>, flat_blocks(total), 256, 0, st, src, C, static_cast<T *>(dst), dst_ld, dst_col, total, rows_out, rows_src, div, mul_hi, mul_lo, add));
   else
     launch_kernel(gather_rows_kernel<float>, flat_blocks(total), 256, 0, st, src, C, static_cast<float *>(dst), dst_ld, dst_col, total, rows_out, rows_src, div, mul_hi, mul_lo, add);
   return launch_status("gather_rows");
 }
 
-extern "C" int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int B, int H, int W, int Cin, int kh, int kw, int ph,
-                                 int pw, int Kpad, void *stream) {
-  MUMPY_REQUIRE(in && out && Kpad >= kh * kw * Cin, "im2col_nhwc: bad arguments");
+extern "C" int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int out_dtype, int B, int H, int W, int Cin, int kh, int kw,
+                                 int ph, int pw, int Kpad, void *stream) {
+  MUMPY_REQUIRE(in && out && Kpad >= kh * kw * Cin && is_16bit(out_dtype), "im2col_nhwc: bad arguments");
   const long total = (long)B * H * W * Kpad;
-  launch_kernel(im2col_kernel, flat_blocks(total), 256, 0, as_stream(stream), in, ld_in, static_cast<__nv_bfloat16 *>(out), total, H, W, Cin, kh, kw, ph, pw, Kpad);
+  MUMPY_WITH_16(out_dtype, T, launch_kernel(im2col_kernel<T>, flat_blocks(total), 256, 0, as_stream(stream), in, ld_in, static_cast<T *>(out), total, H, W, Cin, kh, kw, ph, pw, Kpad));
   return launch_status("im2col_nhwc");
 }
 

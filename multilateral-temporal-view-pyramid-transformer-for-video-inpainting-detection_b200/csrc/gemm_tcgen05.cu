@@ -64,14 +64,15 @@ struct TcParams {
   const float *bias;
   const float *residual;
   void *out;
-  __nv_bfloat16 *aux;     // optional second output (fp32-out mode only): bf16 of act(acc + bias) BEFORE the residual add, row stride ldo
+  uint16_t *aux;          // optional second output (fp32-out mode only): 16-bit act(acc + bias) BEFORE the residual add, row stride ldo
   long ldo;
   long M;
   int N, K;
   int BN;
   int stages;
   int act;
-  int out_bf16;
+  int out_bf16;           // output is 16-bit (bf16, or f16 when `f16` is set)
+  int f16;                // operands (and 16-bit outputs / the side output) are IEEE half instead of bf16
   int tiles_n;
   long num_tiles;
   uint32_t acc_cols;      // TMEM columns per accumulator slot (power of two >= BN)
@@ -158,14 +159,14 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
               x.x += r0.x; x.y += r0.y; x.z += r0.z; x.w += r0.w;
               y.x += r1.x; y.y += r1.y; y.z += r1.z; y.w += r1.w;
             }
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(y.x, y.y), h3 = __floats2bfloat162_rn(y.z, y.w);
             uint4 u;
-            u.x = *reinterpret_cast<uint32_t *>(&h0);
-            u.y = *reinterpret_cast<uint32_t *>(&h1);
-            u.z = *reinterpret_cast<uint32_t *>(&h2);
-            u.w = *reinterpret_cast<uint32_t *>(&h3);
-            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + gm * p.ldo + n0 + col) = u;
+            if (p.f16) {
+              u.x = pack2<__half>(x.x, x.y); u.y = pack2<__half>(x.z, x.w); u.z = pack2<__half>(y.x, y.y); u.w = pack2<__half>(y.z, y.w);
+            } else {
+              u.x = pack2<__nv_bfloat16>(x.x, x.y); u.y = pack2<__nv_bfloat16>(x.z, x.w);
+              u.z = pack2<__nv_bfloat16>(y.x, y.y); u.w = pack2<__nv_bfloat16>(y.z, y.w);
+            }
+            *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.out) + gm * p.ldo + n0 + col) = u;
           }
         }
       } else {
@@ -179,10 +180,12 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st_base + r * 128 + ((c4 ^ (r & 7)) << 4)));
           if (gm < p.M && col < p.BN && n0 + col < p.N) {
             if (p.aux) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
               uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t *>(&h0);
-              pk.y = *reinterpret_cast<uint32_t *>(&h1);
+              if (p.f16) {
+                pk.x = pack2<__half>(x.x, x.y); pk.y = pack2<__half>(x.z, x.w);
+              } else {
+                pk.x = pack2<__nv_bfloat16>(x.x, x.y); pk.y = pack2<__nv_bfloat16>(x.z, x.w);
+              }
               *reinterpret_cast<uint2 *>(p.aux + gm * p.ldo + n0 + col) = pk;
             }
             if (HAS_RES) {
@@ -198,7 +201,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
   }
 }
 
-template <bool kConv>
+// kPair: the two CTAs of a (2,1,1) cluster (one TPC) work on one 256 x BN tile with tcgen05.mma.cta_group::2: CTA r loads
+// A rows [128 r, 128 r + 128) and B rows [BN/2 r, BN/2 r + BN/2) of the tile, the leader (rank 0) issues the M=256 MMAs,
+// each CTA's TMEM receives its own 128 accumulator rows.  Per CTA and k-block that is (128 + BN/2) x 128 B from L2
+// instead of (128 + BN) x 128 B -- the main loop of the 1-CTA kernel is bound by exactly that path (42.5 B/clk/SM).
+template <bool kConv, bool kPair>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -207,10 +214,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t group = kPair ? blockIdx.x >> 1 : blockIdx.x;          // tile-scheduler slot
+  const uint32_t n_groups = kPair ? gridDim.x >> 1 : gridDim.x;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t a_bytes = TC_BM * 128;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128;
+  const uint32_t b_rows = static_cast<uint32_t>(kPair ? p.BN / 2 : p.BN);
+  const uint32_t b_bytes = b_rows * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t full0 = smem_u32(&bars[0]);
   const uint32_t empty0 = smem_u32(&bars[TC_MAX_STAGES]);
@@ -221,23 +232,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (warp == TC_EPI_WARPS && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
+    // pair mode: `full` and `acc_empty` live on the leader and collect arrivals from both CTAs
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full0 + 8 * s, 1);
+      mbar_init(full0 + 8 * s, kPair ? 2 : 1);
       mbar_init(empty0 + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full0 + 8 * s, 1);
-      mbar_init(acc_empty0 + 8 * s, TC_EPI_WARPS);
+      mbar_init(acc_empty0 + 8 * s, kPair ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);
     }
     fence_barrier_init();
   }
   if (warp == TC_EPI_WARPS + 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2 * p.acc_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2 * p.acc_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2 * p.acc_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the previous kernel in the
@@ -248,9 +266,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     // ------------------------------------------------ TMA producer ------------------------------------------------
     if (lane == 0) {
       uint32_t it = 0;
-      for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n0 = static_cast<int>(tile % p.tiles_n) * p.BN;
-        const long m0 = (tile / p.tiles_n) * TC_BM;
+      const uint32_t full_leader = kPair ? mapa_shared(full0, 0) : full0;      // shared::cluster address on rank 0
+      for (long tile = group; tile < p.num_tiles; tile += n_groups) {
+        const int n0 = static_cast<int>(tile % p.tiles_n) * p.BN + static_cast<int>(rank * b_rows);
+        const long m0 = (tile / p.tiles_n) * (kPair ? 2 * TC_BM : TC_BM) + rank * TC_BM;
         int cw = 0, ch = 0, cn = 0;
         if (kConv) {
           cw = static_cast<int>(m0 % p.Wout) + p.lower_w;
@@ -262,8 +281,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           const uint32_t s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
-          mbar_arrive_expect_tx(full0 + 8 * s, stage_bytes);
           const uint32_t sa = tiles + s * stage_bytes;
+          if (kPair) {
+            mbar_arrive_expect_tx_cluster(full_leader + 8 * s, stage_bytes);
+            if (kConv) {
+              const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+              tma_load_im2col_4d_pair(sa, &tmA, full_leader + 8 * s, cb * TC_BK, cw, ch, cn, static_cast<uint16_t>(tap % p.kw),
+                                      static_cast<uint16_t>(tap / p.kw));
+            } else {
+              tma_load_2d_pair(sa, &tmA, full_leader + 8 * s, kb * TC_BK, static_cast<int>(m0));
+            }
+            tma_load_2d_pair(sa + a_bytes, &tmB, full_leader + 8 * s, kb * TC_BK, n0);
+            continue;
+          }
+          mbar_arrive_expect_tx(full0 + 8 * s, stage_bytes);
           if (kConv) {
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
             tma_load_im2col_4d(sa, &tmA, full0 + 8 * s, cb * TC_BK, cw, ch, cn, static_cast<uint16_t>(tap % p.kw),
@@ -277,9 +308,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ------------------------------------------------ MMA issuer --------------------------------------------------
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       uint32_t it = 0, t = 0;
-      for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+      for (long tile = group; tile < p.num_tiles; tile += n_groups, ++t) {
         const uint32_t slot = t & 1, aph = (t >> 1) & 1;
         mbar_wait(acc_empty0 + 8 * slot, aph ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
@@ -295,11 +326,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (kPair) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty0 + 8 * s);      // frees the smem slot once these MMAs have read it
+          if (kPair) umma_commit_pair(empty0 + 8 * s); else umma_commit(empty0 + 8 * s);      // frees the smem slot(s) once these MMAs have read them
         }
-        umma_commit(acc_full0 + 8 * slot);  // accumulator complete
+        if (kPair) umma_commit_pair(acc_full0 + 8 * slot); else umma_commit(acc_full0 + 8 * slot);  // accumulator complete
       }
     }
   } else {
@@ -307,10 +339,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     uint8_t *stage = smem_raw + (tiles - raw) + p.stages * stage_bytes + warp * EPI_STAGE_BYTES;
     const int mode = (p.act == MUMPY_ACT_GELU ? 1 : (p.act == MUMPY_ACT_NONE ? 0 : 2)) | (p.out_bf16 ? 4 : 0) | (p.residual ? 8 : 0);
     uint32_t t = 0;
-    for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+    const uint32_t acc_empty_leader = kPair ? mapa_shared(acc_empty0, 0) : acc_empty0;
+    for (long tile = group; tile < p.num_tiles; tile += n_groups, ++t) {
       const uint32_t slot = t & 1, aph = (t >> 1) & 1;
       const int n0 = static_cast<int>(tile % p.tiles_n) * p.BN;
-      const long m0 = (tile / p.tiles_n) * TC_BM;
+      const long m0 = (tile / p.tiles_n) * (kPair ? 2 * TC_BM : TC_BM) + rank * TC_BM;
       mbar_wait(acc_full0 + 8 * slot, aph);
       tc_fence_after();
       const uint32_t acc = tmem_base + slot * p.acc_cols;
@@ -331,24 +364,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       // this warp is done reading the accumulator: hand the TMEM slot back to the MMA issuer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty0 + 8 * slot);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(acc_empty_leader + 8 * slot); else mbar_arrive(acc_empty0 + 8 * slot);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();     // nobody leaves while the partner can still touch its barriers / tiles
   if (warp == TC_EPI_WARPS + 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * p.acc_cols) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * p.acc_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * p.acc_cols) : "memory");
   }
 }
 
-static int encode_2d_bf16(CUtensorMap *map, const void *ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+static int encode_2d_bf16(CUtensorMap *map, const void *ptr, bool f16, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
                           uint32_t box_inner, uint32_t box_outer) {
   cuuint64_t gdim[2] = {inner, outer};
   cuuint64_t gstride[1] = {row_stride_elems * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
+  CUresult r = g_encode_tiled(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -367,90 +403,144 @@ static int env_int(const char *name) {
 }
 static int g_dbg_bn = -1, g_dbg_stages = -1, g_dbg_mode = -1;
 
-// Tile width: minimise  waves * max(mainloop, epilogue) + min(mainloop, epilogue)  over the divisors of N (accumulators are
-// double buffered, so the epilogue of one tile overlaps the main loop of the next).  Calibration (round-1 measurements,
-// gpurun_out/gemm_knobs*.txt): the main loop of a 1-CTA tile is bound by the L2->SM path, ~42.5 B/clk per SM, i.e.
-// (128 + BN) * 128 B per k-block = (128 + BN) * 1.6 ns, never faster than the tensor pipe (BN * 1.06 ns); an epilogue pass
-// over 32 columns costs a warp ~0.55 us (+0.25 us with an fp32 residual to fetch, +1.1 us for the GELU polynomial).
-static int pick_bn(long M, int N, int nkb, bool has_res, bool gelu) {
-  if (g_dbg_bn < 0) g_dbg_bn = env_int("MUMPY_TC_BN");
-  if (g_dbg_bn > 0 && N % g_dbg_bn == 0) return g_dbg_bn;
+// Tile shape: minimise  waves * max(mainloop, epilogue) + min(mainloop, epilogue)  over the divisors of N and over the
+// 1-CTA (128 x BN) / CTA-pair (256 x BN) variants (accumulators are double buffered, so the epilogue of one tile overlaps the
+// main loop of the next).  Calibration (round-1 measurements, gpurun_out/gemm_knobs*.txt, prof_gemm_fc*_v5): the main loop
+// is bound by the L2->SM path, ~42.5 B/clk per SM: a CTA pulls (128 + rows of B it loads) * 128 B per k-block, i.e.
+// (128 + BN) * 1.6 ns alone or (128 + BN/2) * 1.6 ns in a pair, never faster than the tensor pipe (BN * 1.06 ns); an
+// epilogue pass over 32 columns costs a warp ~0.55 us (+0.25 us with an fp32 residual to fetch, +1.1 us for GELU).
+struct TileChoice {
+  int bn;
+  bool pair;
+};
+// CTA-pair policy: 0 never (default: in the forward the 1-CTA kernel measured as fast or faster -- round-1 bench 18.4 vs
+// 18.8 ms/step -- because both variants are bound by load latency x bytes in flight, not by L2 bytes), 1 cost model decides,
+// 2 whenever legal.  Environment MUMPY_TC_PAIR or mumpy_set_gemm_pair_mode().
+static int g_dbg_pair = -1;
+
+static TileChoice pick_tile(long M, int N, int nkb, bool has_res, bool gelu) {
+  if (g_dbg_bn < 0) {
+    g_dbg_bn = env_int("MUMPY_TC_BN");
+  }
+  if (g_dbg_pair < 0) {
+    const char *v = getenv("MUMPY_TC_PAIR");
+    g_dbg_pair = v ? atoi(v) : 0;
+  }
   static const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
-  const long mt = cdiv(M, TC_BM);
   const double t_chunk = 550.0 + (has_res ? 250.0 : 0.0) + (gelu ? 1100.0 : 0.0);
-  int best = 0;
+  TileChoice best = {0, false};
   double best_cost = 1e30;
-  for (int c : cands) {                            // descending: ties go to the wider tile
-    if (N % c != 0) continue;
-    const long tiles = mt * (N / c);
-    const double waves = (double)cdiv(tiles, g_num_sms);
-    const double load = (128.0 + c) * 1.6, pipe = c * 1.06;
-    const double mma = (double)nkb * (load > pipe ? load : pipe) + 300.0;
-    const double epi = (double)((c + 63) / 64) * t_chunk;
-    const double cost = waves * (mma > epi ? mma : epi) + (mma > epi ? epi : mma);
-    if (cost < best_cost * 0.98) {
-      best_cost = cost;
-      best = c;
+  for (int pair = 0; pair < 2; ++pair) {
+    if (pair && (g_dbg_pair == 0 || g_num_sms < 2)) continue;
+    const long mt = cdiv(M, pair ? 2 * TC_BM : TC_BM);
+    const long slots = pair ? g_num_sms / 2 : g_num_sms;
+    for (int c : cands) {                            // descending: ties go to the wider tile
+      if (N % c != 0) continue;
+      if (g_dbg_bn > 0 && N % g_dbg_bn == 0 && c != g_dbg_bn) continue;
+      if (pair && c % 16 != 0) continue;
+      const long tiles = mt * (N / c);
+      const double waves = (double)cdiv(tiles, slots);
+      const double load = (128.0 + (pair ? c / 2 : c)) * 1.6, pipe = c * 1.06;
+      const double mma = (double)nkb * (load > pipe ? load : pipe) + (pair ? 500.0 : 300.0);
+      const double epi = (double)((c + 63) / 64) * t_chunk;
+      double cost = waves * (mma > epi ? mma : epi) + (mma > epi ? epi : mma);
+      if (pair && g_dbg_pair == 2) cost *= 1e-3;
+      if (cost < best_cost * 0.98) {
+        best_cost = cost;
+        best.bn = c;
+        best.pair = pair != 0;
+      }
     }
   }
-  if (best) return best;
+  if (best.bn) return best;
   for (int c : cands)
-    if (c <= N) return c;                          // no divisor: the tail tile is masked
-  return 16;
+    if (c <= N) return TileChoice{c, false};         // no divisor: the tail tile is masked
+  return TileChoice{16, false};
 }
 
-static bool g_attr_set[2] = {false, false};
+void set_gemm_pair_mode(int mode) { g_dbg_pair = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
+template <typename... KArgs, typename... Args>
+static void launch_pair_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
-static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p, cudaStream_t st) {
+static bool g_attr_set[4] = {false, false, false, false};
+
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p, bool pair, cudaStream_t st) {
   uint32_t cols = 32;
   while (cols < (uint32_t)p.BN) cols <<= 1;
   p.acc_cols = cols;
-  p.idesc = make_idesc_bf16_f32(TC_BM, p.BN);
+  const int bm = pair ? 2 * TC_BM : TC_BM;
+  p.idesc = make_idesc_16_f32(bm, p.BN, p.f16 != 0);
   p.tiles_n = (int)cdiv(p.N, p.BN);
-  p.num_tiles = cdiv(p.M, TC_BM) * p.tiles_n;
+  p.num_tiles = cdiv(p.M, bm) * p.tiles_n;
   if (g_dbg_stages < 0) {
     g_dbg_stages = env_int("MUMPY_TC_STAGES");
     g_dbg_mode = env_int("MUMPY_TC_DEBUG");
   }
   p.debug = g_dbg_mode;
-  const int stage_bytes = TC_BM * 128 + p.BN * 128;
+  const int stage_bytes = TC_BM * 128 + (pair ? p.BN / 2 : p.BN) * 128;
   const int nkb = p.conv ? p.K : (p.K + TC_BK - 1) / TC_BK;
+  const long slots = pair ? g_num_sms / 2 : g_num_sms;
   int stages = TC_SMEM_BUDGET / stage_bytes;
   if (g_dbg_stages > 0 && g_dbg_stages < stages) stages = g_dbg_stages;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  const long kb_per_cta = nkb * cdiv(p.num_tiles, g_num_sms);
+  const long kb_per_cta = nkb * cdiv(p.num_tiles, slots);
   if (stages > kb_per_cta) stages = (int)kb_per_cta;
   if (stages < 1) stages = 1;
   p.stages = stages;
   const int smem = stages * stage_bytes + 1024 + TC_EPI_WARPS * 32 * 128;
-  const int which = p.conv ? 1 : 0;
+  const int which = (p.conv ? 1 : 0) + (pair ? 2 : 0);
   if (!g_attr_set[which]) {
-    cudaError_t e = p.conv ? cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * 32 * 128)
-                           : cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * 32 * 128);
+    const int max_smem = TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * 32 * 128;
+    cudaError_t e;
+    switch (which) {
+      case 0: e = cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+      case 1: e = cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+      case 2: e = cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+      default: e = cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+    }
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
       return MUMPY_ERR_CUDA;
     }
     g_attr_set[which] = true;
   }
-  const unsigned grid = (unsigned)(p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms);
-  if (p.conv)
-    launch_kernel(gemm_tc_kernel<true>, grid, TC_THREADS, smem, st, tmA, tmB, p);
-  else
-    launch_kernel(gemm_tc_kernel<false>, grid, TC_THREADS, smem, st, tmA, tmB, p);
+  const unsigned groups = (unsigned)(p.num_tiles < slots ? p.num_tiles : slots);
+  switch (which) {
+    case 0: launch_kernel(gemm_tc_kernel<false, false>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
+    case 1: launch_kernel(gemm_tc_kernel<true, false>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
+    case 2: launch_pair_kernel(gemm_tc_kernel<false, true>, 2 * groups, TC_THREADS, smem, st, tmA, tmB, p); break;
+    default: launch_pair_kernel(gemm_tc_kernel<true, true>, 2 * groups, TC_THREADS, smem, st, tmA, tmB, p); break;
+  }
   return launch_status("gemm_tc_kernel");
 }
 
 int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, void *aux, long ldo,
-                long M, int N, int K, int out_dtype, int act, cudaStream_t st) {
+                long M, int N, int K, int ab_dtype, int out_dtype, int act, cudaStream_t st) {
   int rc = resolve_driver_entry_points();
   if (rc) return rc;
   MUMPY_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0, "linear(bf16): N, K, lda must be multiples of 8 (N=%d K=%d lda=%ld)", N, K, lda);
   MUMPY_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "linear(bf16): A, W, out must be 16-byte aligned");
-  MUMPY_REQUIRE(out_dtype == MUMPY_BF16 ? (ldo % 8 == 0) : (ldo % 4 == 0), "linear(bf16): ldo alignment");
+  MUMPY_REQUIRE(out_dtype == MUMPY_F32 || out_dtype == ab_dtype, "linear(16-bit): the output is fp32 or the operand type");
+  MUMPY_REQUIRE(out_dtype != MUMPY_F32 ? (ldo % 8 == 0) : (ldo % 4 == 0), "linear(bf16): ldo alignment");
   MUMPY_REQUIRE(M < (1l << 31), "linear(bf16): M too large");
   MUMPY_REQUIRE(!aux || (out_dtype == MUMPY_F32 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ldo % 8 == 0),
                 "linear(bf16): the bf16 side output needs an fp32 main output, 16-byte alignment and ldo %% 8 == 0");
@@ -458,27 +548,29 @@ int linear_bf16(const void *A, long lda, const void *W, const float *bias, const
   p.bias = bias;
   p.residual = residual;
   p.out = out;
-  p.aux = static_cast<__nv_bfloat16 *>(aux);
+  p.aux = static_cast<uint16_t *>(aux);
+  p.f16 = ab_dtype == MUMPY_F16;
   p.ldo = ldo;
   p.M = M;
   p.N = N;
   p.K = K;
-  p.BN = pick_bn(M, N, (K + TC_BK - 1) / TC_BK, residual != nullptr, act == MUMPY_ACT_GELU);
+  const TileChoice tc = pick_tile(M, N, (K + TC_BK - 1) / TC_BK, residual != nullptr, act == MUMPY_ACT_GELU);
+  p.BN = tc.bn;
   p.act = act;
-  p.out_bf16 = (out_dtype == MUMPY_BF16);
+  p.out_bf16 = (out_dtype != MUMPY_F32);
   p.conv = 0;
   CUtensorMap tmA, tmB;
-  rc = encode_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TC_BK, TC_BM);
+  rc = encode_2d_bf16(&tmA, A, p.f16 != 0, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TC_BK, TC_BM);
   if (rc) return rc;
-  rc = encode_2d_bf16(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K, TC_BK, (uint32_t)p.BN);
+  rc = encode_2d_bf16(&tmB, W, p.f16 != 0, (uint64_t)K, (uint64_t)N, (uint64_t)K, TC_BK, (uint32_t)(tc.pair ? p.BN / 2 : p.BN));
   if (rc) return rc;
-  return launch_tc(tmA, tmB, p, st);
+  return launch_tc(tmA, tmB, p, tc.pair, st);
 }
 
 // Implicit-GEMM convolution (stride 1): in (B,H,W,Cin) bf16 NHWC with pixel stride ld_in elements; wpk (Cout, taps*cblocks*64)
 // bf16 with K order (ky,kx,c) and every tap's channels zero padded to a multiple of 64; out (B*H*W, Cout).
 int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, const float *residual, void *out, long ldo, int B,
-              int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int out_dtype, int act, cudaStream_t st) {
+              int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int in_dtype, int out_dtype, int act, cudaStream_t st) {
   int rc = resolve_driver_entry_points();
   if (rc) return rc;
   MUMPY_REQUIRE(Cout % 8 == 0 && ld_in % 8 == 0, "conv(bf16): Cout and ld_in must be multiples of 8");
@@ -495,9 +587,11 @@ int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, co
   p.M = (long)B * H * W;
   p.N = Cout;
   p.K = kh * kw * cblocks;          // k-blocks
-  p.BN = pick_bn(p.M, Cout, p.K, residual != nullptr, act == MUMPY_ACT_GELU);
+  const TileChoice tc = pick_tile(p.M, Cout, p.K, residual != nullptr, act == MUMPY_ACT_GELU);
+  p.BN = tc.bn;
   p.act = act;
-  p.out_bf16 = (out_dtype == MUMPY_BF16);
+  p.out_bf16 = (out_dtype != MUMPY_F32);
+  p.f16 = in_dtype == MUMPY_F16;
   p.conv = 1;
   p.Wout = W;
   p.Hout = H;
@@ -511,7 +605,8 @@ int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, co
   int lower[2] = {-pw, -ph};
   int upper[2] = {pw - (kw - 1), ph - (kh - 1)};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(in), gdim, gstr, lower, upper, TC_BK, TC_BM,
+  MUMPY_REQUIRE(out_dtype == MUMPY_F32 || out_dtype == in_dtype, "conv(16-bit): the output is fp32 or the operand type");
+  CUresult r = g_encode_im2col(&tmA, p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(in), gdim, gstr, lower, upper, TC_BK, TC_BM,
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -520,9 +615,9 @@ int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, co
   }
   // same workaround CUTLASS applies (copy_traits_sm90_im2col.hpp) for small tensors on drivers <= 13.1
   if (g_driver_version <= 13010 && (size_t)B * H * W * ld_in * 2 < 131072) reinterpret_cast<uint64_t *>(&tmA)[1] &= ~(1ull << 21);
-  rc = encode_2d_bf16(&tmB, wpk, (uint64_t)p.K * TC_BK, (uint64_t)Cout, (uint64_t)p.K * TC_BK, TC_BK, (uint32_t)p.BN);
+  rc = encode_2d_bf16(&tmB, wpk, p.f16 != 0, (uint64_t)p.K * TC_BK, (uint64_t)Cout, (uint64_t)p.K * TC_BK, TC_BK, (uint32_t)(tc.pair ? p.BN / 2 : p.BN));
   if (rc) return rc;
-  return launch_tc(tmA, tmB, p, st);
+  return launch_tc(tmA, tmB, p, tc.pair, st);
 }
 
 }  // namespace mumpy

@@ -122,11 +122,10 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restr
           const float rstd = 1.0f / sqrtf(q[r] / C + eps);
           const float o0 = (v[r][u].x - mean[r]) * rstd * g.x + b.x, o1 = (v[r][u].y - mean[r]) * rstd * g.y + b.y;
           const float o2 = (v[r][u].z - mean[r]) * rstd * g.z + b.z, o3 = (v[r][u].w - mean[r]) * rstd * g.w + b.w;
-          if (sizeof(OutT) == 2) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+          if constexpr (sizeof(OutT) == 2) {
             uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t *>(&h0);
-            pk.y = *reinterpret_cast<uint32_t *>(&h1);
+            pk.x = pack2<OutT>(o0, o1);
+            pk.y = pack2<OutT>(o2, o3);
             reinterpret_cast<uint2 *>(out + (row0 + r) * C)[i] = pk;
           } else {
             reinterpret_cast<float4 *>(out + (row0 + r) * C)[i] = make_float4(o0, o1, o2, o3);
@@ -162,8 +161,8 @@ static int launch_ln(Rows rows, const float *gamma, const float *beta, void *out
                      cudaStream_t st) {
   const int warps = 8;
   dim3 grid((unsigned)cdiv(n_rows, warps));
-  if (out_dtype == MUMPY_BF16)
-    launch_kernel(layernorm_kernel<Rows, __nv_bfloat16>, grid, warps * 32, 0, st, rows, gamma, beta, static_cast<__nv_bfloat16 *>(out), n_rows, C, eps);
+  if (is_16bit(out_dtype))
+    MUMPY_WITH_16(out_dtype, T, launch_kernel(layernorm_kernel<Rows, T>, grid, warps * 32, 0, st, rows, gamma, beta, static_cast<T *>(out), n_rows, C, eps));
   else
     launch_kernel(layernorm_kernel<Rows, float>, grid, warps * 32, 0, st, rows, gamma, beta, static_cast<float *>(out), n_rows, C, eps);
   return launch_status("layernorm");
@@ -263,8 +262,8 @@ extern "C" int mumpy_layernorm(const float *x, const float *gamma, const float *
   MUMPY_REQUIRE(x && gamma && beta && out && rows > 0 && C > 0, "layernorm: bad arguments");
   if (C % 4 == 0 && C <= 1024 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
                                    reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
-    if (out_dtype == MUMPY_BF16)
-      dispatch_ln_vec<__nv_bfloat16>(x, gamma, beta, out, rows, C, eps, as_stream(stream));
+    if (is_16bit(out_dtype))
+      MUMPY_WITH_16(out_dtype, T, dispatch_ln_vec<T>(x, gamma, beta, out, rows, C, eps, as_stream(stream)));
     else
       dispatch_ln_vec<float>(x, gamma, beta, out, rows, C, eps, as_stream(stream));
     return launch_status("layernorm_vec");

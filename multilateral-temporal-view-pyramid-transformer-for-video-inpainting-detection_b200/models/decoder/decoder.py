@@ -20,7 +20,7 @@ def _conv(owner, name, conv, x, B, H, W, ld_in=None):
     if Cout == 1 and Cin % 4 == 0 and ld_in in (None, Cin):
         w = owner._packed("hwi:" + name, [conv.weight], lambda: conv.weight.detach().permute(0, 2, 3, 1).contiguous())
         return ops.conv2d_nhwc_cout1(x, w, conv.bias, B, H, W, Cin, kh, kw, ph, pw)
-    if ops.precision() == "bf16" and Cout % 8 == 0 and Cin % 8 == 0 and (ld_in or Cin) % 8 == 0:
+    if ops.tensor_cores() and Cout % 8 == 0 and Cin % 8 == 0 and (ld_in or Cin) % 8 == 0:
         # implicit GEMM on the tensor cores: im2col-mode TMA feeds tcgen05 directly (no im2col buffer)
         cb = (Cin + 63) // 64
 
@@ -28,18 +28,18 @@ def _conv(owner, name, conv, x, B, H, W, ld_in=None):
             w = conv.weight.detach().permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin)
             wp = w.new_zeros(Cout, kh * kw, cb * 64)
             wp[:, :, :Cin] = w
-            return ops.cast_bf16(wp.reshape(Cout, -1).contiguous())
+            return ops.cast16(wp.reshape(Cout, -1).contiguous())
         wq = owner._packed("tcconv:" + name, [conv.weight], make_tc)
-        xb = x if x.dtype == torch.bfloat16 else ops.cast_bf16(x)
+        xb = x if x.dtype == ops.act_dtype() else ops.cast16(x)
         return ops.conv2d_nhwc_bf16(xb, wq, conv.bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in)
-    if ops.precision() == "bf16" and Cout % 8 == 0:
+    if ops.tensor_cores() and Cout % 8 == 0:
         Kpad = (K + 7) // 8 * 8
 
         def make():
             w = conv.weight.detach().permute(0, 2, 3, 1).reshape(Cout, K)
             if Kpad != K:
                 w = torch.cat([w, w.new_zeros(Cout, Kpad - K)], 1)
-            return ops.cast_bf16(w.contiguous())
+            return ops.cast16(w.contiguous())
         wq = owner._packed("tc:" + name, [conv.weight], make)
         cols = ops.im2col_nhwc(x, B, H, W, Cin, kh, kw, ph, pw, Kpad, ld_in)
         return ops.linear(cols, wq, conv.bias).view(B, H, W, Cout)
@@ -170,7 +170,7 @@ class Decoder(PackedModule):
                 parts.append(blk.sum(-1) if self.input_token_temporal_dims[v] == 1 else blk.permute(0, 2, 1).reshape(w.shape[0], -1))
                 c0 += wd
             wp = torch.cat(parts, 1).contiguous()
-            return ops.cast_bf16(wp) if ops.precision() == "bf16" else wp
+            return ops.cast16(wp) if ops.tensor_cores() else wp
         wp = self._packed("rgbw%d" % idx, [conv.weight], make)
         a = torch.empty((B * hw, Kp), dtype=ops.act_dtype(), device=conv.weight.device)
         col = 0

@@ -95,7 +95,7 @@ class CrossSwinBlock(PackedModule):
         x1 = x1.contiguous()
         xn = ops.layernorm(x1, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         ao = self.attn.canvas_attention(xn, B, TH1, W, self.shift_size, self.attn_mask)
-        if ops.precision() == "bf16" and not need_out_fp32:
+        if ops.tensor_cores() and not need_out_fp32:
             if need_out:
                 h, out_op = ops.linear_dual(ao, self.attn._gemm_weight("proj", self.attn.proj.weight), self.attn.proj.bias, x1)
             else:

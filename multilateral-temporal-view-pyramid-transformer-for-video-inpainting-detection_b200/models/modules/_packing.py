@@ -28,14 +28,14 @@ class PackedModule(torch.nn.Module):
             if reshape is not None:
                 w = w.reshape(reshape)
             w = w.contiguous()
-            return ops.cast_bf16(w) if ops.precision() == "bf16" else w
+            return ops.cast16(w) if ops.tensor_cores() else w
         return self._packed("w:" + name, [param], make)
 
 
 def as_operand(x):
     """fp32 activation -> GEMM A operand of the current precision."""
-    if ops.precision() == "bf16" and x.dtype == torch.float32:
-        return ops.cast_bf16(x)
+    if ops.tensor_cores() and x.dtype == torch.float32:
+        return ops.cast16(x)
     return x
 
 

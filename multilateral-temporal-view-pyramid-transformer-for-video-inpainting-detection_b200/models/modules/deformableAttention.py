@@ -65,7 +65,7 @@ class SwinDAttention(PackedModule):
         def make():
             w = torch.cat([self.proj_k.weight.detach().reshape(self.nc, self.nc),
                            self.proj_v.weight.detach().reshape(self.nc, self.nc)], 0).contiguous()
-            return ops.cast_bf16(w) if ops.precision() == "bf16" else w
+            return ops.cast16(w) if ops.tensor_cores() else w
         return self._packed("kv_w", [self.proj_k.weight, self.proj_v.weight], make)
 
     def _kv_bias(self):

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 RS_IDENTITY, RS_UP_ALIGNED, RS_UP_HALFPIX, RS_AVGPOOL2, RS_PIXEL_SHUFFLE2 = 0, 1, 2, 3, 4
 
@@ -19,10 +19,11 @@ launch_count = 0            # libmumpy_b200 kernels launched so far (bench.py re
 
 
 def set_precision(mode: str):
-    """'bf16': tcgen05 GEMMs on bf16 operands with fp32 accumulation; 'fp32': exact fp32 FMA kernels."""
+    """'bf16' / 'fp16': tcgen05 GEMMs on 16-bit operands (bfloat16 or IEEE half: same tensor-core rate, half has 3 more
+    mantissa bits and a narrower range) with fp32 accumulation, residual stream and statistics; 'fp32': exact fp32 FMA kernels."""
     global _precision
-    if mode not in ("bf16", "fp32"):
-        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if mode not in ("bf16", "fp16", "fp32"):
+        raise ValueError("precision must be 'bf16', 'fp16' or 'fp32'")
     _precision = mode
 
 
@@ -32,7 +33,12 @@ def precision() -> str:
 
 def act_dtype():
     """torch dtype of GEMM operands in the current precision mode."""
-    return torch.bfloat16 if _precision == "bf16" else torch.float32
+    return {"bf16": torch.bfloat16, "fp16": torch.float16}.get(_precision, torch.float32)
+
+
+def tensor_cores() -> bool:
+    """True in the 16-bit operand modes (tcgen05 GEMMs / implicit-GEMM convolutions)."""
+    return _precision != "fp32"
 
 
 def code(dtype) -> int:
@@ -40,6 +46,8 @@ def code(dtype) -> int:
         return F32
     if dtype == torch.bfloat16:
         return BF16
+    if dtype == torch.float16:
+        return F16
     raise _lib.MumpyError("unsupported dtype %s" % dtype)
 
 
@@ -86,16 +94,16 @@ def linear(a, w, bias=None, residual=None, act=ACT_NONE, out_dtype=torch.float32
 
 
 def linear_dual(a, w, bias, residual):
-    """bf16 operands only: returns (act-free a @ w.T + bias + residual as fp32, bf16(a @ w.T + bias))."""
+    """16-bit operands only: returns (a @ w.T + bias + residual as fp32, (operand dtype)(a @ w.T + bias))."""
     K = a.shape[-1]
     N = w.shape[0]
     M = a.numel() // K
-    if w.shape[1] != K or a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
-        raise _lib.MumpyError("linear_dual: bf16 operands required")
+    if w.shape[1] != K or a.dtype != w.dtype or a.dtype not in (torch.bfloat16, torch.float16):
+        raise _lib.MumpyError("linear_dual: 16-bit operands of one type required")
     out = torch.empty(a.shape[:-1] + (N,), dtype=torch.float32, device=a.device)
-    aux = torch.empty(a.shape[:-1] + (N,), dtype=torch.bfloat16, device=a.device)
+    aux = torch.empty(a.shape[:-1] + (N,), dtype=a.dtype, device=a.device)
     lib, st = _prep(a, w, bias, residual, out, aux)
-    _lib.check(lib.mumpy_linear_dual(_p(a), K, _p(w), _p(bias), _p(residual), _p(out), _p(aux), N, M, N, K, ACT_NONE, st),
+    _lib.check(lib.mumpy_linear_dual(_p(a), K, _p(w), _p(bias), _p(residual), _p(out), _p(aux), N, M, N, K, code(a.dtype), ACT_NONE, st),
                "mumpy_linear_dual")
     return out, aux
 
@@ -219,11 +227,13 @@ def conv2d_nhwc(x, w_ohwi, bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in=None,
 
 def conv2d_nhwc_bf16(x, w_packed, bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in=None, act=ACT_NONE, out_dtype=torch.float32,
                      residual=None):
-    """Tensor-core implicit GEMM: x (B,H,W,Cin[ld_in]) bf16 NHWC, w_packed (Cout, kh*kw*ceil(Cin/64)*64) bf16."""
+    """Tensor-core implicit GEMM: x (B,H,W,Cin[ld_in]) NHWC and w_packed (Cout, kh*kw*ceil(Cin/64)*64) of one 16-bit type."""
+    if x.dtype != w_packed.dtype:
+        raise _lib.MumpyError("conv2d_nhwc_bf16: activation %s vs filter %s" % (x.dtype, w_packed.dtype))
     out = torch.empty((B, H, W, Cout), dtype=out_dtype, device=x.device)
     lib, st = _prep(x, w_packed, bias, residual, out)
     _lib.check(lib.mumpy_conv2d_nhwc_bf16(_p(x), ld_in or Cin, _p(w_packed), _p(bias), _p(residual), _p(out), Cout, B, H, W, Cin,
-                                          Cout, kh, kw, ph, pw, code(out_dtype), act, st), "mumpy_conv2d_nhwc_bf16")
+                                          Cout, kh, kw, ph, pw, code(x.dtype), code(out_dtype), act, st), "mumpy_conv2d_nhwc_bf16")
     return out
 
 
@@ -236,9 +246,9 @@ def conv2d_nhwc_cout1(x, w_hwi, bias, B, H, W, Cin, kh, kw, ph, pw):
 
 
 def im2col_nhwc(x, B, H, W, Cin, kh, kw, ph, pw, Kpad, ld_in=None):
-    out = torch.empty((B * H * W, Kpad), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((B * H * W, Kpad), dtype=act_dtype(), device=x.device)
     lib, st = _prep(x, out)
-    _lib.check(lib.mumpy_im2col_nhwc(_p(x), ld_in or Cin, _p(out), B, H, W, Cin, kh, kw, ph, pw, Kpad, st),
+    _lib.check(lib.mumpy_im2col_nhwc(_p(x), ld_in or Cin, _p(out), code(out.dtype), B, H, W, Cin, kh, kw, ph, pw, Kpad, st),
                "mumpy_im2col_nhwc")
     return out
 
@@ -322,8 +332,21 @@ def mask_counts(logits, gt=None, want_mask=True):
     return mask, counts
 
 
-def cast_bf16(x):
-    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+def cast16(x, dtype=None):
+    """fp32 -> 16-bit operand (`dtype`, default: the operand type of the current precision mode)."""
+    dtype = dtype or act_dtype()
+    if dtype == torch.float32:
+        raise _lib.MumpyError("cast16 called in fp32 mode")
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
     lib, st = _prep(x, out)
-    _lib.check(lib.mumpy_cast_bf16(_p(x), _p(out), x.numel(), st), "mumpy_cast_bf16")
+    _lib.check(lib.mumpy_cast16(_p(x), _p(out), code(dtype), x.numel(), st), "mumpy_cast16")
     return out
+
+
+def cast_bf16(x):
+    return cast16(x, torch.bfloat16)
+
+
+def set_gemm_pair_mode(mode: int):
+    """CTA-pair (cta_group::2) policy of the tensor-core GEMM: 0 never (default), 1 cost model, 2 whenever legal."""
+    _lib.check(_lib.load().mumpy_set_gemm_pair_mode(int(mode)), "mumpy_set_gemm_pair_mode")

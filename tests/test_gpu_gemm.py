@@ -35,24 +35,50 @@ def test_linear_fp32_exact(M, N, K, epi):
     assert util.maxabs(out, ref) < 2e-5
 
 
-@pytest.mark.parametrize("M,N,K", SHAPES)
-@pytest.mark.parametrize("epi", ["plain", "bias_gelu_bf16out", "bias_residual"])
-def test_linear_tcgen05_bf16(M, N, K, epi):
-    """bf16 operands, fp32 accumulation: compare with the fp32 oracle on the bf16-rounded operands.
-    Tolerance: products are exact in fp32, so only summation order differs (<= ~K * 2^-24 relative) plus one bf16
-    rounding of the result when the output is bf16 (2^-9 relative)."""
+@pytest.fixture
+def pair_mode(request):
+    """CTA-pair policy of the tensor-core GEMM for one test (0 = 1-CTA tiles, 2 = cta_group::2 pairs whenever legal)."""
     ops = _ops()
-    a = util.seeded_input((M, K), 1).bfloat16()
-    w = (util.seeded_input((N, K), 2) / K ** 0.5).bfloat16()
+    ops.set_gemm_pair_mode(request.param)
+    yield request.param
+    ops.set_gemm_pair_mode(0)
+
+
+@pytest.mark.parametrize("pair_mode", [0, 2], indirect=True)
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("epi", ["plain", "bias_gelu_16out", "bias_residual"])
+def test_linear_tcgen05_16bit(M, N, K, epi, dt, pair_mode):
+    """bf16 / f16 operands, fp32 accumulation: compare with the fp32 oracle on the rounded operands.
+    Tolerance: products are exact in fp32, so only summation order differs (<= ~K * 2^-24 relative) plus one rounding of
+    the result when the output is 16-bit (2^-9 relative for bf16, 2^-12 for f16)."""
+    ops = _ops()
+    a = util.seeded_input((M, K), 1).to(dt)
+    w = (util.seeded_input((N, K), 2) / K ** 0.5).to(dt)
     bias = util.seeded_input((N,), 3) if epi != "plain" else None
     res = util.seeded_input((M, N), 4) if epi == "bias_residual" else None
     ref = orc.linear(a.float(), w.float(), bias)
-    if epi == "bias_gelu_bf16out":
+    if epi == "bias_gelu_16out":
         ref = orc.gelu(ref)
     if res is not None:
         ref = ref + res
-    bf16_out = epi == "bias_gelu_bf16out"
+    out16 = epi == "bias_gelu_16out"
     out = ops.linear(a.cuda(), w.cuda(), None if bias is None else bias.cuda(), None if res is None else res.cuda(),
-                     act=ops.ACT_GELU if bf16_out else ops.ACT_NONE, out_dtype=torch.bfloat16 if bf16_out else torch.float32)
-    tol = 2e-2 if bf16_out else 1e-4
+                     act=ops.ACT_GELU if out16 else ops.ACT_NONE, out_dtype=dt if out16 else torch.float32)
+    tol = (2e-2 if dt == torch.bfloat16 else 3e-3) if out16 else 1e-4
     assert util.maxabs(out.float(), ref) < tol * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(3136, 96, 96), (588, 512, 512), (130, 128, 128)])
+def test_linear_dual_outputs(M, N, K, dt):
+    """mumpy_linear_dual: shortcut sum (fp32) and the un-summed branch in operand precision from one pass."""
+    ops = _ops()
+    a = util.seeded_input((M, K), 1).to(dt)
+    w = (util.seeded_input((N, K), 2) / K ** 0.5).to(dt)
+    bias, res = util.seeded_input((N,), 3), util.seeded_input((M, N), 4)
+    branch = orc.linear(a.float(), w.float(), bias)
+    out, aux = ops.linear_dual(a.cuda(), w.cuda(), bias.cuda(), res.cuda())
+    assert out.dtype == torch.float32 and aux.dtype == dt
+    assert util.maxabs(out, branch + res) < 1e-4 * max(1.0, float(branch.abs().max()))
+    assert util.maxabs(aux.float(), branch) < (1e-2 if dt == torch.bfloat16 else 2e-3) * max(1.0, float(branch.abs().max()))

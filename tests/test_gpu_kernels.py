@@ -21,6 +21,15 @@ def _pack_conv(w, Cin):
     return wp.reshape(Cout, -1).bfloat16().contiguous()
 
 
+@pytest.fixture
+def pair_mode(request):
+    ops = _ops()
+    ops.set_gemm_pair_mode(request.param)
+    yield request.param
+    ops.set_gemm_pair_mode(0)
+
+
+@pytest.mark.parametrize("pair_mode", [0, 2], indirect=True)
 @pytest.mark.parametrize("B,H,W,Cin,Cout,kh,kw", [
     (1, 7, 7, 256, 128, 3, 3),        # < 128 KB tensor (driver work-around path)
     (2, 14, 14, 32, 128, 3, 3),       # Cin < 64: channel block zero-filled by TMA
@@ -31,7 +40,7 @@ def _pack_conv(w, Cin):
     (3, 112, 112, 128, 128, 3, 3),    # decoder_5, M tail across image borders
     (5, 7, 7, 128, 64, 3, 3),         # 245 pixels: tiles straddle images
 ])
-def test_conv_implicit_gemm_tcgen05(B, H, W, Cin, Cout, kh, kw):
+def test_conv_implicit_gemm_tcgen05(B, H, W, Cin, Cout, kh, kw, pair_mode):
     ops = _ops()
     x = util.seeded_input((B, Cin, H, W), 1).bfloat16()
     w = (util.seeded_input((Cout, Cin, kh, kw), 2) / (Cin * kh * kw) ** 0.5).bfloat16()
@@ -62,13 +71,14 @@ def test_conv_cout1():
     assert util.maxabs(out.view(2, 1, 24, 20), ref) < 1e-5
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("B,T,H,C,heads,shift", [(2, 3, 14, 64, 2, 3), (2, 1, 14, 96, 3, 0), (1, 3, 7, 128, 4, 0), (3, 3, 28, 128, 4, 3)])
-def test_window_attention_tensor_pipe(B, T, H, C, heads, shift):
+def test_window_attention_tensor_pipe(B, T, H, C, heads, shift, dt):
     """bf16 qkv -> mma.sync kernel vs the oracle's attention on the same bf16-rounded qkv (P is rounded to bf16
     before PV inside the kernel: tolerance 1e-2 on O(1) outputs)."""
     ops = _ops()
     TH, W, ws, N = T * H, H, 7, 49
-    qkv = util.seeded_input((B, TH * W, 3 * C), 1).bfloat16()
+    qkv = util.seeded_input((B, TH * W, 3 * C), 1).to(dt)
     table = 0.5 * util.seeded_input((169, heads), 2)
     bias = orc.relative_position_bias(table, ws)
     mask = orc.shifted_window_mask(TH, W, ws, shift) if shift else None
@@ -87,7 +97,7 @@ def test_window_attention_tensor_pipe(B, T, H, C, heads, shift):
     if shift:
         o = torch.roll(o, (shift, shift), (1, 2))
     out = ops.window_attention(qkv.cuda(), bias.cuda(), None if mask is None else mask.cuda(), B, TH, W, C, heads, ws, shift)
-    assert out.dtype == torch.bfloat16
+    assert out.dtype == dt
     assert util.maxabs(out.float(), o.reshape(B, TH * W, C)) < 2e-2
     # fast path: bias looked up in the raw table, standard shift mask recomputed from region ids
     out2 = ops.window_attention(qkv.cuda(), bias.cuda(), None if mask is None else mask.cuda(), B, TH, W, C, heads, ws, shift,
