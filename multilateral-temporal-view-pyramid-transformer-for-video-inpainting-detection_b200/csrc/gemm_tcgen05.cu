@@ -58,7 +58,7 @@ constexpr int TC_BK = 64;       // 64 bf16 = 128 B = one swizzle span
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
-constexpr int TC_SMEM_BUDGET = 164 * 1024;      // operand ring; + 8 x 4 KB epilogue staging + 1 KB alignment slack
+constexpr int TC_SMEM_BUDGET = 164 * 1024;      // operand ring; + 8 x (4 KB epilogue staging + 512 B bias) + 1 KB alignment slack
 
 struct TcParams {
   const float *bias;
@@ -90,12 +90,13 @@ constexpr int EPI_STAGE_BYTES = 32 * 128;      // per-warp staging tile: 32 rows
 // Phase 2 (coalesced): the warp re-reads the tile row-wise so that every global access is a full 128 B (fp32) or 64 B
 // (bf16) row segment: residual loads, fp32->bf16 packing and the output stores are all coalesced.
 template <int ACT, bool OUT_BF16, bool HAS_RES>
-__device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage, uint32_t acc, int warp, int lane, long m0, int n0) {
+__device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage, const float *bias_s, uint32_t acc, int warp, int lane, long m0,
+                                              int n0) {
   const int quad = warp & 3, half = warp >> 2;
   const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
   const long row0 = m0 + quad * 32;
   const uint32_t st_base = smem_u32(stage);
-  for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+  for (int c0 = half * 32, ci = 0; c0 < p.BN; c0 += 64, ++ci) {
     // residual tile of this chunk, fetched in the coalesced phase-2 layout before anything else so that the global-load
     // latency overlaps the TMEM load and the phase-1 math
     float4 res[8];
@@ -122,20 +123,24 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
     uint32_t v[32];
     tmem_ld32(lane_addr + c0, v);
     if (p.debug == 2) continue;
-    const int nb = n0 + c0;
-    // ---- phase 1 ----
+    // ---- phase 1 ----  (bias of this chunk: staged in shared memory before the accumulator wait, zero when absent)
+    const float4 *bias4 = reinterpret_cast<const float4 *>(bias_s + ci * 32);
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      float4 f = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-      if (p.bias && nb + 4 * g < p.N) {
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + nb + 4 * g));
-        f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
+      float2 f0 = make_float2(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]));
+      float2 f1 = make_float2(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+      {
+        const float4 b = bias4[g];
+        f0 = __fadd2_rn(f0, make_float2(b.x, b.y));
+        f1 = __fadd2_rn(f1, make_float2(b.z, b.w));
       }
       if (ACT == 1) {
-        f.x = gelu_fast(f.x); f.y = gelu_fast(f.y); f.z = gelu_fast(f.z); f.w = gelu_fast(f.w);
+        f0 = gelu_fast2(f0);
+        f1 = gelu_fast2(f1);
       } else if (ACT == 2) {
-        f.x = apply_act(f.x, p.act); f.y = apply_act(f.y, p.act); f.z = apply_act(f.z, p.act); f.w = apply_act(f.w, p.act);
+        f0.x = apply_act(f0.x, p.act); f0.y = apply_act(f0.y, p.act); f1.x = apply_act(f1.x, p.act); f1.y = apply_act(f1.y, p.act);
       }
+      const float4 f = make_float4(f0.x, f0.y, f1.x, f1.y);
       asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + lane * 128 + ((g ^ (lane & 7)) << 4)), "f"(f.x), "f"(f.y),
                    "f"(f.z), "f"(f.w)
                    : "memory");
@@ -146,13 +151,18 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
       if (OUT_BF16) {
         const int c8 = lane & 3;                 // 8 columns (16 B of bf16) per lane, 4 lanes per row, 8 rows per pass
         const int col = c0 + c8 * 8;
+        float4 xs[4], ys[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {          // all shared-memory reads first: their latencies overlap instead of chaining
+          const int r = i * 8 + (lane >> 2);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xs[i].x), "=f"(xs[i].y), "=f"(xs[i].z), "=f"(xs[i].w) : "r"(st_base + r * 128 + (((2 * c8) ^ (r & 7)) << 4)));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ys[i].x), "=f"(ys[i].y), "=f"(ys[i].z), "=f"(ys[i].w) : "r"(st_base + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4)));
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = i * 8 + (lane >> 2);
           const long gm = row0 + r;
-          float4 x, y;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st_base + r * 128 + (((2 * c8) ^ (r & 7)) << 4)));
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(st_base + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4)));
+          float4 x = xs[i], y = ys[i];
           if (gm < p.M && col < p.BN && n0 + col < p.N) {
             if (HAS_RES) {
               const float4 r0 = res[2 * i], r1 = res[2 * i + 1];
@@ -172,12 +182,17 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
       } else {
         const int c4 = lane & 7;                 // 4 columns (16 B of fp32) per lane, 8 lanes per row, 4 rows per pass
         const int col = c0 + c4 * 4;
+        float4 xs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xs[i].x), "=f"(xs[i].y), "=f"(xs[i].z), "=f"(xs[i].w) : "r"(st_base + r * 128 + ((c4 ^ (r & 7)) << 4)));
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + (lane >> 3);
           const long gm = row0 + r;
-          float4 x;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st_base + r * 128 + ((c4 ^ (r & 7)) << 4)));
+          float4 x = xs[i];
           if (gm < p.M && col < p.BN && n0 + col < p.N) {
             if (p.aux) {
               uint2 pk;
@@ -337,6 +352,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   } else {
     // ---------------- epilogue ----------------
     uint8_t *stage = smem_raw + (tiles - raw) + p.stages * stage_bytes + warp * EPI_STAGE_BYTES;
+    float *bias_s = reinterpret_cast<float *>(smem_raw + (tiles - raw) + p.stages * stage_bytes + TC_EPI_WARPS * EPI_STAGE_BYTES) + warp * 128;
     const int mode = (p.act == MUMPY_ACT_GELU ? 1 : (p.act == MUMPY_ACT_NONE ? 0 : 2)) | (p.out_bf16 ? 4 : 0) | (p.residual ? 8 : 0);
     uint32_t t = 0;
     const uint32_t acc_empty_leader = kPair ? mapa_shared(acc_empty0, 0) : acc_empty0;
@@ -344,22 +360,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t slot = t & 1, aph = (t >> 1) & 1;
       const int n0 = static_cast<int>(tile % p.tiles_n) * p.BN;
       const long m0 = (tile / p.tiles_n) * (kPair ? 2 * TC_BM : TC_BM) + rank * TC_BM;
+      // bias values of this warp's column chunks -> shared memory while the accumulator is still being produced
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = (warp >> 2) * 32 + 64 * ci + lane;
+        bias_s[ci * 32 + lane] = (p.bias && c < p.BN && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.0f;
+      }
+      __syncwarp();
       mbar_wait(acc_full0 + 8 * slot, aph);
       tc_fence_after();
       const uint32_t acc = tmem_base + slot * p.acc_cols;
       switch (mode) {
-        case 0: epilogue_tile<0, false, false>(p, stage, acc, warp, lane, m0, n0); break;
-        case 1: epilogue_tile<1, false, false>(p, stage, acc, warp, lane, m0, n0); break;
-        case 2: epilogue_tile<2, false, false>(p, stage, acc, warp, lane, m0, n0); break;
-        case 4: epilogue_tile<0, true, false>(p, stage, acc, warp, lane, m0, n0); break;
-        case 5: epilogue_tile<1, true, false>(p, stage, acc, warp, lane, m0, n0); break;
-        case 6: epilogue_tile<2, true, false>(p, stage, acc, warp, lane, m0, n0); break;
-        case 8: epilogue_tile<0, false, true>(p, stage, acc, warp, lane, m0, n0); break;
-        case 9: epilogue_tile<1, false, true>(p, stage, acc, warp, lane, m0, n0); break;
-        case 10: epilogue_tile<2, false, true>(p, stage, acc, warp, lane, m0, n0); break;
-        case 12: epilogue_tile<0, true, true>(p, stage, acc, warp, lane, m0, n0); break;
-        case 13: epilogue_tile<1, true, true>(p, stage, acc, warp, lane, m0, n0); break;
-        default: epilogue_tile<2, true, true>(p, stage, acc, warp, lane, m0, n0); break;
+        case 0: epilogue_tile<0, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 1: epilogue_tile<1, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 2: epilogue_tile<2, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 4: epilogue_tile<0, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 5: epilogue_tile<1, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 6: epilogue_tile<2, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 8: epilogue_tile<0, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 9: epilogue_tile<1, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 10: epilogue_tile<2, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 12: epilogue_tile<0, true, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 13: epilogue_tile<1, true, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        default: epilogue_tile<2, true, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
       }
       // this warp is done reading the accumulator: hand the TMEM slot back to the MMA issuer
       tc_fence_before();
@@ -504,10 +527,10 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   if (stages > kb_per_cta) stages = (int)kb_per_cta;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  const int smem = stages * stage_bytes + 1024 + TC_EPI_WARPS * 32 * 128;
+  const int smem = stages * stage_bytes + 1024 + TC_EPI_WARPS * (32 * 128 + 512);
   const int which = (p.conv ? 1 : 0) + (pair ? 2 : 0);
   if (!g_attr_set[which]) {
-    const int max_smem = TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * 32 * 128;
+    const int max_smem = TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * (32 * 128 + 512);
     cudaError_t e;
     switch (which) {
       case 0: e = cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;

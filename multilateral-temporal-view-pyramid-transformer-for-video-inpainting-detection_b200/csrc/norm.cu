@@ -68,9 +68,11 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restr
                                                             const float *__restrict__ beta, OutT *__restrict__ out, long n_rows, int C, float eps) {
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
-  const long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
-  if (row0 >= n_rows) return;
   const int nv = C >> 2;
+  const long warp_stride = (long)gridDim.x * (blockDim.x >> 5) * R;
+  // grid-stride over row groups: the grid is sized to the machine (148 SMs x resident CTAs), not to the row count, so that
+  // there is no partial last wave
+  for (long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; row0 < n_rows; row0 += warp_stride) {
   float4 v[R][NV];
   float s[R];
 #pragma unroll
@@ -134,12 +136,14 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restr
       }
     }
   }
+  }
 }
 
 template <typename OutT, int NV, int R>
 static void launch_ln_vec(const float *x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
   const long warps = cdiv(rows, R);
-  launch_kernel(layernorm_vec_kernel<OutT, NV, R>, (unsigned)cdiv(warps, 8), 256, 0, st, x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
+  const long ctas = cdiv(warps, 8);
+  launch_kernel(layernorm_vec_kernel<OutT, NV, R>, (unsigned)(ctas < 148 * 6 ? ctas : 148 * 6), 256, 0, st, x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
 }
 
 template <typename OutT>

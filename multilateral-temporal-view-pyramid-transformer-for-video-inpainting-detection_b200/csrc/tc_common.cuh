@@ -160,22 +160,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// GELU(x) = x * Phi(x) with erfc(|x|/sqrt2) = 2^P(t), t = min(|x|/sqrt2, 5): degree-6 minimax fit of log2(erfc),
-// |error| <= 5.5e-7 absolute in fp32 over the whole real line (below erff's own rounding at bf16 output precision).
-// gelu = relu(x) - 0.5*|x*erfc|.  11 FMA-pipe instructions + one MUFU.EX2 (erff costs ~40 and made the fc1
-// epilogue 2.4x slower than its MMAs).
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 5.0f);
-  float p = 0.000153401316f;
-  p = fmaf(p, t, -0.00372565322f);
-  p = fmaf(p, t, 0.0310176836f);
-  p = fmaf(p, t, -0.149808799f);
-  p = fmaf(p, t, -0.918120487f);
-  p = fmaf(p, t, -1.62793242f);
-  p = fmaf(p, t, 3.06567465e-07f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));
-  return fmaf(-0.5f, fabsf(x * e), fmaxf(x, 0.0f));
+// GELU(x) = relu(x) - |x| * Phi(-|x|), with Phi(-u) = 0.5 erfc(u / sqrt2) = 2^Q(u) on u = min(|x|, 5 sqrt2): degree-6
+// minimax fit of log2 Phi(-u) evaluated in s = -u (so that the last step is one FMA: relu(x) + s * 2^Q), |error| <= 5.5e-7
+// absolute in fp32 over the whole real line (below erff's own rounding at 16-bit output precision).  Two elements per call on
+// the packed fp32x2 pipe of sm_100 (FFMA2): per pair 4 FMNMX + 7 FFMA2 + 2 MUFU.EX2, i.e. 6.5 issue slots per element
+// instead of ~40 for erff (which made the fc1 epilogue 2.4x slower than its MMAs) and 12 for the scalar form.
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  const float2 s = make_float2(fmaxf(-fabsf(x.x), -7.0710678f), fmaxf(-fabsf(x.y), -7.0710678f));
+  float2 p = make_float2(1.9175164197804406e-05f, 1.9175164197804406e-05f);
+  p = __ffma2_rn(p, s, make_float2(0.0006586086819879711f, 0.0006586086819879711f));
+  p = __ffma2_rn(p, s, make_float2(0.0077544208616018295f, 0.0077544208616018295f));
+  p = __ffma2_rn(p, s, make_float2(0.05296541005373001f, 0.05296541005373001f));
+  p = __ffma2_rn(p, s, make_float2(-0.4590602517127991f, -0.4590602517127991f));
+  p = __ffma2_rn(p, s, make_float2(1.1511220932006836f, 1.1511220932006836f));
+  p = __ffma2_rn(p, s, make_float2(-0.9999997019767761f, -0.9999997019767761f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(p.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(p.y));
+  return __ffma2_rn(s, e, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
 }
+__device__ __forceinline__ float gelu_fast(float x) { return gelu_fast2(make_float2(x, x)).x; }
 
 }  // namespace mumpy

@@ -12,8 +12,9 @@ from ... import ops, streams
 from ..modules._packing import PackedModule, require_inference
 
 
-def _conv(owner, name, conv, x, B, H, W, ld_in=None):
-    """Stride-1 nn.Conv2d on an NHWC map x (B,H,W,Cin[ld_in]) -> (B,H,W,Cout) fp32."""
+def _conv(owner, name, conv, x, B, H, W, ld_in=None, out16=False, residual=None):
+    """Stride-1 nn.Conv2d on an NHWC map x (B,H,W,Cin[ld_in]) -> (B,H,W,Cout) fp32 (+ residual, fused into the epilogue).
+    out16: in the tensor-core modes return the result in operand precision (it only feeds another convolution)."""
     Cout, Cin, kh, kw = conv.weight.shape
     ph, pw = conv.padding
     K = kh * kw * Cin
@@ -31,7 +32,8 @@ def _conv(owner, name, conv, x, B, H, W, ld_in=None):
             return ops.cast16(wp.reshape(Cout, -1).contiguous())
         wq = owner._packed("tcconv:" + name, [conv.weight], make_tc)
         xb = x if x.dtype == ops.act_dtype() else ops.cast16(x)
-        return ops.conv2d_nhwc_bf16(xb, wq, conv.bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in)
+        return ops.conv2d_nhwc_bf16(xb, wq, conv.bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in,
+                                    out_dtype=ops.act_dtype() if out16 else torch.float32, residual=residual)
     if ops.tensor_cores() and Cout % 8 == 0:
         Kpad = (K + 7) // 8 * 8
 
@@ -42,9 +44,10 @@ def _conv(owner, name, conv, x, B, H, W, ld_in=None):
             return ops.cast16(w.contiguous())
         wq = owner._packed("tc:" + name, [conv.weight], make)
         cols = ops.im2col_nhwc(x, B, H, W, Cin, kh, kw, ph, pw, Kpad, ld_in)
-        return ops.linear(cols, wq, conv.bias).view(B, H, W, Cout)
+        return ops.linear(cols, wq, conv.bias, residual=None if residual is None else residual.view(B * H * W, Cout)).view(B, H, W, Cout)
     w = owner._packed("ohwi:" + name, [conv.weight], lambda: conv.weight.detach().permute(0, 2, 3, 1).contiguous())
-    return ops.conv2d_nhwc(x, w, conv.bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in)
+    y = ops.conv2d_nhwc(x, w, conv.bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in)
+    return y if residual is None else ops.add(y, residual)
 
 
 class SEB(PackedModule):
@@ -77,9 +80,11 @@ class _GlobalConvModule(PackedModule):
         self.conv_r2 = nn.Conv2d(out_dim, out_dim, kernel_size=(kernel_size[0], 1), padding=(pad0, 0))
 
     def nhwc(self, x, B, H, W):
-        l = _conv(self, "l2", self.conv_l2, _conv(self, "l1", self.conv_l1, x, B, H, W), B, H, W)
-        r = _conv(self, "r2", self.conv_r2, _conv(self, "r1", self.conv_r1, x, B, H, W), B, H, W)
-        return ops.add(l, r)
+        if ops.tensor_cores() and x.dtype == torch.float32:
+            x = ops.cast16(x)                       # one operand copy feeds both branches
+        l = _conv(self, "l2", self.conv_l2, _conv(self, "l1", self.conv_l1, x, B, H, W, out16=True), B, H, W)
+        r = _conv(self, "r2", self.conv_r2, _conv(self, "r1", self.conv_r1, x, B, H, W, out16=True), B, H, W, residual=l)
+        return r
 
     def forward(self, x):
         require_inference(self)
