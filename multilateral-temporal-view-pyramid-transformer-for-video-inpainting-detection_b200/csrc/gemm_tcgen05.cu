@@ -367,6 +367,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         bias_s[ci * 32 + lane] = (p.bias && c < p.BN && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.0f;
       }
       __syncwarp();
+      // pull this warp's part of the fp32 residual tile into L2 while the accumulator is still being produced: one bulk
+      // prefetch per row (the epilogue's residual loads are otherwise DRAM-latency bound, 4 dependent chunks per tile)
+      if (p.residual) {
+        const long gm = m0 + (warp & 3) * 32 + lane;
+        const int cols = min(p.BN, p.N - n0), off = (warp >> 2) * (p.BN / 2);
+        if (gm < p.M && off < cols) {
+          const uint32_t bytes = static_cast<uint32_t>(min(p.BN / 2, cols - off)) * 4u;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.residual + gm * p.ldo + n0 + off), "r"(bytes) : "memory");
+        }
+      }
       mbar_wait(acc_full0 + 8 * slot, aph);
       tc_fence_after();
       const uint32_t acc = tmem_base + slot * p.acc_cols;
