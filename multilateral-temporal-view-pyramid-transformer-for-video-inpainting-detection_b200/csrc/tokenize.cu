@@ -1,75 +1,120 @@
 // CrossThreeViewTokenize for one view (multiTemporalViewEncoder.py:605-618): Conv3d(3->C, kernel=stride=(kt,4,4))
-// is a GEMM over 3*kt*16-element patches (K = 144/96/48), followed by LayerNorm(C).  HBM-bound: each CTA
-// stages 8 horizontally adjacent patches through shared memory with coalesced 128 B row reads.
+// is a GEMM over 3*kt*16-element patches (K = 144/96/48), followed by LayerNorm(C).  fp32 throughout (the tokens seed the
+// fp32 residual stream).  Persistent CTAs: the (K x C) filter matrix stays in shared memory for the CTA's lifetime, each
+// iteration stages one row of S/4 patches (3*kt*4 contiguous image rows, 16-byte coalesced reads) as a K x S/4 tile; a warp
+// owns 8 neighbouring tokens, a lane 4 output channels: per k one 16-byte filter read + two broadcast 16-byte patch reads
+// feed 32 FMAs.  LayerNorm statistics are warp reductions over the channel lanes; stores are 16 bytes, 4C bytes per token
+// contiguous.
 #include "common.cuh"
 
 namespace mumpy {
 
-constexpr int TOK_PER_CTA = 8;
+constexpr int TOK_PER_WARP = 8;
 
-__global__ void __launch_bounds__(128) tokenize_kernel(const float *__restrict__ x, const float *__restrict__ w_kc,
-                                                       const float *__restrict__ bias, const float *__restrict__ gamma,
-                                                       const float *__restrict__ beta, float *__restrict__ out, int T, int S, int kt,
-                                                       int C, float eps) {
+__global__ void __launch_bounds__(512) tokenize_kernel(const float *__restrict__ x, const float *__restrict__ w_kc,
+                                                        const float *__restrict__ bias, const float *__restrict__ gamma,
+                                                        const float *__restrict__ beta, float *__restrict__ out, int T, int S, int kt,
+                                                        int C, float eps, long n_rows) {
   pdl_grid_sync();
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int K = 3 * kt * 16;
-  float *patch = sm;                       // [TOK][K]
-  float *vals = sm + TOK_PER_CTA * K;      // [TOK][C]
   const int Hp = S / 4;
+  const int Hpp = (Hp + TOK_PER_WARP - 1) / TOK_PER_WARP * TOK_PER_WARP;      // patch-tile row length (tokens, padded)
+  float *wsm = sm;                         // [K][C]
+  float *patch = sm + (size_t)K * C;       // [K][Hpp]
   const int To = T / kt;
-  const int groups_per_row = (Hp + TOK_PER_CTA - 1) / TOK_PER_CTA;
-  int gidx = blockIdx.x;
-  const int wg = gidx % groups_per_row; gidx /= groups_per_row;
-  const int hp = gidx % Hp; gidx /= Hp;
-  const int to = gidx % To;
-  const int b = gidx / To;
-  const int wp0 = wg * TOK_PER_CTA;
-  const int ntok = min(TOK_PER_CTA, Hp - wp0);
-
-  // patch element k = ((c*kt + dt)*4 + dy)*4 + dx  (weight layout (C,3,kt,4,4))
-  for (int e = threadIdx.x; e < 3 * kt * 4 * TOK_PER_CTA * 4; e += blockDim.x) {
-    const int dx = e % 4;
-    const int tok = (e / 4) % TOK_PER_CTA;
-    const int khi = e / (4 * TOK_PER_CTA);        // (c*kt + dt)*4 + dy
-    const int dy = khi % 4;
-    const int cdt = khi / 4;
-    const int dt = cdt % kt, c = cdt / kt;
-    float v = 0.0f;
-    if (tok < ntok)
-      v = x[((((long)b * T + to * kt + dt) * 3 + c) * S + hp * 4 + dy) * S + (wp0 + tok) * 4 + dx];
-    patch[tok * K + khi * 4 + dx] = v;
-  }
-  __syncthreads();
-  const int o = threadIdx.x;
-  if (o < C) {
-    float acc[TOK_PER_CTA];
-#pragma unroll
-    for (int t = 0; t < TOK_PER_CTA; ++t) acc[t] = 0.0f;
-    for (int k = 0; k < K; ++k) {
-      const float w = w_kc[(long)k * C + o];
-#pragma unroll
-      for (int t = 0; t < TOK_PER_CTA; ++t) acc[t] = fmaf(patch[t * K + k], w, acc[t]);
-    }
-    const float bo = bias[o];
-#pragma unroll
-    for (int t = 0; t < TOK_PER_CTA; ++t) vals[t * C + o] = acc[t] + bo;
-  }
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int t = warp; t < ntok; t += 4) {
-    const float *v = vals + t * C;
-    float s = 0.0f;
-    for (int i = lane; i < C; i += 32) s += v[i];
-    const float mean = warp_sum(s) / C;
-    float q = 0.0f;
-    for (int i = lane; i < C; i += 32) {
-      const float d = v[i] - mean;
-      q = fmaf(d, d, q);
+  const int C4 = C >> 2;
+  for (int i = threadIdx.x; i < K * C4; i += blockDim.x) reinterpret_cast<float4 *>(wsm)[i] = __ldg(reinterpret_cast<const float4 *>(w_kc) + i);
+  for (int i = threadIdx.x; i < K * (Hpp - Hp); i += blockDim.x) patch[(i / (Hpp - Hp)) * Hpp + Hp + i % (Hpp - Hp)] = 0.0f;   // padded tokens
+  const bool live = lane < C4;
+  float4 bo = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bo, b4 = bo;
+  if (live) {
+    bo = __ldg(reinterpret_cast<const float4 *>(bias) + lane);
+    g4 = __ldg(reinterpret_cast<const float4 *>(gamma) + lane);
+    b4 = __ldg(reinterpret_cast<const float4 *>(beta) + lane);
+  }
+  const int S4 = S >> 2;
+  for (long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int hp = (int)(row % Hp);
+    const long t2 = row / Hp;
+    const int to = (int)(t2 % To);
+    const long b = t2 / To;
+    __syncthreads();                       // previous iteration's readers are done with `patch` (and wsm is visible)
+    // patch element k = ((c*kt + dt)*4 + dy)*4 + dx  (weight layout (C,3,kt,4,4)); image row (c, dt, dy) holds dx fastest
+    for (int e = threadIdx.x; e < 3 * kt * 4 * S4; e += blockDim.x) {
+      const int wp = e % S4;
+      const int khi = e / S4;              // (c*kt + dt)*4 + dy
+      const int dy = khi & 3;
+      const int cdt = khi >> 2;
+      const int dt = cdt % kt, c = cdt / kt;
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(x + ((((long)b * T + to * kt + dt) * 3 + c) * S + hp * 4 + dy) * S) + wp);
+      float *dst = patch + (khi * 4) * Hpp + wp;
+      dst[0] = v.x;
+      dst[Hpp] = v.y;
+      dst[2 * Hpp] = v.z;
+      dst[3 * Hpp] = v.w;
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
-    float *dst = out + (((long)b * To + to) * Hp * Hp + (long)hp * Hp + wp0 + t) * C;
-    for (int i = lane; i < C; i += 32) dst[i] = (v[i] - mean) * rstd * gamma[i] + beta[i];
+    __syncthreads();
+    const int tok0 = warp * TOK_PER_WARP;
+    if (tok0 >= Hp) continue;              // (whole warps only; they still take part in the barriers above)
+    float acc[TOK_PER_WARP][4];
+#pragma unroll
+    for (int t = 0; t < TOK_PER_WARP; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.0f;
+    if (live) {
+      const float4 *w4 = reinterpret_cast<const float4 *>(wsm) + lane;
+      const float4 *p4 = reinterpret_cast<const float4 *>(patch + tok0);
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        const float4 w = w4[(size_t)k * C4];
+        const float4 pa = p4[(size_t)k * (Hpp >> 2)], pb = p4[(size_t)k * (Hpp >> 2) + 1];
+        const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+        for (int t = 0; t < TOK_PER_WARP; ++t) {
+          acc[t][0] = fmaf(pv[t], w.x, acc[t][0]);
+          acc[t][1] = fmaf(pv[t], w.y, acc[t][1]);
+          acc[t][2] = fmaf(pv[t], w.z, acc[t][2]);
+          acc[t][3] = fmaf(pv[t], w.w, acc[t][3]);
+        }
+      }
+    }
+    float s[TOK_PER_WARP];
+#pragma unroll
+    for (int t = 0; t < TOK_PER_WARP; ++t) {
+      acc[t][0] += bo.x; acc[t][1] += bo.y; acc[t][2] += bo.z; acc[t][3] += bo.w;
+      s[t] = live ? (acc[t][0] + acc[t][1]) + (acc[t][2] + acc[t][3]) : 0.0f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int t = 0; t < TOK_PER_WARP; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+    float q[TOK_PER_WARP];
+#pragma unroll
+    for (int t = 0; t < TOK_PER_WARP; ++t) {
+      const float mean = s[t] / C;
+      s[t] = mean;
+      const float d0 = acc[t][0] - mean, d1 = acc[t][1] - mean, d2 = acc[t][2] - mean, d3 = acc[t][3] - mean;
+      q[t] = live ? (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) : 0.0f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int t = 0; t < TOK_PER_WARP; ++t) q[t] += __shfl_xor_sync(0xffffffffu, q[t], o);
+    if (live) {
+      float *orow = out + (((long)b * To + to) * Hp * Hp + (long)hp * Hp + tok0) * C + 4 * lane;
+#pragma unroll
+      for (int t = 0; t < TOK_PER_WARP; ++t) {
+        if (tok0 + t < Hp) {
+          const float rstd = 1.0f / sqrtf(q[t] / C + eps);
+          float4 y;
+          y.x = (acc[t][0] - s[t]) * rstd * g4.x + b4.x;
+          y.y = (acc[t][1] - s[t]) * rstd * g4.y + b4.y;
+          y.z = (acc[t][2] - s[t]) * rstd * g4.z + b4.z;
+          y.w = (acc[t][3] - s[t]) * rstd * g4.w + b4.w;
+          *reinterpret_cast<float4 *>(orow + (long)t * C) = y;
+        }
+      }
+    }
   }
 }
 
@@ -79,12 +124,28 @@ using namespace mumpy;
 
 extern "C" int mumpy_tokenize(const float *x, const float *w_kc, const float *bias, const float *gamma, const float *beta,
                               float *out, int B, int T, int S, int kt, int C, float eps, void *stream) {
-  MUMPY_REQUIRE(x && w_kc && bias && gamma && beta && out && B > 0 && S % 4 == 0 && kt >= 1 && kt <= T, "tokenize: bad arguments");
-  MUMPY_REQUIRE(C <= 128, "tokenize: C=%d > 128 unsupported", C);
+  MUMPY_REQUIRE(x && w_kc && bias && gamma && beta && out && B > 0 && S % 4 == 0 && kt >= 1 && kt <= T, "tokenize: bad arguments (S must be a multiple of 4)");
+  MUMPY_REQUIRE(C <= 128 && C % 4 == 0, "tokenize: C=%d unsupported (multiple of 4, <= 128)", C);
+  MUMPY_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_kc) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(gamma) |
+                  reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "tokenize: buffers must be 16-byte aligned");
   const int Hp = S / 4, To = T / kt, K = 3 * kt * 16;
-  const int groups_per_row = (Hp + TOK_PER_CTA - 1) / TOK_PER_CTA;
-  const long ctas = (long)B * To * Hp * groups_per_row;
-  const size_t smem = (size_t)TOK_PER_CTA * (K + C) * sizeof(float);
-  launch_kernel(tokenize_kernel, (unsigned)ctas, 128, smem, as_stream(stream), x, w_kc, bias, gamma, beta, out, T, S, kt, C, eps);
+  const int warps = (Hp + TOK_PER_WARP - 1) / TOK_PER_WARP;
+  MUMPY_REQUIRE(warps <= 16, "tokenize: S=%d too large (<= 512)", S);
+  const int Hpp = warps * TOK_PER_WARP;
+  const size_t smem = (size_t)K * (C + Hpp) * sizeof(float);
+  MUMPY_REQUIRE(smem <= 227 * 1024, "tokenize: tile of %zu B does not fit shared memory", smem);
+  static size_t granted = 0;
+  if (smem > 48 * 1024 && smem > granted) {
+    cudaError_t e = cudaFuncSetAttribute(tokenize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("tokenize: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+    granted = smem;
+  }
+  const long n_rows = (long)B * To * Hp;
+  const int per_sm = smem > 110 * 1024 ? 1 : 2;
+  const long ctas = n_rows < 148l * per_sm ? n_rows : 148l * per_sm;
+  launch_kernel(tokenize_kernel, (unsigned)ctas, warps * 32, smem, as_stream(stream), x, w_kc, bias, gamma, beta, out, T, S, kt, C, eps, n_rows);
   return launch_status("tokenize");
 }
