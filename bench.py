@@ -384,19 +384,41 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_max = float(t)
 
-        # ---- end-to-end region: pinned host clips -> H2D -> forward -> D2H masks + counts, every step ---------
+        # ---- end-to-end region through the public front end (mumpy_b200.frontend, the test.py loop replacement): every step
+        # uploads B NEW uint8 frames from pinned host memory (one frame per clip: consecutive clips share two of their three
+        # frames), assembles + normalises the clips on the device, runs the forward and reads masks + counts back ----------
+        from mumpy_b200 import frontend
+        host_frames = [torch.randint(0, 256, (B, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(n_in)]
+        dev_frames = torch.empty((B, 224, 224, 3), dtype=torch.uint8, device=device)
+        clip_idx = frontend.clip_frame_indices([B], 3).to(device)
+
+        def step_frames():
+            ops.assemble_clips(dev_frames, clip_idx, frontend.MEAN, frontend.STD, out=x_static)
+            return step()
+
+        dev_frames.copy_(host_frames[0])
+        mask_e, counts_e = step_frames()
+        torch.cuda.synchronize()
+        graph_e = None
+        if not args.no_graph:
+            graph_e = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_e):
+                mask_e, counts_e = step_frames()
+        for i in range(2):
+            dev_frames.copy_(host_frames[i % n_in], non_blocking=True)
+            graph_e.replay() if graph_e is not None else step_frames()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for i in range(K):
-            x_static.copy_(host_in[i % n_in], non_blocking=True)
-            if graph is not None:
-                graph.replay()
-                m, c = mask, counts
+            dev_frames.copy_(host_frames[i % n_in], non_blocking=True)
+            if graph_e is not None:
+                graph_e.replay()
+                m, c = mask_e, counts_e
             else:
-                m, c = step()
+                m, c = step_frames()
             host_mask.copy_(m, non_blocking=True)
             host_counts.copy_(c, non_blocking=True)
         f1.record()
@@ -461,9 +483,10 @@ def main():
                    "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); per-step activation working set is several GB" % (n_in, n_in * B * 9 * 224 * 224 * 4 / 1e6),
                    "residual_stream": "fp32", "gemm": "%s operands, fp32 accumulate (tcgen05)" % args.precision,
                    "branch_concurrency": "views / decoder pyramid levels on 4 forked streams inside the graph"},
-        "e2e": {"value": clips / t_e2e, "unit": "clips/s", "h2d_bytes_per_step": B * 9 * 224 * 224 * 4,
+        "e2e": {"value": clips / t_e2e, "unit": "clips/s", "h2d_bytes_per_step": B * 224 * 224 * 3,
                 "d2h_bytes_per_step": B * 224 * 224 + B * 4 * 8, "ms_per_step": t_e2e / K * 1e3,
-                "api": "mumpy_b200.Encoder/Decoder forward + ops.mask_counts on host-pinned clips"},
+                "api": "mumpy_b200.frontend (uint8 frames from pinned host memory, one new frame per clip; clips assembled + "
+                       "normalised on the device) -> Encoder/Decoder forward -> ops.mask_counts -> masks + counts to pinned host memory"},
         "gpu_launches": launches_per_step * K,
         "roofline": {"bound": "tensor", "achieved": GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12 if world == 1 else GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12,
                      "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12 / peaks["bf16_tflops_sustained"],

@@ -168,6 +168,13 @@ int mumpy_nhwc_to_nchw(const float *in, long ld_in, float *out, int B, int C, in
 /* DAP == mean over groups of `k` consecutive channels (decoder.py:140-143). */
 int mumpy_channel_group_mean(const float *in, float *out, long pixels, int C, int k, void *stream);
 
+/* Clip assembly on the device (test.py:22-25 ToTensor + Normalize; universaldataloader.py:45-48 sliding clip window):
+ * frames (n_frames,H,W,3) uint8 HWC device images; clip_frames (B,T) int32 device frame indices (edge-clamped by the
+ * caller, mumpy_b200.frontend.clip_frame_indices); out (B,T,3,H,W) fp32 = (frame/255 - mean[c]) / std[c], bit-identical to
+ * torchvision's transform.  mean3/std3 are HOST arrays of 3 floats (read during the call). */
+int mumpy_assemble_clips(const unsigned char *frames, const int *clip_frames, float *out, int B, int T, int H, int W,
+                         const float *mean3, const float *std3, void *stream);
+
 /* a20 + measure.py:77-91: thresholded mask (logit > 0 -> 255) and per-clip integer counts
  * [TP, n_pred, n_gt, n_union] (int64, accumulated with atomics; counts must be zeroed by the caller).
  * logits (B, HW) fp32; gt (B, HW) uint8 (non-zero = positive) or NULL; mask (B, HW) uint8 or NULL. */

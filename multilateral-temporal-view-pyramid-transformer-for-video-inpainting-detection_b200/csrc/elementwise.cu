@@ -349,6 +349,40 @@ __global__ void __launch_bounds__(256) conv_cout1_vec_kernel(const float *__rest
   if (live && sub == 0) out[m] = acc + (bias ? bias[0] : 0.0f);
 }
 
+// Clip assembly (test.py:22-25 ToTensor + Normalize, universaldataloader.py:45-48 sliding window): frames are uint8 HWC
+// images resident on the device, every clip names its T frames by index (consecutive clips share T-1 frames, so each
+// frame is uploaded once); out[b,t,c,y,x] = (frame[idx[b,t]][y,x,c] / 255 - mean[c]) / std[c] with the same operation
+// order as torchvision (true divisions), so the result is bit-identical to the reference's CPU transform.
+// One thread per 4 horizontally adjacent pixels: 12 contiguous input bytes, one 16-byte store per channel.
+__global__ void __launch_bounds__(256) assemble_clips_kernel(const unsigned char *__restrict__ frames, const int *__restrict__ clip_frames,
+                                                             float *__restrict__ out, long total4, int T, int HW4, float m0, float m1,
+                                                             float m2, float s0, float s1, float s2) {
+  pdl_grid_sync();
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+  for (; i < total4; i += stride) {
+    const int p4 = (int)(i % HW4);
+    const long bt = i / HW4;                                     // b*T + t
+    const int f = __ldg(clip_frames + bt);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + ((long)f * HW4 + p4) * 12);
+    const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    const unsigned char px[12] = {(unsigned char)(w0), (unsigned char)(w0 >> 8), (unsigned char)(w0 >> 16), (unsigned char)(w0 >> 24),
+                                  (unsigned char)(w1), (unsigned char)(w1 >> 8), (unsigned char)(w1 >> 16), (unsigned char)(w1 >> 24),
+                                  (unsigned char)(w2), (unsigned char)(w2 >> 8), (unsigned char)(w2 >> 16), (unsigned char)(w2 >> 24)};
+    float *dst = out + (bt * 3) * (long)HW4 * 4 + (long)p4 * 4;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float4 v;
+      v.x = ((float)px[c] / 255.0f - mean[c]) / sd[c];
+      v.y = ((float)px[3 + c] / 255.0f - mean[c]) / sd[c];
+      v.z = ((float)px[6 + c] / 255.0f - mean[c]) / sd[c];
+      v.w = ((float)px[9 + c] / 255.0f - mean[c]) / sd[c];
+      *reinterpret_cast<float4 *>(dst + (long)c * HW4 * 4) = v;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) mask_counts_kernel(const float *__restrict__ logits, const unsigned char *__restrict__ gt,
                                                           unsigned char *__restrict__ mask, unsigned long long *__restrict__ counts, int HW) {
   pdl_grid_sync();
@@ -514,6 +548,18 @@ extern "C" int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const fl
   launch_kernel(conv_cout1_kernel, (unsigned)cdiv(pixels, 256), 256, kh * kw * Cin * sizeof(float), as_stream(stream), in, w, bias, out, pixels, H, W,
                                                                                                            Cin, kh, kw, ph, pw);
   return launch_status("conv2d_nhwc_cout1");
+}
+
+extern "C" int mumpy_assemble_clips(const unsigned char *frames, const int *clip_frames, float *out, int B, int T, int H, int W,
+                                    const float *mean3, const float *std3, void *stream) {
+  MUMPY_REQUIRE(frames && clip_frames && out && mean3 && std3 && B > 0 && T > 0 && H > 0 && W > 0, "assemble_clips: bad arguments");
+  MUMPY_REQUIRE((H * W) % 4 == 0 && ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "assemble_clips: H*W must be a multiple of 4 and the buffers 16-byte aligned");
+  const int HW4 = H * W / 4;
+  const long total4 = (long)B * T * HW4;
+  launch_kernel(assemble_clips_kernel, flat_blocks(total4), 256, 0, as_stream(stream), frames, clip_frames, out, total4, T, HW4, mean3[0], mean3[1],
+                mean3[2], std3[0], std3[1], std3[2]);
+  return launch_status("assemble_clips");
 }
 
 extern "C" int mumpy_mask_counts(const float *logits, const unsigned char *gt, unsigned char *mask, long long *counts, int B, int HW,

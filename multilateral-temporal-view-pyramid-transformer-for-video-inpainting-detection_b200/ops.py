@@ -321,6 +321,21 @@ def channel_group_mean(x, pixels, C, k):
     return out
 
 
+def assemble_clips(frames, clip_frames, mean, std, out=None):
+    """frames (n,H,W,3) uint8, clip_frames (B,T) int32 -> normalised clips (B,T,3,H,W) fp32 (ToTensor + Normalize on device)."""
+    if frames.dtype != torch.uint8 or clip_frames.dtype != torch.int32 or frames.shape[-1] != 3:
+        raise _lib.MumpyError("assemble_clips: frames must be uint8 HWC, clip_frames int32")
+    B, T = clip_frames.shape
+    H, W = frames.shape[1], frames.shape[2]
+    if out is None:
+        out = torch.empty((B, T, 3, H, W), dtype=torch.float32, device=frames.device)
+    lib, st = _prep(frames, clip_frames, out)
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _lib.check(lib.mumpy_assemble_clips(_p(frames), _p(clip_frames), _p(out), B, T, H, W, m, s, st), "mumpy_assemble_clips")
+    return out
+
+
 def mask_counts(logits, gt=None, want_mask=True):
     """logits (B,1,H,W) fp32 -> (mask uint8 (B,H,W) in {0,255}, counts int64 (B,4) = [TP, n_pred, n_gt, n_union])."""
     B = logits.shape[0]

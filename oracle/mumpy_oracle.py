@@ -495,6 +495,23 @@ def forward(enc_sd, dec_sd, x, cfg=None, per_clip_pairing=False):
 # --------------------------------------------------------------------------------------------
 # a20 + measure.py:46-91 : mask and per-clip metric
 # --------------------------------------------------------------------------------------------
+def assemble_clips(frames_u8, seq_lengths, length_clip=3, mean=(0.4776, 0.479, 0.4465), std=(0.230, 0.2085, 0.2324)):
+    """One clip per frame, neighbours clamped inside the sequence (universaldataloader.py:45-48), each frame through
+    ToTensor (uint8 HWC -> float CHW / 255) and Normalize ((x - mean) / std per channel) (test.py:22-25).
+    frames_u8 (n,H,W,3) uint8 -> (n, length_clip, 3, H, W) fp32."""
+    k = int(length_clip / 2)
+    mean_t = torch.tensor(mean, dtype=torch.float32).view(3, 1, 1)
+    std_t = torch.tensor(std, dtype=torch.float32).view(3, 1, 1)
+    clips, base = [], 0
+    for n in seq_lengths:
+        for idx in range(n):
+            ids = [max(0, min(n - 1, i)) for i in range(idx - k, idx + k + 1)]
+            fr = [((frames_u8[base + j].permute(2, 0, 1).to(torch.float32).div(255)) - mean_t) / std_t for j in ids]
+            clips.append(torch.stack(fr, 0))
+        base += n
+    return torch.stack(clips, 0)
+
+
 def threshold_mask(logits):
     """test.py:100-106: sigmoid(x) > 0.5  <=>  x > 0 ; uint8 {0,255}."""
     return (logits > 0).to(torch.uint8) * 255

@@ -44,3 +44,25 @@ def test_constructor_signatures():
     assert list(inspect.signature(blocks.Block.__init__).parameters)[1:] == ["dim", "heads", "mlp_dim", "dropout", "drop_path"]
     assert list(inspect.signature(mtv.ThreeViewSwinTransformer.__init__).parameters)[1:4] == [
         "view_configs", "input_token_temporal_dims", "global_encoder_config"]
+
+
+def test_checkpoint_ingestion_roundtrip(tmp_path):
+    """utils/utils.py:286-321 + check_parallel (:156-176): a checkpoint written from DataParallel-wrapped reference modules
+    (keys prefixed `module.`) and a plain one both restore strictly into the mirrors."""
+    import mumpy_b200
+    from mumpy_b200 import checkpoint
+    enc_sd = util.seeded_state_dict(mumpy_b200.Encoder())       # every key of the reference state_dict, buffers included
+    dec_sd = util.seeded_state_dict(mumpy_b200.Decoder())
+    for prefix in ("", "module."):
+        d = tmp_path / ("ckpt_" + (prefix.strip(".") or "plain"))
+        d.mkdir()
+        torch.save({prefix + k: v for k, v in enc_sd.items()}, d / "encoder_3.pt")
+        torch.save({prefix + k: v for k, v in dec_sd.items()}, d / "decoder_3.pt")
+        e, dd = checkpoint.load_checkpoint(str(d), 3)
+        assert list(e.keys()) == list(enc_sd.keys()) and list(dd.keys()) == list(dec_sd.keys())
+        assert all(torch.equal(e[k], enc_sd[k]) for k in enc_sd)
+    enc, dec = mumpy_b200.Encoder(), mumpy_b200.Decoder()
+    enc, dec = checkpoint.restore(enc, dec, str(d), 3)
+    assert not enc.training and not dec.training
+    got = enc.state_dict()
+    assert all(torch.equal(got[k], enc_sd[k]) for k in enc_sd)
