@@ -35,7 +35,9 @@ class CVAModule(nn.Module):
     def __init__(self, dim1, num_heads, window_size=7, temporal_dims=[], qkv_bias=True, qk_scale=None, drop=0.,
                  attn_drop=0., drop_path=0., cur_stage=0):
         super().__init__()
-        self.crossattn = SwinDAttention(dim1, num_heads, attn_drop, n_groups=3)
+        ws = window_size[0] if isinstance(window_size, (tuple, list)) else window_size
+        # the reference leaves SwinDAttention.ws at its default 7 (:131); windows of another size need it set
+        self.crossattn = SwinDAttention(dim1, num_heads, attn_drop, n_groups=3, ws=ws)
         self.drop_path = nn.Identity()
 
     def forward(self, x1, x2, mask=None, return_attention=False):

@@ -19,6 +19,12 @@ class PackedModule(torch.nn.Module):
             with torch.no_grad():
                 hit = (key, fn())
             cache[name] = hit
+            # Packing is enqueued on whatever stream is current (often one of the branch lanes of streams.py) but the packed
+            # tensor is cached and may be consumed from any other stream later: finish it before anyone can enqueue a
+            # consumer.  Once per weight load; never under graph capture (bench.py packs in an eager warm-up step).
+            dev = next((p.device for p in params if p.is_cuda), None)
+            if dev is not None and not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream(dev).synchronize()
         return hit[1]
 
     def _gemm_weight(self, name, param, reshape=None):

@@ -88,6 +88,39 @@ def test_fp16_mode_within_stated_tolerance(model, B):
     assert same > FP16_MASK_IDENTITY
 
 
+@pytest.mark.parametrize("name", ["e2e_256w8_b1", "e2e_512w8_b1"])
+def test_patched_resolution_window8(name):
+    """BASELINE.json configs[3] / SURVEY A10: window 8 at 256x256 and 512x512 (DVI resolution) against captures of the
+    reference classes instantiated with the same patched configuration (oracle/make_golden_hires.py).
+    fp32 mode <= 1e-4 on logits and identical masks; the 16-bit modes within their stated tolerances."""
+    import mumpy_b200
+    g = util.golden(name + ".pt")
+    size, ws, res = g["size"], g["window"], g["res"]
+    enc = mumpy_b200.Encoder(img_size=size, window_size=ws).eval()
+    dec = mumpy_b200.Decoder(shape=res).eval()
+    util.load_seeded(enc.base)            # the fixture seeds the bare ThreeViewSwinTransformer (keys without "base.")
+    util.load_seeded(dec)
+    m = (enc.cuda(), dec.cuda())
+    x = util.seeded_input(g["input_shape"], g["input_seed"])
+    final_x, view_x, ff, logits, feats = _run(m, x, "fp32")
+    assert logits.shape == (1, 1, size, size) and final_x.shape == (1, 2304, res[3], res[3])
+    assert util.maxabs(ff[:, :, ::8, ::8], g["ffinfo_sub"]) < 1e-4
+    for s in range(4):
+        for v in range(3):
+            assert util.maxabs(view_x[s][v][:, :, ::64, :], g["view_sub"][s][v]) < 5e-4, (s, v)
+    assert util.maxabs(final_x, g["final_x"]) < 5e-4
+    assert util.maxabs(logits, g["logits"]) < 1e-4
+    assert util.maxabs(feats[:, :, ::8, ::8], g["x_feats_sub"]) < 1e-4
+    assert int(((logits.cpu() > 0) != (g["logits"] > 0)).sum()) <= int(1e-3 * logits.numel())
+    for mode, tol_max, tol_mean, ident in (("fp16", FP16_LOGIT_MAXABS, FP16_LOGIT_MEANABS, FP16_MASK_IDENTITY),
+                                           ("bf16", BF16_LOGIT_MAXABS, BF16_LOGIT_MEANABS, BF16_MASK_IDENTITY)):
+        _, _, _, lg, _ = _run(m, x, mode)
+        d = (lg.cpu() - g["logits"]).abs()
+        same = float(((lg.cpu() > 0) == (g["logits"] > 0)).float().mean())
+        print("%s %s: logits max-abs %.3e mean-abs %.3e mask identity %.5f" % (name, mode, float(d.max()), float(d.mean()), same))
+        assert float(d.max()) < tol_max and float(d.mean()) < tol_mean and same > ident
+
+
 def test_mask_and_counts(model):
     """a20 + measure.py:77-91: thresholded mask and integer counts from the fused kernel vs the oracle."""
     import mumpy_b200

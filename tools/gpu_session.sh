@@ -1,9 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu18.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu18.log
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench17.json 2> gpurun_out/bench17.err; echo "bench rc=$?"; tail -3 gpurun_out/bench17.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench17.json'))
-print({k:d[k] for k in ('value','ms_per_step','e2e','other_precision','gpu_launches','clocks') if k in d})
-for k in d.get('kernels',[]): print(k)
-PY
+timeout 900 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu20.log 2>&1; echo "pytest rc=$?"; grep -E "identity|passed|failed|rror" gpurun_out/pytest_gpu20.log | head -20
+timeout 900 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_modules.py -m gpu -x -q > gpurun_out/pytest_gpu20b.log 2>&1; echo "pytest(2) rc=$?"; tail -2 gpurun_out/pytest_gpu20b.log
