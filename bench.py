@@ -36,6 +36,7 @@ def parse_args():
     ap.add_argument("--no-kernels", action="store_true", help="skip the isolated-kernel (configs[1]) section")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
     ap.add_argument("--cpu-clips", type=int, default=20, help="clips timed for cpu_baseline (~10 s of host work)")
+    ap.add_argument("--size", type=int, default=224, help="clip resolution: 224 (window 7, the reference) or 512 (window 8, configs[3])")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"], help="16-bit operand type of the headline run")
     ap.add_argument("--no-fp16", action="store_true", help="skip the extra fp16-operand measurement")
     return ap.parse_args()
@@ -140,12 +141,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_model(device, precision="bf16"):
+def build_model(device, precision="bf16", size=224):
     import torch
     import mumpy_b200
     from tests import util
     mumpy_b200.set_precision(precision)
-    enc, dec = mumpy_b200.Encoder().eval(), mumpy_b200.Decoder().eval()
+    if size == 224:
+        enc, dec = mumpy_b200.Encoder().eval(), mumpy_b200.Decoder().eval()
+    else:                                  # patched-resolution configuration: window 8
+        enc = mumpy_b200.Encoder(img_size=size, window_size=8).eval()
+        dec = mumpy_b200.Decoder(shape=[size // 4, size // 8, size // 16, size // 32]).eval()
     util.load_seeded(enc)
     util.load_seeded(dec)
     return enc.to(device), dec.to(device)
@@ -314,14 +319,16 @@ def main():
     peaks = load_peaks()
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
-    enc, dec = build_model(device, args.precision)
+    enc, dec = build_model(device, args.precision, args.size)
+    S = args.size
+    gflop_per_clip = GFLOP_PER_CLIP if S == 224 else {512: 902.3, 448: 685.3}.get(S, GFLOP_PER_CLIP * (S / 224.0) ** 2)
     n_in = 4                                            # rotate 4 distinct input batches (4 x 57.8 MB > 126 MB L2)
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    host_in = [torch.randn((B, 3, 3, 224, 224), generator=g).pin_memory() for _ in range(n_in)]
+    host_in = [torch.randn((B, 3, 3, S, S), generator=g).pin_memory() for _ in range(n_in)]
     dev_in = [h.to(device) for h in host_in]
-    gt = (torch.rand((B, 224, 224), generator=g) > 0.7).to(torch.uint8).to(device)
+    gt = (torch.rand((B, S, S), generator=g) > 0.7).to(torch.uint8).to(device)
     x_static = torch.empty_like(dev_in[0])
-    host_mask = torch.empty((B, 224, 224), dtype=torch.uint8).pin_memory()
+    host_mask = torch.empty((B, S, S), dtype=torch.uint8).pin_memory()
     host_counts = torch.empty((B, 4), dtype=torch.int64).pin_memory()
 
     def step():
@@ -372,7 +379,7 @@ def main():
             m, c = run_step(i)
             all_counts.append(c.clone())
         if world > 1:                                    # the path's only exchange: 3 x fp64 metric sums
-            sums_dev = ev.local_sums(torch.cat(all_counts, 0), 224 * 224).to(device)
+            sums_dev = ev.local_sums(torch.cat(all_counts, 0), S * S).to(device)
             dist.all_reduce(sums_dev)
         e1.record()
         torch.cuda.synchronize()
@@ -388,8 +395,8 @@ def main():
         # uploads B NEW uint8 frames from pinned host memory (one frame per clip: consecutive clips share two of their three
         # frames), assembles + normalises the clips on the device, runs the forward and reads masks + counts back ----------
         from mumpy_b200 import frontend
-        host_frames = [torch.randint(0, 256, (B, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(n_in)]
-        dev_frames = torch.empty((B, 224, 224, 3), dtype=torch.uint8, device=device)
+        host_frames = [torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(n_in)]
+        dev_frames = torch.empty((B, S, S, 3), dtype=torch.uint8, device=device)
         clip_idx = frontend.clip_frame_indices([B], 3).to(device)
 
         def step_frames():
@@ -478,20 +485,21 @@ def main():
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": t_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "global_batch": B * world, "parallelism": "clip-sharded dp%d" % world,
+        "config": {"workload": WORKLOAD if S == 224 else "configs[3]: full Mumpy forward at %dx%d (window 8, SURVEY A10), synthetic clips, key-seeded weights" % (S, S),
+                   "clips_per_gpu_per_step": B, "global_batch": B * world, "parallelism": "clip-sharded dp%d" % world,
                    "launch": "CUDA graph" if graph is not None else "eager",
-                   "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); per-step activation working set is several GB" % (n_in, n_in * B * 9 * 224 * 224 * 4 / 1e6),
+                   "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); per-step activation working set is several GB" % (n_in, n_in * B * 9 * S * S * 4 / 1e6),
                    "residual_stream": "fp32", "gemm": "%s operands, fp32 accumulate (tcgen05)" % args.precision,
                    "branch_concurrency": "views / decoder pyramid levels on 4 forked streams inside the graph"},
-        "e2e": {"value": clips / t_e2e, "unit": "clips/s", "h2d_bytes_per_step": B * 224 * 224 * 3,
-                "d2h_bytes_per_step": B * 224 * 224 + B * 4 * 8, "ms_per_step": t_e2e / K * 1e3,
+        "e2e": {"value": clips / t_e2e, "unit": "clips/s", "h2d_bytes_per_step": B * S * S * 3,
+                "d2h_bytes_per_step": B * S * S + B * 4 * 8, "ms_per_step": t_e2e / K * 1e3,
                 "api": "mumpy_b200.frontend (uint8 frames from pinned host memory, one new frame per clip; clips assembled + "
                        "normalised on the device) -> Encoder/Decoder forward -> ops.mask_counts -> masks + counts to pinned host memory"},
         "gpu_launches": launches_per_step * K,
-        "roofline": {"bound": "tensor", "achieved": GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12 if world == 1 else GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12,
-                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12 / peaks["bf16_tflops_sustained"],
+        "roofline": {"bound": "tensor", "achieved": gflop_per_clip * 1e9 * (B * K) / t_max / 1e12 if world == 1 else gflop_per_clip * 1e9 * (B * K) / t_max / 1e12,
+                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": gflop_per_clip * 1e9 * (B * K) / t_max / 1e12 / peaks["bf16_tflops_sustained"],
                      "traffic": None, "per": "GPU", "kernel": "whole step (gemm_tc_kernel dominates; per-kernel rooflines under `kernels`)",
-                     "flops_per_clip": GFLOP_PER_CLIP * 1e9, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)"},
+                     "flops_per_clip": gflop_per_clip * 1e9, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)"},
         "clocks": clocks,
     }
     if live is not None:
@@ -503,13 +511,13 @@ def main():
             "share_of_kernel_time": live["share_of_kernel_time"], "serial_kernel_time_ms": live["kernel_time_ms"],
             "traffic": 46.7e6, "traffic_note": "dram read+write of the largest-share launch (fc1 M=18816 N=2048 K=512, 98 MB algorithmic: the bf16 "
                                                "output stays in L2), ncu --set full, profiles/r1_gemm_fc1_ncu.txt",
-            "whole_step": {"achieved": GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12,
-                           "frac": GFLOP_PER_CLIP * 1e9 * (B * K) / t_max / 1e12 / peaks["bf16_tflops_sustained"],
-                           "flops_per_clip": GFLOP_PER_CLIP * 1e9}})
+            "whole_step": {"achieved": gflop_per_clip * 1e9 * (B * K) / t_max / 1e12,
+                           "frac": gflop_per_clip * 1e9 * (B * K) / t_max / 1e12 / peaks["bf16_tflops_sustained"],
+                           "flops_per_clip": gflop_per_clip * 1e9}})
     if other is not None:
         line["other_precision"] = other
     if rank == 0:
-        if world == 1:
+        if world == 1 and S == 224:
             cps, dt, threads = cpu_forward_clips_per_s(args.cpu_clips)
             line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
                                     "sample": "%d single-clip fp32 forwards (batch 1) of the oracle port of the reference, %.1f s" % (args.cpu_clips, dt)}

@@ -1,3 +1,7 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu20.log 2>&1; echo "pytest rc=$?"; grep -E "identity|passed|failed|rror" gpurun_out/pytest_gpu20.log | head -20
-timeout 900 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_modules.py -m gpu -x -q > gpurun_out/pytest_gpu20b.log 2>&1; echo "pytest(2) rc=$?"; tail -2 gpurun_out/pytest_gpu20b.log
+timeout 900 python bench.py --size 512 --batch 8 --steps 10 --warmup 3 > gpurun_out/bench_512.json 2> gpurun_out/bench_512.err; echo "bench512 rc=$?"; tail -3 gpurun_out/bench_512.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_512.json'))
+print({k:d[k] for k in ('value','ms_per_step','e2e','other_precision','roofline','config') if k in d})
+PY
