@@ -230,7 +230,7 @@ def kernel_section(peaks, device):
     return out
 
 
-OPS_TIMED = ["linear", "linear_dual", "linear_into", "layernorm", "patch_merge_norm", "window_attention", "mha_short", "tokenize", "faf",
+OPS_TIMED = ["linear", "linear_dual", "linear_into", "layernorm", "patch_merge_norm", "window_attention", "mha_short", "tokenize", "faf", "faf16", "assemble_clips",
              "cva_offsets", "cva_sample", "cva_attention", "cva_residual", "gather_rows", "conv2d_nhwc", "conv2d_nhwc_bf16",
              "conv2d_nhwc_cout1", "im2col_nhwc", "groupnorm_nhwc", "resample_nhwc", "mul_add", "add", "nchw_to_nhwc", "nhwc_to_nchw",
              "channel_group_mean", "mask_counts", "cast16"]

@@ -107,6 +107,13 @@ int mumpy_tokenize(const float *x, const float *w_kc, const float *bias, const f
 int mumpy_faf(const float *x, const float *dct, float *ws, float *out, int B, int T, int frame, int S,
               const int *band_lo_hi6, void *stream);
 
+/* The same transform on the tensor cores (16-bit modes): the four DCT passes run as tcgen05 GEMMs over split operands
+ * (a = a_hi + a_lo in `dtype`, three partial products accumulated in fp32: error 2.9e-5 (bf16) / 2.5e-6 (f16) on outputs ~3),
+ * with a repack kernel (per-image transpose, band masks, hi/lo split) between them.  dcat / dtcat (S, 3S) of `dtype` =
+ * [D_hi | D_lo | D_hi] for D and for D^T; ws16: 9*B*S x 3S 16-bit values; ws32: 9*B*S*S floats. */
+int mumpy_faf16(const float *x, const void *dcat, const void *dtcat, void *ws16, float *ws32, float *out, int B, int T,
+                int frame, int S, const int *band_lo_hi6, int dtype, void *stream);
+
 /* SwinDAttention pieces (deformableAttention.py:324-405); windows are addressed on canvases.
  * offsets: q (B*L1, C) fp32 canvas of the query view -> pix (N1, groups, P, 2) fp32 sampling positions in pixel
  *          units (y,x) of an aligned-corners ws x ws grid (:334-356).  dw_w (Cg,25), dw_b, ln_g, ln_b (Cg), pw (2,Cg). */

@@ -27,6 +27,7 @@ SIGNATURES = {
     "mumpy_mha_short": [vp, vp, ci, cl, ci, ci, ci, vp],
     "mumpy_tokenize": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
     "mumpy_faf": [vp, vp, vp, vp, ci, ci, ci, ci, ctypes.POINTER(ci), vp],
+    "mumpy_faf16": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ctypes.POINTER(ci), ci, vp],
     "mumpy_cva_offsets": [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_cva_sample": [vp, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_cva_attention": [vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],

@@ -58,6 +58,80 @@ struct StoreBands {
   }
 };
 
+// ---- tensor-core path (16-bit modes): the four DCT passes as tcgen05 GEMMs on split operands -------------------------
+// a = a_hi + a_lo with both halves in the 16-bit operand type; a.b ~ a_hi.b_hi + a_hi.b_lo + a_lo.b_hi accumulated in fp32 is
+// one GEMM over the K-concatenation  A' = [a_hi | a_hi | a_lo],  W' = [w_hi | w_lo | w_hi]  (K' = 3S): max-abs error vs the
+// fp64 transform 2.9e-5 (bf16 halves) / 2.5e-6 (f16 halves, = fp32's own rounding) on outputs of magnitude ~3, far below
+// the operand rounding of the convolutions that consume the result.  Between the GEMMs a repack kernel transposes each
+// S x S image (the next pass contracts over the other index), applies the band masks, splits into halves and writes the
+// K-concatenated operand; the last repack writes the (B,9,S,S) result.
+struct RepackParams {
+  const float *in;          // fp32 images, row-major R x C
+  long group_stride;        // image z lives at in + (z / group) * group_stride + (z % group) * R * C
+  int group;
+  int R, C;
+  int transpose;            // output element (orow, ocol) = transpose ? (c, r) : (r, c)
+  int n_img;                // input images
+  int n_bands;              // 1, or 3: output image band*n_img + z keeps lo[band] <= r + c <= hi[band]
+  int lo[3], hi[3];
+  void *out16;              // split mode: rows of 3*OC 16-bit values [hi | hi | lo]
+  float *out32;             // final mode: fp32, output image (z % n_img3 ... ) remapped to (b, band*3 + c)
+  int final_imgs;           // final mode: images per band (= 3B); 0 otherwise
+};
+
+template <typename T16>
+__global__ void __launch_bounds__(256) faf_repack_kernel(const RepackParams p) {
+  pdl_grid_sync();
+  __shared__ float tile[32][33];
+  const int z = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float *img = p.in + (long)(z / p.group) * p.group_stride + (long)(z % p.group) * p.R * p.C;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < p.R && c < p.C) ? img[(long)r * p.C + c] : 0.0f;
+  }
+  __syncthreads();
+  const int OR = p.transpose ? p.C : p.R, OC = p.transpose ? p.R : p.C;
+  for (int i = ty; i < 32; i += 8) {
+    // output row index runs over i, output column over tx (coalesced along the output row)
+    const int r = p.transpose ? r0 + tx : r0 + i;
+    const int c = p.transpose ? c0 + i : c0 + tx;
+    if (r >= p.R || c >= p.C) continue;
+    const float v = p.transpose ? tile[tx][i] : tile[i][tx];
+    const int orow = p.transpose ? c : r, ocol = p.transpose ? r : c;
+    if (p.out32) {
+      const int band = z / p.final_imgs, im = z % p.final_imgs;
+      const long oimg = (long)(im / 3) * 9 + band * 3 + im % 3;
+      p.out32[(oimg * OR + orow) * OC + ocol] = v;
+    } else {
+      T16 *o = static_cast<T16 *>(p.out16);
+      for (int b = 0; b < p.n_bands; ++b) {
+        float m = v;
+        if (p.n_bands > 1 && (r + c < p.lo[b] || r + c > p.hi[b])) m = 0.0f;
+        const T16 h = from_f32<T16>(m);
+        const T16 l = from_f32<T16>(m - to_f32(h));
+        T16 *row = o + (((long)b * p.n_img + z) * OR + orow) * 3 * OC;
+        row[ocol] = h;
+        row[OC + ocol] = h;
+        row[2 * OC + ocol] = l;
+      }
+    }
+  }
+}
+
+int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, void *aux, long ldo,
+                long M, int N, int K, int ab_dtype, int out_dtype, int act, cudaStream_t st);
+
+static int faf_repack(const RepackParams &p, int n_img, int dtype, cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(p.C, 32), (unsigned)cdiv(p.R, 32), (unsigned)n_img);
+  if (dtype == MUMPY_F16)
+    launch_kernel(faf_repack_kernel<__half>, grid, 256, 0, st, p);
+  else
+    launch_kernel(faf_repack_kernel<__nv_bfloat16>, grid, 256, 0, st, p);
+  return launch_status("faf_repack");
+}
+
 }  // namespace mumpy
 
 using namespace mumpy;
@@ -83,4 +157,66 @@ extern "C" int mumpy_faf(const float *x, const float *dct, float *ws, float *out
   if (rc) return rc;
   // 4. Y[m,n] = sum_k D[k,m] U[k,n]
   return launch_gemm_simt(Strided{dct, 0, 1, S}, Strided{u, SS, 1, S}, StoreBands{out, S, n_img}, S, S, S, 3 * n_img, st, "faf pass 4");
+}
+
+// Tensor-core FAF.  dcat (S, 3S) = [D_hi | D_lo | D_hi], dtcat (S, 3S) = the same for D^T, both of `dtype`;
+// ws16: 9*B*S rows x 3S 16-bit values; ws32: 9*B*S*S floats.
+extern "C" int mumpy_faf16(const float *x, const void *dcat, const void *dtcat, void *ws16, float *ws32, float *out, int B, int T,
+                           int frame, int S, const int *band_lo_hi6, int dtype, void *stream) {
+  MUMPY_REQUIRE(x && dcat && dtcat && ws16 && ws32 && out && band_lo_hi6 && B > 0 && frame >= 0 && frame < T, "faf16: bad arguments");
+  MUMPY_REQUIRE(is_16bit(dtype) && S % 8 == 0, "faf16: 16-bit operand type and S %% 8 == 0 required");
+  cudaStream_t st = as_stream(stream);
+  const int n_img = B * 3;
+  const long SS = (long)S * S;
+  RepackParams p = {};
+  p.R = S;
+  p.C = S;
+  p.out16 = ws16;
+  // P0: frame `frame` of x -> [x_hi | x_hi | x_lo], rows (img, i)
+  p.in = x;
+  p.group = 3;
+  p.group_stride = (long)T * 3 * SS;
+  p.in += (long)frame * 3 * SS;
+  p.transpose = 0;
+  p.n_img = n_img;
+  p.n_bands = 1;
+  int rc = faf_repack(p, n_img, dtype, st);
+  if (rc) return rc;
+  // G1: T1[(img,i), k] = sum_j x[i,j] D[k,j]
+  rc = linear_bf16(ws16, 3 * S, dcat, nullptr, nullptr, ws32, nullptr, S, (long)n_img * S, S, 3 * S, dtype, MUMPY_F32, MUMPY_ACT_NONE, st);
+  if (rc) return rc;
+  // P1: transpose -> rows (img, k), columns i
+  p.in = ws32;
+  p.group = 1;
+  p.group_stride = SS;
+  p.transpose = 1;
+  rc = faf_repack(p, n_img, dtype, st);
+  if (rc) return rc;
+  // G2: Xf^T[(img,k), k'] = sum_i T1[i,k] D[k',i]
+  rc = linear_bf16(ws16, 3 * S, dcat, nullptr, nullptr, ws32, nullptr, S, (long)n_img * S, S, 3 * S, dtype, MUMPY_F32, MUMPY_ACT_NONE, st);
+  if (rc) return rc;
+  // P2: transpose + band masks -> rows (band, img, k'), columns k of F_band o Xf
+  p.n_bands = 3;
+  for (int b = 0; b < 3; ++b) {
+    p.lo[b] = band_lo_hi6[2 * b];
+    p.hi[b] = band_lo_hi6[2 * b + 1];
+  }
+  rc = faf_repack(p, n_img, dtype, st);
+  if (rc) return rc;
+  // G3: U[(band,img,k'), j] = sum_k (F o Xf)[k',k] D[k,j]
+  rc = linear_bf16(ws16, 3 * S, dtcat, nullptr, nullptr, ws32, nullptr, S, 3l * n_img * S, S, 3 * S, dtype, MUMPY_F32, MUMPY_ACT_NONE, st);
+  if (rc) return rc;
+  // P3: transpose -> rows (band, img, j), columns k'
+  p.n_bands = 1;
+  p.n_img = 3 * n_img;
+  rc = faf_repack(p, 3 * n_img, dtype, st);
+  if (rc) return rc;
+  // G4: Y^T[(band,img,j), i] = sum_k' U[k',j] D[k',i]
+  rc = linear_bf16(ws16, 3 * S, dtcat, nullptr, nullptr, ws32, nullptr, S, 3l * n_img * S, S, 3 * S, dtype, MUMPY_F32, MUMPY_ACT_NONE, st);
+  if (rc) return rc;
+  // P4: transpose into out (B, 9, S, S), channel = band*3 + rgb
+  p.out16 = nullptr;
+  p.out32 = out;
+  p.final_imgs = n_img;
+  return faf_repack(p, 3 * n_img, dtype, st);
 }

@@ -463,15 +463,21 @@ static TileChoice pick_tile(long M, int N, int nkb, bool has_res, bool gelu) {
   const double t_chunk = 550.0 + (has_res ? 250.0 : 0.0) + (gelu ? 1100.0 : 0.0);
   TileChoice best = {0, false};
   double best_cost = 1e30;
+  // N values whose only divisors among the candidates are narrow (e.g. 224 = 7 x 32, the DCT passes) may also take a wide
+  // tile with a masked tail: TMA zero-fills the weight rows beyond N and the epilogue masks the columns
+  int widest_div = 0;
+  for (int c : cands)
+    if (N % c == 0 && c > widest_div) widest_div = c;
   for (int pair = 0; pair < 2; ++pair) {
     if (pair && (g_dbg_pair == 0 || g_num_sms < 2)) continue;
     const long mt = cdiv(M, pair ? 2 * TC_BM : TC_BM);
     const long slots = pair ? g_num_sms / 2 : g_num_sms;
     for (int c : cands) {                            // descending: ties go to the wider tile
-      if (N % c != 0) continue;
+      const bool divides = N % c == 0;
+      if (!divides && !(widest_div < 64 && c >= 64 && c < N + 64)) continue;
       if (g_dbg_bn > 0 && N % g_dbg_bn == 0 && c != g_dbg_bn) continue;
       if (pair && c % 16 != 0) continue;
-      const long tiles = mt * (N / c);
+      const long tiles = mt * cdiv(N, c);
       const double waves = (double)cdiv(tiles, slots);
       const double load = (128.0 + (pair ? c / 2 : c)) * 1.6, pipe = c * 1.06;
       const double mma = (double)nkb * (load > pipe ? load : pipe) + (pair ? 500.0 : 300.0);

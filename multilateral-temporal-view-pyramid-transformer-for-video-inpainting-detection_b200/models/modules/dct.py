@@ -52,10 +52,31 @@ class FAF(nn.Module):
             self._dct = self._dct.to(device)
         return self._dct
 
+    def _split_operands(self, device):
+        """[D_hi | D_lo | D_hi] and the same for D^T in the operand type of the current 16-bit mode (cached per device / mode)."""
+        key = (str(device), ops.precision())
+        cache = self.__dict__.setdefault("_split_cache", {})
+        if key not in cache:
+            d = self._dct_on(device)
+            dt16 = ops.act_dtype()
+
+            def cat(m):
+                hi = m.to(dt16)
+                lo = (m - hi.float()).to(dt16)
+                return torch.cat([hi, lo, hi], dim=1).contiguous()
+            cache[key] = (cat(d), cat(d.t().contiguous()))
+            if not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream(device).synchronize()       # cached across streams, like _packing.PackedModule
+        return cache[key]
+
     def frame(self, x, frame=1):
         """x (B,T,3,S,S) -> FAF of one frame, (B,9,S,S), channel = band*3 + rgb."""
         require_inference(self)
-        return ops.faf(x.contiguous(), self._dct_on(x.device), [f.band for f in self.filters], frame)
+        bands = [f.band for f in self.filters]
+        if ops.tensor_cores() and self.size % 8 == 0:
+            dcat, dtcat = self._split_operands(x.device)
+            return ops.faf16(x.contiguous(), dcat, dtcat, bands, frame)
+        return ops.faf(x.contiguous(), self._dct_on(x.device), bands, frame)
 
     def forward(self, x):
         """x (B,T,3,S,S) -> (B,T,9,S,S) like the reference; the encoder only needs frame 1 and calls frame()."""

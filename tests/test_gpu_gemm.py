@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 SHAPES = [  # (M, N, K) drawn from the model: qkv / proj / fc1 / fc2 / merge / embed, with ragged M and K tails
     (49, 96, 96), (3136, 288, 96), (3136, 384, 96), (3136, 96, 384), (9408, 384, 128), (2352, 1024, 256),
-    (588, 1536, 512), (588, 512, 2048), (147, 3072, 1024), (147, 768, 2560), (1000, 256, 576), (130, 64, 72),
+    (588, 1536, 512), (588, 512, 2048), (147, 3072, 1024), (147, 768, 2560), (1000, 256, 576), (130, 64, 72), (1344, 224, 672),
 ]
 
 

@@ -117,3 +117,21 @@ def test_fast_gelu_epilogue_accuracy():
     ref = orc.gelu(a.bfloat16().float() @ w.bfloat16().float().t())
     out = ops.linear(a.bfloat16().cuda(), w.bfloat16().cuda(), act=ops.ACT_GELU)
     assert util.maxabs(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+@pytest.mark.parametrize("size,B", [(224, 2), (56, 3)])
+def test_faf_tensor_core_path(mode, size, B):
+    """FAF in the 16-bit modes: four tcgen05 GEMMs on hi/lo-split operands vs the fp32 oracle (dct.py:71-79).
+    Split arithmetic keeps ~16 (bf16) / ~22 (f16) mantissa bits: tolerance 1e-4 / 2e-5 on outputs of magnitude ~3."""
+    import mumpy_b200
+    from mumpy_b200.models.modules.dct import FAF
+    x = util.seeded_input((B, 3, 3, size, size), 17)
+    ref = orc.faf_middle(x)
+    mumpy_b200.set_precision(mode)
+    try:
+        y = FAF(size).eval().frame(x.cuda(), 1)
+    finally:
+        mumpy_b200.set_precision("bf16")
+    assert y.shape == ref.shape
+    assert util.maxabs(y, ref) < (1e-4 if mode == "bf16" else 2e-5)
