@@ -21,8 +21,10 @@ def _conv(owner, name, conv, x, B, H, W, ld_in=None, out16=False, residual=None)
     if Cout == 1 and Cin % 4 == 0 and ld_in in (None, Cin):
         w = owner._packed("hwi:" + name, [conv.weight], lambda: conv.weight.detach().permute(0, 2, 3, 1).contiguous())
         return ops.conv2d_nhwc_cout1(x, w, conv.bias, B, H, W, Cin, kh, kw, ph, pw)
-    if ops.tensor_cores() and Cout % 8 == 0 and Cin % 8 == 0 and (ld_in or Cin) % 8 == 0:
-        # implicit GEMM on the tensor cores: im2col-mode TMA feeds tcgen05 directly (no im2col buffer)
+    if ops.tensor_cores() and Cout % 8 == 0 and (ld_in or Cin) % 8 == 0:
+        # implicit GEMM on the tensor cores: im2col-mode TMA feeds tcgen05 directly (no im2col buffer).  Cin itself may be
+        # anything (the 9-channel frequency map): the tensor map's channel extent is Cin, TMA zero-fills the rest of the
+        # 64-channel block, only the pixel stride has to be 16-byte aligned
         cb = (Cin + 63) // 64
 
         def make_tc():
@@ -191,13 +193,13 @@ class Decoder(PackedModule):
         y = ops.linear(a, wp, conv.bias)
         return ops.groupnorm_nhwc(y, gn.weight, gn.bias, B, hw, y.shape[-1], gn.num_groups, ops.ACT_RELU, gn.eps).view(B, h, h, -1)
 
-    def _freq_stage(self, name, x, B, H, W, pooled=False):
+    def _freq_stage(self, name, x, B, H, W, pooled=False, ld_in=None):
         """AvgPool2 -> Conv3x3 -> GroupNorm -> Sigmoid (:147-181). x NHWC (B,H,W,C) (already pooled if `pooled`)."""
         seq = getattr(self, name)
         if not pooled:
             x = ops.resample_nhwc(x, B, H, W, x.shape[-1], ops.RS_AVGPOOL2)
             H, W = H // 2, W // 2
-        c = _conv(self, name, seq[1], x, B, H, W)
+        c = _conv(self, name, seq[1], x, B, H, W, ld_in=ld_in)
         return ops.groupnorm_nhwc(c, seq[2].weight, seq[2].bias, B, H * W, c.shape[-1], seq[2].num_groups, ops.ACT_SIGMOID, seq[2].eps)
 
     def _dec_stage(self, name, x, B, H, W, dap=False):
@@ -225,8 +227,13 @@ class Decoder(PackedModule):
         # with their SEB / global-conv modules; the decoder_2..5 chain follows on lane 0.  Hand-overs are events.
         with streams.region(x.device) as reg:
             with reg.lane(3):
-                f_in = ops.nchw_to_nhwc(ffinfo.contiguous().float(), pool2=True)            # AvgPool2 of decoder_frequency_0
-                freq0 = self._freq_stage("decoder_frequency_0", f_in, B, S // 2, S // 2, pooled=True)
+                # AvgPool2 of decoder_frequency_0 fused into the layout change; pixel stride padded to 16 channels so that the
+                # 9-channel map can feed the TMA convolution (the padding is never read)
+                cf = ffinfo.shape[1]
+                ldf = (cf + 7) // 8 * 8
+                f_in = torch.empty((B, S // 2, S // 2, ldf), dtype=torch.float32, device=x.device)
+                ops.nchw_to_nhwc(ffinfo.contiguous().float(), pool2=True, out=f_in, ld_out=ldf)
+                freq0 = self._freq_stage("decoder_frequency_0", f_in, B, S // 2, S // 2, pooled=True, ld_in=ldf)
                 reg.publish("freq0", freq0)
                 freq1 = self._freq_stage("decoder_frequency_1", freq0, B, S // 2, S // 2)
                 reg.publish("freq1", freq1)

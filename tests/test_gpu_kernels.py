@@ -61,6 +61,19 @@ def test_conv_reads_channel_slice_of_wider_map():
     assert util.maxabs(out, ref) < 2e-4 * max(1.0, float(ref.abs().max()))
 
 
+def test_conv_odd_channel_count_with_padded_pixel_stride():
+    """decoder_frequency_0: 9 input channels at a pixel stride of 16 -- the tensor map's channel extent is 9, TMA zero-fills
+    the rest of the 64-channel block, the (garbage) padding channels are never read."""
+    ops = _ops()
+    B, H, W, Cin, ld, Cout = 2, 28, 28, 9, 16, 128
+    x = util.seeded_input((B, H, W, ld), 1).bfloat16()
+    x[..., Cin:] = float("nan")
+    w = (util.seeded_input((Cout, Cin, 3, 3), 2) / (Cin * 9) ** 0.5).bfloat16()
+    ref = orc.conv2d(x[..., :Cin].float().permute(0, 3, 1, 2), w.float(), None, (1, 1)).permute(0, 2, 3, 1)
+    out = ops.conv2d_nhwc_bf16(x.cuda(), _pack_conv(w.float(), Cin).cuda(), None, B, H, W, Cin, Cout, 3, 3, 1, 1, ld_in=ld)
+    assert util.maxabs(out, ref) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
 def test_conv_cout1():
     ops = _ops()
     x = util.seeded_input((2, 32, 24, 20), 1)
