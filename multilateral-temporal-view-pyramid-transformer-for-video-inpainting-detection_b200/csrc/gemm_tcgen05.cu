@@ -56,7 +56,8 @@ int resolve_driver_entry_points() {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;       // 64 bf16 = 128 B = one swizzle span
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 12;
+constexpr int TC_EPI_GROUPS = TC_EPI_WARPS / 4;      // warps per TMEM lane quadrant: each takes every TC_EPI_GROUPS-th 32-column chunk
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr int TC_SMEM_BUDGET = 164 * 1024;      // operand ring; + 8 x (4 KB epilogue staging + 512 B bias) + 1 KB alignment slack
 
@@ -96,7 +97,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
   const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
   const long row0 = m0 + quad * 32;
   const uint32_t st_base = smem_u32(stage);
-  for (int c0 = half * 32, ci = 0; c0 < p.BN; c0 += 64, ++ci) {
+  for (int c0 = half * 32, ci = 0; c0 < p.BN; c0 += 32 * TC_EPI_GROUPS, ++ci) {
     // residual tile of this chunk, fetched in the coalesced phase-2 layout before anything else so that the global-load
     // latency overlaps the TMEM load and the phase-1 math
     float4 res[8];
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       // bias values of this warp's column chunks -> shared memory while the accumulator is still being produced
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
-        const int c = (warp >> 2) * 32 + 64 * ci + lane;
+        const int c = (warp >> 2) * 32 + 32 * TC_EPI_GROUPS * ci + lane;
         bias_s[ci * 32 + lane] = (p.bias && c < p.BN && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.0f;
       }
       __syncwarp();
@@ -371,10 +372,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       // prefetch per row (the epilogue's residual loads are otherwise DRAM-latency bound, 4 dependent chunks per tile)
       if (p.residual) {
         const long gm = m0 + (warp & 3) * 32 + lane;
-        const int cols = min(p.BN, p.N - n0), off = (warp >> 2) * (p.BN / 2);
-        if (gm < p.M && off < cols) {
-          const uint32_t bytes = static_cast<uint32_t>(min(p.BN / 2, cols - off)) * 4u;
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.residual + gm * p.ldo + n0 + off), "r"(bytes) : "memory");
+        const int cols = min(p.BN, p.N - n0), off = (warp >> 2) * 32;     // each warp group pulls 32-column slices, strided like its chunks
+        if (gm < p.M && off < cols && (warp >> 2) == 0) {
+          const uint32_t bytes = static_cast<uint32_t>(cols) * 4u;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.residual + gm * p.ldo + n0), "r"(bytes) : "memory");
         }
       }
       mbar_wait(acc_full0 + 8 * slot, aph);

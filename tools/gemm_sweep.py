@@ -71,11 +71,12 @@ for key, cnt in log.items():
         name = "lin M=%d N=%d K=%d act=%d %s%s" % (M, N, K, act, "bf16" if odt == torch.bfloat16 else "f32", "+res" if has_res else "")
     else:
         _, B_, H, W, Cin, Cout, kh, kw = key
-        xin = torch.randn((B_, H, W, Cin), device=dev).bfloat16()
+        ld = (Cin + 7) // 8 * 8
+        xin = torch.randn((B_, H, W, ld), device=dev).bfloat16()
         cb = (Cin + 63) // 64
         wq = (torch.randn((Cout, kh * kw * cb * 64), device=dev) / (Cin * kh * kw) ** 0.5).bfloat16()
         bias = torch.zeros(Cout, device=dev)
-        t = timed(lambda: orig_conv(xin, wq, bias, B_, H, W, Cin, Cout, kh, kw, (kh - 1) // 2, (kw - 1) // 2))
+        t = timed(lambda: orig_conv(xin, wq, bias, B_, H, W, Cin, Cout, kh, kw, (kh - 1) // 2, (kw - 1) // 2, ld_in=ld))
         M = B_ * H * W
         flops = 2.0 * M * Cout * Cin * kh * kw
         byts = 2 * M * Cin + 2 * wq.numel() + 4 * M * Cout
