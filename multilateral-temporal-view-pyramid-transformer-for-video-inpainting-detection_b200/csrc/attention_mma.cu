@@ -179,9 +179,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // tasks with a two-stage cp.async ring, so the q/k/v gather of task i+1 (49 x 64 B row segments each, straight from
 // the canvas-ordered qkv matrix) is in flight while task i runs on the tensor pipe.  K and V fragments are loaded
 // once per task into registers and reused by the four 16-row query tiles.
-constexpr int WATT_WARPS = 8;
+constexpr int WATT_WARPS = 16;
+constexpr int WATT_STAGES = 1;           // q/k/v tile sets per warp (2 = the warp prefetches its next task while computing)
+constexpr bool WATT_KV_REGS = false;     // keep the K / V fragments of a task in registers across its four query tiles
 constexpr int WATT_STAGE_BYTES = 3 * ATT_TILE_BYTES;
-constexpr int WATT_WARP_BYTES = 2 * WATT_STAGE_BYTES + 2 * 64 * (int)sizeof(int);
+constexpr int WATT_WARP_BYTES = WATT_STAGES * WATT_STAGE_BYTES + WATT_STAGES * 64 * (int)sizeof(int);
 
 // MODE 0: gathered bias (nH,N,N) + optional mask tensor (nW,N,N) through global loads.
 // MODE 1: bias from the raw relative_position_bias_table (T,nH), staged for all heads in shared memory; the mask is the
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t *wbase = att_smem + warp * WATT_WARP_BYTES;
-  int *rows_base = reinterpret_cast<int *>(wbase + 2 * WATT_STAGE_BYTES);
+  int *rows_base = reinterpret_cast<int *>(wbase + WATT_STAGES * WATT_STAGE_BYTES);
   float *tbl_all = reinterpret_cast<float *>(att_smem + WATT_WARPS * WATT_WARP_BYTES);      // [heads][T], pre-divided by the scale
   if (MODE == 1) {
     for (int i = threadIdx.x; i < TBL * heads; i += blockDim.x) {
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
     }
   }
   // rows >= N of every tile stay zero for the whole kernel (only rows < N are ever copied)
-  for (int i = lane; i < 2 * WATT_STAGE_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(wbase)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = lane; i < WATT_STAGES * WATT_STAGE_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(wbase)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
   const int wpr = W / WS, wrows = TH / WS;
@@ -258,14 +260,22 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
     }
   };
 
-  if (first < n_tasks) issue(first, 0);
-  cp_async_commit();
-  int stage = 0;
-  for (long task = first; task < n_tasks; task += total_warps, stage ^= 1) {
-    const long next = task + total_warps;
-    if (next < n_tasks) issue(next, stage ^ 1);
+  if (WATT_STAGES == 2) {
+    if (first < n_tasks) issue(first, 0);
     cp_async_commit();
-    cp_async_wait<1>();
+  }
+  int stage = 0;
+  for (long task = first; task < n_tasks; task += total_warps, stage ^= (WATT_STAGES - 1)) {
+    if (WATT_STAGES == 2) {
+      const long next = task + total_warps;
+      if (next < n_tasks) issue(next, stage ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {                        // single tile set: the other 15 warps of the SM cover this warp's load latency
+      issue(task, 0);
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
     __syncwarp();
 
     const long win = task / heads;
@@ -278,14 +288,16 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
     const bool masked = MODE == 1 && mshift > 0 && (last_r || last_c);
     const float *tbl = tbl_all + h * TBL;
 
-    uint32_t kf[NT][4], vf[4][2][4];
+    uint32_t kf[WATT_KV_REGS ? NT : 1][4], vf[WATT_KV_REGS ? 4 : 1][2][4];
+    if (WATT_KV_REGS) {
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) ldsm_x4(sK + tile_off(nt * 8 + (lane & 7), lane >> 3), kf[nt][0], kf[nt][1], kf[nt][2], kf[nt][3]);
+      for (int nt = 0; nt < NT; ++nt) ldsm_x4(sK + tile_off(nt * 8 + (lane & 7), lane >> 3), kf[nt % (WATT_KV_REGS ? NT : 1)][0], kf[nt % (WATT_KV_REGS ? NT : 1)][1], kf[nt % (WATT_KV_REGS ? NT : 1)][2], kf[nt % (WATT_KV_REGS ? NT : 1)][3]);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const int tok = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      for (int kk = 0; kk < 4; ++kk) {
+        const int tok = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-      for (int dp = 0; dp < 2; ++dp) ldsm_x4_t(sV + tile_off(tok, dp * 2 + (lane >> 4)), vf[kk][dp][0], vf[kk][dp][1], vf[kk][dp][2], vf[kk][dp][3]);
+        for (int dp = 0; dp < 2; ++dp) ldsm_x4_t(sV + tile_off(tok, dp * 2 + (lane >> 4)), vf[kk % (WATT_KV_REGS ? 4 : 1)][dp][0], vf[kk % (WATT_KV_REGS ? 4 : 1)][dp][1], vf[kk % (WATT_KV_REGS ? 4 : 1)][dp][2], vf[kk % (WATT_KV_REGS ? 4 : 1)][dp][3]);
+      }
     }
     // region ids of this lane's key columns (standard shift mask), only for windows that hold masked pairs
     int regj[16];
@@ -336,8 +348,10 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        mma_16<T>(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], kf[nt][0], kf[nt][1]);
-        mma_16<T>(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], kf[nt][2], kf[nt][3]);
+        if (!WATT_KV_REGS) ldsm_x4(sK + tile_off(nt * 8 + (lane & 7), lane >> 3), kf[0][0], kf[0][1], kf[0][2], kf[0][3]);
+        const int ki = WATT_KV_REGS ? nt : 0;
+        mma_16<T>(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], kf[ki][0], kf[ki][1]);
+        mma_16<T>(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], kf[ki][2], kf[ki][3]);
       }
       float m_lo = -INFINITY, m_hi = -INFINITY;
 #pragma unroll
@@ -386,8 +400,13 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
           const uint32_t a3 = two ? pack2<T>(s[(2 * kk + 1) & 7][2], s[(2 * kk + 1) & 7][3]) : 0u;
 #pragma unroll
           for (int dp = 0; dp < 2; ++dp) {
-            mma_16<T>(o[dp * 2], a0, a1, a2, a3, vf[kk][dp][0], vf[kk][dp][1]);
-            mma_16<T>(o[dp * 2 + 1], a0, a1, a2, a3, vf[kk][dp][2], vf[kk][dp][3]);
+            const int vi = WATT_KV_REGS ? kk : 0;
+            if (!WATT_KV_REGS) {
+              const int tok = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+              ldsm_x4_t(sV + tile_off(tok, dp * 2 + (lane >> 4)), vf[0][dp][0], vf[0][dp][1], vf[0][dp][2], vf[0][dp][3]);
+            }
+            mma_16<T>(o[dp * 2], a0, a1, a2, a3, vf[vi][dp][0], vf[vi][dp][1]);
+            mma_16<T>(o[dp * 2 + 1], a0, a1, a2, a3, vf[vi][dp][2], vf[vi][dp][3]);
           }
         }
       }
