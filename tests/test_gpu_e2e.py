@@ -131,3 +131,44 @@ def test_mask_and_counts(model):
     mask, counts = mumpy_b200.ops.mask_counts(logits.cuda(), gt.to(torch.uint8).cuda())
     assert torch.equal(mask.cpu(), orc.threshold_mask(logits)[:, 0])
     assert torch.equal(counts.cpu(), orc.clip_counts(logits[:, 0] > 0, gt))
+
+
+def test_graph_replay_and_lanes_are_deterministic(model):
+    """The forward captured in a CUDA graph (fork/join lanes become parallel branches, as bench.py runs it) replays to
+    exactly the eager result, the eager result is reproducible run to run, and the single-stream schedule
+    (streams.set_enabled(False)) gives the same bits: every kernel is deterministic and the lanes only reorder
+    independent work."""
+    import mumpy_b200
+    from mumpy_b200 import streams
+    enc, dec = model
+    g = util.golden("e2e_b2.pt")
+    x = util.seeded_input(g["input_shape"], g["input_seed"]).cuda()
+    mumpy_b200.set_precision("bf16")
+
+    def fwd():
+        final_x, view_x, ff = enc(x)
+        return dec(final_x, view_x, ff)[0]
+
+    with torch.no_grad():
+        a = fwd().clone()
+        b = fwd().clone()
+        assert torch.equal(a, b)
+        streams.set_enabled(False)
+        try:
+            c = fwd().clone()
+        finally:
+            streams.set_enabled(True)
+        assert torch.equal(a, c)
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fwd()
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fwd()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, a)
