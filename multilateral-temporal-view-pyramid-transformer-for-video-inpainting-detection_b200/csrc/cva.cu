@@ -21,19 +21,28 @@ __global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restric
                                                           const float *__restrict__ ln_b, const float *__restrict__ pw,
                                                           float *__restrict__ pix, int TH1, int W, int C, int groups, int ws) {
   pdl_grid_sync();
-  extern __shared__ float tile[];   // [P][Cg] query window, then [25][Cg] depthwise taps (tap-major: conflict-free per lane)
+  // [(ws+4)^2][Cg] query window with a zero border of 2 pixels (the depthwise conv's padding: no bounds tests in the tap loop),
+  // then [25][Cg] depthwise taps (tap-major: conflict-free per lane), then [P][2] raw offsets
+  extern __shared__ float tile[];
   const int P = ws * ws;
   const int Cg = C / groups;
-  float *wsm = tile + P * Cg;
+  const int wp = ws + 4;
+  float *wsm = tile + wp * wp * Cg;
+  float *off = wsm + 25 * Cg;
   const int win = blockIdx.x, g = blockIdx.y;
   const int nW1 = (TH1 / ws) * (W / ws);
   const int b = win / nW1, n = win % nW1;
   const long L1 = (long)TH1 * W;
   const int cg4 = Cg >> 2;
-  for (int e = threadIdx.x; e < P * cg4; e += blockDim.x) {
-    const int p = e / cg4, c4 = e - p * cg4;
-    const long row = b * L1 + window_token_row(n, p, TH1, W, ws, 0);
-    reinterpret_cast<float4 *>(tile)[e] = __ldg(reinterpret_cast<const float4 *>(q + row * C + g * Cg) + c4);
+  for (int e = threadIdx.x; e < wp * wp * cg4; e += blockDim.x) {
+    const int pp = e / cg4, c4 = e - pp * cg4;
+    const int yy = pp / wp - 2, xx = pp % wp - 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < ws && xx >= 0 && xx < ws) {
+      const long row = b * L1 + window_token_row(n, yy * ws + xx, TH1, W, ws, 0);
+      v = __ldg(reinterpret_cast<const float4 *>(q + row * C + g * Cg) + c4);
+    }
+    reinterpret_cast<float4 *>(tile)[e] = v;
   }
   for (int e = threadIdx.x; e < 25 * Cg; e += blockDim.x) {
     const int c = e / 25, tap = e - c * 25;
@@ -41,10 +50,26 @@ __global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restric
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // per-lane channel constants (bias, LayerNorm affine, 1x1 weights); for narrow groups the 25 taps live in registers too
+  float cb[MAXC], cgam[MAXC], cbet[MAXC], cwy[MAXC], cwx[MAXC];
+  constexpr bool kTapRegs = MAXC <= 2;
+  float wreg[kTapRegs ? MAXC : 1][25];
+#pragma unroll
+  for (int u = 0; u < MAXC; ++u) {
+    const int c = lane + 32 * u;
+    const bool ok = c < Cg;
+    cb[u] = ok ? __ldg(dw_b + c) : 0.0f;
+    cgam[u] = ok ? __ldg(ln_g + c) : 0.0f;
+    cbet[u] = ok ? __ldg(ln_b + c) : 0.0f;
+    cwy[u] = ok ? __ldg(pw + c) : 0.0f;
+    cwx[u] = ok ? __ldg(pw + Cg + c) : 0.0f;
+    if (kTapRegs) {
+#pragma unroll
+      for (int t = 0; t < 25; ++t) wreg[u][t] = ok ? wsm[t * Cg + c] : 0.0f;
+    }
+  }
   for (int p = warp; p < P; p += nwarps) {
     const int pi = p / ws, pj = p % ws;
-    const int a0 = max(0, 2 - pi), a1 = min(5, ws + 2 - pi);
-    const int b0 = max(0, 2 - pj), b1 = min(5, ws + 2 - pj);
     float val[MAXC];
     float s = 0.0f;
 #pragma unroll
@@ -52,12 +77,13 @@ __global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restric
       const int c = lane + 32 * u;
       float acc = 0.0f;
       if (c < Cg) {
-        for (int a = a0; a < a1; ++a) {
-          const float *trow = tile + ((pi + a - 2) * ws + pj - 2) * Cg + c;
-          const float *wrow = wsm + a * 5 * Cg + c;
-          for (int bb = b0; bb < b1; ++bb) acc = fmaf(trow[bb * Cg], wrow[bb * Cg], acc);
-        }
-        acc += __ldg(dw_b + c);
+        const float *t0 = tile + (pi * wp + pj) * Cg + c;      // top-left tap of the zero-padded window
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 5; ++bb)
+            acc = fmaf(t0[(a * wp + bb) * Cg], kTapRegs ? wreg[u][a * 5 + bb] : wsm[(a * 5 + bb) * Cg + c], acc);
+        acc += cb[u];
         s += acc;
       }
       val[u] = acc;
@@ -66,8 +92,7 @@ __global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restric
     float v = 0.0f;
 #pragma unroll
     for (int u = 0; u < MAXC; ++u) {
-      const int c = lane + 32 * u;
-      if (c < Cg) {
+      if (lane + 32 * u < Cg) {
         const float d = val[u] - mean;
         v = fmaf(d, d, v);
       }
@@ -76,25 +101,31 @@ __global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restric
     float oy = 0.0f, ox = 0.0f;
 #pragma unroll
     for (int u = 0; u < MAXC; ++u) {
-      const int c = lane + 32 * u;
-      if (c < Cg) {
-        const float a = gelu_erf((val[u] - mean) * rstd * __ldg(ln_g + c) + __ldg(ln_b + c));
-        oy = fmaf(a, __ldg(pw + c), oy);
-        ox = fmaf(a, __ldg(pw + Cg + c), ox);
+      if (lane + 32 * u < Cg) {
+        const float a = gelu_erf((val[u] - mean) * rstd * cgam[u] + cbet[u]);
+        oy = fmaf(a, cwy[u], oy);
+        ox = fmaf(a, cwx[u], ox);
       }
     }
     oy = warp_sum(oy);
     ox = warp_sum(ox);
     if (lane == 0) {
-      const float inv = 1.0f / (float)ws;
-      const float ref_y = ((pi + 0.5f) / ws) * 2.0f - 1.0f;
-      const float ref_x = ((pj + 0.5f) / ws) * 2.0f - 1.0f;
-      const float pos_y = tanhf(oy) * inv * 2.0f + ref_y;
-      const float pos_x = tanhf(ox) * inv * 2.0f + ref_x;
-      float *o = pix + (((long)win * groups + g) * P + p) * 2;
-      o[0] = ((pos_y + 1.0f) / 2.0f) * (ws - 1);
-      o[1] = ((pos_x + 1.0f) / 2.0f) * (ws - 1);
+      off[2 * p] = oy;
+      off[2 * p + 1] = ox;
     }
+  }
+  __syncthreads();
+  // one thread per pixel: pix = ((tanh(o) * (1/ws) * 2 + ref) + 1) / 2 * (ws-1)
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const int pi = p / ws, pj = p % ws;
+    const float inv = 1.0f / (float)ws;
+    const float ref_y = ((pi + 0.5f) / ws) * 2.0f - 1.0f;
+    const float ref_x = ((pj + 0.5f) / ws) * 2.0f - 1.0f;
+    const float pos_y = tanhf(off[2 * p]) * inv * 2.0f + ref_y;
+    const float pos_x = tanhf(off[2 * p + 1]) * inv * 2.0f + ref_x;
+    float *o = pix + (((long)win * groups + g) * P + p) * 2;
+    o[0] = ((pos_y + 1.0f) / 2.0f) * (ws - 1);
+    o[1] = ((pos_x + 1.0f) / 2.0f) * (ws - 1);
   }
 }
 
@@ -209,7 +240,7 @@ extern "C" int mumpy_cva_offsets(const float *q, const float *dw_w, const float 
   const int Cg = C / groups;
   MUMPY_REQUIRE(Cg <= 256 && Cg % 4 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0, "cva_offsets: group width %d unsupported (<= 256, multiple of 4)", Cg);
   const int N1 = B * (TH1 / ws) * (W / ws);
-  const size_t smem = (size_t)(ws * ws + 25) * Cg * sizeof(float);
+  const size_t smem = ((size_t)((ws + 4) * (ws + 4) + 25) * Cg + 2 * ws * ws) * sizeof(float);
   cudaStream_t st = as_stream(stream);
   if (Cg <= 32) return launch_cva_offsets<1>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups, ws, smem, st);
   if (Cg <= 64) return launch_cva_offsets<2>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups, ws, smem, st);

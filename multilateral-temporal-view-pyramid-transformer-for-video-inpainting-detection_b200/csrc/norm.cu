@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restr
   const int lane = threadIdx.x & 31;
   const int nv = C >> 2;
   const long warp_stride = (long)gridDim.x * (blockDim.x >> 5) * R;
-  // grid-stride over row groups: the grid is sized to the machine (148 SMs x resident CTAs), not to the row count, so that
-  // there is no partial last wave
+  // grid-stride over row groups (the grid covers every row group up to 148 x 64 CTAs: one pass per warp measured ~10 %
+  // faster than a grid capped at the resident CTA count)
   for (long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; row0 < n_rows; row0 += warp_stride) {
   float4 v[R][NV];
   float s[R];
@@ -143,7 +143,7 @@ template <typename OutT, int NV, int R>
 static void launch_ln_vec(const float *x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
   const long warps = cdiv(rows, R);
   const long ctas = cdiv(warps, 8);
-  launch_kernel(layernorm_vec_kernel<OutT, NV, R>, (unsigned)(ctas < 148 * 6 ? ctas : 148 * 6), 256, 0, st, x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
+  launch_kernel(layernorm_vec_kernel<OutT, NV, R>, (unsigned)(ctas < 148 * 64 ? ctas : 148 * 64), 256, 0, st, x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
 }
 
 template <typename OutT>
