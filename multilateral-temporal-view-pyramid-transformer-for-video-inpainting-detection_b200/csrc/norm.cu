@@ -60,104 +60,104 @@ __global__ void __launch_bounds__(256) layernorm_kernel(Rows rows, const float *
   }
 }
 
-// Plain rows, C % 4 == 0, C <= 1024: rows live in registers as float4 (NV vectors per lane per row); a warp normalises
-// R rows at once so that every lane keeps 8 independent 16-byte loads in flight whatever the row width (C = 96 .. 1024):
-// one coalesced global read, exact two-pass statistics, one coalesced write (8-byte bf16x4 or 16-byte fp32x4 per lane).
-template <typename OutT, int NV, int R>
+// Plain rows, C % 4 == 0, C <= 1024: rows live in registers as float4.  LPR lanes share a row (8 / 16 / 32, so that a lane
+// holds NV = C/4/LPR = 3..8 vectors and the statistics need only log2(LPR) shuffle steps -- with a full warp per 96..256-wide
+// row the kernel was issue-bound on shuffles, ncu: 2.3 IPC at 37 % of HBM); a warp handles 32/LPR rows side by side and RI such
+// groups per iteration to keep ~8 independent 16-byte loads in flight per lane.  Exact two-pass statistics, coalesced 128-byte
+// (LPR = 8) or longer row segments, 8-byte (16-bit x 4) or 16-byte (fp32 x 4) stores.
+template <typename OutT, int LPR, int NV, int RI>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
                                                             const float *__restrict__ beta, OutT *__restrict__ out, long n_rows, int C, float eps) {
   pdl_grid_sync();
+  constexpr int RPW = (32 / LPR) * RI;                     // rows per warp iteration
   const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, grp = lane / LPR;
   const int nv = C >> 2;
-  const long warp_stride = (long)gridDim.x * (blockDim.x >> 5) * R;
-  // grid-stride over row groups (the grid covers every row group up to 148 x 64 CTAs: one pass per warp measured ~10 %
-  // faster than a grid capped at the resident CTA count)
-  for (long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; row0 < n_rows; row0 += warp_stride) {
-  float4 v[R][NV];
-  float s[R];
+  const long warp_stride = (long)gridDim.x * (blockDim.x >> 5) * RPW;
+  for (long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < n_rows; row0 += warp_stride) {
+    float4 v[RI][NV];
+    float s[RI], q[RI];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    s[r] = 0.0f;
-    const bool live = row0 + r < n_rows;
-    const float4 *xr = reinterpret_cast<const float4 *>(x + (row0 + r) * C);
+    for (int r = 0; r < RI; ++r) {
+      const long row = row0 + r * (32 / LPR) + grp;
+      const float4 *xr = reinterpret_cast<const float4 *>(x + row * C);
+      s[r] = 0.0f;
 #pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      const int i = lane + 32 * u;
-      v[r][u] = (live && i < nv) ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-#pragma unroll
-    for (int u = 0; u < NV; ++u) s[r] += (v[r][u].x + v[r][u].y) + (v[r][u].z + v[r][u].w);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
-  float mean[R], q[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    mean[r] = s[r] / C;
-    q[r] = 0.0f;
-#pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      if (lane + 32 * u < nv) {
-        const float a = v[r][u].x - mean[r], b = v[r][u].y - mean[r], c = v[r][u].z - mean[r], d = v[r][u].w - mean[r];
-        q[r] += (a * a + b * b) + (c * c + d * d);
+      for (int u = 0; u < NV; ++u) {
+        const int i = sub + LPR * u;
+        v[r][u] = (row < n_rows && i < nv) ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
+    for (int r = 0; r < RI; ++r)
 #pragma unroll
-    for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
-  const float4 *g4 = reinterpret_cast<const float4 *>(gamma), *b4 = reinterpret_cast<const float4 *>(beta);
+      for (int u = 0; u < NV; ++u) s[r] += (v[r][u].x + v[r][u].y) + (v[r][u].z + v[r][u].w);
 #pragma unroll
-  for (int u = 0; u < NV; ++u) {
-    const int i = lane + 32 * u;
-    if (i < nv) {
-      const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+    for (int o = LPR / 2; o > 0; o >>= 1)
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (row0 + r < n_rows) {
-          const float rstd = 1.0f / sqrtf(q[r] / C + eps);
-          const float o0 = (v[r][u].x - mean[r]) * rstd * g.x + b.x, o1 = (v[r][u].y - mean[r]) * rstd * g.y + b.y;
-          const float o2 = (v[r][u].z - mean[r]) * rstd * g.z + b.z, o3 = (v[r][u].w - mean[r]) * rstd * g.w + b.w;
+      for (int r = 0; r < RI; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      s[r] = s[r] / C;                                     // mean
+      q[r] = 0.0f;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        if (sub + LPR * u < nv) {
+          const float a = v[r][u].x - s[r], b = v[r][u].y - s[r], c = v[r][u].z - s[r], d = v[r][u].w - s[r];
+          q[r] += (a * a + b * b) + (c * c + d * d);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < RI; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+#pragma unroll
+    for (int r = 0; r < RI; ++r) q[r] = 1.0f / sqrtf(q[r] / C + eps);      // rstd
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int i = sub + LPR * u;
+      if (i >= nv) continue;
+      const float4 g4 = __ldg(reinterpret_cast<const float4 *>(gamma) + i), b4 = __ldg(reinterpret_cast<const float4 *>(beta) + i);
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        const long row = row0 + r * (32 / LPR) + grp;
+        if (row < n_rows) {
+          const float rstd = q[r];
+          const float o0 = (v[r][u].x - s[r]) * rstd * g4.x + b4.x, o1 = (v[r][u].y - s[r]) * rstd * g4.y + b4.y;
+          const float o2 = (v[r][u].z - s[r]) * rstd * g4.z + b4.z, o3 = (v[r][u].w - s[r]) * rstd * g4.w + b4.w;
           if constexpr (sizeof(OutT) == 2) {
             uint2 pk;
             pk.x = pack2<OutT>(o0, o1);
             pk.y = pack2<OutT>(o2, o3);
-            reinterpret_cast<uint2 *>(out + (row0 + r) * C)[i] = pk;
+            reinterpret_cast<uint2 *>(out + row * C)[i] = pk;
           } else {
-            reinterpret_cast<float4 *>(out + (row0 + r) * C)[i] = make_float4(o0, o1, o2, o3);
+            reinterpret_cast<float4 *>(out + row * C)[i] = make_float4(o0, o1, o2, o3);
           }
         }
       }
     }
   }
-  }
 }
 
-template <typename OutT, int NV, int R>
+template <typename OutT, int LPR, int NV, int RI>
 static void launch_ln_vec(const float *x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
-  const long warps = cdiv(rows, R);
+  const long warps = cdiv(rows, (32 / LPR) * RI);
   const long ctas = cdiv(warps, 8);
-  launch_kernel(layernorm_vec_kernel<OutT, NV, R>, (unsigned)(ctas < 148 * 64 ? ctas : 148 * 64), 256, 0, st, x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
+  launch_kernel(layernorm_vec_kernel<OutT, LPR, NV, RI>, (unsigned)(ctas < 148 * 64 ? ctas : 148 * 64), 256, 0, st, x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
 }
 
 template <typename OutT>
 static void dispatch_ln_vec(const float *x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
-  const int nvl = (C / 4 + 31) / 32;      // float4 vectors per lane per row
-  switch (nvl) {
-    case 1: launch_ln_vec<OutT, 1, 8>(x, gamma, beta, out, rows, C, eps, st); break;
-    case 2: launch_ln_vec<OutT, 2, 4>(x, gamma, beta, out, rows, C, eps, st); break;
-    case 3: launch_ln_vec<OutT, 3, 2>(x, gamma, beta, out, rows, C, eps, st); break;
-    case 4: launch_ln_vec<OutT, 4, 2>(x, gamma, beta, out, rows, C, eps, st); break;
-    case 5:
-    case 6: launch_ln_vec<OutT, 6, 1>(x, gamma, beta, out, rows, C, eps, st); break;
-    default: launch_ln_vec<OutT, 8, 1>(x, gamma, beta, out, rows, C, eps, st); break;
-  }
+  const int nv = C / 4;                 // float4 vectors per row
+  if (nv <= 24) launch_ln_vec<OutT, 8, 3, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 32) launch_ln_vec<OutT, 8, 4, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 48) launch_ln_vec<OutT, 16, 3, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 64) launch_ln_vec<OutT, 16, 4, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 96) launch_ln_vec<OutT, 32, 3, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 128) launch_ln_vec<OutT, 32, 4, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 192) launch_ln_vec<OutT, 32, 6, 1>(x, gamma, beta, out, rows, C, eps, st);
+  else launch_ln_vec<OutT, 32, 8, 1>(x, gamma, beta, out, rows, C, eps, st);
 }
 
 template <typename Rows>
