@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__
   const int wpr = W / ws;
   const long base_row = b2 * L2 + (long)(n2 / wpr) * ws * W + (n2 % wpr) * ws;      // canvas row of the window's pixel (0,0)
   const int C4 = C >> 2;
-  for (int e = threadIdx.x; e < P * C4; e += blockDim.x) {
+  // blockIdx.y splits the window's P*C/4 work items when there are too few windows to fill the machine
+  const int items = P * C4, per = (items + gridDim.y - 1) / gridDim.y;
+  const int e_end = min(items, (int)(blockIdx.y + 1) * per);
+  for (int e = blockIdx.y * per + threadIdx.x; e < e_end; e += blockDim.x) {
     const int p = e / C4, c = (e - p * C4) * 4;
     const int g = c / Cg;                                  // Cg % 4 == 0: the four channels share a group
     const float2 pp = __ldg(reinterpret_cast<const float2 *>(pix + (((long)qw * groups + g) * P + p) * 2));
@@ -190,25 +193,43 @@ __global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__
   }
 }
 
-// x_new = h + window_partition(h) (window-major, added at flat position) + reinterpret_(C,P)->(P,C)(y)
+// x_new = h + window_partition(h) (window-major, added at flat position) + reinterpret_(C,P)->(P,C)(y):
+// flat element f = p*C + c of window (b, n)'s (P, C) block receives  h[canvas(n, p), c]  and  y[(win*P + f % P), f / P]  -- the
+// raw reshape of a (C, P) tensor (deformableAttention.py:403) is a transposed read of the token-major y.  One CTA per
+// window: y's (P, C) block is staged in shared memory (coalesced read) so that the transposed access never touches DRAM
+// with a stride; everything else is 16-byte coalesced.
 __global__ void __launch_bounds__(256) cva_residual_kernel(const float *__restrict__ h, const float *__restrict__ y,
-                                                           float *__restrict__ x_new, long total, int TH1, int W, int C, int ws) {
+                                                           float *__restrict__ x_new, int TH1, int W, int C, int ws) {
   pdl_grid_sync();
+  extern __shared__ float ysm[];      // [P][C + 1]
   const int P = ws * ws;
   const long L1 = (long)TH1 * W;
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (; idx < total; idx += stride) {
-    const int c = (int)(idx % C);
-    const long tok = idx / C;
-    const long b = tok / L1;
-    const int l = (int)(tok % L1);
-    const int n = l / P, p = l % P;
+  const int nW = (int)(L1 / P);
+  const long win = blockIdx.x;
+  const long b = win / nW;
+  const int n = (int)(win - b * nW);
+  const int C4 = C >> 2, ldy = C + 1;
+  const float4 *y4 = reinterpret_cast<const float4 *>(y + win * P * C);
+  for (int e = threadIdx.x; e < P * C4; e += blockDim.x) {
+    const int p = e / C4, c = (e - p * C4) * 4;
+    const float4 v = __ldg(y4 + e);
+    float *d = ysm + p * ldy + c;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const long blk = (b * L1 + (long)n * P) * C;      // flat offset of this window's (P, C) block in window-major order
+  for (int e = threadIdx.x; e < P * C4; e += blockDim.x) {
+    const int p = e / C4, c = (e - p * C4) * 4;
     const long wrow = b * L1 + window_token_row(n, p, TH1, W, ws, 0);
-    const int f = p * C + c;                 // flat index inside the window's (C,P) channel-major block
-    const int cc = f / P, pp = f % P;
-    const long win = b * (L1 / P) + n;
-    x_new[idx] = h[idx] + h[wrow * C + c] + y[(win * P + pp) * C + cc];
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(h + blk) + e);
+    const float4 hw = __ldg(reinterpret_cast<const float4 *>(h + wrow * C + c));
+    const int f = p * C + c;
+    float4 o;
+    o.x = a.x + hw.x + ysm[(f % P) * ldy + f / P];
+    o.y = a.y + hw.y + ysm[((f + 1) % P) * ldy + (f + 1) / P];
+    o.z = a.z + hw.z + ysm[((f + 2) % P) * ldy + (f + 2) / P];
+    o.w = a.w + hw.w + ysm[((f + 3) % P) * ldy + (f + 3) / P];
+    reinterpret_cast<float4 *>(x_new + blk)[e] = o;
   }
 }
 
@@ -258,20 +279,38 @@ extern "C" int mumpy_cva_sample(const void *x2, int x2_dtype, const float *pix, 
   const int N1 = B * (TH1 / ws) * (W / ws);
   const int N2 = B * (TH2 / ws) * (W / ws);
   cudaStream_t st = as_stream(stream);
+  int ysplit = (int)cdiv(148 * 4, N2);
+  const int max_split = (int)cdiv((long)ws * ws * (C / 4), 256);
+  if (ysplit > max_split) ysplit = max_split;
+  const dim3 sgrid((unsigned)N2, (unsigned)(ysplit < 1 ? 1 : ysplit));
   if (is_16bit(x2_dtype))
-    MUMPY_WITH_16(x2_dtype, T, launch_kernel(cva_sample_kernel<T, T>, N2, 256, 0, st, static_cast<const T *>(x2), pix, static_cast<T *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing));
+    MUMPY_WITH_16(x2_dtype, T, launch_kernel(cva_sample_kernel<T, T>, sgrid, 256, 0, st, static_cast<const T *>(x2), pix, static_cast<T *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing));
   else if (is_16bit(out_dtype))
-    MUMPY_WITH_16(out_dtype, T, launch_kernel(cva_sample_kernel<float, T>, N2, 256, 0, st, static_cast<const float *>(x2), pix, static_cast<T *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing));
+    MUMPY_WITH_16(out_dtype, T, launch_kernel(cva_sample_kernel<float, T>, sgrid, 256, 0, st, static_cast<const float *>(x2), pix, static_cast<T *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing));
   else
-    launch_kernel(cva_sample_kernel<float, float>, N2, 256, 0, st, static_cast<const float *>(x2), pix, static_cast<float *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
+    launch_kernel(cva_sample_kernel<float, float>, sgrid, 256, 0, st, static_cast<const float *>(x2), pix, static_cast<float *>(sampled), N1, TH1, TH2, W, C, groups, ws, per_clip_pairing);
   return launch_status("cva_sample");
 }
 
 extern "C" int mumpy_cva_residual(const float *h, const float *y, float *x_new, int B, int TH1, int W, int C, int ws,
                                   void *stream) {
   MUMPY_REQUIRE(h && y && x_new && h != x_new && B > 0, "cva_residual: bad arguments (must be out of place)");
-  const long total = (long)B * TH1 * W * C;
-  const int blocks = (int)(cdiv(total, 256) < 148 * 16 ? cdiv(total, 256) : 148 * 16);
-  launch_kernel(cva_residual_kernel, blocks, 256, 0, as_stream(stream), h, y, x_new, total, TH1, W, C, ws);
+  MUMPY_REQUIRE(C % 4 == 0 && TH1 % ws == 0 && W % ws == 0 &&
+                    ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x_new)) & 15) == 0,
+                "cva_residual: C %% 4 == 0, whole windows and 16-byte aligned buffers required");
+  const int P = ws * ws;
+  const size_t smem = (size_t)P * (C + 1) * sizeof(float);
+  MUMPY_REQUIRE(smem <= 227 * 1024, "cva_residual: window block of %zu B does not fit shared memory", smem);
+  static size_t granted = 0;
+  if (smem > 48 * 1024 && smem > granted) {
+    cudaError_t e = cudaFuncSetAttribute(cva_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("cva_residual: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+    granted = smem;
+  }
+  const long wins = (long)B * (TH1 / ws) * (W / ws);
+  launch_kernel(cva_residual_kernel, (unsigned)wins, 256, smem, as_stream(stream), h, y, x_new, TH1, W, C, ws);
   return launch_status("cva_residual");
 }

@@ -84,15 +84,19 @@ __global__ void __launch_bounds__(256) faf_repack_kernel(const RepackParams p) {
   pdl_grid_sync();
   __shared__ float tile[32][33];
   const int z = blockIdx.z;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const float *img = p.in + (long)(z / p.group) * p.group_stride + (long)(z % p.group) * p.R * p.C;
+  const int OR = p.transpose ? p.C : p.R, OC = p.transpose ? p.R : p.C;
+  // one CTA per 32-row band of an image, walking the column tiles (a CTA per 32 x 32 tile was launch-bound: 14 k CTAs of
+  // 1 k elements each)
+  for (int c0 = blockIdx.x * 32; c0 < p.C; c0 += gridDim.x * 32) {
+  __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int r = r0 + i, c = c0 + tx;
     tile[i][tx] = (r < p.R && c < p.C) ? img[(long)r * p.C + c] : 0.0f;
   }
   __syncthreads();
-  const int OR = p.transpose ? p.C : p.R, OC = p.transpose ? p.R : p.C;
   for (int i = ty; i < 32; i += 8) {
     // output row index runs over i, output column over tx (coalesced along the output row)
     const int r = p.transpose ? r0 + tx : r0 + i;
@@ -118,13 +122,14 @@ __global__ void __launch_bounds__(256) faf_repack_kernel(const RepackParams p) {
       }
     }
   }
+  }
 }
 
 int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, void *aux, long ldo,
                 long M, int N, int K, int ab_dtype, int out_dtype, int act, cudaStream_t st);
 
 static int faf_repack(const RepackParams &p, int n_img, int dtype, cudaStream_t st) {
-  dim3 grid((unsigned)cdiv(p.C, 32), (unsigned)cdiv(p.R, 32), (unsigned)n_img);
+  dim3 grid(1, (unsigned)cdiv(p.R, 32), (unsigned)n_img);
   if (dtype == MUMPY_F16)
     launch_kernel(faf_repack_kernel<__half>, grid, 256, 0, st, p);
   else

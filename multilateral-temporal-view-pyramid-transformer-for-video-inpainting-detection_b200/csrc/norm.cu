@@ -9,6 +9,8 @@ struct PlainRows {
   int C;
   static constexpr int kSegs = 1;
   __device__ __forceinline__ const float *seg(long row, int) const { return x + row * C; }
+  // float4 vector i of the (kSegs * C)-wide row
+  __device__ __forceinline__ const float4 *vec(long row, int i) const { return reinterpret_cast<const float4 *>(x + row * C) + i; }
 };
 
 // PatchMerging: output token (b, r', c') = cat of canvas tokens (2r'+dy, 2c'+dx), segment q: dy = q&1, dx = q>>1
@@ -24,6 +26,11 @@ struct MergeRows {
     const int r2 = (int)(t % H2);
     const long b = t / H2;
     return x + ((b * TH + 2 * r2 + (q & 1)) * W + 2 * c2 + (q >> 1)) * C;
+  }
+  __device__ __forceinline__ const float4 *vec(long row, int i) const {
+    const int nvseg = C >> 2;
+    const int q = i / nvseg;
+    return reinterpret_cast<const float4 *>(seg(row, q)) + (i - q * nvseg);
   }
 };
 
@@ -65,8 +72,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(Rows rows, const float *
 // row the kernel was issue-bound on shuffles, ncu: 2.3 IPC at 37 % of HBM); a warp handles 32/LPR rows side by side and RI such
 // groups per iteration to keep ~8 independent 16-byte loads in flight per lane.  Exact two-pass statistics, coalesced 128-byte
 // (LPR = 8) or longer row segments, 8-byte (16-bit x 4) or 16-byte (fp32 x 4) stores.
-template <typename OutT, int LPR, int NV, int RI>
-__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+template <typename Rows, typename OutT, int LPR, int NV, int RI>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const Rows rows, const float *__restrict__ gamma,
                                                             const float *__restrict__ beta, OutT *__restrict__ out, long n_rows, int C, float eps) {
   pdl_grid_sync();
   constexpr int RPW = (32 / LPR) * RI;                     // rows per warp iteration
@@ -80,12 +87,11 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restr
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
       const long row = row0 + r * (32 / LPR) + grp;
-      const float4 *xr = reinterpret_cast<const float4 *>(x + row * C);
       s[r] = 0.0f;
 #pragma unroll
       for (int u = 0; u < NV; ++u) {
         const int i = sub + LPR * u;
-        v[r][u] = (row < n_rows && i < nv) ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[r][u] = (row < n_rows && i < nv) ? *rows.vec(row, i) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
@@ -140,24 +146,25 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restr
   }
 }
 
-template <typename OutT, int LPR, int NV, int RI>
-static void launch_ln_vec(const float *x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
+// `C` below is the full normalised width (4 x the canvas width for MergeRows)
+template <typename Rows, typename OutT, int LPR, int NV, int RI>
+static void launch_ln_vec(const Rows &x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
   const long warps = cdiv(rows, (32 / LPR) * RI);
   const long ctas = cdiv(warps, 8);
-  launch_kernel(layernorm_vec_kernel<OutT, LPR, NV, RI>, (unsigned)(ctas < 148 * 64 ? ctas : 148 * 64), 256, 0, st, x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
+  launch_kernel(layernorm_vec_kernel<Rows, OutT, LPR, NV, RI>, (unsigned)(ctas < 148 * 64 ? ctas : 148 * 64), 256, 0, st, x, gamma, beta, static_cast<OutT *>(out), rows, C, eps);
 }
 
-template <typename OutT>
-static void dispatch_ln_vec(const float *x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
+template <typename Rows, typename OutT>
+static void dispatch_ln_vec(const Rows &x, const float *gamma, const float *beta, void *out, long rows, int C, float eps, cudaStream_t st) {
   const int nv = C / 4;                 // float4 vectors per row
-  if (nv <= 24) launch_ln_vec<OutT, 8, 3, 2>(x, gamma, beta, out, rows, C, eps, st);
-  else if (nv <= 32) launch_ln_vec<OutT, 8, 4, 2>(x, gamma, beta, out, rows, C, eps, st);
-  else if (nv <= 48) launch_ln_vec<OutT, 16, 3, 2>(x, gamma, beta, out, rows, C, eps, st);
-  else if (nv <= 64) launch_ln_vec<OutT, 16, 4, 2>(x, gamma, beta, out, rows, C, eps, st);
-  else if (nv <= 96) launch_ln_vec<OutT, 32, 3, 2>(x, gamma, beta, out, rows, C, eps, st);
-  else if (nv <= 128) launch_ln_vec<OutT, 32, 4, 2>(x, gamma, beta, out, rows, C, eps, st);
-  else if (nv <= 192) launch_ln_vec<OutT, 32, 6, 1>(x, gamma, beta, out, rows, C, eps, st);
-  else launch_ln_vec<OutT, 32, 8, 1>(x, gamma, beta, out, rows, C, eps, st);
+  if (nv <= 24) launch_ln_vec<Rows, OutT, 8, 3, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 32) launch_ln_vec<Rows, OutT, 8, 4, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 48) launch_ln_vec<Rows, OutT, 16, 3, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 64) launch_ln_vec<Rows, OutT, 16, 4, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 96) launch_ln_vec<Rows, OutT, 32, 3, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 128) launch_ln_vec<Rows, OutT, 32, 4, 2>(x, gamma, beta, out, rows, C, eps, st);
+  else if (nv <= 192) launch_ln_vec<Rows, OutT, 32, 6, 1>(x, gamma, beta, out, rows, C, eps, st);
+  else launch_ln_vec<Rows, OutT, 32, 8, 1>(x, gamma, beta, out, rows, C, eps, st);
 }
 
 template <typename Rows>
@@ -267,9 +274,9 @@ extern "C" int mumpy_layernorm(const float *x, const float *gamma, const float *
   if (C % 4 == 0 && C <= 1024 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
                                    reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
     if (is_16bit(out_dtype))
-      MUMPY_WITH_16(out_dtype, T, dispatch_ln_vec<T>(x, gamma, beta, out, rows, C, eps, as_stream(stream)));
+      MUMPY_WITH_16(out_dtype, T, dispatch_ln_vec<PlainRows, T>(PlainRows{x, C}, gamma, beta, out, rows, C, eps, as_stream(stream)));
     else
-      dispatch_ln_vec<float>(x, gamma, beta, out, rows, C, eps, as_stream(stream));
+      dispatch_ln_vec<PlainRows, float>(PlainRows{x, C}, gamma, beta, out, rows, C, eps, as_stream(stream));
     return launch_status("layernorm_vec");
   }
   return launch_ln(PlainRows{x, C}, gamma, beta, out, out_dtype, rows, C, eps, as_stream(stream));
@@ -279,7 +286,16 @@ extern "C" int mumpy_patch_merge_norm(const float *x, const float *gamma, const 
                                       int TH, int W, int C, float eps, void *stream) {
   MUMPY_REQUIRE(x && gamma && beta && out && B > 0 && TH % 2 == 0 && W % 2 == 0, "patch_merge_norm: bad arguments");
   const long rows = (long)B * (TH / 2) * (W / 2);
-  return launch_ln(MergeRows{x, C, TH, W}, gamma, beta, out, out_dtype, rows, C, eps, as_stream(stream));
+  const MergeRows mr{x, C, TH, W};
+  if (C % 4 == 0 && 4 * C <= 1024 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
+                                       reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
+    if (is_16bit(out_dtype))
+      MUMPY_WITH_16(out_dtype, T, dispatch_ln_vec<MergeRows, T>(mr, gamma, beta, out, rows, 4 * C, eps, as_stream(stream)));
+    else
+      dispatch_ln_vec<MergeRows, float>(mr, gamma, beta, out, rows, 4 * C, eps, as_stream(stream));
+    return launch_status("patch_merge_norm_vec");
+  }
+  return launch_ln(mr, gamma, beta, out, out_dtype, rows, C, eps, as_stream(stream));
 }
 
 extern "C" int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *stats_ws, float *out,
