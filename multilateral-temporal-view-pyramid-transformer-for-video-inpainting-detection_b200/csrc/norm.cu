@@ -185,8 +185,9 @@ static int launch_ln(Rows rows, const float *gamma, const float *beta, void *out
 //     a fixed order (deterministic);  (3) groupnorm_apply_kernel normalises + activates with float4 accesses.
 constexpr int GN_SMEM_FLOATS = 12 * 1024;      // 48 KB staging
 
-__global__ void __launch_bounds__(256) gn_partial_kernel(const float *__restrict__ x, float *__restrict__ partial, int HW, int C, int groups, int pix,
-                                                         int nchunks) {
+// generic fallback (any C): one warp per group, scalar indexing
+__global__ void __launch_bounds__(256) gn_partial_generic_kernel(const float *__restrict__ x, float *__restrict__ partial, int HW, int C, int groups,
+                                                                 int pix, int nchunks) {
   pdl_grid_sync();
   extern __shared__ float tile[];   // [pix][C]
   const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
@@ -218,14 +219,76 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float *__restrict
   }
 }
 
-__global__ void gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ stats, int total_bg, int HW, int cg, int pix, int nchunks,
-                                   float eps) {
+// C/4 divides 256 (C = 32 ... 1024, powers of two): a thread owns one channel quad (one group, cg % 4 == 0) and every
+// (256 / (C/4))-th pixel of the staged chunk: float4 shared-memory reads, no index arithmetic per element; the per-thread
+// partials are combined per group in a fixed order (deterministic).  Exact two-pass (mean, then M2 about the chunk mean).
+__global__ void __launch_bounds__(256) gn_partial_kernel(const float *__restrict__ x, float *__restrict__ partial, int HW, int C, int groups, int pix,
+                                                         int nchunks) {
   pdl_grid_sync();
-  const int bg = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ float tile[];   // [pix][C]
+  __shared__ float red[256];
+  __shared__ float gmean[64];
+  const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
+  const int p0 = chunk * pix;
+  const int np = min(pix, HW - p0);
+  const float4 *src = reinterpret_cast<const float4 *>(x + ((long)b * HW + p0) * C);
+  float4 *t4 = reinterpret_cast<float4 *>(tile);
+  const int C4 = C >> 2;
+  const int nvec = np * C4;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) t4[i] = src[i];
+  __syncthreads();
+  const int cg = C / groups, cqg = cg >> 2;           // channel quads per group
+  const int lanes_p = 256 / C4;
+  const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cnt = cqg * lanes_p;                       // partials per group
+  const float inv_n = 1.0f / (float)(np * cg);
+  float s = 0.0f;
+  for (int p = pl; p < np; p += lanes_p) {
+    const float4 v = t4[p * C4 + c4];
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int g = warp; g < groups; g += 8) {
+    float a = 0.0f;
+    for (int k = lane; k < cnt; k += 32) a += red[(k / cqg) * C4 + g * cqg + (k % cqg)];
+    a = warp_sum(a);
+    if (lane == 0) gmean[g] = a * inv_n;
+  }
+  __syncthreads();
+  const float mean = gmean[(c4 * 4) / cg];
+  float q = 0.0f;
+  for (int p = pl; p < np; p += lanes_p) {
+    const float4 v = t4[p * C4 + c4];
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  red[threadIdx.x] = q;
+  __syncthreads();
+  for (int g = warp; g < groups; g += 8) {
+    float a = 0.0f;
+    for (int k = lane; k < cnt; k += 32) a += red[(k / cqg) * C4 + g * cqg + (k % cqg)];
+    a = warp_sum(a);
+    if (lane == 0) {
+      float *o = partial + (((long)b * groups + g) * nchunks + chunk) * 2;
+      o[0] = gmean[g];
+      o[1] = a;
+    }
+  }
+}
+
+// one warp per (image, group): every lane folds its chunks (lane, lane+32, ...) with Chan's parallel-variance update, then the
+// 32 lane results are merged pairwise in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ stats, int total_bg, int HW, int cg,
+                                                          int pix, int nchunks, float eps) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int bg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (bg >= total_bg) return;
   const float *p = partial + (long)bg * nchunks * 2;
   float n_a = 0.0f, mean_a = 0.0f, m2_a = 0.0f;
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = lane; c < nchunks; c += 32) {
     const float n_b = (float)(min(pix, HW - c * pix) * cg);
     const float mean_b = p[2 * c], m2_b = p[2 * c + 1];
     const float n_ab = n_a + n_b;
@@ -234,8 +297,23 @@ __global__ void gn_finalize_kernel(const float *__restrict__ partial, float *__r
     m2_a += m2_b + delta * delta * (n_a * n_b / n_ab);
     n_a = n_ab;
   }
-  stats[2 * bg] = mean_a;
-  stats[2 * bg + 1] = 1.0f / sqrtf(m2_a / n_a + eps);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float n_b = __shfl_down_sync(0xffffffffu, n_a, o);
+    const float mean_b = __shfl_down_sync(0xffffffffu, mean_a, o);
+    const float m2_b = __shfl_down_sync(0xffffffffu, m2_a, o);
+    const float n_ab = n_a + n_b;
+    if (n_b > 0.0f) {
+      const float delta = mean_b - mean_a;
+      mean_a += delta * (n_b / n_ab);
+      m2_a += m2_b + delta * delta * (n_a * n_b / n_ab);
+      n_a = n_ab;
+    }
+  }
+  if (lane == 0) {
+    stats[2 * bg] = mean_a;
+    stats[2 * bg + 1] = 1.0f / sqrtf(m2_a / n_a + eps);
+  }
 }
 
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float *__restrict__ x, const float *__restrict__ stats,
@@ -311,10 +389,19 @@ extern "C" int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const fl
   const int nchunks = (int)cdiv(HW, pix);
   float *stats = stats_ws;                                  // 2 * B * groups
   float *partial = stats_ws + 2 * (long)B * groups;         // 2 * B * groups * nchunks
-  launch_kernel(gn_partial_kernel, B * nchunks, 256, (size_t)pix * C * sizeof(float), st, x, partial, HW, C, groups, pix, nchunks);
+  const int C4 = C / 4;
+  static bool gn_attr = false;
+  if (!gn_attr) {        // 48 KB of dynamic staging + the static reduction arrays exceed the default 48 KB window
+    cudaFuncSetAttribute(gn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_SMEM_FLOATS * (int)sizeof(float));
+    gn_attr = true;
+  }
+  if (C4 <= 256 && 256 % C4 == 0 && groups <= 64)
+    launch_kernel(gn_partial_kernel, B * nchunks, 256, (size_t)pix * C * sizeof(float), st, x, partial, HW, C, groups, pix, nchunks);
+  else
+    launch_kernel(gn_partial_generic_kernel, B * nchunks, 256, (size_t)pix * C * sizeof(float), st, x, partial, HW, C, groups, pix, nchunks);
   int rc = launch_status("gn_partial");
   if (rc) return rc;
-  launch_kernel(gn_finalize_kernel, (unsigned)cdiv(B * groups, 128), 128, 0, st, partial, stats, B * groups, HW, C / groups, pix, nchunks, eps);
+  launch_kernel(gn_finalize_kernel, (unsigned)cdiv(B * groups, 8), 256, 0, st, partial, stats, B * groups, HW, C / groups, pix, nchunks, eps);
   rc = launch_status("gn_finalize");
   if (rc) return rc;
   const long total4 = (long)B * HW * C / 4;
