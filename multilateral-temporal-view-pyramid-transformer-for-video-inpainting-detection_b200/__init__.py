@@ -10,9 +10,21 @@ identifier); `import mumpy_b200` (repo root shim) resolves to it.  Layout:
   evaluate.py           clip-sharded evaluation: thresholded masks, per-clip F1/IoU counts, NCCL reduction
   build.py              nvcc recipe for the shared library
 """
-from . import ops  # noqa: F401
+from . import ops, streams  # noqa: F401
 from .ops import precision, set_precision  # noqa: F401
 from .models.encoder.encoder import Encoder  # noqa: F401
 from .models.decoder.decoder import Decoder  # noqa: F401
 
-__all__ = ["Encoder", "Decoder", "ops", "set_precision", "precision"]
+
+
+def forward(encoder, decoder, x):
+    """test.py:94-95 as one call: `feats, views, dct = encoder(x); return decoder(feats, views, dct)` inside ONE stream region,
+    so that the decoder's pyramid / frequency branches start as soon as their stage features exist and overlap the
+    encoder's tail (stage 3 and the 12 small global blocks) instead of waiting for the encoder's join.  Same results, bit for
+    bit, as the two separate calls (tests/test_gpu_e2e.py).  Returns (logits (B,1,S,S), x_feats (B,32,S,S))."""
+    with streams.region(x.device):
+        final_x, view_x, ffinfo = encoder(x)
+        return decoder(final_x, view_x, ffinfo)
+
+
+__all__ = ["Encoder", "Decoder", "forward", "ops", "streams", "set_precision", "precision"]

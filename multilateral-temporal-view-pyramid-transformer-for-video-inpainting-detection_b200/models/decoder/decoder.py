@@ -223,10 +223,13 @@ class Decoder(PackedModule):
         xh = x.permute(0, 2, 3, 1)
         xh = xh if xh.is_contiguous() else ops.nchw_to_nhwc(x.contiguous())            # (B,n,n,2304)
         S = ffinfo.shape[-1]
-        # Independent branches run on lanes (streams.py): lane 3 the frequency pyramid, lanes 0-2 the rgb pyramid levels
-        # with their SEB / global-conv modules; the decoder_2..5 chain follows on lane 0.  Hand-overs are events.
+        # Independent branches run on lanes (streams.py): lane 3 the frequency pyramid, lanes 0-1 the rgb pyramid levels with
+        # their SEB / global-conv modules, the decoder_2..5 chain follows on lane 0.  Hand-overs are events; inputs that another
+        # lane produced (stage features, the frequency map) are awaited with need_tensor, final_x with need_main, so that inside
+        # an outer region (mumpy_b200.forward) these branches overlap the encoder's tail.  Lane 2 is left to the heaviest view.
         with streams.region(x.device) as reg:
             with reg.lane(3):
+                reg.need_tensor(ffinfo)
                 # AvgPool2 of decoder_frequency_0 fused into the layout change; pixel stride padded to 16 channels so that the
                 # 9-channel map can feed the TMA convolution (the padding is never read)
                 cf = ffinfo.shape[1]
@@ -244,33 +247,23 @@ class Decoder(PackedModule):
                 freq4 = self._freq_stage("decoder_frequency_4", freq3, B, S // 16, S // 16)
                 reg.publish("freq4", freq4)
             with reg.lane(0):
+                reg.need_tensor(*view_x[3])
                 rgb4 = self._rgb_stage(3, view_x[3], B, s3)
                 reg.publish("rgb4", rgb4)
             with reg.lane(1):
+                reg.need_tensor(*view_x[2])
                 rgb3 = self._rgb_stage(2, view_x[2], B, s2)
                 reg.publish("rgb3", rgb3)
-            with reg.lane(2):
+                reg.need_tensor(*view_x[1])
                 rgb2 = self._rgb_stage(1, view_x[1], B, s1)
                 reg.publish("rgb2", rgb2)
             c2, c3, c4 = rgb2.shape[-1], rgb3.shape[-1], rgb4.shape[-1]
 
-            with reg.lane(0):
-                cin = c4 + xh.shape[-1]
-                cat0 = torch.empty((B, s3, s3, cin), dtype=torch.float32, device=x.device)    # cat[rgb4, x] (:204)
-                ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_IDENTITY, out=cat0, ld_out=cin, out_col=0)
-                ops.resample_nhwc(xh, B, s3, s3, xh.shape[-1], ops.RS_IDENTITY, out=cat0, ld_out=cin, out_col=c4)
-                gcn0 = self.gcm1.nhwc(cat0, B, s3, s3)
-                reg.need("freq4")
-                g0 = ops.mul_add(gcn0, freq4)
-                out1 = ops.resample_nhwc(g0, B, s3, s3, g0.shape[-1], ops.RS_PIXEL_SHUFFLE2)  # ecre (:205)
             with reg.lane(1):
                 reg.need("rgb4")
                 seb1 = self.seb1.nhwc(rgb3, rgb4, B, s3, s3)
                 gcn1 = self.gcm2.nhwc(seb1, B, s2, s2)
                 reg.publish("gcn1", gcn1)
-            with reg.lane(2):
-                reg.need("rgb3")
-                reg.need("rgb4")
                 cat2 = torch.empty((B, s2, s2, c3 + c4), dtype=torch.float32, device=x.device)  # cat[rgb3, up2(rgb4)] (:210)
                 ops.resample_nhwc(rgb3, B, s2, s2, c3, ops.RS_IDENTITY, out=cat2, ld_out=c3 + c4, out_col=0)
                 ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_UP_HALFPIX, 2, out=cat2, ld_out=c3 + c4, out_col=c3)
@@ -278,6 +271,7 @@ class Decoder(PackedModule):
                 gcn2 = self.gcm3.nhwc(seb2, B, s1, s1)
                 reg.publish("gcn2", gcn2)
             with reg.lane(0):
+                reg.need_tensor(*view_x[0])
                 rgb1 = self._rgb_stage(0, view_x[0], B, s0)
                 reg.need("rgb2")
                 reg.need("rgb3")
@@ -289,6 +283,17 @@ class Decoder(PackedModule):
                 seb3 = self.seb3.nhwc(rgb1, cat3, B, s1, s1)
                 gcn3 = self.gcm4.nhwc(seb3, B, s0, s0)
 
+                # the only part that needs the encoder's final tokens (produced on the caller's stream)
+                reg.need_main()
+                cin = c4 + xh.shape[-1]
+                cat0 = torch.empty((B, s3, s3, cin), dtype=torch.float32, device=x.device)    # cat[rgb4, x] (:204)
+                ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_IDENTITY, out=cat0, ld_out=cin, out_col=0)
+                ops.resample_nhwc(xh, B, s3, s3, xh.shape[-1], ops.RS_IDENTITY, out=cat0, ld_out=cin, out_col=c4)
+                gcn0 = self.gcm1.nhwc(cat0, B, s3, s3)
+                reg.need("freq4")
+                g0 = ops.mul_add(gcn0, freq4)
+                out1 = ops.resample_nhwc(g0, B, s3, s3, g0.shape[-1], ops.RS_PIXEL_SHUFFLE2)  # ecre (:205)
+
                 reg.need("gcn1")
                 reg.need("freq3")
                 d = self._dec_stage("decoder_2", ops.mul_add(gcn1, freq3, out1), B, s2, s2)        # (:218)
@@ -299,6 +304,7 @@ class Decoder(PackedModule):
                 d = self._dec_stage("decoder_4", ops.mul_add(gcn3, freq1, d), B, s0, s0)           # (:220)
                 reg.need("freq0")
                 feats = self._dec_stage("decoder_5", ops.mul_add(d, freq0), B, 2 * s0, 2 * s0, dap=True)   # (:221-222) (B,S,S,32)
+            reg.wait_lanes()          # hand the result back to the caller's stream (the lanes stay forked in a nested region)
         Sf = 4 * s0
         mask = _conv(self, "final_out", self.final_out, feats, B, Sf, Sf)                  # (B,S,S,1) == (B,1,S,S)
         x_feats = ops.nhwc_to_nchw(feats, B, Sf, Sf, feats.shape[-1])

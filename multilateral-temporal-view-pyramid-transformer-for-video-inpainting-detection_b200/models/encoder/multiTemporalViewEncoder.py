@@ -217,10 +217,13 @@ class MultiViewBasicLayer(nn.Module):
 
     def forward(self, x):
         out = []
-        with streams.region(x[0].device):
+        with streams.region(x[0].device) as reg:
             for blk in self.blocks:
                 x = blk(x)
                 out = x.copy()
+            for v in range(len(out)):            # the stage features are consumed across lanes (decoder pyramid): publish them
+                with reg.lane(v):
+                    reg.publish_tensor(out[v])
             if self.downsample is not None:
                 x = self.downsample(x)
         return x, out
@@ -320,11 +323,20 @@ class ThreeViewSwinTransformer(PackedModule):
         with streams.region(x.device) as reg:
             with reg.lane(3):
                 ffinfo = self.faf.frame(x, 1)                              # == faf(x)[:, 1]  
+                reg.publish_tensor(ffinfo)
             toks = self.tokenize(x)
             # align_temporal_dimension_across_views + vmap over the size-1 dim == flatten (t, n) (:701-708,737)
             xs = [t.reshape(B, -1, t.shape[-1]) for t in toks]
             xs, outs = self.layers(xs)
-        out_x = [[t.unsqueeze(1) for t in stage] for stage in outs]
+            out_x = [[t.unsqueeze(1) for t in stage] for stage in outs]
+            # the temporal global encoder runs on the caller's stream as soon as the three view lanes have delivered stage 3;
+            # inside an outer region (mumpy_b200.forward) the frequency lane and the decoder's branches keep running beside it
+            reg.wait_lanes([0, 1, 2])
+            g = self._global_part(xs, B)
+        return g, out_x, ffinfo
+
+    def _global_part(self, xs, B):
+        x = xs[0]
         # merge_views_along_channel_axis + globalembedding (:710-718,740); rows ordered (b, n, t)
         T = max(self.input_token_temporal_dims)
         n = xs[0].shape[1]
@@ -340,4 +352,4 @@ class ThreeViewSwinTransformer(PackedModule):
         g = ops.linear(merged, self._gemm_weight("globalembedding", self.globalembedding.weight), self.globalembedding.bias)
         # vmap(globalblocks, in_dims=2) == blocks on (B*n, T, 768)  (:741)
         g = self.globalblocks(g.view(B * n, T, -1))
-        return g.view(B, n, -1), out_x, ffinfo                          # == cat over t on the channel axis (:745)
+        return g.view(B, n, -1)                                          # == cat over t on the channel axis (:745)

@@ -11,7 +11,10 @@ without waiting for other streams):
     different stream is still pending;
   * everything produced inside a region is only used by the caller after the region's join.
 Regions nest: only the outermost one forks and joins, inner ones (e.g. a three-view block called from the encoder)
-just pick lanes.  No torch computation happens here; streams and events only.
+just pick lanes and hand results over with events (`publish_tensor` / `need_tensor` / `wait_lanes` / `need_main`).  Wrapping
+`encoder(x)` and `decoder(...)` in ONE outer region (mumpy_b200.forward does) therefore lets the decoder's pyramid and
+frequency branches start as soon as their stage features exist and overlap the encoder's tail (stage 3 and the 12 small
+global blocks).  No torch computation happens here; streams and events only.
 """
 import contextlib
 import os
@@ -66,6 +69,46 @@ class Region:
         """Called on the consuming lane before the first use of what `key` published."""
         if self.parallel:
             torch.cuda.current_stream().wait_event(self.events[key])
+
+    def publish_tensor(self, *tensors):
+        """Like publish(), keyed by the tensors' storage: called on the lane that produced them, lets any other lane (or the
+        caller's stream) `need_tensor()` them later without knowing who produced them (views share the key)."""
+        for t in tensors:
+            if t is not None:
+                self.publish(("t", t.data_ptr()), t)
+
+    def need_tensor(self, *tensors):
+        """Waits (on the current stream) for every tensor that was `publish_tensor`-ed in this region; others are assumed to be
+        ordered already (produced on the current stream, or before the region forked)."""
+        if not self.parallel:
+            return
+        cur = torch.cuda.current_stream()
+        for t in tensors:
+            ev = self.events.get(("t", t.data_ptr())) if t is not None else None
+            if ev is not None:
+                cur.wait_event(ev)
+
+    def wait_lanes(self, lanes=None):
+        """The current stream waits for everything enqueued so far on the given lanes (default: all) -- a one-way join that
+        leaves the lanes running; used where a nested region must hand results back to the caller's stream."""
+        if not self.parallel:
+            return
+        cur = torch.cuda.current_stream()
+        for i in (range(N_LANES) if lanes is None else lanes):
+            if self.lanes[i % N_LANES] != cur:
+                ev = torch.cuda.Event()
+                ev.record(self.lanes[i % N_LANES])
+                cur.wait_event(ev)
+
+    def need_main(self):
+        """The current lane waits for everything enqueued so far on the caller's stream (results produced there after the fork)."""
+        if not self.parallel:
+            return
+        cur = torch.cuda.current_stream()
+        if cur != self.main:
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            cur.wait_event(ev)
 
     def hold(self, *tensors):
         """Keeps tensors alive until the join (inputs of work that is still pending on a lane)."""

@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu30.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu30.log | cut -c1-200
-timeout 300 python tools/op_breakdown.py 32 > gpurun_out/op_breakdown_v10.txt 2>&1; grep -E "groupnorm|serial step" gpurun_out/op_breakdown_v10.txt | head
-timeout 600 python bench.py --steps 20 --warmup 3 --no-kernels --no-fp16 > gpurun_out/bench26.json 2> gpurun_out/bench26.err; echo "bench rc=$?"; cut -c1-180 gpurun_out/bench26.json
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu31.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu31.log | cut -c1-250
+timeout 600 python bench.py --steps 20 --warmup 3 --no-kernels --no-fp16 > gpurun_out/bench27.json 2> gpurun_out/bench27.err; echo "bench rc=$?"; cut -c1-180 gpurun_out/bench27.json; tail -3 gpurun_out/bench27.err
+timeout 600 python bench.py --steps 20 --warmup 3 --no-kernels --no-fp16 --batch 1 > gpurun_out/bench27_b1.json 2> /dev/null; cut -c60-180 gpurun_out/bench27_b1.json
