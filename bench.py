@@ -189,13 +189,13 @@ def kernel_section(peaks, device):
         out.append({"kernel": "cva_sample_kernel (stage-0 v2<-v3, B=64)", "bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3})
         del x2, pix
-        # (ii) DCT branch (64,3,3,224,224) -> (64,9,224,224), dense fp32: 8 matmuls of 224^3 per image-channel
+        # (ii) DCT branch (64,3,3,224,224) -> (64,9,224,224): 8 matmuls of 224^3 per image-channel (bf16 mode: split operands)
         x = torch.randn((B, 3, 3, 224, 224), device=device)
         faf = FAF(224).eval()
         t = timed(lambda: faf.frame(x, 1), reps=3)
         flops = B * 3 * 8 * 2 * 224 ** 3
         byts = B * 224 * 224 * (3 * 4 + 9 * 4)
-        out.append({"kernel": "mumpy_faf (4 fp32 GEMM passes, B=64)", "bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        out.append({"kernel": "mumpy_faf16 (4 tcgen05 GEMM passes on split bf16 operands + 5 repack kernels, B=64)", "bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3, "dense_tflops_fp32": flops / t / 1e12})
         del x
         # (iii) Swin stage-0 (view 3) GEMMs at B=64: M = 64*9408, C = 128
@@ -510,7 +510,7 @@ def main():
             "achieved": live["achieved"], "frac": live["achieved"] / peaks["bf16_tflops_sustained"],
             "avg_launch_us": live["avg_launch_us"], "flops_per_launch_avg": live["flops_per_step"] / live["launches_per_step"],
             "share_of_kernel_time": live["share_of_kernel_time"], "serial_kernel_time_ms": live["kernel_time_ms"],
-            "traffic": 46.7e6, "traffic_note": "dram read+write of the largest-share launch (fc1 M=18816 N=2048 K=512, 98 MB algorithmic: the bf16 "
+            "traffic": 45.0e6, "traffic_note": "dram read+write of the largest-share launch (fc1 M=18816 N=2048 K=512, 98 MB algorithmic: the bf16 "
                                                "output stays in L2), ncu --set full, profiles/r1_gemm_fc1_ncu.txt",
             "whole_step": {"achieved": gflop_per_clip * 1e9 * (B * K) / t_max / 1e12,
                            "frac": gflop_per_clip * 1e9 * (B * K) / t_max / 1e12 / peaks["bf16_tflops_sustained"],
