@@ -58,6 +58,8 @@ int mumpy_set_pdl(int enabled);
 /* CTA-pair (tcgen05 cta_group::2, 256 x BN tiles on a (2,1,1) cluster) policy of the bf16 GEMM / implicit-GEMM convolution:
  * 0 never (default), 1 the tile cost model decides, 2 whenever the shape allows.  Environment: MUMPY_TC_PAIR. */
 int mumpy_set_gemm_pair_mode(int mode);
+/* Tuning aid: force the GEMM tile width (a divisor of N; 0 = the cost model decides).  Environment: MUMPY_TC_BN. */
+int mumpy_set_gemm_tile(int bn);
 
 /* nn.Linear / 1x1 conv:  out = act(A . W^T + bias) (+ residual).   swinTransformer.py:45-51,142,164,365;
  * blocks.py:28-34,56,71; deformableAttention.py:333,361-362,402; multiTemporalViewEncoder.py:283,740;
