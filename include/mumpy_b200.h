@@ -60,6 +60,9 @@ int mumpy_set_pdl(int enabled);
 int mumpy_set_gemm_pair_mode(int mode);
 /* Tuning aid: force the GEMM tile width (a divisor of N; 0 = the cost model decides).  Environment: MUMPY_TC_BN. */
 int mumpy_set_gemm_tile(int bn);
+/* Kernel used by mumpy_window_attention in the 16-bit modes when the bias comes from the relative-position table:
+ * 1 (default) tcgen05 / TMEM (two windows per 128-row accumulator), 0 the per-warp mma.sync kernel.  Environment: MUMPY_ATT_TC. */
+int mumpy_set_attention_tc(int enabled);
 
 /* nn.Linear / 1x1 conv:  out = act(A . W^T + bias) (+ residual).   swinTransformer.py:45-51,142,164,365;
  * blocks.py:28-34,56,71; deformableAttention.py:333,361-362,402; multiTemporalViewEncoder.py:283,740;

@@ -19,6 +19,7 @@ SIGNATURES = {
     "mumpy_init": [ci],
     "mumpy_set_pdl": [ci],
     "mumpy_set_gemm_pair_mode": [ci],
+    "mumpy_set_attention_tc": [ci],
     "mumpy_set_gemm_tile": [ci],
     "mumpy_linear": [vp, cl, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, ci, vp],
     "mumpy_linear_dual": [vp, cl, vp, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, vp],

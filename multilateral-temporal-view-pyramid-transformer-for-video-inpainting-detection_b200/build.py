@@ -26,7 +26,7 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-           "-Xcompiler", "-fPIC", "-o", OUT] + sources()
+           "-Xcompiler", "-fPIC", "-o", OUT] + os.environ.get("MUMPY_NVCC_FLAGS", "").split() + sources()      # e.g. -DWTC_TIMING
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

@@ -36,6 +36,7 @@ int launch_status(const char *what) {
 
 int resolve_driver_entry_points();
 void set_gemm_pair_mode(int mode);
+void set_attention_tc(int enabled);
 void set_gemm_tile_override(int bn);
 int linear_f32(const float *A, long lda, const float *W, const float *bias, const float *residual, float *out, long ldo,
                long M, int N, int K, int act, cudaStream_t st);
@@ -77,6 +78,11 @@ extern "C" const char *mumpy_last_error(void) { return g_err; }
 
 extern "C" int mumpy_set_gemm_pair_mode(int mode) {
   set_gemm_pair_mode(mode);
+  return MUMPY_OK;
+}
+
+extern "C" int mumpy_set_attention_tc(int enabled) {
+  set_attention_tc(enabled);
   return MUMPY_OK;
 }
 

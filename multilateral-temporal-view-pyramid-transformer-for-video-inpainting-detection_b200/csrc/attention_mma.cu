@@ -233,10 +233,11 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
   const long first = (long)blockIdx.x * WATT_WARPS + warp;
 
   auto issue = [&](long task, int stage) {
-    const long win = task / heads;
-    const int h = (int)(task - win * heads);
-    const long b = win / nW;
-    const int n = (int)(win - b * nW);
+    // 32-bit index arithmetic (the host checks n_tasks < 2^31): a 64-bit division by a run-time value is a ~100-instruction call
+    const unsigned win = (unsigned)task / (unsigned)heads;
+    const int h = (int)((unsigned)task - win * (unsigned)heads);
+    const unsigned b = win / (unsigned)nW;
+    const int n = (int)(win - b * (unsigned)nW);
     const int wr = n / wpr, wc = n - wr * wpr;
     int *rows = rows_base + stage * 64;
 #pragma unroll
@@ -278,9 +279,9 @@ __global__ void __launch_bounds__(WATT_WARPS * 32, 1) window_attention_mma_kerne
     }
     __syncwarp();
 
-    const long win = task / heads;
-    const int h = (int)(task - win * heads);
-    const int n = (int)(win % nW);
+    const unsigned win = (unsigned)task / (unsigned)heads;
+    const int h = (int)((unsigned)task - win * (unsigned)heads);
+    const int n = (int)(win % (unsigned)nW);
     const int wr = n / wpr, wc = n - wr * wpr;
     const int *rows = rows_base + stage * 64;
     const uint32_t sQ = smem_addr(wbase + stage * WATT_STAGE_BYTES), sK = sQ + ATT_TILE_BYTES, sV = sK + ATT_TILE_BYTES;
@@ -580,11 +581,24 @@ static int watt_smem_attr(K kernel, size_t bytes) {
   return MUMPY_OK;
 }
 
+int window_attention_tc(const void *qkv, const float *rel_table, int standard_mask, void *out, int dtype, int B, int TH, int W, int C, int heads,
+                        int ws, int shift, cudaStream_t st);
+
+static int g_att_tc = -1;      // -1: read MUMPY_ATT_TC on first use (default on)
+void set_attention_tc(int enabled) { g_att_tc = enabled ? 1 : 0; }
+static bool attention_tc_enabled() {
+  if (g_att_tc < 0) {
+    const char *e = getenv("MUMPY_ATT_TC");
+    g_att_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_att_tc == 1;
+}
+
 template <typename T>
 static int window_attention_mma_t(const void *qkv, const float *bias, const float *mask, const float *rel_table, int standard_mask, void *out, int B,
                                   int TH, int W, int C, int heads, int ws, int shift, cudaStream_t st) {
   const long n_tasks = (long)B * (TH / ws) * (W / ws) * heads;
-  MUMPY_REQUIRE((long)B * TH * W < (1l << 31), "window_attention(16-bit): too many tokens");
+  MUMPY_REQUIRE((long)B * TH * W < (1l << 31) && n_tasks < (1l << 31), "window_attention(16-bit): too many tokens");
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -595,6 +609,8 @@ static int window_attention_mma_t(const void *qkv, const float *bias, const floa
   const long want = cdiv(n_tasks, WATT_WARPS);
   const unsigned grid = (unsigned)(want < num_sms ? want : num_sms);
   const bool table_mode = rel_table != nullptr && (mask == nullptr || standard_mask);
+  if (table_mode && (ws == 7 || ws == 8) && heads * 32 == C && attention_tc_enabled())
+    return window_attention_tc(qkv, rel_table, mask != nullptr, out, std::is_same<T, __half>::value ? MUMPY_F16 : MUMPY_BF16, B, TH, W, C, heads, ws, shift, st);
   const int Tn = (2 * ws - 1) * (2 * ws - 1);
   const size_t smem = (size_t)WATT_WARPS * WATT_WARP_BYTES + (table_mode ? (size_t)Tn * heads * sizeof(float) : 0);
   MUMPY_REQUIRE(smem <= 227 * 1024, "window_attention(16-bit): %d heads need %zu B of shared memory", heads, smem);

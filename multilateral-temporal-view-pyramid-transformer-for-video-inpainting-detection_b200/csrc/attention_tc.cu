@@ -1,0 +1,377 @@
+// Swin window attention on tcgen05 (16-bit modes, relative-position table + standard shift mask; swinTransformer.py:117-149,
+// 233-252).  One CTA of 128 threads works on a PAIR of windows and one head at a time: the 2 x 64 (49 or 64 live) query rows
+// fill the 128 lanes of a tensor-memory accumulator, thread r owns query row r from the gather to the store.
+//
+//   S  = Q K^T : two 128x64x32 MMAs (keys of window A -> columns 0-63, keys of window B -> columns 64-127).  Row r only
+//                reads the 64 columns of its own window; the other half is the price of using one 128-row atom.
+//   softmax    : the thread reads its row with tcgen05.ld and walks the keys with compile-time indices, so the
+//                relative-position bias is one shared-memory load at an immediate offset per key (no index arithmetic),
+//                the shift mask one bit test; exp2 with log2e folded into the scale and the table.
+//   O  = P V   : P (16-bit) goes back to shared memory in the K-major 128-byte-swizzled layout the MMA reads (it re-uses
+//                the Q tile, whose padding rows stay zero), V is stored transposed (dims x keys) when it is gathered;
+//                two 128x32x64 MMAs (V of window A -> columns 0-31, of window B -> 32-63), row r reads its window's half.
+//
+// Window partition and the cyclic shift are folded into the gather / scatter row index, as in the mma.sync kernel.
+// 40 KB of tiles + the per-head bias table per CTA and 128 TMEM columns: four CTAs per SM cover each other's latencies.
+#include <cstdio>
+#include <type_traits>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace mumpy {
+
+#ifdef WTC_TIMING
+#define WTC_T(i) ts_[i] = clock64()
+#else
+#define WTC_T(i)
+#endif
+
+constexpr int WTC_THREADS = 128;
+constexpr int WTC_Q_BYTES = 128 * 64;         // query rows of both windows: 128 rows x 64 B (d = 32), 64-byte swizzle
+constexpr int WTC_K_BYTES = 64 * 64;          // keys of one window: 64 rows x 64 B, 64-byte swizzle (K-major B operand)
+constexpr int WTC_V_BYTES = 64 * 64;          // values of one window, same layout (read as an MN-major B operand)
+constexpr int WTC_P_BYTES = 128 * 128;        // probabilities: 128 rows x 64 keys, 128-byte swizzle
+constexpr int WTC_TILE_BYTES = WTC_Q_BYTES + 2 * WTC_K_BYTES + 2 * WTC_V_BYTES + WTC_P_BYTES;
+constexpr int WTC_TMEM_COLS = 128;
+
+__device__ __forceinline__ void wtc_cp_async_16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void wtc_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 64-byte-swizzled operand tile with a 64-byte row pitch (8-row groups 512 B apart).  As a K-major operand (q, k) the 32
+// dims of a row are the K extent (two k-steps 32 B apart); read as an MN-major B operand (v) the rows are the K index (keys)
+// and the 32 dims the N extent: canonical layouts ((8,m),(T,2)):((4T,SBO),(1,T)) and ((T,4,m),(8,k)):((1,T,LBO),(4T,SBO)),
+// T = 8 elements, SBO = 512 B, layout type SWIZZLE_64B = 4.
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
+template <int WS>
+__device__ __forceinline__ int wtc_token_row(int wr, int wc, int p, int TH, int W, int shift) {
+  int r = wr * WS + p / WS + shift;
+  int c = wc * WS + p % WS + shift;
+  if (r >= TH) r -= TH;
+  if (c >= W) c -= W;
+  return r * W + c;
+}
+
+template <typename T, int WS>
+__global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(const T *__restrict__ qkv, const float *__restrict__ rel_table,
+                                                                              T *__restrict__ out, int TH, int W, int C, int heads, int shift,
+                                                                              int mshift, int n_win, int n_tiles, int per_cta) {
+  pdl_grid_sync();
+  constexpr int N = WS * WS;
+  constexpr int TBL = (2 * WS - 1) * (2 * WS - 1);
+  constexpr int OFF = (WS - 1) * 2 * WS;
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr float kC = 0.17677669529663687f * kLog2e;          // 32^-0.5 * log2(e)
+  constexpr bool kF16 = std::is_same<T, __half>::value;
+  extern __shared__ uint8_t wtc_raw[];
+  const uint32_t base = (smem_u32(wtc_raw) + 1023u) & ~1023u;
+  uint8_t *gen = wtc_raw + (base - smem_u32(wtc_raw));
+  const uint32_t sQ = base, sK = sQ + WTC_Q_BYTES, sV = sK + 2 * WTC_K_BYTES, sP = sV + 2 * WTC_V_BYTES;
+  float *tbl_all = reinterpret_cast<float *>(gen + WTC_TILE_BYTES);              // [heads][TBL], times log2(e)
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int half = tid >> 6, p = tid & 63;
+
+  for (int i = tid; i < WTC_TILE_BYTES / 16; i += WTC_THREADS) reinterpret_cast<uint4 *>(gen)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < TBL * heads; i += WTC_THREADS) {
+    const int hh = i / TBL, e = i - hh * TBL;
+    tbl_all[i] = __ldg(rel_table + (long)e * heads + hh) * kLog2e;
+  }
+  const uint32_t bar_s = smem_u32(&bars[0]), bar_o = smem_u32(&bars[1]);
+  if (tid == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(WTC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();          // the zero fill is read by the MMAs
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+  const int wpr = W / WS, wrows = TH / WS;
+  const int nW = wrows * wpr;
+  const int L = TH * W;
+  const uint32_t idesc_s = make_idesc_16_f32(128, 64, kF16);
+  const uint32_t idesc_o = make_idesc_16_f32(128, 32, kF16) | (1u << 16);       // B (= V) is MN-major: dims contiguous per key
+  const uint64_t dQ = make_sw64_desc(sQ), dP = make_kmajor_sw128_desc(sP);
+  auto a_of = [](int t) { return (t / WS) * (2 * WS - 1) + t % WS; };
+  const int pc = min(p, N - 1);
+  const int a_i = a_of(pc) + OFF;
+  const uint32_t sw = static_cast<uint32_t>(tid & 7);
+  const uint32_t p_row = sP + tid * 128;
+
+  // per-tile state of this thread's row: canvas token, liveness, shift-mask bits
+  struct RowState {
+    int pair, h;
+    long row;
+    bool valid, masked;
+    unsigned long long mbits;
+  };
+  auto locate = [&](int pair, int h, RowState &rs) {
+    rs.h = h;
+    if (pair == rs.pair) return;
+    rs.pair = pair;
+    const int win = 2 * pair + half;
+    rs.valid = p < N && win < n_win;
+    const int wclamped = min(win, n_win - 1);
+    const int b = wclamped / nW, n = wclamped - b * nW;
+    const int wr = n / wpr, wc = n - wr * wpr;
+    rs.row = (long)b * L + wtc_token_row<WS>(wr, wc, pc, TH, W, shift);
+    const bool last_r = wr == wrows - 1, last_c = wc == wpr - 1;
+    rs.masked = mshift > 0 && (last_r || last_c);
+    if (rs.masked) {
+      // keys in the same shift region as this query (region = row part x column part of the window, swinTransformer.py:236-247)
+      const unsigned long long r1 = (1ull << (WS * (WS - mshift))) - 1ull;             // keys with jr < WS - mshift
+      unsigned long long c1 = 0;
+      for (int r = 0; r < WS; ++r) c1 |= ((1ull << (WS - mshift)) - 1ull) << (r * WS);  // keys with jc < WS - mshift
+      const bool i_r1 = pc / WS < WS - mshift, i_c1 = pc % WS < WS - mshift;
+      const unsigned long long same_r = last_r ? (i_r1 ? r1 : ~r1) : ~0ull;
+      const unsigned long long same_c = last_c ? (i_c1 ? c1 : ~c1) : ~0ull;
+      rs.mbits = ~(same_r & same_c);
+    }
+  };
+  // Gather: a warp fetches the q / k / v segments of its own 32 rows, four lanes per row (64 contiguous bytes, 8 rows per
+  // instruction) -- the token row of the lane's gather row comes from its owner by shuffle.  Destination rows are 64 B with
+  // 16-byte chunks XOR (row >> 1) & 3: the SWIZZLE_64B pattern for a 64-byte row pitch.
+  const int lane = tid & 31;
+  const uint32_t g_chunk = static_cast<uint32_t>(lane & 3);
+  auto gather = [&](const RowState &rs, int which, uint32_t tile_base) {       // which: 0 q, 1 k, 2 v (element offset which * C)
+    const int enc = rs.valid ? (int)rs.row : -1;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int r_in_warp = pass * 8 + (lane >> 2);
+      const int row = __shfl_sync(0xffffffffu, enc, r_in_warp);
+      if (row >= 0) {
+        const uint32_t r = static_cast<uint32_t>((tid & 32) + r_in_warp);      // row inside the window's 64-row tile
+        const T *src = qkv + (long)row * 3 * C + which * C + rs.h * 32 + g_chunk * 8;
+        wtc_cp_async_16(tile_base + r * 64 + ((g_chunk ^ ((r >> 1) & 3)) << 4), src);
+      }
+    }
+  };
+  auto issue_qk = [&](const RowState &rs) {
+    gather(rs, 0, sQ + half * (64 * 64));
+    gather(rs, 1, sK + half * WTC_K_BYTES);
+  };
+  auto issue_v = [&](const RowState &rs) { gather(rs, 2, sV + half * WTC_V_BYTES); };
+
+  const int t_begin = blockIdx.x * per_cta;
+  const int t_end = min(n_tiles, t_begin + per_cta);
+  RowState cur;
+  cur.pair = -1;
+  cur.valid = cur.masked = false;
+  cur.mbits = 0;
+  cur.row = 0;
+  cur.h = 0;
+  if (t_begin < t_end) {
+    locate(t_begin / heads, t_begin % heads, cur);
+    issue_qk(cur);
+    issue_v(cur);
+  }
+  uint32_t phase = 0;
+#ifdef WTC_TIMING
+  long long ts_[8];
+#endif
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    // Software pipeline: the next tile's q/k gather is issued as soon as S is complete (it lands during the softmax), its v
+    // gather as soon as O is complete (it lands during the next tile's S and softmax).
+    WTC_T(0);
+    const bool has_next = tile + 1 < t_end;
+    RowState nxt = cur;
+    if (has_next) {
+      const bool wrap = cur.h + 1 == heads;            // heads of one window pair are consecutive tiles
+      locate(cur.pair + (wrap ? 1 : 0), wrap ? 0 : cur.h + 1, nxt);
+    }
+    wtc_cp_async_wait_all();
+    fence_proxy_async_smem();
+    __syncthreads();
+    WTC_T(1);
+    // ---- S = Q K^T
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int w2 = 0; w2 < 2; ++w2) {
+        const uint64_t dK = make_sw64_desc(sK + w2 * WTC_K_BYTES);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma_bf16(tmem + w2 * 64, dQ + 2 * k, dK + 2 * k, idesc_s, k);
+      }
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, phase);
+    tc_fence_after();
+    WTC_T(2);
+    if (has_next) issue_qk(nxt);
+    WTC_T(3);
+    // ---- softmax of this thread's row (exp2 domain)
+    uint32_t s_lo[32], s_hi[32];
+    tmem_ld32(t_row + half * 64, s_lo);
+    tmem_ld32(t_row + half * 64 + 32, s_hi);
+    float inv = 0.0f;
+    if (cur.valid) {
+      const float *tb = tbl_all + cur.h * TBL + a_i;
+      float s[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) s[j] = fmaf(__uint_as_float(j < 32 ? s_lo[j & 31] : s_hi[j & 31]), kC, tb[-a_of(j)]);
+      if (cur.masked) {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          if ((cur.mbits >> j) & 1ull) s[j] += -100.0f * kLog2e;
+      }
+      float m = s[0];
+#pragma unroll
+      for (int j = 1; j < N; ++j) m = fmaxf(m, s[j]);
+      float sum = 0.0f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        s[j] = ex2_approx(s[j] - m);
+        sum += s[j];
+      }
+      inv = 1.0f / sum;
+#pragma unroll
+      for (uint32_t c = 0; c * 8 < N; ++c) {            // (chunks past the last key stay zero from the initial fill)
+        uint32_t w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j0 = c * 8 + 2 * e;
+          w4[e] = j0 < N ? pack2<T>(s[j0 < N ? j0 : 0], j0 + 1 < N ? s[j0 + 1 < N ? j0 + 1 : 0] : 0.0f) : 0u;
+        }
+        sts_v4(p_row + ((c ^ sw) << 4), w4[0], w4[1], w4[2], w4[3]);
+      }
+    }
+    WTC_T(4);
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    WTC_T(5);
+    // ---- O = P V
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int w2 = 0; w2 < 2; ++w2) {
+        const uint64_t dV = make_sw64_desc(sV + w2 * WTC_V_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + w2 * 32, dP + 2 * k, dV + (16 * 64 / 16) * k, idesc_o, k);      // 16 keys = 1024 B per k-step
+      }
+      umma_commit(bar_o);
+    }
+    mbar_wait(bar_o, phase);
+    tc_fence_after();
+    WTC_T(6);
+    phase ^= 1;
+    if (has_next) issue_v(nxt);
+    uint32_t o[32];
+    tmem_ld32(t_row + half * 32, o);
+    // The row's 32 outputs go through this warp's (now idle) rows of the P tile so that the global stores use the gather's
+    // mapping: four lanes write the 64 contiguous bytes of one token.
+    if (cur.valid) {
+#pragma unroll
+      for (uint32_t c = 0; c < 4; ++c)
+        sts_v4(p_row + ((c ^ sw) << 4), pack2<T>(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv),
+               pack2<T>(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv),
+               pack2<T>(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv),
+               pack2<T>(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv));
+    }
+    __syncwarp();
+    {
+      const int enc = cur.valid ? (int)cur.row : -1;
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int r_in_warp = pass * 8 + (lane >> 2);
+        const int row = __shfl_sync(0xffffffffu, enc, r_in_warp);
+        if (row >= 0) {
+          const uint32_t r = static_cast<uint32_t>((tid & ~31) + r_in_warp);          // row of the P tile
+          uint4 w;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(sP + r * 128 + ((g_chunk ^ (r & 7)) << 4)));
+          *reinterpret_cast<uint4 *>(out + (long)row * C + cur.h * 32 + g_chunk * 8) = w;
+        }
+      }
+    }
+    __syncwarp();
+    WTC_T(7);
+#ifdef WTC_TIMING
+    if (blockIdx.x == 0 && tid == 0 && tile < t_begin + 4)
+      printf("tile %d: sync1 %lld  S %lld  scatter %lld  softmax %lld  sync2 %lld  PV %lld  store %lld\n", tile, ts_[1] - ts_[0], ts_[2] - ts_[1], ts_[3] - ts_[2], ts_[4] - ts_[3], ts_[5] - ts_[4], ts_[6] - ts_[5], ts_[7] - ts_[6]);
+#endif
+    tc_fence_before();      // (the barrier at the top of the next iteration orders these accumulator reads before the next S)
+    cur = nxt;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(WTC_TMEM_COLS) : "memory");
+  }
+}
+
+template <typename T, int WS>
+static int launch_wtc(const T *qkv, const float *rel_table, T *out, int B, int TH, int W, int C, int heads, int shift, int mshift, cudaStream_t st) {
+  const int nW = (TH / WS) * (W / WS);
+  const long n_win = (long)B * nW;
+  const long n_tiles = ((n_win + 1) / 2) * heads;
+  MUMPY_REQUIRE(n_tiles < (1l << 30) && (long)B * TH * W < (1l << 31), "window_attention(tcgen05): too many tokens");
+  const size_t smem = 1024 + WTC_TILE_BYTES + (size_t)(2 * WS - 1) * (2 * WS - 1) * heads * sizeof(float);
+  static size_t granted = 0;
+  if (smem > granted) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel<T, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("window_attention(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+    granted = smem;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  // resident CTAs per SM: 512 TMEM columns / 128, 64 K registers / (128 threads x 128), 227 KB of shared memory (+1 KB reserved per CTA)
+  const long by_smem = (227 * 1024) / (long)(smem + 1024);
+  const long per_sm = by_smem < 1 ? 1 : (by_smem > 512 / WTC_TMEM_COLS ? 512 / WTC_TMEM_COLS : by_smem);
+  const long slots = (long)num_sms * per_sm;
+  const long per_cta = cdiv(n_tiles, n_tiles < slots ? n_tiles : slots);
+  const unsigned grid = (unsigned)cdiv(n_tiles, per_cta);
+  launch_kernel(window_attention_tc_kernel<T, WS>, grid, WTC_THREADS, smem, st, qkv, rel_table, out, TH, W, C, heads, shift, mshift, (int)n_win,
+                (int)n_tiles, (int)per_cta);
+  return launch_status("window_attention_tc");
+}
+
+// table-mode window attention (relative_position_bias_table + optional standard shift mask) on tcgen05; ws 7 or 8
+int window_attention_tc(const void *qkv, const float *rel_table, int standard_mask, void *out, int dtype, int B, int TH, int W, int C, int heads,
+                        int ws, int shift, cudaStream_t st) {
+  const int mshift = standard_mask ? shift : 0;
+  if (dtype == MUMPY_F16) {
+    if (ws == 7) return launch_wtc<__half, 7>(static_cast<const __half *>(qkv), rel_table, static_cast<__half *>(out), B, TH, W, C, heads, shift, mshift, st);
+    return launch_wtc<__half, 8>(static_cast<const __half *>(qkv), rel_table, static_cast<__half *>(out), B, TH, W, C, heads, shift, mshift, st);
+  }
+  if (ws == 7) return launch_wtc<__nv_bfloat16, 7>(static_cast<const __nv_bfloat16 *>(qkv), rel_table, static_cast<__nv_bfloat16 *>(out), B, TH, W, C, heads, shift, mshift, st);
+  return launch_wtc<__nv_bfloat16, 8>(static_cast<const __nv_bfloat16 *>(qkv), rel_table, static_cast<__nv_bfloat16 *>(out), B, TH, W, C, heads, shift, mshift, st);
+}
+
+}  // namespace mumpy

@@ -377,6 +377,11 @@ def cast_bf16(x):
     return cast16(x, torch.bfloat16)
 
 
+def set_attention_tc(enabled: bool):
+    """16-bit table-mode window attention: True (default) the tcgen05 / TMEM kernel, False the per-warp mma.sync kernel."""
+    _lib.check(_lib.load().mumpy_set_attention_tc(int(bool(enabled))), "mumpy_set_attention_tc")
+
+
 def set_gemm_pair_mode(mode: int):
     """CTA-pair (cta_group::2) policy of the tensor-core GEMM: 0 never (default), 1 cost model, 2 whenever legal."""
     _lib.check(_lib.load().mumpy_set_gemm_pair_mode(int(mode)), "mumpy_set_gemm_pair_mode")

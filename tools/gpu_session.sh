@@ -1,3 +1,5 @@
-cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu32.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu32.log | cut -c1-200
-timeout 600 python bench.py --steps 30 --warmup 3 --no-kernels --no-fp16 > gpurun_out/bench28.json 2> gpurun_out/bench28.err; echo "bench rc=$?"; cut -c1-180 gpurun_out/bench28.json
+set -x
+cd /root/repo
+timeout 300 python tools/att_bench.py 2>&1 | tail -20
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+timeout 600 python bench.py --no-kernels 2>&1 | tail -1 | cut -c1-400
