@@ -198,7 +198,24 @@ def kernel_section(peaks, device):
         out.append({"kernel": "mumpy_faf16 (4 tcgen05 GEMM passes on split bf16 operands + 5 repack kernels, B=64)", "bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3, "dense_tflops_fp32": flops / t / 1e12})
         del x
-        # (iii) Swin stage-0 (view 3) GEMMs at B=64: M = 64*9408, C = 128
+        # (iii) one Swin window-attention stage: stage 0 of view 3 at B=64 (canvas 168 x 56, C = 128, 4 heads, 12288 windows of 49
+        #       tokens), plain and shifted; table-mode bias + region-id shift mask, tcgen05 kernel.  Algorithmic bytes: qkv read + out write.
+        TH, W, C, heads = 168, 56, 128, 4
+        qkv = torch.randn((B, TH * W, 3 * C), device=device).bfloat16()
+        table = (torch.randn((169, heads), device=device) * 0.5).contiguous()
+        coords = torch.stack(torch.meshgrid(torch.arange(7), torch.arange(7), indexing="ij")).flatten(1)
+        rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0) + 6
+        bias = table[(rel[..., 0] * 13 + rel[..., 1]).to(device).view(-1)].view(49, 49, heads).permute(2, 0, 1).contiguous()
+        for shift in (0, 3):
+            mask = torch.zeros((TH // 7) * (W // 7), 49, 49, device=device) if shift else None      # (placeholder: standard_mask recomputes it)
+            t = timed(lambda: ops.window_attention(qkv, bias, mask, B, TH, W, C, heads, 7, shift, rel_table=table, standard_mask=shift > 0))
+            byts = 2 * qkv.numel() + 2 * qkv.numel() // 3
+            flops = 2.0 * 2 * B * (TH // 7) * (W // 7) * heads * 49 * 49 * 32
+            out.append({"kernel": "window_attention_tc_kernel (stage 0 of view 3, B=64, shift %d)" % shift, "bound": "hbm", "achieved": byts / t / 1e9,
+                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3,
+                        "tflops": flops / t / 1e12})
+        del qkv
+        # (iv) Swin stage-0 (view 3) GEMMs at B=64: M = 64*9408, C = 128
         M = B * 9408
         a = torch.randn((M, 128), device=device).bfloat16()
         for name, N, K in (("qkv", 384, 128), ("fc1+GELU", 512, 128), ("fc2", 128, 512)):

@@ -1,18 +1,24 @@
 // Swin window attention on tcgen05 (16-bit modes, relative-position table + standard shift mask; swinTransformer.py:117-149,
 // 233-252).  One CTA of 128 threads works on a PAIR of windows and one head at a time: the 2 x 64 (49 or 64 live) query rows
-// fill the 128 lanes of a tensor-memory accumulator, thread r owns query row r from the gather to the store.
+// fill the 128 lanes of a tensor-memory accumulator, thread r owns query row r from the softmax to the store.
 //
+//   gather     : q, k and v rows (64 B per token and head) come straight from the canvas-ordered qkv matrix with 16-byte
+//                cp.async, four lanes per token; window partition and the cyclic shift are folded into the row index.  All
+//                three tiles use a 64-byte row pitch with the 64-byte swizzle: q and k are K-major operands, v is read as an
+//                MN-major B operand (keys x dims, no transpose anywhere).
 //   S  = Q K^T : two 128x64x32 MMAs (keys of window A -> columns 0-63, keys of window B -> columns 64-127).  Row r only
 //                reads the 64 columns of its own window; the other half is the price of using one 128-row atom.
 //   softmax    : the thread reads its row with tcgen05.ld and walks the keys with compile-time indices, so the
 //                relative-position bias is one shared-memory load at an immediate offset per key (no index arithmetic),
 //                the shift mask one bit test; exp2 with log2e folded into the scale and the table.
-//   O  = P V   : P (16-bit) goes back to shared memory in the K-major 128-byte-swizzled layout the MMA reads (it re-uses
-//                the Q tile, whose padding rows stay zero), V is stored transposed (dims x keys) when it is gathered;
-//                two 128x32x64 MMAs (V of window A -> columns 0-31, of window B -> 32-63), row r reads its window's half.
+//   O  = P V   : P (16-bit pairs) is written back into the thread's own lane of tensor memory (tcgen05.st) and the MMAs take
+//                their A operand from there; two 128x32x64 MMAs (V of window A -> columns 0-31, of window B -> 32-63), row r
+//                reads its window's half, scales by 1/sum and stores through a shared-memory transpose (64 contiguous bytes
+//                per four lanes).
 //
-// Window partition and the cyclic shift are folded into the gather / scatter row index, as in the mma.sync kernel.
-// 40 KB of tiles + the per-head bias table per CTA and 128 TMEM columns: four CTAs per SM cover each other's latencies.
+// Software pipeline per CTA: the next tile's q/k gather is issued when S completes, its v gather when O has been read.
+// 24 KB of tiles + the per-head bias table per CTA, 128 TMEM columns, 128 registers: four CTAs per SM cover each other's
+// MMA round trips and memory latencies.  (-DWTC_TIMING prints per-phase clock64() deltas of CTA 0.)
 #include <cstdio>
 #include <type_traits>
 
@@ -31,8 +37,8 @@ constexpr int WTC_THREADS = 128;
 constexpr int WTC_Q_BYTES = 128 * 64;         // query rows of both windows: 128 rows x 64 B (d = 32), 64-byte swizzle
 constexpr int WTC_K_BYTES = 64 * 64;          // keys of one window: 64 rows x 64 B, 64-byte swizzle (K-major B operand)
 constexpr int WTC_V_BYTES = 64 * 64;          // values of one window, same layout (read as an MN-major B operand)
-constexpr int WTC_P_BYTES = 128 * 128;        // probabilities: 128 rows x 64 keys, 128-byte swizzle
-constexpr int WTC_TILE_BYTES = WTC_Q_BYTES + 2 * WTC_K_BYTES + 2 * WTC_V_BYTES + WTC_P_BYTES;
+constexpr int WTC_TILE_BYTES = WTC_Q_BYTES + 2 * WTC_K_BYTES + 2 * WTC_V_BYTES;
+constexpr int WTC_P_COL = 64;                 // probabilities (16-bit pairs, 32 columns) inside the accumulator allocation
 constexpr int WTC_TMEM_COLS = 128;
 
 __device__ __forceinline__ void wtc_cp_async_16(uint32_t dst, const void *src) {
@@ -42,6 +48,26 @@ __device__ __forceinline__ void wtc_cp_async_wait_all() { asm volatile("cp.async
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+      "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (row i in lane i, 16-bit elements packed two per column) comes from tensor memory
+__device__ __forceinline__ void umma_bf16_tmem_a(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -86,7 +112,7 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
   extern __shared__ uint8_t wtc_raw[];
   const uint32_t base = (smem_u32(wtc_raw) + 1023u) & ~1023u;
   uint8_t *gen = wtc_raw + (base - smem_u32(wtc_raw));
-  const uint32_t sQ = base, sK = sQ + WTC_Q_BYTES, sV = sK + 2 * WTC_K_BYTES, sP = sV + 2 * WTC_V_BYTES;
+  const uint32_t sQ = base, sK = sQ + WTC_Q_BYTES, sV = sK + 2 * WTC_K_BYTES;
   float *tbl_all = reinterpret_cast<float *>(gen + WTC_TILE_BYTES);              // [heads][TBL], times log2(e)
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
@@ -120,12 +146,11 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
   const int L = TH * W;
   const uint32_t idesc_s = make_idesc_16_f32(128, 64, kF16);
   const uint32_t idesc_o = make_idesc_16_f32(128, 32, kF16) | (1u << 16);       // B (= V) is MN-major: dims contiguous per key
-  const uint64_t dQ = make_sw64_desc(sQ), dP = make_kmajor_sw128_desc(sP);
+  const uint64_t dQ = make_sw64_desc(sQ);
   auto a_of = [](int t) { return (t / WS) * (2 * WS - 1) + t % WS; };
   const int pc = min(p, N - 1);
   const int a_i = a_of(pc) + OFF;
-  const uint32_t sw = static_cast<uint32_t>(tid & 7);
-  const uint32_t p_row = sP + tid * 128;
+  const uint32_t o_row = sV + tid * 64, o_sw = static_cast<uint32_t>((tid >> 1) & 3);      // output staging (see the epilogue)
 
   // per-tile state of this thread's row: canvas token, liveness, shift-mask bits
   struct RowState {
@@ -233,6 +258,9 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     tmem_ld32(t_row + half * 64, s_lo);
     tmem_ld32(t_row + half * 64 + 32, s_hi);
     float inv = 0.0f;
+    uint32_t pk[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) pk[e] = 0u;
     if (cur.valid) {
       const float *tb = tbl_all + cur.h * TBL + a_i;
       float s[N];
@@ -254,19 +282,13 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
       }
       inv = 1.0f / sum;
 #pragma unroll
-      for (uint32_t c = 0; c * 8 < N; ++c) {            // (chunks past the last key stay zero from the initial fill)
-        uint32_t w4[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j0 = c * 8 + 2 * e;
-          w4[e] = j0 < N ? pack2<T>(s[j0 < N ? j0 : 0], j0 + 1 < N ? s[j0 + 1 < N ? j0 + 1 : 0] : 0.0f) : 0u;
-        }
-        sts_v4(p_row + ((c ^ sw) << 4), w4[0], w4[1], w4[2], w4[3]);
-      }
+      for (int e = 0; 2 * e < N; ++e) pk[e] = pack2<T>(s[2 * e], 2 * e + 1 < N ? s[2 * e + 1 < N ? 2 * e + 1 : 0] : 0.0f);
     }
+    // P goes into this thread's own lane of tensor memory (columns 64-95, inside the S block the row has finished reading):
+    // the PV MMAs take their A operand from there, so the probabilities never touch shared memory.
+    tmem_st32(t_row + WTC_P_COL, pk);
     WTC_T(4);
     tc_fence_before();
-    fence_proxy_async_smem();
     __syncthreads();
     WTC_T(5);
     // ---- O = P V
@@ -276,7 +298,8 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
       for (int w2 = 0; w2 < 2; ++w2) {
         const uint64_t dV = make_sw64_desc(sV + w2 * WTC_V_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + w2 * 32, dP + 2 * k, dV + (16 * 64 / 16) * k, idesc_o, k);      // 16 keys = 1024 B per k-step
+        for (int k = 0; k < 4; ++k)      // per k-step: 16 keys = 8 packed columns of P, 1024 B of V
+          umma_bf16_tmem_a(tmem + w2 * 32, tmem + WTC_P_COL + 8 * k, dV + (16 * 64 / 16) * k, idesc_o, k);
       }
       umma_commit(bar_o);
     }
@@ -284,15 +307,14 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     tc_fence_after();
     WTC_T(6);
     phase ^= 1;
-    if (has_next) issue_v(nxt);
     uint32_t o[32];
     tmem_ld32(t_row + half * 32, o);
-    // The row's 32 outputs go through this warp's (now idle) rows of the P tile so that the global stores use the gather's
-    // mapping: four lanes write the 64 contiguous bytes of one token.
+    // The row's 32 outputs go through this warp's rows of the V tile (PV is complete, the next v gather not yet issued) so that
+    // the global stores use the gather's mapping: four lanes write the 64 contiguous bytes of one token.
     if (cur.valid) {
 #pragma unroll
       for (uint32_t c = 0; c < 4; ++c)
-        sts_v4(p_row + ((c ^ sw) << 4), pack2<T>(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv),
+        sts_v4(o_row + ((c ^ o_sw) << 4), pack2<T>(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv),
                pack2<T>(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv),
                pack2<T>(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv),
                pack2<T>(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv));
@@ -305,14 +327,15 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
         const int r_in_warp = pass * 8 + (lane >> 2);
         const int row = __shfl_sync(0xffffffffu, enc, r_in_warp);
         if (row >= 0) {
-          const uint32_t r = static_cast<uint32_t>((tid & ~31) + r_in_warp);          // row of the P tile
+          const uint32_t r = static_cast<uint32_t>((tid & ~31) + r_in_warp);
           uint4 w;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(sP + r * 128 + ((g_chunk ^ (r & 7)) << 4)));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(sV + r * 64 + ((g_chunk ^ ((r >> 1) & 3)) << 4)));
           *reinterpret_cast<uint4 *>(out + (long)row * C + cur.h * 32 + g_chunk * 8) = w;
         }
       }
     }
     __syncwarp();
+    if (has_next) issue_v(nxt);       // (same warp, same rows: ordered after the staging reads)
     WTC_T(7);
 #ifdef WTC_TIMING
     if (blockIdx.x == 0 && tid == 0 && tile < t_begin + 4)

@@ -84,15 +84,27 @@ def test_conv_cout1():
     assert util.maxabs(out.view(2, 1, 24, 20), ref) < 1e-5
 
 
-@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("B,T,H,C,heads,shift", [(2, 3, 14, 64, 2, 3), (2, 1, 14, 96, 3, 0), (1, 3, 7, 128, 4, 0), (3, 3, 28, 128, 4, 3)])
-def test_window_attention_tensor_pipe(B, T, H, C, heads, shift, dt):
-    """bf16 qkv -> mma.sync kernel vs the oracle's attention on the same bf16-rounded qkv (P is rounded to bf16
-    before PV inside the kernel: tolerance 1e-2 on O(1) outputs)."""
+@pytest.fixture
+def attention_tc(request):
+    """Table-mode kernel for one test: True = tcgen05 / TMEM (default), False = per-warp mma.sync."""
     ops = _ops()
-    TH, W, ws, N = T * H, H, 7, 49
+    ops.set_attention_tc(request.param)
+    yield request.param
+    ops.set_attention_tc(True)
+
+
+@pytest.mark.parametrize("attention_tc", [True, False], indirect=True)
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,T,H,C,heads,shift,ws", [(2, 3, 14, 64, 2, 3, 7), (2, 1, 14, 96, 3, 0, 7), (1, 3, 7, 128, 4, 0, 7), (3, 3, 28, 128, 4, 3, 7),
+                                                    (1, 1, 7, 32, 1, 0, 7), (2, 3, 16, 64, 2, 4, 8), (1, 1, 8, 96, 3, 0, 8)])
+def test_window_attention_tensor_pipe(B, T, H, C, heads, shift, ws, dt, attention_tc):
+    """16-bit qkv -> tensor-pipe kernels (tcgen05 two-windows-per-accumulator kernel in table mode, mma.sync otherwise) vs the
+    oracle's attention on the same rounded qkv (P is rounded to 16 bits before PV inside the kernels: tolerance 2e-2 on O(1)
+    outputs).  Covers odd window counts (an unpaired last window), one-window inputs, odd head counts and window size 8."""
+    ops = _ops()
+    TH, W, N = T * H, H, ws * ws
     qkv = util.seeded_input((B, TH * W, 3 * C), 1).to(dt)
-    table = 0.5 * util.seeded_input((169, heads), 2)
+    table = 0.5 * util.seeded_input(((2 * ws - 1) ** 2, heads), 2)
     bias = orc.relative_position_bias(table, ws)
     mask = orc.shifted_window_mask(TH, W, ws, shift) if shift else None
     x = qkv.float().view(B, TH, W, 3 * C)
