@@ -198,6 +198,13 @@ def kernel_section(peaks, device):
         out.append({"kernel": "mumpy_faf16 (4 tcgen05 GEMM passes on split bf16 operands + 5 repack kernels, B=64)", "bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3, "dense_tflops_fp32": flops / t / 1e12})
         del x
+        # (ii-b) loader front end: PIL-exact bicubic resize of 64 native-resolution DAVIS frames (480 x 854 RGB uint8) to 224 x 224
+        frames = torch.randint(0, 256, (B, 480, 854, 3), dtype=torch.uint8, device=device)
+        t = timed(lambda: ops.resize_u8(frames, 224, 224, ops.RESIZE_BICUBIC))
+        byts = frames.numel() + B * 224 * 224 * 3
+        out.append({"kernel": "resize_horizontal_kernel + resize_vertical_kernel (bicubic 480x854 -> 224x224, B=64)", "bound": "hbm",
+                    "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3})
+        del frames
         # (iii) one Swin window-attention stage: stage 0 of view 3 at B=64 (canvas 168 x 56, C = 128, 4 heads, 12288 windows of 49
         #       tokens), plain and shifted; table-mode bias + region-id shift mask, tcgen05 kernel.  Algorithmic bytes: qkv read + out write.
         TH, W, C, heads = 168, 56, 128, 4

@@ -187,6 +187,22 @@ int mumpy_channel_group_mean(const float *in, float *out, long pixels, int C, in
 int mumpy_assemble_clips(const unsigned char *frames, const int *clip_frames, float *out, int B, int T, int H, int W,
                          const float *mean3, const float *std3, void *stream);
 
+/* Frame resize of the loader on the device (dataloaders/universaldataset.py:68-79: PIL `img.resize(self.inputRes)`), bit-identical
+ * to Pillow's 8-bit resampler.  filter: MUMPY_RESIZE_BICUBIC (Pillow >= 7 default; two separable passes, 22-bit fixed-point
+ * coefficients, uint8 intermediate) or MUMPY_RESIZE_NEAREST (default of the pillow==4.0.0 pinned by requirements.txt:9).
+ *
+ * mumpy_resize_taps (HOST only, no GPU needed): per-axis tables exactly as Pillow builds them in double precision.
+ *   bicubic: bounds = out_size x [first source index, tap count], coefs = out_size x ksize int32 (22 fractional bits);
+ *            call with coefs = NULL to get *ksize only.   nearest: bounds = out_size source indices, coefs unused, *ksize = 1.
+ * mumpy_resize_u8: in (n,in_h,in_w,C) uint8 -> out (n,out_h,out_w,C) uint8, C <= 4; the tables are DEVICE copies of the above
+ *   (_h for the width axis, _v for the height axis); tmp = n*in_h*out_w*C bytes, needed when both sizes change. */
+#define MUMPY_RESIZE_NEAREST 0
+#define MUMPY_RESIZE_BICUBIC 3
+int mumpy_resize_taps(int in_size, int out_size, int filter, int *bounds, int *coefs, int coef_capacity, int *ksize);
+int mumpy_resize_u8(const unsigned char *in, unsigned char *out, unsigned char *tmp, int n, int in_h, int in_w, int out_h, int out_w,
+                    int channels, int filter, const int *bounds_h, const int *coefs_h, int ksize_h, const int *bounds_v,
+                    const int *coefs_v, int ksize_v, void *stream);
+
 /* a20 + measure.py:77-91: thresholded mask (logit > 0 -> 255) and per-clip integer counts
  * [TP, n_pred, n_gt, n_union] (int64, accumulated with atomics; counts must be zeroed by the caller).
  * logits (B, HW) fp32; gt (B, HW) uint8 (non-zero = positive) or NULL; mask (B, HW) uint8 or NULL. */

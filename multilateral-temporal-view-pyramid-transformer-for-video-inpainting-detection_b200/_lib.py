@@ -47,6 +47,8 @@ SIGNATURES = {
     "mumpy_nhwc_to_nchw": [vp, cl, vp, ci, ci, ci, ci, vp],
     "mumpy_channel_group_mean": [vp, vp, cl, ci, ci, vp],
     "mumpy_assemble_clips": [vp, vp, vp, ci, ci, ci, ci, ctypes.POINTER(cf), ctypes.POINTER(cf), vp],
+    "mumpy_resize_taps": [ci, ci, ci, vp, vp, ci, vp],
+    "mumpy_resize_u8": [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp, vp, ci, vp],
     "mumpy_mask_counts": [vp, vp, vp, vp, ci, ci, vp],
     "mumpy_cast16": [vp, vp, ci, cl, vp],
 }

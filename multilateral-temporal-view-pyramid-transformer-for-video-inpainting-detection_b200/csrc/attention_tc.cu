@@ -271,16 +271,18 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
         for (int j = 0; j < N; ++j)
           if ((cur.mbits >> j) & 1ull) s[j] += -100.0f * kLog2e;
       }
-      float m = s[0];
+      // four interleaved partial maxima / sums: the reductions are dependent chains, and a CTA has one warp per scheduler
+      float m4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-      for (int j = 1; j < N; ++j) m = fmaxf(m, s[j]);
-      float sum = 0.0f;
+      for (int j = 4; j < N; ++j) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         s[j] = ex2_approx(s[j] - m);
-        sum += s[j];
+        sum4[j & 3] += s[j];
       }
-      inv = 1.0f / sum;
+      inv = 1.0f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
 #pragma unroll
       for (int e = 0; 2 * e < N; ++e) pk[e] = pack2<T>(s[2 * e], 2 * e + 1 < N ? s[2 * e + 1 < N ? 2 * e + 1 : 0] : 0.0f);
     }

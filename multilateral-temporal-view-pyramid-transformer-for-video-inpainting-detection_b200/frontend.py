@@ -2,7 +2,9 @@
 the host (universaldataloader.py:45-48: frames idx-1, idx, idx+1 clamped to the sequence), converts it with
 ToTensor + Normalize (test.py:22-25) and uploads 1.8 MB of fp32 per clip.  Consecutive clips share two of their three
 frames, so here every frame is uploaded ONCE as uint8 HWC (150 KB at 224x224) and the clips are assembled and normalised on
-the GPU by mumpy_assemble_clips (bit-identical to the torchvision transform).
+the GPU by mumpy_assemble_clips (bit-identical to the torchvision transform).  Frames may also be handed over at their native
+resolution: ClipAssembler.from_native resizes them on the device with mumpy_resize_u8, bit-identical to the PIL resize of the
+loader.
 """
 import torch
 
@@ -37,6 +39,14 @@ class ClipAssembler:
         self.frames = frames.to(device, non_blocking=True).contiguous()
         self.index = clip_frame_indices(seq_lengths, length_clip).to(device)
         self.mean, self.std = mean, std
+
+    @classmethod
+    def from_native(cls, frames, seq_lengths, device, size=224, resample=ops.RESIZE_BICUBIC, chunk=64, **kw):
+        """frames at their native resolution ((n, H0, W0, 3) uint8, e.g. 480 x 854 DAVIS frames): uploaded as they are and resized
+        to size x size on the device exactly as the loader's `img.resize(self.inputRes)` does on the host
+        (universaldataset.py:68-79; `resample` = PIL filter code: bicubic is Pillow >= 7's default, nearest pillow 4.0.0's)."""
+        small = [ops.resize_u8(frames[i:i + chunk].to(device, non_blocking=True), size, size, resample) for i in range(0, frames.shape[0], chunk)]
+        return cls(torch.cat(small, 0), seq_lengths, device, **kw)
 
     def __len__(self):
         return self.index.shape[0]

@@ -351,6 +351,52 @@ def assemble_clips(frames, clip_frames, mean, std, out=None):
     return out
 
 
+RESIZE_NEAREST, RESIZE_BICUBIC = 0, 3          # PIL's filter codes
+_taps_cache = {}
+
+
+def resize_taps(in_size, out_size, filter=RESIZE_BICUBIC):
+    """Per-axis resampling tables exactly as Pillow builds them (host computation inside the library, no GPU needed).
+    bicubic -> (bounds int32 (out,2) = [first source index, taps], coefs int32 (out,ksize), ksize); nearest -> (index int32 (out,), None, 1)."""
+    lib = _lib.load()
+    ks = ctypes.c_int(0)
+    if filter == RESIZE_NEAREST:
+        idx = torch.empty(out_size, dtype=torch.int32)
+        _lib.check(lib.mumpy_resize_taps(int(in_size), int(out_size), int(filter), idx.data_ptr(), None, 0, ctypes.addressof(ks)), "mumpy_resize_taps")
+        return idx, None, 1
+    bounds = torch.empty((out_size, 2), dtype=torch.int32)
+    _lib.check(lib.mumpy_resize_taps(int(in_size), int(out_size), int(filter), bounds.data_ptr(), None, 0, ctypes.addressof(ks)), "mumpy_resize_taps")
+    coefs = torch.empty((out_size, ks.value), dtype=torch.int32)
+    _lib.check(lib.mumpy_resize_taps(int(in_size), int(out_size), int(filter), bounds.data_ptr(), coefs.data_ptr(), coefs.numel(),
+                                     ctypes.addressof(ks)), "mumpy_resize_taps")
+    return bounds, coefs, ks.value
+
+
+def _device_taps(in_size, out_size, filter, device):
+    key = (in_size, out_size, filter, str(device))
+    if key not in _taps_cache:
+        b, c, k = resize_taps(in_size, out_size, filter)
+        _taps_cache[key] = (b.to(device), None if c is None else c.to(device), k)
+    return _taps_cache[key]
+
+
+def resize_u8(frames, out_h, out_w, filter=RESIZE_BICUBIC):
+    """frames (n,H,W,C) uint8 on the device -> (n,out_h,out_w,C) uint8, bit-identical to PIL.Image.resize((out_w,out_h), filter)
+    of every frame (universaldataset.py:68-79)."""
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] > 4 or not frames.is_cuda:
+        raise _lib.MumpyError("resize_u8: frames must be a (n,H,W,C<=4) uint8 CUDA tensor")
+    frames = frames.contiguous()
+    n, H, W, C = frames.shape
+    out = torch.empty((n, out_h, out_w, C), dtype=torch.uint8, device=frames.device)
+    bh, ch, kh = _device_taps(W, out_w, filter, frames.device)
+    bv, cv, kv = _device_taps(H, out_h, filter, frames.device)
+    tmp = torch.empty((n, H, out_w, C), dtype=torch.uint8, device=frames.device) if (filter != RESIZE_NEAREST and H != out_h and W != out_w) else None
+    lib, st = _prep(frames, out)
+    _lib.check(lib.mumpy_resize_u8(_p(frames), _p(out), _p(tmp), n, H, W, out_h, out_w, C, int(filter), _p(bh), _p(ch), kh, _p(bv), _p(cv), kv, st),
+               "mumpy_resize_u8")
+    return out
+
+
 def mask_counts(logits, gt=None, want_mask=True):
     """logits (B,1,H,W) fp32 -> (mask uint8 (B,H,W) in {0,255}, counts int64 (B,4) = [TP, n_pred, n_gt, n_union])."""
     B = logits.shape[0]
