@@ -151,10 +151,13 @@ int mumpy_conv2d_nhwc(const float *in, long ld_in, const float *w, const float *
 /* tensor-core implicit-GEMM convolution ('same', stride 1): in (B,H,W,Cin) bf16 NHWC with pixel stride ld_in (a channel
  * slice of a wider map is allowed); w_packed (Cout, kh*kw*ceil(Cin/64)*64) bf16, K order (ky,kx,c), each tap's channels
  * zero padded to a multiple of 64; out (B*H*W, Cout) fp32|bf16 = act(conv + bias) (+ residual).  The A tiles are
- * fetched by an im2col-mode TMA tensor map (padding = zero fill), no im2col buffer is materialised. */
+ * fetched by an im2col-mode TMA tensor map (padding = zero fill), no im2col buffer is materialised.
+ * splitk_ws (optional, caller-owned, 16-byte aligned, splitk_ws_bytes long): when the map is small and the reduction long
+ * (gcm1: 32 x 7 x 7 pixels, K = 7 * 2560) the k-blocks are split over otherwise idle SMs -- as many ranges as fit the
+ * workspace at B*H*W*Cout*4 bytes each -- and summed by a second kernel that applies bias / act / residual. */
 int mumpy_conv2d_nhwc_bf16(const void *in, long ld_in, const void *w_packed, const float *bias, const float *residual,
                            void *out, long ld_out, int B, int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw,
-                           int in_dtype, int out_dtype, int act, void *stream);
+                           int in_dtype, int out_dtype, int act, float *splitk_ws, long splitk_ws_bytes, void *stream);
 /* Cout == 1 convolution (final_out 3x3, decoder.py:95): in (B,H,W,Cin) fp32 contiguous, w (kh,kw,Cin), out (B,H,W). */
 int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const float *bias, float *out, int B, int H, int W, int Cin,
                             int kh, int kw, int ph, int pw, void *stream);

@@ -36,7 +36,7 @@ SIGNATURES = {
     "mumpy_cva_residual": [vp, vp, vp, ci, ci, ci, ci, ci, vp],
     "mumpy_gather_rows": [vp, ci, vp, ci, cl, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_conv2d_nhwc": [vp, cl, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
-    "mumpy_conv2d_nhwc_bf16": [vp, cl, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_conv2d_nhwc_bf16": [vp, cl, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, cl, vp],
     "mumpy_conv2d_nhwc_cout1": [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_im2col_nhwc": [vp, cl, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_groupnorm_nhwc": [vp, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, cf, ci, vp],

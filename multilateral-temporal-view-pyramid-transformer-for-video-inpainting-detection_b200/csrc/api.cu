@@ -44,7 +44,8 @@ int linear_bf16(const void *A, long lda, const void *W, const float *bias, const
                 long M, int N, int K, int ab_dtype, int out_dtype, int act, cudaStream_t st);
 
 int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, const float *residual, void *out, long ldo, int B,
-              int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int in_dtype, int out_dtype, int act, cudaStream_t st);
+              int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int in_dtype, int out_dtype, int act, float *splitk_ws,
+              long splitk_ws_bytes, cudaStream_t st);
 
 template <typename T>
 __global__ void cast16_kernel(const float *__restrict__ in, T *__restrict__ out, long n) {
@@ -136,10 +137,10 @@ extern "C" int mumpy_linear_dual(const void *A, long lda, const void *W, const f
 
 extern "C" int mumpy_conv2d_nhwc_bf16(const void *in, long ld_in, const void *w_packed, const float *bias, const float *residual,
                                       void *out, long ld_out, int B, int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw,
-                                      int in_dtype, int out_dtype, int act, void *stream) {
+                                      int in_dtype, int out_dtype, int act, float *splitk_ws, long splitk_ws_bytes, void *stream) {
   MUMPY_REQUIRE(in && w_packed && out && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && is_16bit(in_dtype), "conv2d_nhwc_bf16: bad arguments");
-  return conv_bf16(in, ld_in, w_packed, bias, residual, out, ld_out, B, H, W, Cin, Cout, kh, kw, ph, pw, in_dtype, out_dtype, act,
-                   as_stream(stream));
+  return conv_bf16(in, ld_in, w_packed, bias, residual, out, ld_out, B, H, W, Cin, Cout, kh, kw, ph, pw, in_dtype, out_dtype, act, splitk_ws,
+                   splitk_ws_bytes, as_stream(stream));
 }
 
 extern "C" int mumpy_cast16(const float *in, void *out, int out_dtype, long n, void *stream) {

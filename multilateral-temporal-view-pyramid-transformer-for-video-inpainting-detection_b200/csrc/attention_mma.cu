@@ -609,7 +609,8 @@ static int window_attention_mma_t(const void *qkv, const float *bias, const floa
   const long want = cdiv(n_tasks, WATT_WARPS);
   const unsigned grid = (unsigned)(want < num_sms ? want : num_sms);
   const bool table_mode = rel_table != nullptr && (mask == nullptr || standard_mask);
-  if (table_mode && (ws == 7 || ws == 8) && heads * 32 == C && attention_tc_enabled())
+  // tcgen05 kernel unless the per-CTA copy of the bias table gets large (>= 32 heads: few windows, the staging dominates)
+  if (table_mode && (ws == 7 || ws == 8) && heads * 32 == C && (2 * ws - 1) * (2 * ws - 1) * heads * 4 <= 16 * 1024 && attention_tc_enabled())
     return window_attention_tc(qkv, rel_table, mask != nullptr, out, std::is_same<T, __half>::value ? MUMPY_F16 : MUMPY_BF16, B, TH, W, C, heads, ws, shift, st);
   const int Tn = (2 * ws - 1) * (2 * ws - 1);
   const size_t smem = (size_t)WATT_WARPS * WATT_WARP_BYTES + (table_mode ? (size_t)Tn * heads * sizeof(float) : 0);

@@ -80,6 +80,9 @@ struct TcParams {
   uint32_t idesc;
   // conv mode (A through the im2col tensor map)
   int debug;
+  // split-K: a tile index also selects one of k_splits ranges of k-blocks; partial sums go to out + split * split_stride
+  int k_splits;
+  long split_stride;
   int conv;
   int Wout, Hout, lower_w, lower_h, kw, cblocks;
 };
@@ -92,7 +95,7 @@ constexpr int EPI_STAGE_BYTES = 32 * 128;      // per-warp staging tile: 32 rows
 // (bf16) row segment: residual loads, fp32->bf16 packing and the output stores are all coalesced.
 template <int ACT, bool OUT_BF16, bool HAS_RES>
 __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage, const float *bias_s, uint32_t acc, int warp, int lane, long m0,
-                                              int n0) {
+                                              int n0, long out_shift) {
   const int quad = warp & 3, half = warp >> 2;
   const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
   const long row0 = m0 + quad * 32;
@@ -177,7 +180,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
               u.x = pack2<__nv_bfloat16>(x.x, x.y); u.y = pack2<__nv_bfloat16>(x.z, x.w);
               u.z = pack2<__nv_bfloat16>(y.x, y.y); u.w = pack2<__nv_bfloat16>(y.z, y.w);
             }
-            *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.out) + gm * p.ldo + n0 + col) = u;
+            *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.out) + out_shift + gm * p.ldo + n0 + col) = u;
           }
         }
       } else {
@@ -208,7 +211,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
               const float4 r0 = res[i];
               x.x += r0.x; x.y += r0.y; x.z += r0.z; x.w += r0.w;
             }
-            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + gm * p.ldo + n0 + col) = x;
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + out_shift + gm * p.ldo + n0 + col) = x;
           }
         }
       }
@@ -283,7 +286,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     if (lane == 0) {
       uint32_t it = 0;
       const uint32_t full_leader = kPair ? mapa_shared(full0, 0) : full0;      // shared::cluster address on rank 0
-      for (long tile = group; tile < p.num_tiles; tile += n_groups) {
+      for (long tile_s = group; tile_s < p.num_tiles; tile_s += n_groups) {
+        const long tile = tile_s / p.k_splits;
+        const int ks = static_cast<int>(tile_s - tile * p.k_splits);
+        const int kb0 = static_cast<int>((long)ks * nkb / p.k_splits), kb1 = static_cast<int>((long)(ks + 1) * nkb / p.k_splits);
         const int n0 = static_cast<int>(tile % p.tiles_n) * p.BN + static_cast<int>(rank * b_rows);
         const long m0 = (tile / p.tiles_n) * (kPair ? 2 * TC_BM : TC_BM) + rank * TC_BM;
         int cw = 0, ch = 0, cn = 0;
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           ch = static_cast<int>(r % p.Hout) + p.lower_h;
           cn = static_cast<int>(r / p.Hout);
         }
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -326,12 +332,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     // ------------------------------------------------ MMA issuer --------------------------------------------------
     if (lane == 0 && rank == 0) {
       uint32_t it = 0, t = 0;
-      for (long tile = group; tile < p.num_tiles; tile += n_groups, ++t) {
+      for (long tile_s = group; tile_s < p.num_tiles; tile_s += n_groups, ++t) {
+        const int ks = static_cast<int>(tile_s % p.k_splits);
+        const int kb0 = static_cast<int>((long)ks * nkb / p.k_splits), kb1 = static_cast<int>((long)(ks + 1) * nkb / p.k_splits);
         const uint32_t slot = t & 1, aph = (t >> 1) & 1;
         mbar_wait(acc_empty0 + 8 * slot, aph ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + slot * p.acc_cols;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(full0 + 8 * s, ph);
@@ -342,8 +350,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr>>4) field
-            if (kPair) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (kPair) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (kPair) umma_commit_pair(empty0 + 8 * s); else umma_commit(empty0 + 8 * s);      // frees the smem slot(s) once these MMAs have read them
         }
@@ -357,7 +365,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int mode = (p.act == MUMPY_ACT_GELU ? 1 : (p.act == MUMPY_ACT_NONE ? 0 : 2)) | (p.out_bf16 ? 4 : 0) | (p.residual ? 8 : 0);
     uint32_t t = 0;
     const uint32_t acc_empty_leader = kPair ? mapa_shared(acc_empty0, 0) : acc_empty0;
-    for (long tile = group; tile < p.num_tiles; tile += n_groups, ++t) {
+    for (long tile_s = group; tile_s < p.num_tiles; tile_s += n_groups, ++t) {
+      const long tile = tile_s / p.k_splits;
+      const long out_shift = (tile_s - tile * p.k_splits) * p.split_stride;
       const uint32_t slot = t & 1, aph = (t >> 1) & 1;
       const int n0 = static_cast<int>(tile % p.tiles_n) * p.BN;
       const long m0 = (tile / p.tiles_n) * (kPair ? 2 * TC_BM : TC_BM) + rank * TC_BM;
@@ -382,18 +392,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc_fence_after();
       const uint32_t acc = tmem_base + slot * p.acc_cols;
       switch (mode) {
-        case 0: epilogue_tile<0, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        case 1: epilogue_tile<1, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        case 2: epilogue_tile<2, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        case 4: epilogue_tile<0, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        case 5: epilogue_tile<1, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        case 6: epilogue_tile<2, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        case 8: epilogue_tile<0, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        case 9: epilogue_tile<1, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        case 10: epilogue_tile<2, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        case 12: epilogue_tile<0, true, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        case 13: epilogue_tile<1, true, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
-        default: epilogue_tile<2, true, true>(p, stage, bias_s, acc, warp, lane, m0, n0); break;
+        case 0: epilogue_tile<0, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        case 1: epilogue_tile<1, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        case 2: epilogue_tile<2, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        case 4: epilogue_tile<0, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        case 5: epilogue_tile<1, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        case 6: epilogue_tile<2, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        case 8: epilogue_tile<0, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        case 9: epilogue_tile<1, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        case 10: epilogue_tile<2, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        case 12: epilogue_tile<0, true, true>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        case 13: epilogue_tile<1, true, true>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        default: epilogue_tile<2, true, true>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
       }
       // this warp is done reading the accumulator: hand the TMEM slot back to the MMA issuer
       tc_fence_before();
@@ -531,7 +541,8 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   const int bm = pair ? 2 * TC_BM : TC_BM;
   p.idesc = make_idesc_16_f32(bm, p.BN, p.f16 != 0);
   p.tiles_n = (int)cdiv(p.N, p.BN);
-  p.num_tiles = cdiv(p.M, bm) * p.tiles_n;
+  if (p.k_splits < 1) p.k_splits = 1;
+  p.num_tiles = cdiv(p.M, bm) * p.tiles_n * p.k_splits;
   if (g_dbg_stages < 0) {
     g_dbg_stages = env_int("MUMPY_TC_STAGES");
     g_dbg_mode = env_int("MUMPY_TC_DEBUG");
@@ -543,7 +554,7 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   int stages = TC_SMEM_BUDGET / stage_bytes;
   if (g_dbg_stages > 0 && g_dbg_stages < stages) stages = g_dbg_stages;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  const long kb_per_cta = nkb * cdiv(p.num_tiles, slots);
+  const long kb_per_cta = (nkb / p.k_splits) * cdiv(p.num_tiles, slots);
   if (stages > kb_per_cta) stages = (int)kb_per_cta;
   if (stages < 1) stages = 1;
   p.stages = stages;
@@ -610,10 +621,55 @@ int linear_bf16(const void *A, long lda, const void *W, const float *bias, const
   return launch_tc(tmA, tmB, p, tc.pair, st);
 }
 
+// Second half of a split-K GEMM: out = act(sum_s partial[s] + bias) (+ residual), four columns per thread.  The partial
+// sums (k_splits x M x N fp32, written by gemm_tc_kernel's plain epilogue) are still in L2 when this runs.
+template <typename OutT>
+__global__ void splitk_reduce_kernel(const float *__restrict__ partial, int S, long stride, const float *__restrict__ bias,
+                                     const float *__restrict__ residual, OutT *__restrict__ out, long ldo, long M, int N, int act) {
+  pdl_grid_sync();
+  const int n4 = N >> 2;
+  const long total = M * n4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long m = i / n4;
+    const int c = (int)(i - m * n4) << 2;
+    float4 a = *reinterpret_cast<const float4 *>(partial + m * N + c);
+    for (int s = 1; s < S; ++s) {
+      const float4 b = *reinterpret_cast<const float4 *>(partial + s * stride + m * N + c);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (act == MUMPY_ACT_GELU) {
+      const float2 lo = gelu_fast2(make_float2(a.x, a.y)), hi = gelu_fast2(make_float2(a.z, a.w));
+      a = make_float4(lo.x, lo.y, hi.x, hi.y);
+    } else if (act != MUMPY_ACT_NONE) {
+      a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
+    }
+    if (residual) {
+      const float4 r = *reinterpret_cast<const float4 *>(residual + m * ldo + c);
+      a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+    }
+    if constexpr (sizeof(OutT) == 4) {
+      *reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + m * ldo + c) = a;
+    } else {
+      uint2 u;
+      u.x = pack2<OutT>(a.x, a.y);
+      u.y = pack2<OutT>(a.z, a.w);
+      *reinterpret_cast<uint2 *>(out + m * ldo + c) = u;
+    }
+  }
+}
+
 // Implicit-GEMM convolution (stride 1): in (B,H,W,Cin) bf16 NHWC with pixel stride ld_in elements; wpk (Cout, taps*cblocks*64)
 // bf16 with K order (ky,kx,c) and every tap's channels zero padded to a multiple of 64; out (B*H*W, Cout).
+// splitk_ws / splitk_ws_bytes: optional caller-owned fp32 workspace; when the tile grid would leave most SMs idle (small
+// maps with a long reduction, e.g. 32 x 7 x 7 pixels and K = 7 * 2560) the reduction is split across CTAs and reduced by a
+// second kernel.
 int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, const float *residual, void *out, long ldo, int B,
-              int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int in_dtype, int out_dtype, int act, cudaStream_t st) {
+              int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int in_dtype, int out_dtype, int act, float *splitk_ws,
+              long splitk_ws_bytes, cudaStream_t st) {
   int rc = resolve_driver_entry_points();
   if (rc) return rc;
   MUMPY_REQUIRE(Cout % 8 == 0 && ld_in % 8 == 0, "conv(bf16): Cout and ld_in must be multiples of 8");
@@ -630,11 +686,34 @@ int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, co
   p.M = (long)B * H * W;
   p.N = Cout;
   p.K = kh * kw * cblocks;          // k-blocks
-  const TileChoice tc = pick_tile(p.M, Cout, p.K, residual != nullptr, act == MUMPY_ACT_GELU);
+  TileChoice tc = pick_tile(p.M, Cout, p.K, residual != nullptr, act == MUMPY_ACT_GELU);
   p.BN = tc.bn;
   p.act = act;
   p.out_bf16 = (out_dtype != MUMPY_F32);
   p.f16 = in_dtype == MUMPY_F16;
+  int splits = 1;
+  if (splitk_ws && (reinterpret_cast<uintptr_t>(splitk_ws) & 15) == 0 && Cout % 4 == 0) {
+    // widest tile (the A tile is fetched once per k-block), then as many k ranges as there are idle SMs, >= 8 k-blocks each
+    const int bn = Cout <= 256 && Cout % 16 == 0 ? Cout : tc.bn;
+    const long tiles = cdiv(p.M, TC_BM) * cdiv(Cout, bn);
+    long s = g_num_sms / tiles;
+    if (s > p.K / 8) s = p.K / 8;
+    if (s > splitk_ws_bytes / (long)(p.M * Cout * sizeof(float))) s = splitk_ws_bytes / (long)(p.M * Cout * sizeof(float));
+    if (s >= 2) {
+      splits = (int)s;
+      tc.bn = bn;
+      tc.pair = false;
+      p.BN = bn;
+      p.bias = nullptr;
+      p.residual = nullptr;
+      p.act = MUMPY_ACT_NONE;
+      p.out = splitk_ws;
+      p.out_bf16 = 0;
+      p.ldo = Cout;
+      p.k_splits = splits;
+      p.split_stride = p.M * Cout;
+    }
+  }
   p.conv = 1;
   p.Wout = W;
   p.Hout = H;
@@ -660,7 +739,17 @@ int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, co
   if (g_driver_version <= 13010 && (size_t)B * H * W * ld_in * 2 < 131072) reinterpret_cast<uint64_t *>(&tmA)[1] &= ~(1ull << 21);
   rc = encode_2d_bf16(&tmB, wpk, p.f16 != 0, (uint64_t)p.K * TC_BK, (uint64_t)Cout, (uint64_t)p.K * TC_BK, TC_BK, (uint32_t)(tc.pair ? p.BN / 2 : p.BN));
   if (rc) return rc;
-  return launch_tc(tmA, tmB, p, tc.pair, st);
+  rc = launch_tc(tmA, tmB, p, tc.pair, st);
+  if (rc || splits == 1) return rc;
+  const long total = p.M * (Cout / 4);
+  const unsigned grid = (unsigned)(cdiv(total, 256) < 148l * 8 ? cdiv(total, 256) : 148l * 8);
+  if (out_dtype == MUMPY_F32)
+    launch_kernel(splitk_reduce_kernel<float>, grid, 256, 0, st, splitk_ws, splits, p.split_stride, bias, residual, static_cast<float *>(out), ldo, p.M, Cout, act);
+  else if (out_dtype == MUMPY_F16)
+    launch_kernel(splitk_reduce_kernel<__half>, grid, 256, 0, st, splitk_ws, splits, p.split_stride, bias, residual, static_cast<__half *>(out), ldo, p.M, Cout, act);
+  else
+    launch_kernel(splitk_reduce_kernel<__nv_bfloat16>, grid, 256, 0, st, splitk_ws, splits, p.split_stride, bias, residual, static_cast<__nv_bfloat16 *>(out), ldo, p.M, Cout, act);
+  return launch_status("splitk_reduce_kernel");
 }
 
 }  // namespace mumpy

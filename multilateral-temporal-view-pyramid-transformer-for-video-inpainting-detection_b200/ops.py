@@ -4,6 +4,7 @@ PyTorch is used here for device memory and the current stream only; every comput
 kernel.  All tensors must live on a CUDA device and be contiguous -- anything else raises (no fallback).
 """
 import ctypes
+import os
 
 import torch
 
@@ -240,15 +241,26 @@ def conv2d_nhwc(x, w_ohwi, bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in=None,
     return out
 
 
+CONV_SPLIT_K = os.environ.get("MUMPY_CONV_SPLITK", "1") != "0"      # split-K for small-map / long-reduction convolutions
+
+
 def conv2d_nhwc_bf16(x, w_packed, bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_in=None, act=ACT_NONE, out_dtype=torch.float32,
-                     residual=None):
+                     residual=None, split_k=None):
     """Tensor-core implicit GEMM: x (B,H,W,Cin[ld_in]) NHWC and w_packed (Cout, kh*kw*ceil(Cin/64)*64) of one 16-bit type."""
     if x.dtype != w_packed.dtype:
         raise _lib.MumpyError("conv2d_nhwc_bf16: activation %s vs filter %s" % (x.dtype, w_packed.dtype))
     out = torch.empty((B, H, W, Cout), dtype=out_dtype, device=x.device)
+    # split-K workspace for small maps with a long reduction (few 128-row tiles, >= 32 k-blocks): one fp32 partial per k range
+    ws = None
+    m_tiles, kblocks = (B * H * W + 127) // 128, kh * kw * ((Cin + 63) // 64)
+    if split_k is None:
+        split_k = CONV_SPLIT_K
+    if split_k and m_tiles * 2 <= 148 and kblocks >= 32 and Cout % 16 == 0 and Cout <= 256:
+        ws = torch.empty((min(148 // m_tiles, kblocks // 8), B * H * W, Cout), dtype=torch.float32, device=x.device)
     lib, st = _prep(x, w_packed, bias, residual, out)
     _lib.check(lib.mumpy_conv2d_nhwc_bf16(_p(x), ld_in or Cin, _p(w_packed), _p(bias), _p(residual), _p(out), Cout, B, H, W, Cin,
-                                          Cout, kh, kw, ph, pw, code(x.dtype), code(out_dtype), act, st), "mumpy_conv2d_nhwc_bf16")
+                                          Cout, kh, kw, ph, pw, code(x.dtype), code(out_dtype), act, _p(ws),
+                                          0 if ws is None else ws.numel() * 4, st), "mumpy_conv2d_nhwc_bf16")
     return out
 
 

@@ -13,12 +13,12 @@ def _ops():
     return mumpy_b200.ops
 
 
-def _pack_conv(w, Cin):
+def _pack_conv(w, Cin, dt=torch.bfloat16):
     Cout, _, kh, kw = w.shape
     cb = (Cin + 63) // 64
     wp = torch.zeros(Cout, kh * kw, cb * 64)
     wp[:, :, :Cin] = w.permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin)
-    return wp.reshape(Cout, -1).bfloat16().contiguous()
+    return wp.reshape(Cout, -1).to(dt).contiguous()
 
 
 @pytest.fixture
@@ -49,6 +49,28 @@ def test_conv_implicit_gemm_tcgen05(B, H, W, Cin, Cout, kh, kw, pair_mode):
     xn = x.permute(0, 2, 3, 1).contiguous().cuda()
     out = ops.conv2d_nhwc_bf16(xn, _pack_conv(w.float(), Cin).cuda(), bias.cuda(), B, H, W, Cin, Cout, kh, kw, (kh - 1) // 2, (kw - 1) // 2)
     assert util.maxabs(out, ref) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kh,kw", [(4, 7, 7, 2560, 128, 1, 7), (32, 7, 7, 640, 128, 7, 1), (2, 14, 14, 512, 256, 3, 3)])
+def test_conv_split_k_matches_single_pass(B, H, W, Cin, Cout, kh, kw, dt):
+    """Small maps with a long reduction run split-K (partials in a caller-owned workspace + a reduce kernel that applies bias /
+    residual / output rounding): same result as the one-pass kernel up to fp32 summation order, and vs the oracle."""
+    ops = _ops()
+    x = util.seeded_input((B, Cin, H, W), 1).to(dt)
+    w = (util.seeded_input((Cout, Cin, kh, kw), 2) / (Cin * kh * kw) ** 0.5).to(dt)
+    bias, res = util.seeded_input((Cout,), 3), util.seeded_input((B, H, W, Cout), 4)
+    ref = orc.conv2d(x.float(), w.float(), bias, ((kh - 1) // 2, (kw - 1) // 2)).permute(0, 2, 3, 1) + res
+    xn, wp = x.permute(0, 2, 3, 1).contiguous().cuda(), _pack_conv(w.float(), Cin, dt).cuda()
+    args = (xn, wp, bias.cuda(), B, H, W, Cin, Cout, kh, kw, (kh - 1) // 2, (kw - 1) // 2)
+    one = ops.conv2d_nhwc_bf16(*args, residual=res.cuda(), split_k=False)
+    two = ops.conv2d_nhwc_bf16(*args, residual=res.cuda(), split_k=True)
+    scale = max(1.0, float(ref.abs().max()))
+    assert util.maxabs(two, ref) < 2e-4 * scale
+    assert util.maxabs(two, one) < 1e-4 * scale          # fp32 summation order over K = 17920
+    lo1 = ops.conv2d_nhwc_bf16(*args, out_dtype=dt, split_k=False)
+    lo2 = ops.conv2d_nhwc_bf16(*args, out_dtype=dt, split_k=True)
+    assert lo2.dtype == dt and util.maxabs(lo2.float(), lo1.float()) <= (2 ** -7 if dt == torch.bfloat16 else 2 ** -10) * scale
 
 
 def test_conv_reads_channel_slice_of_wider_map():
