@@ -257,6 +257,9 @@ def conv2d_nhwc_bf16(x, w_packed, bias, B, H, W, Cin, Cout, kh, kw, ph, pw, ld_i
         split_k = CONV_SPLIT_K
     if split_k and m_tiles * 2 <= 148 and kblocks >= 32 and Cout % 16 == 0 and Cout <= 256:
         ws = torch.empty((min(148 // m_tiles, kblocks // 8), B * H * W, Cout), dtype=torch.float32, device=x.device)
+        if ws.shape[0] >= 2:
+            global launch_count
+            launch_count += 1        # + the reduce kernel
     lib, st = _prep(x, w_packed, bias, residual, out)
     _lib.check(lib.mumpy_conv2d_nhwc_bf16(_p(x), ld_in or Cin, _p(w_packed), _p(bias), _p(residual), _p(out), Cout, B, H, W, Cin,
                                           Cout, kh, kw, ph, pw, code(x.dtype), code(out_dtype), act, _p(ws),
@@ -403,6 +406,9 @@ def resize_u8(frames, out_h, out_w, filter=RESIZE_BICUBIC):
     bh, ch, kh = _device_taps(W, out_w, filter, frames.device)
     bv, cv, kv = _device_taps(H, out_h, filter, frames.device)
     tmp = torch.empty((n, H, out_w, C), dtype=torch.uint8, device=frames.device) if (filter != RESIZE_NEAREST and H != out_h and W != out_w) else None
+    if tmp is not None:
+        global launch_count
+        launch_count += 1            # horizontal + vertical pass
     lib, st = _prep(frames, out)
     _lib.check(lib.mumpy_resize_u8(_p(frames), _p(out), _p(tmp), n, H, W, out_h, out_w, C, int(filter), _p(bh), _p(ch), kh, _p(bv), _p(cv), kv, st),
                "mumpy_resize_u8")

@@ -1,3 +1,3 @@
 set -x
 cd /root/repo
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -15
