@@ -22,6 +22,10 @@ import os
 import torch
 
 N_LANES = 4
+# CUDA stream priority per lane (lower = scheduled first; stream capture records it on the graph's kernel nodes).  Measured on
+# B200 at batch 32: ANY unequal assignment is slower than equal priorities -- view 3's lane (60 % of the encoder's work) high:
+# 1995 -> 1873 clips/s; the light lanes high instead: 1987 -> 1856 -- so the default is equal; MUMPY_LANE_PRIO overrides.
+LANE_PRIORITY = [int(v) for v in os.environ.get("MUMPY_LANE_PRIO", "0,0,0,0").split(",")]
 _lanes = {}            # device index -> [torch.cuda.Stream]
 _active = {}           # device index -> Region
 enabled = os.environ.get("MUMPY_STREAMS", "1") != "0"      # MUMPY_STREAMS=0: one serial chain (A/B measurements)
@@ -42,7 +46,7 @@ class Region:
         if self.parallel:
             idx = device.index if device.index is not None else torch.cuda.current_device()
             if idx not in _lanes:
-                _lanes[idx] = [torch.cuda.Stream(device=idx) for _ in range(N_LANES)]
+                _lanes[idx] = [torch.cuda.Stream(device=idx, priority=LANE_PRIORITY[i]) for i in range(N_LANES)]
             self.lanes = _lanes[idx]
             self.main = torch.cuda.current_stream(idx)
             for s in self.lanes:
