@@ -79,10 +79,10 @@ struct TcParams {
   uint32_t acc_cols;      // TMEM columns per accumulator slot (power of two >= BN)
   uint32_t idesc;
   // conv mode (A through the im2col tensor map)
-  int debug;
-  // split-K: a tile index also selects one of k_splits ranges of k-blocks; partial sums go to out + split * split_stride
-  int k_splits;
-  long split_stride;
+  // (the struct is kept at its size: ptxas places part of a larger parameter block on the stack and the epilogue spills)
+  short debug;
+  short k_splits;         // split-K (kSplit kernels): a tile index also selects one of k_splits ranges of k-blocks; the partial
+                          // sums of range s go to out + s * M * N (fp32, ldo = N)
   int conv;
   int Wout, Hout, lower_w, lower_h, kw, cblocks;
 };
@@ -224,7 +224,9 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
 // A rows [128 r, 128 r + 128) and B rows [BN/2 r, BN/2 r + BN/2) of the tile, the leader (rank 0) issues the M=256 MMAs,
 // each CTA's TMEM receives its own 128 accumulator rows.  Per CTA and k-block that is (128 + BN/2) x 128 B from L2
 // instead of (128 + BN) x 128 B -- the main loop of the 1-CTA kernel is bound by exactly that path (42.5 B/clk/SM).
-template <bool kConv, bool kPair>
+// kSplit: split-K instantiation (conv only): kept apart so that the plain kernels carry none of its index arithmetic (the
+// epilogue warps are at the register limit: one more live 64-bit value spills)
+template <bool kConv, bool kPair, bool kSplit = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -287,9 +289,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       uint32_t it = 0;
       const uint32_t full_leader = kPair ? mapa_shared(full0, 0) : full0;      // shared::cluster address on rank 0
       for (long tile_s = group; tile_s < p.num_tiles; tile_s += n_groups) {
-        const long tile = tile_s / p.k_splits;
-        const int ks = static_cast<int>(tile_s - tile * p.k_splits);
-        const int kb0 = static_cast<int>((long)ks * nkb / p.k_splits), kb1 = static_cast<int>((long)(ks + 1) * nkb / p.k_splits);
+        const long tile = kSplit ? tile_s / p.k_splits : tile_s;
+        const int ks = kSplit ? static_cast<int>(tile_s - tile * p.k_splits) : 0;
+        const int kb0 = kSplit ? static_cast<int>((long)ks * nkb / p.k_splits) : 0;
+        const int kb1 = kSplit ? static_cast<int>((long)(ks + 1) * nkb / p.k_splits) : nkb;
         const int n0 = static_cast<int>(tile % p.tiles_n) * p.BN + static_cast<int>(rank * b_rows);
         const long m0 = (tile / p.tiles_n) * (kPair ? 2 * TC_BM : TC_BM) + rank * TC_BM;
         int cw = 0, ch = 0, cn = 0;
@@ -333,8 +336,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     if (lane == 0 && rank == 0) {
       uint32_t it = 0, t = 0;
       for (long tile_s = group; tile_s < p.num_tiles; tile_s += n_groups, ++t) {
-        const int ks = static_cast<int>(tile_s % p.k_splits);
-        const int kb0 = static_cast<int>((long)ks * nkb / p.k_splits), kb1 = static_cast<int>((long)(ks + 1) * nkb / p.k_splits);
+        const int ks = kSplit ? static_cast<int>(tile_s % p.k_splits) : 0;
+        const int kb0 = kSplit ? static_cast<int>((long)ks * nkb / p.k_splits) : 0;
+        const int kb1 = kSplit ? static_cast<int>((long)(ks + 1) * nkb / p.k_splits) : nkb;
         const uint32_t slot = t & 1, aph = (t >> 1) & 1;
         mbar_wait(acc_empty0 + 8 * slot, aph ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
@@ -366,8 +370,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     uint32_t t = 0;
     const uint32_t acc_empty_leader = kPair ? mapa_shared(acc_empty0, 0) : acc_empty0;
     for (long tile_s = group; tile_s < p.num_tiles; tile_s += n_groups, ++t) {
-      const long tile = tile_s / p.k_splits;
-      const long out_shift = (tile_s - tile * p.k_splits) * p.split_stride;
+      const long tile = kSplit ? tile_s / p.k_splits : tile_s;
+      const long out_shift = kSplit ? (tile_s - tile * p.k_splits) * (p.M * p.N) : 0;
       const uint32_t slot = t & 1, aph = (t >> 1) & 1;
       const int n0 = static_cast<int>(tile % p.tiles_n) * p.BN;
       const long m0 = (tile / p.tiles_n) * (kPair ? 2 * TC_BM : TC_BM) + rank * TC_BM;
@@ -532,7 +536,7 @@ static void launch_pair_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-static bool g_attr_set[4] = {false, false, false, false};
+static bool g_attr_set[5] = {false, false, false, false, false};
 
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p, bool pair, cudaStream_t st) {
   uint32_t cols = 32;
@@ -547,7 +551,7 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
     g_dbg_stages = env_int("MUMPY_TC_STAGES");
     g_dbg_mode = env_int("MUMPY_TC_DEBUG");
   }
-  p.debug = g_dbg_mode;
+  p.debug = (short)g_dbg_mode;
   const int stage_bytes = TC_BM * 128 + (pair ? p.BN / 2 : p.BN) * 128;
   const int nkb = p.conv ? p.K : (p.K + TC_BK - 1) / TC_BK;
   const long slots = pair ? g_num_sms / 2 : g_num_sms;
@@ -559,7 +563,7 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   if (stages < 1) stages = 1;
   p.stages = stages;
   const int smem = stages * stage_bytes + 1024 + TC_EPI_WARPS * (32 * 128 + 512);
-  const int which = (p.conv ? 1 : 0) + (pair ? 2 : 0);
+  const int which = p.k_splits > 1 ? 4 : (p.conv ? 1 : 0) + (pair ? 2 : 0);      // split-K: conv, single-CTA tiles only
   if (!g_attr_set[which]) {
     const int max_smem = TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * (32 * 128 + 512);
     cudaError_t e;
@@ -567,7 +571,8 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
       case 0: e = cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
       case 1: e = cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
       case 2: e = cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
-      default: e = cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+      case 3: e = cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+      default: e = cudaFuncSetAttribute(gemm_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
     }
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
@@ -580,7 +585,8 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
     case 0: launch_kernel(gemm_tc_kernel<false, false>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
     case 1: launch_kernel(gemm_tc_kernel<true, false>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
     case 2: launch_pair_kernel(gemm_tc_kernel<false, true>, 2 * groups, TC_THREADS, smem, st, tmA, tmB, p); break;
-    default: launch_pair_kernel(gemm_tc_kernel<true, true>, 2 * groups, TC_THREADS, smem, st, tmA, tmB, p); break;
+    case 3: launch_pair_kernel(gemm_tc_kernel<true, true>, 2 * groups, TC_THREADS, smem, st, tmA, tmB, p); break;
+    default: launch_kernel(gemm_tc_kernel<true, false, true>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
   }
   return launch_status("gemm_tc_kernel");
 }
@@ -710,8 +716,7 @@ int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, co
       p.out = splitk_ws;
       p.out_bf16 = 0;
       p.ldo = Cout;
-      p.k_splits = splits;
-      p.split_stride = p.M * Cout;
+      p.k_splits = (short)splits;
     }
   }
   p.conv = 1;
@@ -744,11 +749,11 @@ int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, co
   const long total = p.M * (Cout / 4);
   const unsigned grid = (unsigned)(cdiv(total, 256) < 148l * 8 ? cdiv(total, 256) : 148l * 8);
   if (out_dtype == MUMPY_F32)
-    launch_kernel(splitk_reduce_kernel<float>, grid, 256, 0, st, splitk_ws, splits, p.split_stride, bias, residual, static_cast<float *>(out), ldo, p.M, Cout, act);
+    launch_kernel(splitk_reduce_kernel<float>, grid, 256, 0, st, splitk_ws, splits, p.M * Cout, bias, residual, static_cast<float *>(out), ldo, p.M, Cout, act);
   else if (out_dtype == MUMPY_F16)
-    launch_kernel(splitk_reduce_kernel<__half>, grid, 256, 0, st, splitk_ws, splits, p.split_stride, bias, residual, static_cast<__half *>(out), ldo, p.M, Cout, act);
+    launch_kernel(splitk_reduce_kernel<__half>, grid, 256, 0, st, splitk_ws, splits, p.M * Cout, bias, residual, static_cast<__half *>(out), ldo, p.M, Cout, act);
   else
-    launch_kernel(splitk_reduce_kernel<__nv_bfloat16>, grid, 256, 0, st, splitk_ws, splits, p.split_stride, bias, residual, static_cast<__nv_bfloat16 *>(out), ldo, p.M, Cout, act);
+    launch_kernel(splitk_reduce_kernel<__nv_bfloat16>, grid, 256, 0, st, splitk_ws, splits, p.M * Cout, bias, residual, static_cast<__nv_bfloat16 *>(out), ldo, p.M, Cout, act);
   return launch_status("splitk_reduce_kernel");
 }
 
