@@ -295,19 +295,28 @@ def timed_serial_step(enc, dec, x, gt):
     was = streams.enabled
     streams.set_enabled(False)
     orig = {n: getattr(ops, n) for n in OPS_TIMED}
+    best = None
     try:
-        one_step()                               # un-instrumented pass: the eager allocator pool holds every block afterwards
+        for _ in range(2):                       # un-instrumented passes: the eager allocator pool holds every block afterwards
+            one_step()
         torch.cuda.synchronize()
         for n in OPS_TIMED:
             setattr(ops, n, wrap(n, orig[n]))
-        torch.cuda._sleep(int(0.2 * 1.9e9))
-        one_step()
-        torch.cuda.synchronize()
+        # A host hiccup longer than the park (allocator growth, a slow first call) leaks launch latency into the intervals and
+        # can only inflate them: take the attempt with the smallest total.
+        for attempt in range(3):
+            del recs[:]
+            torch.cuda._sleep(int(0.3 * 1.9e9))
+            one_step()
+            torch.cuda.synchronize()
+            cur = [(n, shp, fl, e0.elapsed_time(e1) * 1e-3) for n, shp, fl, e0, e1 in recs]
+            if best is None or sum(r[3] for r in cur) < sum(r[3] for r in best):
+                best = cur
     finally:
         for n in OPS_TIMED:
             setattr(ops, n, orig[n])
         streams.set_enabled(was)
-    return [(n, shp, fl, e0.elapsed_time(e1) * 1e-3) for n, shp, fl, e0, e1 in recs]
+    return best
 
 
 def gemm_kernel_live(enc, dec, x, gt, peaks):
