@@ -202,7 +202,7 @@ def kernel_section(peaks, device):
         frames = torch.randint(0, 256, (B, 480, 854, 3), dtype=torch.uint8, device=device)
         t = timed(lambda: ops.resize_u8(frames, 224, 224, ops.RESIZE_BICUBIC))
         byts = frames.numel() + B * 224 * 224 * 3
-        out.append({"kernel": "resize_horizontal_kernel + resize_vertical_kernel (bicubic 480x854 -> 224x224, B=64)", "bound": "hbm",
+        out.append({"kernel": "resize_horizontal_rows_kernel + resize_vertical_kernel (bicubic 480x854 -> 224x224, B=64)", "bound": "hbm",
                     "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3})
         del frames
         # (iii) one Swin window-attention stage: stage 0 of view 3 at B=64 (canvas 168 x 56, C = 128, 4 heads, 12288 windows of 49

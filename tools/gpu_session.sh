@@ -1,4 +1,4 @@
 set -x
 cd /root/repo
-timeout 600 python bench.py --no-kernels --no-fp16 --steps 10 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('nofp16', d['value'], d['roofline']['share_of_kernel_time'], d['roofline']['serial_kernel_time_ms'], d['roofline']['achieved'])"
-timeout 600 python bench.py --no-kernels --steps 10 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('withfp16', d['value'], d['roofline']['share_of_kernel_time'], d['roofline']['serial_kernel_time_ms'], d['roofline']['achieved'])"
+timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench_final.json; cut -c1-200 gpurun_out/bench_final.json
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_frontend.py tests/test_gpu_kernels.py -x -q -m gpu -k "resize or window_attention or split_k or native" 2>&1 | tail -12
