@@ -1,7 +1,10 @@
 // Deformable cross-view attention (SwinDAttention, deformableAttention.py:324-405): offset network, bilinear
 // sampling of the key/value windows and the raw-reshape residual.  All three are HBM/L2-bound gathers on the
 // token canvases; the k/v/out projections run through mumpy_linear and the softmax core is in attention.cu.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace mumpy {
 
@@ -19,7 +22,7 @@ template <int MAXC>   // channels per lane = Cg/32 <= MAXC
 __global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restrict__ q, const float *__restrict__ dw_w,
                                                           const float *__restrict__ dw_b, const float *__restrict__ ln_g,
                                                           const float *__restrict__ ln_b, const float *__restrict__ pw,
-                                                          float *__restrict__ pix, int TH1, int W, int C, int groups, int ws) {
+                                                          float *__restrict__ pix, int N1, int TH1, int W, int C, int groups, int ws) {
   pdl_grid_sync();
   // [(ws+4)^2][Cg] query window with a zero border of 2 pixels (the depthwise conv's padding: no bounds tests in the tap loop),
   // then [25][Cg] depthwise taps (tap-major: conflict-free per lane), then [P][2] raw offsets
@@ -29,21 +32,13 @@ __global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restric
   const int wp = ws + 4;
   float *wsm = tile + wp * wp * Cg;
   float *off = wsm + 25 * Cg;
-  const int win = blockIdx.x, g = blockIdx.y;
+  // Persistent over the windows of one group (blockIdx.y): the taps, the per-lane channel constants and the zero border of
+  // the tile are set up once per CTA -- with a CTA per (window, group) that set-up cost more than the 49 x Cg x 25 FMAs.
+  const int g = blockIdx.y;
   const int nW1 = (TH1 / ws) * (W / ws);
-  const int b = win / nW1, n = win % nW1;
   const long L1 = (long)TH1 * W;
   const int cg4 = Cg >> 2;
-  for (int e = threadIdx.x; e < wp * wp * cg4; e += blockDim.x) {
-    const int pp = e / cg4, c4 = e - pp * cg4;
-    const int yy = pp / wp - 2, xx = pp % wp - 2;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (yy >= 0 && yy < ws && xx >= 0 && xx < ws) {
-      const long row = b * L1 + window_token_row(n, yy * ws + xx, TH1, W, ws, 0);
-      v = __ldg(reinterpret_cast<const float4 *>(q + row * C + g * Cg) + c4);
-    }
-    reinterpret_cast<float4 *>(tile)[e] = v;
-  }
+  for (int e = threadIdx.x; e < wp * wp * cg4; e += blockDim.x) reinterpret_cast<float4 *>(tile)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int e = threadIdx.x; e < 25 * Cg; e += blockDim.x) {
     const int c = e / 25, tap = e - c * 25;
     wsm[tap * Cg + c] = __ldg(dw_w + e);
@@ -68,6 +63,15 @@ __global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restric
       for (int t = 0; t < 25; ++t) wreg[u][t] = ok ? wsm[t * Cg + c] : 0.0f;
     }
   }
+  for (int win = blockIdx.x; win < N1; win += gridDim.x) {
+  const int b = win / nW1, n = win % nW1;
+  __syncthreads();                       // the previous window's readers are done with the tile and the offsets
+  for (int e = threadIdx.x; e < P * cg4; e += blockDim.x) {      // interior pixels only: the border stays zero
+    const int pp = e / cg4, c4 = e - pp * cg4;
+    const long row = b * L1 + window_token_row(n, pp, TH1, W, ws, 0);
+    reinterpret_cast<float4 *>(tile)[((pp / ws + 2) * wp + pp % ws + 2) * cg4 + c4] = __ldg(reinterpret_cast<const float4 *>(q + row * C + g * Cg) + c4);
+  }
+  __syncthreads();
   for (int p = warp; p < P; p += nwarps) {
     const int pi = p / ws, pj = p % ws;
     float val[MAXC];
@@ -126,6 +130,104 @@ __global__ void __launch_bounds__(256) cva_offsets_kernel(const float *__restric
     float *o = pix + (((long)win * groups + g) * P + p) * 2;
     o[0] = ((pos_y + 1.0f) / 2.0f) * (ws - 1);
     o[1] = ((pos_x + 1.0f) / 2.0f) * (ws - 1);
+  }
+  }
+}
+
+// Register-resident variant (the one that runs for window sizes 7 and 8): a WARP per (window, group), persistent.
+//   phase A, lane = channel: the channel's WS x WS window lives in registers, the depthwise 5x5 is fully unrolled with the
+//            out-of-window taps dropped at compile time (841 of 1225 FMAs for WS = 7, no shared-memory reads, no address
+//            arithmetic); conv outputs go to a [pixel][channel] tile in shared memory;
+//   phase B, lane = pixel: LayerNorm over the channels, GELU, the 1x1 (Cg -> 2), tanh and the pixel-coordinate map -- no
+//            shuffles, two rounds for 49 pixels.
+// Against the CTA-per-unit kernel above (a warp per pixel: 25 LDS + 25 FMA + ~50 integer instructions + 20 shuffles per
+// pixel) this is ~4x fewer instructions; the op sits on the critical path at the start of every stage.
+template <int WS>
+__global__ void __launch_bounds__(128, 2) cva_offsets_reg_kernel(const float *__restrict__ q, const float *__restrict__ dw_w,
+                                                              const float *__restrict__ dw_b, const float *__restrict__ ln_g,
+                                                              const float *__restrict__ ln_b, const float *__restrict__ pw,
+                                                              float *__restrict__ pix, int N1, int TH1, int W, int C, int groups) {
+  pdl_grid_sync();
+  constexpr int P = WS * WS;
+  extern __shared__ float cr_smem[];
+  const int Cg = C / groups;
+  const int pitch = Cg + 1;                              // [pixel][channel] tile, odd pitch: conflict-free in both phases
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *prm = cr_smem;                                  // [4][Cg]: LayerNorm gamma, beta, 1x1 weights (y, x)
+  float *tile = cr_smem + 4 * Cg + warp * (P * pitch);
+  for (int i = threadIdx.x; i < Cg; i += blockDim.x) {
+    prm[i] = __ldg(ln_g + i);
+    prm[Cg + i] = __ldg(ln_b + i);
+    prm[2 * Cg + i] = __ldg(pw + i);
+    prm[3 * Cg + i] = __ldg(pw + Cg + i);
+  }
+  __syncthreads();
+  const int wpr = W / WS;
+  const int nW1 = (TH1 / WS) * wpr;
+  const long L1 = (long)TH1 * W;
+  const long n_units = (long)N1 * groups;
+  for (long unit = (long)blockIdx.x * 4 + warp; unit < n_units; unit += (long)gridDim.x * 4) {
+    const int win = (int)(unit / groups), g = (int)(unit - (long)win * groups);
+    const int b = win / nW1, n = win - b * nW1;
+    const int wr = n / wpr, wc = n - wr * wpr;
+    const float *qbase = q + (b * L1 + (long)(wr * WS) * W + wc * WS) * C + g * Cg;
+    // ---- phase A
+    for (int cc = 0; cc < Cg; cc += 32) {
+      const int c = cc + lane;
+      if (c < Cg) {
+        float in[P], w[25];
+#pragma unroll
+        for (int t = 0; t < 25; ++t) w[t] = __ldg(dw_w + c * 25 + t);
+#pragma unroll
+        for (int p = 0; p < P; ++p) in[p] = __ldg(qbase + ((long)(p / WS) * W + p % WS) * C + c);
+        const float bias = __ldg(dw_b + c);
+#pragma unroll
+        for (int pi = 0; pi < WS; ++pi)
+#pragma unroll
+          for (int pj = 0; pj < WS; ++pj) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+#pragma unroll
+              for (int bb = 0; bb < 5; ++bb) {
+                const int y = pi + a - 2, x = pj + bb - 2;
+                if (y >= 0 && y < WS && x >= 0 && x < WS) acc = fmaf(in[y * WS + x], w[a * 5 + bb], acc);
+              }
+            tile[(pi * WS + pj) * pitch + c] = acc + bias;
+          }
+      }
+    }
+    __syncwarp();
+    // ---- phase B
+    for (int p = lane; p < P; p += 32) {
+      const float *v = tile + p * pitch;
+      float s = 0.0f;
+      for (int c = 0; c < Cg; ++c) s += v[c];
+      const float mean = s / Cg;
+      float var = 0.0f;
+      for (int c = 0; c < Cg; ++c) {
+        const float d = v[c] - mean;
+        var = fmaf(d, d, var);
+      }
+      const float rstd = 1.0f / sqrtf(var / Cg + 1e-5f);
+      float oy = 0.0f, ox = 0.0f;
+      for (int c = 0; c < Cg; c += 2) {              // (Cg is a multiple of 4) two channels per step on the packed-fp32 GELU:
+        // |error| <= 5.5e-7 against the erf form (tc_common.cuh), far below what the sampling positions can resolve
+        const float2 a = gelu_fast2(make_float2((v[c] - mean) * rstd * prm[c] + prm[Cg + c], (v[c + 1] - mean) * rstd * prm[c + 1] + prm[Cg + c + 1]));
+        oy = fmaf(a.y, prm[2 * Cg + c + 1], fmaf(a.x, prm[2 * Cg + c], oy));
+        ox = fmaf(a.y, prm[3 * Cg + c + 1], fmaf(a.x, prm[3 * Cg + c], ox));
+      }
+      const int pi = p / WS, pj = p % WS;
+      const float inv = 1.0f / (float)WS;
+      const float ref_y = ((pi + 0.5f) / WS) * 2.0f - 1.0f;
+      const float ref_x = ((pj + 0.5f) / WS) * 2.0f - 1.0f;
+      const float pos_y = tanhf(oy) * inv * 2.0f + ref_y;
+      const float pos_x = tanhf(ox) * inv * 2.0f + ref_x;
+      float *o = pix + (unit * P + p) * 2;
+      o[0] = ((pos_y + 1.0f) / 2.0f) * (WS - 1);
+      o[1] = ((pos_x + 1.0f) / 2.0f) * (WS - 1);
+    }
+    __syncwarp();
   }
 }
 
@@ -249,8 +351,11 @@ static int launch_cva_offsets(const float *q, const float *dw_w, const float *dw
     }
     granted = smem;
   }
-  dim3 grid((unsigned)N1, (unsigned)groups);
-  launch_kernel(cva_offsets_kernel<MAXC>, grid, 256, smem, st, q, dw_w, dw_b, ln_g, ln_b, pw, pix, TH1, W, C, groups, ws);
+  // resident CTAs: 8 x 256 threads per SM, shared memory permitting
+  const long per_sm = (220 * 1024) / (long)(smem + 1024) < 8 ? ((220 * 1024) / (long)(smem + 1024) < 1 ? 1 : (220 * 1024) / (long)(smem + 1024)) : 8;
+  const long want = cdiv(148 * per_sm, groups);
+  dim3 grid((unsigned)(N1 < want ? N1 : want), (unsigned)groups);
+  launch_kernel(cva_offsets_kernel<MAXC>, grid, 256, smem, st, q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups, ws);
   return launch_status("cva_offsets");
 }
 
@@ -261,8 +366,37 @@ extern "C" int mumpy_cva_offsets(const float *q, const float *dw_w, const float 
   const int Cg = C / groups;
   MUMPY_REQUIRE(Cg <= 256 && Cg % 4 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0, "cva_offsets: group width %d unsupported (<= 256, multiple of 4)", Cg);
   const int N1 = B * (TH1 / ws) * (W / ws);
-  const size_t smem = ((size_t)((ws + 4) * (ws + 4) + 25) * Cg + 2 * ws * ws) * sizeof(float);
   cudaStream_t st = as_stream(stream);
+  static int use_reg = -1;                 // MUMPY_CVA_REG=0 forces the CTA-per-unit kernel (A/B measurements)
+  if (use_reg < 0) {
+    const char *e = getenv("MUMPY_CVA_REG");
+    use_reg = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_reg && (ws == 7 || ws == 8)) {
+    const size_t rsmem = ((size_t)4 * Cg + 4 * (size_t)ws * ws * (Cg + 1)) * sizeof(float);
+    if (rsmem <= 200 * 1024) {
+      cudaError_t e = cudaSuccess;
+      static size_t granted7 = 0, granted8 = 0;
+      size_t &granted = ws == 7 ? granted7 : granted8;
+      if (rsmem > 48 * 1024 && rsmem > granted) {
+        e = ws == 7 ? cudaFuncSetAttribute(cva_offsets_reg_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem)
+                    : cudaFuncSetAttribute(cva_offsets_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+        if (e != cudaSuccess) {
+          set_error("cva_offsets: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+          return MUMPY_ERR_CUDA;
+        }
+        granted = rsmem;
+      }
+      const long units = (long)N1 * groups;
+      long per_sm = (220 * 1024) / (long)(rsmem + 1024);
+      per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);             // 2 CTAs x 4 warps: ~250 registers per thread (window, taps, interleaved accumulators)
+      const long ctas = cdiv(units, 4) < 148 * per_sm ? cdiv(units, 4) : 148 * per_sm;
+      if (ws == 7) launch_kernel(cva_offsets_reg_kernel<7>, (unsigned)ctas, 128, rsmem, st, q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups);
+      else launch_kernel(cva_offsets_reg_kernel<8>, (unsigned)ctas, 128, rsmem, st, q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups);
+      return launch_status("cva_offsets");
+    }
+  }
+  const size_t smem = ((size_t)((ws + 4) * (ws + 4) + 25) * Cg + 2 * ws * ws) * sizeof(float);
   if (Cg <= 32) return launch_cva_offsets<1>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups, ws, smem, st);
   if (Cg <= 64) return launch_cva_offsets<2>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups, ws, smem, st);
   if (Cg <= 128) return launch_cva_offsets<4>(q, dw_w, dw_b, ln_g, ln_b, pw, pix, N1, TH1, W, C, groups, ws, smem, st);
