@@ -102,7 +102,6 @@ template <typename T, int WS>
 __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(const T *__restrict__ qkv, const float *__restrict__ rel_table,
                                                                               T *__restrict__ out, int TH, int W, int C, int heads, int shift,
                                                                               int mshift, int n_win, int n_tiles, int per_cta) {
-  pdl_grid_sync();
   constexpr int N = WS * WS;
   constexpr int TBL = (2 * WS - 1) * (2 * WS - 1);
   constexpr int OFF = (WS - 1) * 2 * WS;
@@ -206,6 +205,9 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
   };
   auto issue_v = [&](const RowState &rs) { gather(rs, 2, sV + half * WTC_V_BYTES); };
 
+  // Everything above touches only shared / tensor memory and the (constant) bias table: under programmatic dependent launch it
+  // overlaps the tail of the kernel that produces qkv; the first read of qkv comes after this wait.
+  pdl_grid_sync();
   const int t_begin = blockIdx.x * per_cta;
   const int t_end = min(n_tiles, t_begin + per_cta);
   RowState cur;

@@ -147,7 +147,6 @@ __global__ void __launch_bounds__(128, 2) cva_offsets_reg_kernel(const float *__
                                                               const float *__restrict__ dw_b, const float *__restrict__ ln_g,
                                                               const float *__restrict__ ln_b, const float *__restrict__ pw,
                                                               float *__restrict__ pix, int N1, int TH1, int W, int C, int groups) {
-  pdl_grid_sync();
   constexpr int P = WS * WS;
   extern __shared__ float cr_smem[];
   const int Cg = C / groups;
@@ -161,6 +160,7 @@ __global__ void __launch_bounds__(128, 2) cva_offsets_reg_kernel(const float *__
     prm[2 * Cg + i] = __ldg(pw + i);
     prm[3 * Cg + i] = __ldg(pw + Cg + i);
   }
+  pdl_grid_sync();                                       // (the parameters above are constants: staged while the producer of q drains)
   __syncthreads();
   const int wpr = W / WS;
   const int nW1 = (TH1 / WS) * wpr;

@@ -1,3 +1,4 @@
 cd /root/repo
-echo REG; timeout 120 python tools/cva_one.py 2>&1 | tail -4
-timeout 900 python -m pytest tests/test_gpu_modules.py tests/test_gpu_e2e.py -x -q -m gpu 2>&1 | tail -3
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+timeout 600 python bench.py --no-kernels --no-fp16 2>&1 | tail -1 | cut -c1-140
+timeout 600 python bench.py --no-kernels --no-fp16 2>&1 | tail -1 | cut -c1-140
