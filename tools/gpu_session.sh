@@ -1,6 +1,7 @@
 set -x
 cd /root/repo
-timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench_final.json; cut -c1-200 gpurun_out/bench_final.json
-timeout 600 python bench.py --size 512 --batch 8 --no-kernels --no-fp16 --steps 10 2>&1 | tail -1 > gpurun_out/bench_512.json; cut -c1-200 gpurun_out/bench_512.json
-timeout 600 python tools/op_breakdown.py 32 > gpurun_out/op_breakdown.txt 2>&1; head -3 gpurun_out/op_breakdown.txt
-timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py 32 > gpurun_out/ncu_launch.log 2>&1; tail -2 gpurun_out/ncu_launch.log
+timeout 600 python bench.py --no-kernels --no-fp16 --steps 20 2>&1 | tail -1 > gpurun_out/scale_n1.json
+for n in 2 4 8; do
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 3 --no-kernels --no-fp16 2>&1 | tail -1 > gpurun_out/scale_n$n.json
+done
+for n in 1 2 4 8; do cut -c1-160 gpurun_out/scale_n$n.json; done
