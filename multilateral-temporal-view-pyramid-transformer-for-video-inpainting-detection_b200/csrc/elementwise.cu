@@ -349,6 +349,69 @@ __global__ void __launch_bounds__(256) conv_cout1_vec_kernel(const float *__rest
   if (live && sub == 0) out[m] = acc + (bias ? bias[0] : 0.0f);
 }
 
+// Cout == 1, 3x3 'same': LPP lanes per pixel column, every thread produces COUT1_ROWS vertically adjacent outputs from one
+// pass over the COUT1_ROWS + 2 input rows of its column (three float4 loads per row, each reused by up to three outputs; the
+// nine weight float4 of its channel quad live in registers) -- half the loads and ~2.5x fewer instructions per output than
+// one thread per (pixel, quad).  Four neighbouring columns per LPP = 8 warp: 512 contiguous bytes per load instruction.
+constexpr int COUT1_ROWS = 4;
+template <int LPP>
+__global__ void __launch_bounds__(256) conv_cout1_rows_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
+                                                              float *__restrict__ out, long units, int H, int W) {
+  pdl_grid_sync();
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long u = gid / LPP;                      // unit = (image, row tile, column)
+  const int sub = (int)(gid % LPP);
+  const bool live = u < units;
+  const long uu = live ? u : 0;
+  const int x = (int)(uu % W);
+  const long r = uu / W;
+  const int tiles = (H + COUT1_ROWS - 1) / COUT1_ROWS;
+  const int y0 = (int)(r % tiles) * COUT1_ROWS;
+  const long b = r / tiles;
+  const float4 *in4 = reinterpret_cast<const float4 *>(in);
+  float4 wt[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wt[t] = __ldg(reinterpret_cast<const float4 *>(w) + t * LPP + sub);
+  float acc[COUT1_ROWS];
+#pragma unroll
+  for (int i = 0; i < COUT1_ROWS; ++i) acc[i] = 0.0f;
+#pragma unroll
+  for (int ry = 0; ry < COUT1_ROWS + 2; ++ry) {
+    const int yy = y0 + ry - 1;
+    if (yy < 0 || yy >= H) continue;
+    const float4 *row = in4 + ((b * H + yy) * W) * LPP + sub;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v[3];
+    v[0] = x > 0 ? __ldg(row + (long)(x - 1) * LPP) : zero;
+    v[1] = __ldg(row + (long)x * LPP);
+    v[2] = x + 1 < W ? __ldg(row + (long)(x + 1) * LPP) : zero;
+#pragma unroll
+    for (int i = 0; i < COUT1_ROWS; ++i) {
+      const int ky = ry - i;                     // input row ry feeds output row i through filter row ky
+      if (ky < 0 || ky > 2) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 f = wt[ky * 3 + kx];
+        acc[i] = fmaf(v[kx].x, f.x, acc[i]);
+        acc[i] = fmaf(v[kx].y, f.y, acc[i]);
+        acc[i] = fmaf(v[kx].z, f.z, acc[i]);
+        acc[i] = fmaf(v[kx].w, f.w, acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < COUT1_ROWS; ++i) {
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  if (live && sub == 0) {
+    const float bv = bias ? bias[0] : 0.0f;
+#pragma unroll
+    for (int i = 0; i < COUT1_ROWS; ++i)
+      if (y0 + i < H) out[(b * H + y0 + i) * W + x] = acc[i] + bv;
+  }
+}
+
 // Clip assembly (test.py:22-25 ToTensor + Normalize, universaldataloader.py:45-48 sliding window): frames are uint8 HWC
 // images resident on the device, every clip names its T frames by index (consecutive clips share T-1 frames, so each
 // frame is uploaded once); out[b,t,c,y,x] = (frame[idx[b,t]][y,x,c] / 255 - mean[c]) / std[c] with the same operation
@@ -538,6 +601,13 @@ extern "C" int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const fl
   if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w)) & 15) == 0 && (Cin == 32 || Cin == 64 || Cin == 128 || Cin == 16)) {
     cudaStream_t st = as_stream(stream);
     const int lpp = Cin / 4;
+    if (kh == 3 && kw == 3 && ph == 1 && pw == 1 && (lpp == 8 || lpp == 4)) {
+      const long units = (long)B * ((H + COUT1_ROWS - 1) / COUT1_ROWS) * W;
+      const unsigned rgrid = (unsigned)cdiv(units * lpp, 256);
+      if (lpp == 8) launch_kernel(conv_cout1_rows_kernel<8>, rgrid, 256, 0, st, in, w, bias, out, units, H, W);
+      else launch_kernel(conv_cout1_rows_kernel<4>, rgrid, 256, 0, st, in, w, bias, out, units, H, W);
+      return launch_status("conv2d_nhwc_cout1_rows");
+    }
     const unsigned grid = (unsigned)cdiv(pixels * lpp, 256);
     if (lpp == 4) launch_kernel(conv_cout1_vec_kernel<4>, grid, 256, 0, st, in, w, bias, out, pixels, H, W, kh, kw, ph, pw);
     else if (lpp == 8) launch_kernel(conv_cout1_vec_kernel<8>, grid, 256, 0, st, in, w, bias, out, pixels, H, W, kh, kw, ph, pw);

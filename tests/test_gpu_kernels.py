@@ -96,14 +96,17 @@ def test_conv_odd_channel_count_with_padded_pixel_stride():
     assert util.maxabs(out, ref) < 2e-4 * max(1.0, float(ref.abs().max()))
 
 
-def test_conv_cout1():
+@pytest.mark.parametrize("B,Cin,H,W", [(2, 32, 24, 20), (3, 32, 22, 19), (1, 16, 5, 7), (2, 64, 9, 12), (1, 32, 224, 224)])
+def test_conv_cout1(B, Cin, H, W):
+    """final_out (decoder.py:95): 3x3, one output channel.  Row-tiled kernel for 16 / 32 input channels (incl. heights that are
+    not a multiple of the four-row tile and one-pixel borders), per-pixel kernel otherwise."""
     ops = _ops()
-    x = util.seeded_input((2, 32, 24, 20), 1)
-    w = util.seeded_input((1, 32, 3, 3), 2) / 17.0
+    x = util.seeded_input((B, Cin, H, W), 1)
+    w = util.seeded_input((1, Cin, 3, 3), 2) / 17.0
     b = util.seeded_input((1,), 3)
     ref = orc.conv2d(x, w, b, (1, 1))
-    out = ops.conv2d_nhwc_cout1(x.permute(0, 2, 3, 1).contiguous().cuda(), w.permute(0, 2, 3, 1).contiguous().cuda(), b.cuda(), 2, 24, 20, 32, 3, 3, 1, 1)
-    assert util.maxabs(out.view(2, 1, 24, 20), ref) < 1e-5
+    out = ops.conv2d_nhwc_cout1(x.permute(0, 2, 3, 1).contiguous().cuda(), w.permute(0, 2, 3, 1).contiguous().cuda(), b.cuda(), B, H, W, Cin, 3, 3, 1, 1)
+    assert util.maxabs(out.view(B, 1, H, W), ref) < 1e-5
 
 
 @pytest.fixture
