@@ -1,3 +1,5 @@
+set -x
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_e2e.py -x -q -m gpu -k "cout1 or fp32_mode or decoder" 2>&1 | tail -3
-timeout 600 python tools/op_breakdown.py 32 2>&1 | grep -i "cout1\|serial step"
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench_final.json; cut -c1-200 gpurun_out/bench_final.json
