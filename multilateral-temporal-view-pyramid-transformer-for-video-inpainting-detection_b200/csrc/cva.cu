@@ -248,14 +248,23 @@ __global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__
   const long L2 = (long)TH2 * W;
   const int wpr = W / ws;
   const long base_row = b2 * L2 + (long)(n2 / wpr) * ws * W + (n2 % wpr) * ws;      // canvas row of the window's pixel (0,0)
-  const int C4 = C >> 2;
-  // blockIdx.y splits the window's P*C/4 work items when there are too few windows to fill the machine
+  const int C4 = C >> 2, Cg4 = Cg >> 2;
+  // blockIdx.y splits the window's P*C/4 work items when there are too few windows to fill the machine.  The kernel is
+  // instruction-bound (ncu: 3 IPC), so the (pixel, channel quad) of an item is stepped incrementally -- no division in the
+  // loop -- and all addresses are 32-bit offsets from the window's first pixel.
   const int items = P * C4, per = (items + gridDim.y - 1) / gridDim.y;
   const int e_end = min(items, (int)(blockIdx.y + 1) * per);
-  for (int e = blockIdx.y * per + threadIdx.x; e < e_end; e += blockDim.x) {
-    const int p = e / C4, c = (e - p * C4) * 4;
-    const int g = c / Cg;                                  // Cg % 4 == 0: the four channels share a group
-    const float2 pp = __ldg(reinterpret_cast<const float2 *>(pix + (((long)qw * groups + g) * P + p) * 2));
+  const int e0 = blockIdx.y * per + threadIdx.x;
+  int p = e0 / C4, c4 = e0 - p * C4;
+  const int step_p = blockDim.x / C4, step_c = blockDim.x - step_p * C4;
+  const InT *wbase = x2 + base_row * C;                                   // pixel (0,0) of the kv window
+  const float *pbase = pix + (long)qw * groups * P * 2;
+  OutT *obase = sampled + (long)j * P * C;
+  for (int e = e0; e < e_end; e += blockDim.x) {
+    const int c = c4 * 4;
+    int g = 0;
+    for (int t = Cg4; t <= c4; t += Cg4) ++g;                              // Cg % 4 == 0: the four channels share a group
+    const float2 pp = __ldg(reinterpret_cast<const float2 *>(pbase + (g * P + p) * 2));
     const float py = pp.x, px = pp.y;
     const float fy = floorf(py), fx = floorf(px);
     const int y0 = (int)fy, x0 = (int)fx;
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__
         const int yy = y0 + dy, xx = x0 + dx;
         if (yy < 0 || yy >= ws || xx < 0 || xx >= ws) continue;
         const float wgt = (dy ? wy1 : wy0) * (dx ? wx1 : wx0);
-        const InT *src = x2 + (base_row + (long)yy * W + xx) * C + c;
+        const InT *src = wbase + (yy * W + xx) * C + c;
         float4 v;
         if (sizeof(InT) == 4) {
           v = __ldg(reinterpret_cast<const float4 *>(src));
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__
         acc.x = fmaf(v.x, wgt, acc.x); acc.y = fmaf(v.y, wgt, acc.y); acc.z = fmaf(v.z, wgt, acc.z); acc.w = fmaf(v.w, wgt, acc.w);
       }
     }
-    OutT *dst = sampled + ((long)j * P + p) * C + c;
+    OutT *dst = obase + p * C + c;
     if constexpr (sizeof(OutT) == 2) {
       uint2 pk;
       pk.x = pack2<OutT>(acc.x, acc.y);
@@ -291,6 +300,12 @@ __global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__
       *reinterpret_cast<uint2 *>(dst) = pk;
     } else {
       *reinterpret_cast<float4 *>(dst) = acc;
+    }
+    p += step_p;
+    c4 += step_c;
+    if (c4 >= C4) {
+      c4 -= C4;
+      ++p;
     }
   }
 }
