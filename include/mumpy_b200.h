@@ -165,9 +165,11 @@ int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const float *bias, 
 int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int out_dtype, int B, int H, int W, int Cin, int kh, int kw,
                       int ph, int pw, int Kpad, void *stream);
 /* GroupNorm + activation; stats over (H*W, C/groups) per (b, group), exact two-pass per pixel chunk + Chan combine.
- * stats_ws: 2*B*groups*(1 + nchunks) floats, nchunks = ceil(HW / min(64, 12288 / C, HW)). */
+ * stats_ws: 2*B*groups*(1 + nchunks) floats, nchunks = ceil(HW / min(64, 12288 / C, HW)).
+ * quad_mean != 0: the output holds the mean of every 4 consecutive activated channels (C/4 per pixel; decoder.py:140-143 DAP =
+ * PixelShuffle(2) -> AvgPool2d(2), which commutes with the bilinear upsample that follows) -- ld_out / out_col then count those. */
 int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *stats_ws, float *out,
-                         long ld_out, int out_col, int B, int HW, int C, int groups, float eps, int act, void *stream);
+                         long ld_out, int out_col, int B, int HW, int C, int groups, float eps, int act, int quad_mean, void *stream);
 /* out[..., col:col+Cout] = resample(in) (* mul) (+ add); mul/add are (B,Ho,Wo,Cout) contiguous or NULL. */
 int mumpy_resample_nhwc(const float *in, const float *mul, const float *add, float *out, long ld_out, int out_col,
                         int B, int H, int W, int C, int mode, int scale, void *stream);

@@ -39,7 +39,7 @@ SIGNATURES = {
     "mumpy_conv2d_nhwc_bf16": [vp, cl, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, cl, vp],
     "mumpy_conv2d_nhwc_cout1": [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_im2col_nhwc": [vp, cl, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
-    "mumpy_groupnorm_nhwc": [vp, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, cf, ci, vp],
+    "mumpy_groupnorm_nhwc": [vp, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, cf, ci, ci, vp],
     "mumpy_resample_nhwc": [vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_mul_add": [vp, vp, vp, vp, cl, vp],
     "mumpy_add": [vp, vp, vp, cl, vp],

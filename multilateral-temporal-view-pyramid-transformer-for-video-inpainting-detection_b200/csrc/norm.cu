@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float *__restric
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float *__restrict__ x, const float *__restrict__ stats,
                                                               const float *__restrict__ gamma, const float *__restrict__ beta,
                                                               float *__restrict__ out, long ld_out, int out_col, long total4, int HW,
-                                                              int C, int groups, int act) {
+                                                              int C, int groups, int act, int quad_mean) {
   pdl_grid_sync();
   const int cg = C / groups;
   const int C4 = C / 4;
@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float *__res
     o.y = apply_act((v.y - mean) * rstd * g.y + bt.y, act);
     o.z = apply_act((v.z - mean) * rstd * g.z + bt.z, act);
     o.w = apply_act((v.w - mean) * rstd * g.w + bt.w, act);
-    *reinterpret_cast<float4 *>(out + pix * ld_out + out_col + c) = o;
+    if (quad_mean) out[pix * ld_out + out_col + (c >> 2)] = (o.x + o.y + o.z + o.w) * 0.25f;      // DAP: mean of 4 consecutive channels
+    else *reinterpret_cast<float4 *>(out + pix * ld_out + out_col + c) = o;
   }
 }
 
@@ -378,9 +379,10 @@ extern "C" int mumpy_patch_merge_norm(const float *x, const float *gamma, const 
 
 extern "C" int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *stats_ws, float *out,
                                     long ld_out, int out_col, int B, int HW, int C, int groups, float eps, int act,
-                                    void *stream) {
+                                    int quad_mean, void *stream) {
   MUMPY_REQUIRE(x && gamma && beta && stats_ws && out && C % groups == 0, "groupnorm_nhwc: bad arguments");
-  MUMPY_REQUIRE((C / groups) % 4 == 0 && ld_out % 4 == 0 && out_col % 4 == 0, "groupnorm_nhwc: channels per group, ld_out, out_col must be multiples of 4");
+  MUMPY_REQUIRE((C / groups) % 4 == 0 && (quad_mean || (ld_out % 4 == 0 && out_col % 4 == 0)),
+                "groupnorm_nhwc: channels per group, ld_out, out_col must be multiples of 4");
   MUMPY_REQUIRE(C <= GN_SMEM_FLOATS, "groupnorm_nhwc: C too large");
   cudaStream_t st = as_stream(stream);
   int pix = GN_SMEM_FLOATS / C;
@@ -406,6 +408,6 @@ extern "C" int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const fl
   if (rc) return rc;
   const long total4 = (long)B * HW * C / 4;
   const int blocks = (int)(cdiv(total4, 256) < 148 * 16 ? cdiv(total4, 256) : 148 * 16);
-  launch_kernel(groupnorm_apply_kernel, blocks, 256, 0, st, x, stats, gamma, beta, out, ld_out, out_col, total4, HW, C, groups, act);
+  launch_kernel(groupnorm_apply_kernel, blocks, 256, 0, st, x, stats, gamma, beta, out, ld_out, out_col, total4, HW, C, groups, act, quad_mean);
   return launch_status("groupnorm_apply");
 }

@@ -207,10 +207,12 @@ class Decoder(PackedModule):
         mean (:140-143) is taken before the upsample (they commute)."""
         seq = getattr(self, name)
         c = _conv(self, name, seq[0], x, B, H, W)
-        g = ops.groupnorm_nhwc(c, seq[1].weight, seq[1].bias, B, H * W, c.shape[-1], seq[1].num_groups, ops.ACT_RELU, seq[1].eps)
+        k = self.dap_k ** 2 if dap else 1
+        fused = k == 4 and c.shape[-1] % 4 == 0          # the DAP mean of 4 consecutive channels comes out of the GroupNorm apply pass
+        g = ops.groupnorm_nhwc(c, seq[1].weight, seq[1].bias, B, H * W, c.shape[-1], seq[1].num_groups, ops.ACT_RELU, seq[1].eps,
+                               quad_mean=fused)
         C = g.shape[-1]
-        if dap:
-            k = self.dap_k ** 2
+        if dap and not fused:
             g = ops.channel_group_mean(g, B * H * W, C, k)
             C //= k
         return ops.resample_nhwc(g, B, H, W, C, ops.RS_UP_ALIGNED, 2)

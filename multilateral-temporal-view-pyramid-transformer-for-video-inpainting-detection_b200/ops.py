@@ -283,17 +283,20 @@ def im2col_nhwc(x, B, H, W, Cin, kh, kw, ph, pw, Kpad, ld_in=None):
     return out
 
 
-def groupnorm_nhwc(x, gamma, beta, B, HW, C, groups, act, eps=1e-5, out=None, ld_out=None, out_col=0):
+def groupnorm_nhwc(x, gamma, beta, B, HW, C, groups, act, eps=1e-5, out=None, ld_out=None, out_col=0, quad_mean=False):
+    """GroupNorm + activation on an NHWC map; quad_mean=True returns the mean of every 4 consecutive activated channels (the
+    decoder's DAP, decoder.py:140-143) as (..., C/4) without materialising the normalised map."""
+    Co = C // 4 if quad_mean else C
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty(tuple(x.shape[:-1]) + (Co,), dtype=torch.float32, device=x.device)
     pix = max(1, min(64, 12288 // C, HW))
     nchunks = (HW + pix - 1) // pix
     stats = torch.empty((2 * B * groups * (1 + nchunks),), dtype=torch.float32, device=x.device)
     lib, st = _prep(x, gamma, beta, stats, out)
     global launch_count
     launch_count += 2            # partial statistics + finalize + apply
-    _lib.check(lib.mumpy_groupnorm_nhwc(_p(x), _p(gamma), _p(beta), _p(stats), _p(out), ld_out or C, out_col, B, HW, C,
-                                        groups, eps, act, st), "mumpy_groupnorm_nhwc")
+    _lib.check(lib.mumpy_groupnorm_nhwc(_p(x), _p(gamma), _p(beta), _p(stats), _p(out), ld_out or Co, out_col, B, HW, C,
+                                        groups, eps, act, int(quad_mean), st), "mumpy_groupnorm_nhwc")
     return out
 
 

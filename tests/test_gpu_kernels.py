@@ -185,3 +185,19 @@ def test_faf_tensor_core_path(mode, size, B):
         mumpy_b200.set_precision("bf16")
     assert y.shape == ref.shape
     assert util.maxabs(y, ref) < (1e-4 if mode == "bf16" else 2e-5)
+
+
+def test_groupnorm_quad_mean_is_the_dap_of_the_plain_output():
+    """decoder_5 tail: GroupNorm -> ReLU -> DAP (mean over each 4 consecutive channels, decoder.py:140-143) in one apply pass
+    equals the two-kernel form (GroupNorm map, then channel_group_mean)."""
+    ops = _ops()
+    B, H, W, C, groups = 2, 12, 10, 128, 8
+    x = util.seeded_input((B, H, W, C), 1).cuda()
+    gam, bet = util.seeded_input((C,), 2).cuda(), util.seeded_input((C,), 3).cuda()
+    full = ops.groupnorm_nhwc(x, gam, bet, B, H * W, C, groups, ops.ACT_RELU)
+    ref = ops.channel_group_mean(full, B * H * W, C, 4).view(B, H, W, C // 4)
+    ref2 = torch.relu(torch.nn.functional.group_norm(x.cpu().permute(0, 3, 1, 2), groups, gam.cpu(), bet.cpu())).permute(0, 2, 3, 1)
+    ref2 = ref2.reshape(B, H, W, C // 4, 4).mean(-1)
+    out = ops.groupnorm_nhwc(x, gam, bet, B, H * W, C, groups, ops.ACT_RELU, quad_mean=True)
+    assert out.shape == (B, H, W, C // 4)
+    assert util.maxabs(out, ref) < 1e-6 and util.maxabs(out, ref2) < 1e-5
