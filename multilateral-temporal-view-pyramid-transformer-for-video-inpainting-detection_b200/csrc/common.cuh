@@ -51,6 +51,20 @@ static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 }
 static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
+// q = i / d, r = i % d for a flat element index: 32-bit arithmetic when the caller knows the index fits (`small`, uniform
+// across the grid) -- a 64-bit division by a run-time value is a ~100-instruction routine, which made several flat kernels
+// instruction-bound.
+__device__ __forceinline__ void divmod_idx(long i, int d, bool small, long &q, int &r) {
+  if (small) {
+    const unsigned qq = (unsigned)i / (unsigned)d;
+    q = qq;
+    r = (int)((unsigned)i - qq * (unsigned)d);
+  } else {
+    q = i / d;
+    r = (int)(i - q * d);
+  }
+}
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);

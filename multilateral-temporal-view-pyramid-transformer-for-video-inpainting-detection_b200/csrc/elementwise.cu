@@ -44,11 +44,12 @@ __global__ void __launch_bounds__(256) gather_rows_vec_kernel(const float *__res
   pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
+  const bool small = total4 < (1l << 31);
   for (; i < total4; i += stride) {
-    const int c4 = (int)(i % C4);
-    const long r = i / C4;
-    const long b = r / rows_out;
-    const int q = (int)(r - b * rows_out);
+    int c4, q;
+    long r, b;
+    divmod_idx(i, C4, small, r, c4);
+    divmod_idx(r, rows_out, small, b, q);
     const long srow = b * rows_src + (q / div) * mul_hi + (q % div) * mul_lo + add;
     const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + srow * C4 + c4);
     store4(dst + r * dst_ld + dst_col + 4 * c4, v);
@@ -136,22 +137,25 @@ __global__ void __launch_bounds__(256) resample_kernel(const float *__restrict__
   }
 }
 
-// 4 channels per thread for every mode but pixel-shuffle (C, ld_out, out_col multiples of 4)
+// 4 channels per thread for every mode but pixel-shuffle (C, ld_out, out_col multiples of 4).  Idx = uint32_t whenever the
+// element count allows: the index decomposition is three divisions by run-time values per element, and 64-bit ones cost
+// ~100 instructions each (the kernel was instruction-bound at a third of HBM bandwidth).
+template <typename Idx>
 __global__ void __launch_bounds__(256) resample_vec_kernel(const float *__restrict__ in, const float *__restrict__ mul,
                                                            const float *__restrict__ add, float *__restrict__ out, long ld_out, int out_col,
                                                            long total4, int H, int W, int C4, int Ho, int Wo, int mode, int scale) {
   pdl_grid_sync();
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
+  Idx i = (Idx)blockIdx.x * blockDim.x + threadIdx.x;
+  const Idx stride = (Idx)gridDim.x * blockDim.x;
   const float4 *in4 = reinterpret_cast<const float4 *>(in);
-  for (; i < total4; i += stride) {
-    const int c4 = (int)(i % C4);
-    long t = i / C4;
-    const int wo = (int)(t % Wo);
-    t /= Wo;
-    const int ho = (int)(t % Ho);
-    const long b = t / Ho;
-    const float4 *img = in4 + b * H * W * C4 + c4;
+  for (; i < (Idx)total4; i += stride) {
+    const Idx pixel = i / (Idx)C4;
+    const int c4 = (int)(i - pixel * (Idx)C4);
+    const Idx row = pixel / (Idx)Wo;
+    const int wo = (int)(pixel - row * (Idx)Wo);
+    const Idx b = row / (Idx)Ho;
+    const int ho = (int)(row - b * (Idx)Ho);
+    const float4 *img = in4 + (long)b * H * W * C4 + c4;
     float4 v;
     if (mode == MUMPY_RS_IDENTITY) {
       v = __ldg(img + ((long)ho * W + wo) * C4);
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(256) resample_vec_kernel(const float *__restri
       const float4 m = __ldg(reinterpret_cast<const float4 *>(add) + i);
       v.x += m.x; v.y += m.y; v.z += m.z; v.w += m.w;
     }
-    *reinterpret_cast<float4 *>(out + (i / C4) * ld_out + out_col + 4 * c4) = v;
+    *reinterpret_cast<float4 *>(out + (long)pixel * ld_out + out_col + 4 * c4) = v;
   }
 }
 
@@ -533,7 +537,10 @@ extern "C" int mumpy_resample_nhwc(const float *in, const float *mul, const floa
   const long total = (long)B * Ho * Wo * Co;
   if (mode != MUMPY_RS_PIXEL_SHUFFLE2 && C % 4 == 0 && ld_out % 4 == 0 && out_col % 4 == 0 &&
       ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mul) | reinterpret_cast<uintptr_t>(add)) & 15) == 0) {
-    launch_kernel(resample_vec_kernel, flat_blocks(total / 4), 256, 0, as_stream(stream), in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale);
+    if (total / 4 < (1l << 31) - (1l << 24))
+      launch_kernel(resample_vec_kernel<uint32_t>, flat_blocks(total / 4), 256, 0, as_stream(stream), in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale);
+    else
+      launch_kernel(resample_vec_kernel<long>, flat_blocks(total / 4), 256, 0, as_stream(stream), in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale);
     return launch_status("resample_vec");
   }
   launch_kernel(resample_kernel, flat_blocks(total), 256, 0, as_stream(stream), in, mul, add, out, ld_out, out_col, total, H, W, C, Ho, Wo, Co, mode, scale);

@@ -325,10 +325,13 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float *__res
   const int C4 = C / 4;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
+  const bool small = total4 < (1l << 31);
   for (; i < total4; i += stride) {
-    const int c = (int)(i % C4) * 4;
-    const long pix = i / C4;
-    const long b = pix / HW;
+    int c, prem;
+    long pix, b;
+    divmod_idx(i, C4, small, pix, c);
+    c *= 4;
+    divmod_idx(pix, HW, small, b, prem);
     const float4 v = reinterpret_cast<const float4 *>(x)[i];
     const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + c)), bt = __ldg(reinterpret_cast<const float4 *>(beta + c));
     const float *st = stats + 2 * (b * groups + c / cg);          // cg % 4 == 0: the four channels share a group
