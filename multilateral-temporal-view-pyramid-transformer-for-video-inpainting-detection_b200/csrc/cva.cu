@@ -315,10 +315,14 @@ __global__ void __launch_bounds__(256) cva_sample_kernel(const InT *__restrict__
 // raw reshape of a (C, P) tensor (deformableAttention.py:403) is a transposed read of the token-major y.  One CTA per
 // window: y's (P, C) block is staged in shared memory (coalesced read) so that the transposed access never touches DRAM
 // with a stride; everything else is 16-byte coalesced.
+// WS > 0: compile-time window size (7 or 8) -- the loop body has a dozen divisions by P and ws, which as run-time values made
+// the kernel instruction-bound; WS == 0: generic.
+template <int WS>
 __global__ void __launch_bounds__(256) cva_residual_kernel(const float *__restrict__ h, const float *__restrict__ y,
-                                                           float *__restrict__ x_new, int TH1, int W, int C, int ws) {
+                                                           float *__restrict__ x_new, int TH1, int W, int C, int ws_rt) {
   pdl_grid_sync();
   extern __shared__ float ysm[];      // [P][C + 1]
+  const int ws = WS > 0 ? WS : ws_rt;
   const int P = ws * ws;
   const long L1 = (long)TH1 * W;
   const int nW = (int)(L1 / P);
@@ -450,9 +454,12 @@ extern "C" int mumpy_cva_residual(const float *h, const float *y, float *x_new, 
   const int P = ws * ws;
   const size_t smem = (size_t)P * (C + 1) * sizeof(float);
   MUMPY_REQUIRE(smem <= 227 * 1024, "cva_residual: window block of %zu B does not fit shared memory", smem);
-  static size_t granted = 0;
+  static size_t granted_ws[3] = {0, 0, 0};
+  size_t &granted = granted_ws[ws == 7 ? 0 : (ws == 8 ? 1 : 2)];
   if (smem > 48 * 1024 && smem > granted) {
-    cudaError_t e = cudaFuncSetAttribute(cva_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ws == 7 ? cudaFuncSetAttribute(cva_residual_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : ws == 8 ? cudaFuncSetAttribute(cva_residual_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(cva_residual_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("cva_residual: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MUMPY_ERR_CUDA;
@@ -460,6 +467,8 @@ extern "C" int mumpy_cva_residual(const float *h, const float *y, float *x_new, 
     granted = smem;
   }
   const long wins = (long)B * (TH1 / ws) * (W / ws);
-  launch_kernel(cva_residual_kernel, (unsigned)wins, 256, smem, as_stream(stream), h, y, x_new, TH1, W, C, ws);
+  if (ws == 7) launch_kernel(cva_residual_kernel<7>, (unsigned)wins, 256, smem, as_stream(stream), h, y, x_new, TH1, W, C, ws);
+  else if (ws == 8) launch_kernel(cva_residual_kernel<8>, (unsigned)wins, 256, smem, as_stream(stream), h, y, x_new, TH1, W, C, ws);
+  else launch_kernel(cva_residual_kernel<0>, (unsigned)wins, 256, smem, as_stream(stream), h, y, x_new, TH1, W, C, ws);
   return launch_status("cva_residual");
 }
