@@ -55,6 +55,13 @@ const char *mumpy_last_error(void);
 /* Programmatic dependent launch of the library's kernels (default on; environment MUMPY_PDL=0 disables): each kernel
  * may be scheduled while its predecessor in the stream drains and synchronises on it in-kernel (griddepcontrol.wait). */
 int mumpy_set_pdl(int enabled);
+/* fp16 range guard.  In the "fp16" precision mode every fp32 -> IEEE-half conversion saturates to +-65504 instead of producing
+ * inf, and the kernels that create new magnitudes in operand precision (GEMM / convolution epilogues, casts, gathers, LayerNorm,
+ * the DCT repack) OR 1 into the caller-owned device word registered here whenever they had to saturate.  The caller reads the
+ * word back with the step's results (ops.f16_overflowed(), evaluate.py raises) -- the reference computes in fp32
+ * (test.py:94-95), so leaving the half range must be loud, never silent.  NULL disables reporting (saturation stays).
+ * Synchronous (cudaMemcpyToSymbol); call once per device, outside stream capture. */
+int mumpy_set_f16_overflow_flag(unsigned int *flag_dev);
 /* CTA-pair (tcgen05 cta_group::2, 256 x BN tiles on a (2,1,1) cluster) policy of the bf16 GEMM / implicit-GEMM convolution:
  * 0 never (default), 1 the tile cost model decides, 2 whenever the shape allows.  Environment: MUMPY_TC_PAIR. */
 int mumpy_set_gemm_pair_mode(int mode);

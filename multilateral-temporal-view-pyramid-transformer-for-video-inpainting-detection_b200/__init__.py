@@ -11,7 +11,7 @@ identifier); `import mumpy_b200` (repo root shim) resolves to it.  Layout:
   build.py              nvcc recipe for the shared library
 """
 from . import ops, streams  # noqa: F401
-from .ops import precision, set_precision  # noqa: F401
+from .ops import check_f16_range, f16_overflowed, precision, set_precision  # noqa: F401
 from .models.encoder.encoder import Encoder  # noqa: F401
 from .models.decoder.decoder import Decoder  # noqa: F401
 
@@ -22,9 +22,13 @@ def forward(encoder, decoder, x):
     so that the decoder's pyramid / frequency branches start as soon as their stage features exist and overlap the
     encoder's tail (stage 3 and the 12 small global blocks) instead of waiting for the encoder's join.  Same results, bit for
     bit, as the two separate calls (tests/test_gpu_e2e.py).  Returns (logits (B,1,S,S), x_feats (B,32,S,S))."""
-    with streams.region(x.device):
+    # The input conversion (non-contiguous or non-fp32 clips) must be enqueued BEFORE the region forks its lanes: the
+    # frequency lane and the tokenizer lanes read x without any further hand-over.
+    x = x.contiguous().float()
+    with streams.region(x.device) as reg:
+        reg.hold(x)
         final_x, view_x, ffinfo = encoder(x)
         return decoder(final_x, view_x, ffinfo)
 
 
-__all__ = ["Encoder", "Decoder", "forward", "ops", "streams", "set_precision", "precision"]
+__all__ = ["Encoder", "Decoder", "forward", "ops", "streams", "set_precision", "precision", "f16_overflowed", "check_f16_range"]

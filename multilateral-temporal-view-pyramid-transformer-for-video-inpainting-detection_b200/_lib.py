@@ -18,6 +18,7 @@ SIGNATURES = {
     "mumpy_abi_version": [],
     "mumpy_init": [ci],
     "mumpy_set_pdl": [ci],
+    "mumpy_set_f16_overflow_flag": [vp],
     "mumpy_set_gemm_pair_mode": [ci],
     "mumpy_set_attention_tc": [ci],
     "mumpy_set_gemm_tile": [ci],

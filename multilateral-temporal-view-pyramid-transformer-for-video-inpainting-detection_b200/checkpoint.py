@@ -39,6 +39,9 @@ def restore(encoder, decoder, model_dir, epoch=3, device=None):
     enc_sd, dec_sd = load_checkpoint(model_dir, epoch)
     encoder.load_state_dict(enc_sd, strict=True)
     decoder.load_state_dict(dec_sd, strict=True)
+    from .models.modules._packing import invalidate_packed
+    invalidate_packed(encoder)
+    invalidate_packed(decoder)
     if device is not None:
         encoder.to(device)
         decoder.to(device)

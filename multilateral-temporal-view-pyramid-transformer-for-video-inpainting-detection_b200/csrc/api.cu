@@ -47,12 +47,31 @@ int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, co
               int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int in_dtype, int out_dtype, int act, float *splitk_ws,
               long splitk_ws_bytes, cudaStream_t st);
 
+// setters of the per-translation-unit fp16 overflow flag pointers (common.cuh); filled by static initialisers
+static F16FlagSetter *flag_setters(int **count) {
+  static F16FlagSetter fns[32];
+  static int n = 0;
+  *count = &n;
+  return fns;
+}
+void register_f16_flag_setter(F16FlagSetter fn) {
+  int *n;
+  F16FlagSetter *fns = flag_setters(&n);
+  if (*n < 32) fns[(*n)++] = fn;
+}
+
 template <typename T>
 __global__ void cast16_kernel(const float *__restrict__ in, T *__restrict__ out, long n) {
   pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) out[i] = from_f32<T>(in[i]);
+  float amax = 0.0f;
+  for (; i < n; i += stride) {
+    const float v = in[i];
+    amax = fmaxf(amax, fabsf(v));
+    out[i] = from_f32<T>(v);
+  }
+  if (is_half_t<T>::value) f16_guard(amax);
 }
 
 template <typename T>
@@ -60,13 +79,16 @@ __global__ void cast16_vec_kernel(const float4 *__restrict__ in, uint2 *__restri
   pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
+  float amax = 0.0f;
   for (; i < n4; i += stride) {
     const float4 v = __ldg(in + i);
+    amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fmaxf(fabsf(v.y), fabsf(v.z)), fabsf(v.w)));
     uint2 pk;
     pk.x = pack2<T>(v.x, v.y);
     pk.y = pack2<T>(v.z, v.w);
     out[i] = pk;
   }
+  if (is_half_t<T>::value) f16_guard(amax);
 }
 
 }  // namespace mumpy
@@ -89,6 +111,19 @@ extern "C" int mumpy_set_attention_tc(int enabled) {
 
 extern "C" int mumpy_set_gemm_tile(int bn) {
   set_gemm_tile_override(bn);
+  return MUMPY_OK;
+}
+
+extern "C" int mumpy_set_f16_overflow_flag(unsigned int *flag_dev) {
+  int *n;
+  F16FlagSetter *fns = flag_setters(&n);
+  for (int i = 0; i < *n; ++i) {
+    cudaError_t e = fns[i](flag_dev);
+    if (e != cudaSuccess) {
+      set_error("mumpy_set_f16_overflow_flag: %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+  }
   return MUMPY_OK;
 }
 

@@ -72,7 +72,15 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
-template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+// fp32 -> IEEE half always SATURATES to +-65504 (cvt.satfinite) instead of producing inf: a value beyond the half range can then
+// never turn into inf - inf = NaN further down the forward.  Saturation alone would be silent, so the kernels that create new
+// magnitudes in operand precision (GEMM / conv epilogues, casts, gathers, LayerNorm, the DCT repack) also track the largest
+// |value| they converted and report it through f16_guard() below.
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  return __ushort_as_half(h);
+}
 
 // two fp32 -> one 32-bit word of two 16-bit operands (round to nearest even) and back, for either operand type
 template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
@@ -81,8 +89,9 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, f
   return *reinterpret_cast<uint32_t *>(&h);
 }
 template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
-  __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t *>(&h);
+  uint32_t u;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));
+  return u;
 }
 template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t u);
 template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) {
@@ -93,6 +102,32 @@ template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
   const __half2 h = *reinterpret_cast<const __half2 *>(&u);
   return __half22float2(h);
 }
+// ---- fp16 range guard ("fp16" precision mode) ----
+// A caller-owned device word (mumpy_set_f16_overflow_flag) that kernels OR 1 into when they had to saturate: the host reads
+// it with the step's results (ops.f16_overflowed / evaluate.py raise), so leaving the half range is loud, never silent.
+// The pointer lives in one __device__ variable per translation unit (the library is built without relocatable device code);
+// every unit that includes this header registers its setter with api.cu.
+static __device__ unsigned int *tu_f16_flag = nullptr;
+typedef cudaError_t (*F16FlagSetter)(unsigned int *);
+void register_f16_flag_setter(F16FlagSetter fn);
+static cudaError_t tu_set_f16_flag(unsigned int *p) { return cudaMemcpyToSymbol(tu_f16_flag, &p, sizeof(p)); }
+namespace {
+struct F16FlagRegistrar {
+  F16FlagRegistrar() { register_f16_flag_setter(&tu_set_f16_flag); }
+};
+static F16FlagRegistrar f16_flag_registrar_;
+}  // namespace
+constexpr float kHalfMax = 65504.0f;
+// amax = largest |fp32 value| this thread converted to IEEE half (track with fmaxf(amax, fabsf(v)); NaN-transparent)
+__device__ __forceinline__ void f16_guard(float amax) {
+  if (amax > kHalfMax) {
+    unsigned int *f = tu_f16_flag;
+    if (f) atomicOr(f, 1u);
+  }
+}
+template <typename T> struct is_half_t { static constexpr bool value = false; };
+template <> struct is_half_t<__half> { static constexpr bool value = true; };
+
 static inline bool is_16bit(int dtype) { return dtype == MUMPY_BF16 || dtype == MUMPY_F16; }
 // runs `...` with T bound to the 16-bit operand type that `dtype` (MUMPY_BF16 / MUMPY_F16) names
 #define MUMPY_WITH_16(dtype, T, ...)       \

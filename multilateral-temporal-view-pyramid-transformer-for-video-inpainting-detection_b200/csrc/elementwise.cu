@@ -17,14 +17,18 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restric
   pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
+  float amax = 0.0f;
   for (; i < total; i += stride) {
     const int c = (int)(i % C);
     const long r = i / C;
     const long b = r / rows_out;
     const int q = (int)(r % rows_out);
     const long srow = b * rows_src + (q / div) * mul_hi + (q % div) * mul_lo + add;
-    dst[r * dst_ld + dst_col + c] = from_f32<OutT>(src[srow * C + c]);
+    const float v = src[srow * C + c];
+    amax = fmaxf(amax, fabsf(v));
+    dst[r * dst_ld + dst_col + c] = from_f32<OutT>(v);
   }
+  if (is_half_t<OutT>::value) f16_guard(amax);
 }
 
 __device__ __forceinline__ void store4(float *dst, float4 v) { *reinterpret_cast<float4 *>(dst) = v; }
@@ -45,6 +49,7 @@ __global__ void __launch_bounds__(256) gather_rows_vec_kernel(const float *__res
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   const bool small = total4 < (1l << 31);
+  float amax = 0.0f;
   for (; i < total4; i += stride) {
     int c4, q;
     long r, b;
@@ -52,8 +57,10 @@ __global__ void __launch_bounds__(256) gather_rows_vec_kernel(const float *__res
     divmod_idx(r, rows_out, small, b, q);
     const long srow = b * rows_src + (q / div) * mul_hi + (q % div) * mul_lo + add;
     const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + srow * C4 + c4);
+    amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fmaxf(fabsf(v.y), fabsf(v.z)), fabsf(v.w)));
     store4(dst + r * dst_ld + dst_col + 4 * c4, v);
   }
+  if (is_half_t<OutT>::value) f16_guard(amax);
 }
 
 template <typename OutT>
@@ -63,6 +70,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ i
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   const int K = kh * kw * Cin;
+  float amax = 0.0f;
   for (; i < total; i += stride) {
     const int k = (int)(i % Kpad);
     const long m = i / Kpad;
@@ -78,8 +86,10 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ i
       const int yy = y + ky - ph, xx = x + kx - pw;
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = in[((b * H + yy) * W + xx) * ld_in + c];
     }
+    amax = fmaxf(amax, fabsf(v));
     out[i] = from_f32<OutT>(v);
   }
+  if (is_half_t<OutT>::value) f16_guard(amax);
 }
 
 // source index + weights of nn.Upsample(bilinear) along one axis (ATen area_pixel_compute_source_index)

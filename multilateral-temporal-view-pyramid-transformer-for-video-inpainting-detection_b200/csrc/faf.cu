@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) faf_repack_kernel(const RepackParams p) {
       for (int b = 0; b < p.n_bands; ++b) {
         float m = v;
         if (p.n_bands > 1 && (r + c < p.lo[b] || r + c > p.hi[b])) m = 0.0f;
+        if (is_half_t<T16>::value && fabsf(m) > kHalfMax) f16_guard(fabsf(m));      // DCT coefficient beyond the half range
         const T16 h = from_f32<T16>(m);
         const T16 l = from_f32<T16>(m - to_f32(h));
         T16 *row = o + (((long)b * p.n_img + z) * OR + orow) * 3 * OC;

@@ -100,6 +100,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
   const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
   const long row0 = m0 + quad * 32;
   const uint32_t st_base = smem_u32(stage);
+  float amax = 0.0f;          // largest |value| converted to IEEE half by this thread (fp16 range guard, common.cuh)
   for (int c0 = half * 32, ci = 0; c0 < p.BN; c0 += 32 * TC_EPI_GROUPS, ++ci) {
     // residual tile of this chunk, fetched in the coalesced phase-2 layout before anything else so that the global-load
     // latency overlaps the TMEM load and the phase-1 math
@@ -175,6 +176,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
             }
             uint4 u;
             if (p.f16) {
+              amax = fmaxf(fmaxf(fmaxf(amax, fabsf(x.x)), fmaxf(fabsf(x.y), fabsf(x.z))), fmaxf(fmaxf(fabsf(x.w), fabsf(y.x)), fmaxf(fabsf(y.y), fmaxf(fabsf(y.z), fabsf(y.w)))));
               u.x = pack2<__half>(x.x, x.y); u.y = pack2<__half>(x.z, x.w); u.z = pack2<__half>(y.x, y.y); u.w = pack2<__half>(y.z, y.w);
             } else {
               u.x = pack2<__nv_bfloat16>(x.x, x.y); u.y = pack2<__nv_bfloat16>(x.z, x.w);
@@ -201,6 +203,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
             if (p.aux) {
               uint2 pk;
               if (p.f16) {
+                amax = fmaxf(fmaxf(amax, fabsf(x.x)), fmaxf(fmaxf(fabsf(x.y), fabsf(x.z)), fabsf(x.w)));
                 pk.x = pack2<__half>(x.x, x.y); pk.y = pack2<__half>(x.z, x.w);
               } else {
                 pk.x = pack2<__nv_bfloat16>(x.x, x.y); pk.y = pack2<__nv_bfloat16>(x.z, x.w);
@@ -218,6 +221,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
     }
     __syncwarp();
   }
+  f16_guard(amax);
 }
 
 // kPair: the two CTAs of a (2,1,1) cluster (one TPC) work on one 256 x BN tile with tcgen05.mma.cta_group::2: CTA r loads
@@ -660,6 +664,7 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, int S, l
     if constexpr (sizeof(OutT) == 4) {
       *reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + m * ldo + c) = a;
     } else {
+      if (is_half_t<OutT>::value) f16_guard(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
       uint2 u;
       u.x = pack2<OutT>(a.x, a.y);
       u.y = pack2<OutT>(a.z, a.w);

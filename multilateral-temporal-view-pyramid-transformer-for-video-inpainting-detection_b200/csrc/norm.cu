@@ -58,13 +58,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(Rows rows, const float *
   }
   const float rstd = 1.0f / sqrtf(warp_sum(v) / CT + eps);
   OutT *o = out + row * CT;
+  float amax = 0.0f;
   for (int q = 0; q < Rows::kSegs; ++q) {
     const float *p = rows.seg(row, q);
     for (int i = lane; i < C; i += 32) {
       const int c = q * C + i;
-      o[c] = from_f32<OutT>((p[i] - mean) * rstd * gamma[c] + beta[c]);
+      const float y = (p[i] - mean) * rstd * gamma[c] + beta[c];
+      amax = fmaxf(amax, fabsf(y));
+      o[c] = from_f32<OutT>(y);
     }
   }
+  if (is_half_t<OutT>::value) f16_guard(amax);
 }
 
 // Plain rows, C % 4 == 0, C <= 1024: rows live in registers as float4.  LPR lanes share a row (8 / 16 / 32, so that a lane
@@ -81,6 +85,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const Rows rows, con
   const int sub = lane % LPR, grp = lane / LPR;
   const int nv = C >> 2;
   const long warp_stride = (long)gridDim.x * (blockDim.x >> 5) * RPW;
+  [[maybe_unused]] float amax = 0.0f;
   for (long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < n_rows; row0 += warp_stride) {
     float4 v[RI][NV];
     float s[RI], q[RI];
@@ -133,6 +138,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const Rows rows, con
           const float o0 = (v[r][u].x - s[r]) * rstd * g4.x + b4.x, o1 = (v[r][u].y - s[r]) * rstd * g4.y + b4.y;
           const float o2 = (v[r][u].z - s[r]) * rstd * g4.z + b4.z, o3 = (v[r][u].w - s[r]) * rstd * g4.w + b4.w;
           if constexpr (sizeof(OutT) == 2) {
+            if constexpr (is_half_t<OutT>::value) amax = fmaxf(fmaxf(amax, fabsf(o0)), fmaxf(fmaxf(fabsf(o1), fabsf(o2)), fabsf(o3)));
             uint2 pk;
             pk.x = pack2<OutT>(o0, o1);
             pk.y = pack2<OutT>(o2, o3);
@@ -144,6 +150,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const Rows rows, con
       }
     }
   }
+  if constexpr (is_half_t<OutT>::value) f16_guard(amax);
 }
 
 // `C` below is the full normalised width (4 x the canvas width for MergeRows)

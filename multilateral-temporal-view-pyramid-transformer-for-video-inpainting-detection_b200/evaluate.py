@@ -96,5 +96,9 @@ class ShardedEvaluator:
             n_pixels = logits.shape[-1] * logits.shape[-2]
             rows.append(self.counts_fn(logits, gt))
         counts = torch.cat(rows, 0) if rows else torch.zeros((0, 4), dtype=torch.int64)
+        if counts.is_cuda:
+            from . import ops
+            counts = counts.cpu()                      # the shard's results are on the host: the range flag is final too
+            ops.check_f16_range(device)                # 'fp16' mode left the half range -> raise, never report silently
         f1, iou, n = reduce_means(local_sums(counts, n_pixels or 1), device)
         return {"f1": f1, "iou": iou, "n_valid": n, "counts": counts, "shard": (lo, hi)}

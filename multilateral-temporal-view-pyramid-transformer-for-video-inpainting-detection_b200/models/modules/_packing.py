@@ -10,7 +10,19 @@ import torch
 from ... import ops
 
 
+def invalidate_packed(module):
+    """Drops every cached kernel-side copy below `module`.  Needed after in-place updates through `.data` (p.data.copy_(w),
+    EMA updates ...), which do not bump Parameter._version; load_state_dict and checkpoint.restore call it themselves.
+    CUDA graphs captured earlier hold raw pointers to the old copies and must be re-captured (also after set_precision)."""
+    for m in module.modules():
+        m.__dict__.pop("_pack_cache", None)
+
+
 class PackedModule(torch.nn.Module):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.register_load_state_dict_post_hook(lambda mod, incompatible: invalidate_packed(mod))
+
     def _packed(self, name, params, fn):
         key = tuple((p.data_ptr(), p._version, p.device) for p in params) + (ops.precision(),)
         cache = self.__dict__.setdefault("_pack_cache", {})

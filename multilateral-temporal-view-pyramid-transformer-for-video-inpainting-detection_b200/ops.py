@@ -14,8 +14,13 @@ F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 RS_IDENTITY, RS_UP_ALIGNED, RS_UP_HALFPIX, RS_AVGPOOL2, RS_PIXEL_SHUFFLE2 = 0, 1, 2, 3, 4
 
-_precision = "bf16"
+# Default operand precision: IEEE half.  Same tcgen05 kernels and speed as bfloat16, three more mantissa bits on every GEMM /
+# attention operand: the mode that meets the north star's >= 99.9 % thresholded-mask identity (bf16: 99.6 %).  Its narrower
+# range is guarded: conversions saturate and report through the overflow flag below (f16_overflowed()).
+DEFAULT_PRECISION = "fp16"
+_precision = DEFAULT_PRECISION
 _bound_device = None
+_overflow_flags = {}        # device index -> int32 tensor registered with mumpy_set_f16_overflow_flag
 launch_count = 0            # libmumpy_b200 kernels launched so far (bench.py reports the per-step delta as gpu_launches)
 
 
@@ -69,6 +74,10 @@ def _prep(*tensors):
     lib = _lib.load()
     if dev != _bound_device:
         _lib.check(lib.mumpy_init(dev), "mumpy_init")
+        if dev not in _overflow_flags:
+            _overflow_flags[dev] = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", dev))
+            torch.cuda.synchronize(dev)
+        _lib.check(lib.mumpy_set_f16_overflow_flag(_overflow_flags[dev].data_ptr()), "mumpy_set_f16_overflow_flag")
         _bound_device = dev
     launch_count += 1
     return lib, torch.cuda.current_stream(dev).cuda_stream
@@ -76,6 +85,31 @@ def _prep(*tensors):
 
 def _p(t):
     return None if t is None else t.data_ptr()
+
+
+def f16_overflow_flag(device=None):
+    """The int32 device word the kernels OR 1 into when an fp32 value beyond the IEEE-half range was converted (and saturated)
+    in 'fp16' mode; None before the first library call on that device.  Copy it back with a step's results to check cheaply."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    return _overflow_flags.get(dev)
+
+
+def f16_overflowed(device=None, reset=True) -> bool:
+    """True when any kernel since the last reset had to saturate an fp32 -> half conversion (synchronises the device)."""
+    flag = f16_overflow_flag(device)
+    if flag is None:
+        return False
+    hit = bool(flag.item())
+    if hit and reset:
+        flag.zero_()
+    return hit
+
+
+def check_f16_range(device=None):
+    """Raises MumpyError when the 'fp16' mode left the half range since the last check -- loud, never silent."""
+    if f16_overflowed(device):
+        raise _lib.MumpyError("fp16 operand overflow: an activation beyond +-65504 was saturated; results are not trustworthy. "
+                              "Use set_precision('bf16') (same speed, wider range, ~99.6 % mask identity) or 'fp32' for this model.")
 
 
 # ------------------------------------------------------------------------------------------------ GEMM / norms

@@ -1,5 +1,7 @@
 """GPU: the full forward (Encoder -> Decoder, the path test.py:94-95 drives) through the C ABI against the reference
-captures.  fp32 mode: <= 1e-4 on logits and identical masks.  bf16 mode: stated tolerance + mask identity fraction."""
+captures.  fp32 mode: <= 1e-4 on logits and identical masks.  fp16 mode (the default and the mode bench.py reports):
+max-abs <= 5e-3, mean-abs <= 6e-4, >= 99.9 % identical thresholded masks (the north star's bar).  bf16 mode (opt-in):
+its own stated, weaker tolerance."""
 import pytest
 import torch
 
@@ -9,9 +11,11 @@ pytestmark = pytest.mark.gpu
 
 # bf16-mode tolerances (tcgen05 GEMMs on bf16 operands, fp32 accumulation / residual stream / statistics),
 # measured on B200 with the key-seeded weights, logit std 0.18:
-BF16_LOGIT_MAXABS = 6e-2
-BF16_LOGIT_MEANABS = 6e-3
-BF16_MASK_IDENTITY = 0.97
+# bf16 is the opt-in wide-range mode; it does NOT meet the north star's >= 99.9 % mask identity (8 mantissa bits on every
+# operand: measured 1.0e-2 / 1.3e-2 max-abs, 1.9e-3 mean-abs, 99.60 % identity) -- the default / benchmarked mode is fp16 (below).
+BF16_LOGIT_MAXABS = 3e-2
+BF16_LOGIT_MEANABS = 3e-3
+BF16_MASK_IDENTITY = 0.994
 
 
 @pytest.fixture(scope="module")
@@ -34,7 +38,7 @@ def _run(model, x, mode):
         torch.cuda.synchronize()
         return final_x, view_x, ff, logits, feats
     finally:
-        mumpy_b200.set_precision("bf16")
+        mumpy_b200.set_precision(mumpy_b200.ops.DEFAULT_PRECISION)
 
 
 @pytest.mark.parametrize("B", [1, 2])

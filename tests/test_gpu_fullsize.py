@@ -27,7 +27,7 @@ def model():
     return enc.cuda(), dec.cuda()
 
 
-@pytest.mark.parametrize("mode,tol,identity", [("fp32", 2e-5, 0.9999), ("fp16", 4e-3, 0.999), ("bf16", 6e-2, 0.97)])
+@pytest.mark.parametrize("mode,tol,identity", [("fp32", 2e-5, 0.9999), ("fp16", 4e-3, 0.999), ("bf16", 3e-2, 0.994)])
 def test_batch32_rows_equal_single_clip_forwards(model, mode, tol, identity):
     """configs[2] shape.  fp32 mode: the only batch dependence is fp32 summation order (split-K ranges, tile widths).  16-bit
     modes: tile choices change with M, rounding points do not, so the tolerances of the golden-vector tests apply with room."""
@@ -49,7 +49,7 @@ def test_batch32_rows_equal_single_clip_forwards(model, mode, tol, identity):
                 assert same >= identity, (mode, i, same)
     finally:
         mtv.set_per_clip_pairing(False)
-        mumpy_b200.set_precision("bf16")
+        mumpy_b200.set_precision(mumpy_b200.ops.DEFAULT_PRECISION)
 
 
 def test_batch32_mask_counts_identity(model):
@@ -124,7 +124,7 @@ def test_faf_b32_scaling_and_frame_independence():
                 assert torch.equal(faf.frame((x * 2).contiguous(), 1), y * 2)
                 assert torch.equal(faf.frame(x[5:6].contiguous(), 1), y[5:6])
         finally:
-            mumpy_b200.set_precision("bf16")
+            mumpy_b200.set_precision(mumpy_b200.ops.DEFAULT_PRECISION)
 
 
 def test_resize_b64_native_frames():

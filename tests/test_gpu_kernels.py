@@ -182,7 +182,7 @@ def test_faf_tensor_core_path(mode, size, B):
     try:
         y = FAF(size).eval().frame(x.cuda(), 1)
     finally:
-        mumpy_b200.set_precision("bf16")
+        mumpy_b200.set_precision(mumpy_b200.ops.DEFAULT_PRECISION)
     assert y.shape == ref.shape
     assert util.maxabs(y, ref) < (1e-4 if mode == "bf16" else 2e-5)
 

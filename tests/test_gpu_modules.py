@@ -20,7 +20,7 @@ def fp32_mode():
     import mumpy_b200
     mumpy_b200.set_precision("fp32")
     yield
-    mumpy_b200.set_precision("bf16")
+    mumpy_b200.set_precision(mumpy_b200.ops.DEFAULT_PRECISION)
 
 
 def _build(cls, ctor):
