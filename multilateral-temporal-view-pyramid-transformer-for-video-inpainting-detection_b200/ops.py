@@ -90,7 +90,9 @@ def _p(t):
 def f16_overflow_flag(device=None):
     """The int32 device word the kernels OR 1 into when an fp32 value beyond the IEEE-half range was converted (and saturated)
     in 'fp16' mode; None before the first library call on that device.  Copy it back with a step's results to check cheaply."""
-    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    dev = None if device is None else torch.device(device).index      # torch.device("cuda") has no index: the current device
+    if dev is None:
+        dev = torch.cuda.current_device()
     return _overflow_flags.get(dev)
 
 
