@@ -280,7 +280,7 @@ def kernel_section(peaks, device, dt=None):
     return out
 
 
-OPS_TIMED = ["linear", "linear_dual", "linear_into", "layernorm", "patch_merge_norm", "window_attention", "mha_short", "tokenize", "faf", "faf16", "assemble_clips",
+OPS_TIMED = ["linear", "linear_dual", "linear_into", "ln_linear", "layernorm", "patch_merge_norm", "window_attention", "mha_short", "tokenize", "faf", "faf16", "assemble_clips",
              "cva_offsets", "cva_sample", "cva_attention", "cva_residual", "gather_rows", "conv2d_nhwc", "conv2d_nhwc_bf16",
              "conv2d_nhwc_cout1", "im2col_nhwc", "groupnorm_nhwc", "resample_nhwc", "mul_add", "add", "nchw_to_nhwc", "nhwc_to_nchw",
              "channel_group_mean", "mask_counts", "cast16"]
@@ -298,6 +298,9 @@ def timed_serial_step(enc, dec, x, gt):
         if name in ("linear", "linear_dual") and a[0].dtype != torch.float32:
             K_ = a[0].shape[-1]
             return 2.0 * (a[0].numel() // K_) * a[1].shape[0] * K_
+        if name == "ln_linear":                  # (x, gamma, beta, eps, w, ...): LayerNorm fused into the consuming GEMM
+            K_ = a[0].shape[-1]
+            return 2.0 * (a[0].numel() // K_) * a[4].shape[0] * K_
         if name == "conv2d_nhwc_bf16":
             B_, H, W_, Cin, Cout, kh, kw = a[3:10]
             return 2.0 * B_ * H * W_ * Cout * Cin * kh * kw

@@ -78,6 +78,19 @@ int mumpy_set_attention_tc(int enabled);
  * residual (M,N) fp32 with row stride ldo or NULL (may alias out); out (M,N) of `out_dtype`, row stride ldo. */
 int mumpy_linear(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out,
                  long ldo, long M, int N, int K, int ab_dtype, int out_dtype, int act, void *stream);
+
+/* LayerNorm fused into the nn.Linear that consumes it (16-bit operand modes only):
+ *   out = act( LayerNorm(x; gamma, beta, eps) . W^T + bias )
+ * replaces `self.norm1(x)` + `self.qkv(x)` (swinTransformer.py:266,142; multiTemporalViewEncoder.py:246,
+ * WindowAttention.forward) and `self.norm2(x)` + `self.fc1(x)` + `self.act(x)` (swinTransformer.py:305,47-48) of a Swin /
+ * CrossSwin block: the normalised rows are produced in shared memory as the tcgen05 A operand and never written to global memory.
+ * x (M,K) fp32 row-major (the residual stream), gamma/beta (K) fp32, W (N,K) row-major of `w_dtype` (MUMPY_BF16 / MUMPY_F16),
+ * bias (N) fp32 or NULL, out (M,N) of `w_dtype` with row stride ldo; act MUMPY_ACT_NONE or MUMPY_ACT_GELU.
+ * Shapes: K in {96,128,192,256,384,512} and N a multiple of 64 or 96 (mumpy_ln_linear_supported returns 1); anything else is an error --
+ * the caller then runs mumpy_layernorm + mumpy_linear.  Statistics are exact two-pass fp32, bit-identical to mumpy_layernorm. */
+int mumpy_ln_linear_supported(int N, int K);
+int mumpy_ln_linear(const float *x, const float *gamma, const float *beta, float eps, const void *W, const float *bias, void *out,
+                    long ldo, long M, int N, int K, int w_dtype, int act, void *stream);
 /* Same GEMM on bf16 operands with two results: out = act(A . W^T + bias) + residual (fp32) and
  * aux16 = (operand type)(act(A . W^T + bias)) -- the un-summed W-MSA branch that CrossSwinBlock returns as the next view's
  * key/value source (multiTemporalViewEncoder.py:275-276) together with the shortcut sum, in one pass. */

@@ -43,6 +43,10 @@ int linear_f32(const float *A, long lda, const float *W, const float *bias, cons
 int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, void *aux, long ldo,
                 long M, int N, int K, int ab_dtype, int out_dtype, int act, cudaStream_t st);
 
+bool ln_linear_supported(int N, int K);
+int ln_linear_16(const float *x, const float *gamma, const float *beta, float eps, const void *W, const float *bias, void *out, long ldo,
+                 long M, int N, int K, int w_dtype, int act, cudaStream_t st);
+
 int conv_bf16(const void *in, long ld_in, const void *wpk, const float *bias, const float *residual, void *out, long ldo, int B,
               int H, int W, int Cin, int Cout, int kh, int kw, int ph, int pw, int in_dtype, int out_dtype, int act, float *splitk_ws,
               long splitk_ws_bytes, cudaStream_t st);
@@ -162,6 +166,14 @@ extern "C" int mumpy_linear(const void *A, long lda, const void *W, const float 
   if (is_16bit(ab_dtype)) return linear_bf16(A, lda, W, bias, residual, out, nullptr, ldo, M, N, K, ab_dtype, out_dtype, act, as_stream(stream));
   set_error("linear: unknown dtype %d", ab_dtype);
   return MUMPY_ERR_ARG;
+}
+
+extern "C" int mumpy_ln_linear_supported(int N, int K) { return ln_linear_supported(N, K) ? 1 : 0; }
+
+extern "C" int mumpy_ln_linear(const float *x, const float *gamma, const float *beta, float eps, const void *W, const float *bias, void *out,
+                               long ldo, long M, int N, int K, int w_dtype, int act, void *stream) {
+  MUMPY_REQUIRE(x && gamma && beta && W && out && M > 0 && N > 0 && K > 0 && is_16bit(w_dtype), "ln_linear: bad arguments (M=%ld N=%d K=%d)", M, N, K);
+  return ln_linear_16(x, gamma, beta, eps, W, bias, out, ldo, M, N, K, w_dtype, act, as_stream(stream));
 }
 
 extern "C" int mumpy_linear_dual(const void *A, long lda, const void *W, const float *bias, const float *residual, float *out,

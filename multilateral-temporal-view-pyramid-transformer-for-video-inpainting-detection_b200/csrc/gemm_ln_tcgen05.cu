@@ -1,0 +1,414 @@
+// LayerNorm fused into the GEMM that consumes it (16-bit modes):
+//   out[m, n] = act( LN(x[m, :]) . W[n, :] + bias[n] )          x (M,K) fp32 residual stream, W (N,K) 16-bit, out 16-bit
+// i.e. norm1 -> qkv (swinTransformer.py:266 + :142) and norm2 -> fc1 + GELU (:305 + :47-48) of every Swin block whose
+// width fits (K = C in {96, 128, 192, 256, 384, 512}).  The normalised operand never exists in global memory:
+//
+//   * a work item is (128-row tile, group of `ng` N-tiles).  The 12 epilogue warps first normalise the item's 128 rows
+//     (exact two-pass fp32 statistics, the arithmetic of layernorm_vec_kernel: same lanes-per-row split, same summation
+//     order, so the operand is bit-identical to the unfused path) and write them as 16-bit K-major SWIZZLE_128B tiles
+//     straight into shared memory -- the whole 128 x K A operand stays resident (K = 512: 128 KB) for all N-tiles of the item;
+//   * warp 12 streams only the weight tiles (BN x 64) through a TMA / mbarrier ring, warp 13 issues tcgen05.mma
+//     (M = 128, N = BN, K = 16) into double-buffered TMEM accumulators, the epilogue warps drain them (bias, GELU, 16-bit
+//     pack through a 2 KB per-warp swizzled staging tile, 64-byte coalesced row segments).
+//
+// Versus layernorm_vec_kernel + gemm_tc_kernel this removes one kernel, the 16-bit write + re-reads of the normalised
+// matrix, and the A half of the main loop's L2 -> SM traffic (the GEMM main loop is bound by the ~42.5 B/clk/SM L2 path).
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+#include "tc_epilogue.cuh"
+
+namespace mumpy {
+
+int resolve_driver_entry_points();
+int tc_encode_2d_16(CUtensorMap *map, const void *ptr, bool f16, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                    uint32_t box_inner, uint32_t box_outer);
+int tc_num_sms();
+
+constexpr int LG_BM = 128;
+constexpr int LG_BK = 64;
+constexpr int LG_MAX_STAGES = 8;
+constexpr int LG_EPI_WARPS = 12;
+constexpr int LG_EPI_GROUPS = LG_EPI_WARPS / 4;
+constexpr int LG_THREADS = (LG_EPI_WARPS + 2) * 32;
+constexpr int LG_STAGING = EPI16_STAGING;           // per-warp staging tile: 32 rows x 32 columns of 16-bit outputs
+constexpr int LG_BIAS = 128 * 4;                    // per-warp bias slice (up to 4 chunks of 32 columns)
+constexpr int LG_A_KB_BYTES = LG_BM * 128;          // one 64-column k-block of the resident A operand
+constexpr int LG_SMEM_TOTAL = 226 * 1024;       // dynamic part; the barriers / TMEM slot are static shared memory
+
+struct LgParams {
+  const float *x;
+  const float *gamma;
+  const float *beta;
+  const float *bias;
+  uint16_t *out;
+  long M;
+  long ldo;
+  long num_items;
+  int N, K;
+  int BN;
+  int stages;
+  int act;
+  int f16;
+  int ng;             // N-tiles per work item
+  int n_groups;       // work items per 128-row tile (ng * n_groups = N / BN)
+  int nkb;            // 64-column k-blocks (the last one may be partial: K = 96)
+  uint32_t acc_cols;
+  uint32_t idesc;
+  float eps;
+  int debug;          // development: bit 0 skips the LayerNorm prologue, bit 1 the epilogue, bit 2 the MMAs, bit 3 the TMA loads (timing attribution only)
+};
+
+// N-tile visited at step `nt` of work item `item`: every 128-row tile starts its sweep over the group's N-tiles at a different
+// offset.  Without it all ~148 CTAs request the SAME weight tile from L2 at the same time (one wave, identical schedules) and
+// the few L2 slices holding it serialise them: measured 1 us per k-block instead of 0.2.
+__device__ __forceinline__ int lg_ntile(const LgParams &p, long item, int nt) {
+  const int rot = static_cast<int>((item / p.n_groups) % p.ng);
+  const int g = static_cast<int>(item % p.n_groups);
+  int t = nt + rot;
+  if (t >= p.ng) t -= p.ng;
+  return g * p.ng + t;
+}
+
+__device__ __forceinline__ void lg_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Normalises rows [m0, m0 + 128) into the resident A operand.  LPR lanes share a row and hold NV float4 each (K = 16 LPR NV),
+// 32/LPR rows side by side in a warp, RI such groups in flight -- layernorm_vec_kernel's scheme (norm.cu).
+template <typename OutT, int LPR, int NV, int RI>
+__device__ __forceinline__ float lg_normalise_rows(const LgParams &p, uint32_t a_base, long m0, int warp, int lane) {
+  constexpr int G = 32 / LPR;
+  constexpr int RPW = G * RI;
+  static_assert(LG_BM % RPW == 0, "row groups must tile the 128-row block");
+  const int sub = lane % LPR, grp = lane / LPR;
+  const int C = p.K;
+  float amax = 0.0f;
+  for (int r0 = warp * RPW; r0 < LG_BM; r0 += LG_EPI_WARPS * RPW) {
+    float4 v[RI][NV];
+    float s[RI], q[RI];
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      const long row = m0 + r0 + r * G + grp;
+#pragma unroll
+      for (int u = 0; u < NV; ++u)
+        v[r][u] = row < p.M ? *(reinterpret_cast<const float4 *>(p.x + row * C) + sub + LPR * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      s[r] = 0.0f;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) s[r] += (v[r][u].x + v[r][u].y) + (v[r][u].z + v[r][u].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < RI; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      s[r] = s[r] / C;
+      q[r] = 0.0f;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const float a = v[r][u].x - s[r], b = v[r][u].y - s[r], c = v[r][u].z - s[r], d = v[r][u].w - s[r];
+        q[r] += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < RI; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+#pragma unroll
+    for (int r = 0; r < RI; ++r) q[r] = 1.0f / sqrtf(q[r] / C + p.eps);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int i = sub + LPR * u;                  // float4 index in the row: columns 4i .. 4i+3
+      const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma) + i), b4 = __ldg(reinterpret_cast<const float4 *>(p.beta) + i);
+      // k-block i/16, 16-byte chunk (i%16)/2 of the 128-byte row, low / high half of the chunk
+      const uint32_t col_off = static_cast<uint32_t>(i >> 4) * LG_A_KB_BYTES + static_cast<uint32_t>(i & 1) * 8u;
+      const uint32_t chunk = static_cast<uint32_t>(i & 15) >> 1;
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        const uint32_t rt = static_cast<uint32_t>(r0 + r * G + grp);
+        const float rstd = q[r];
+        const float o0 = (v[r][u].x - s[r]) * rstd * g4.x + b4.x, o1 = (v[r][u].y - s[r]) * rstd * g4.y + b4.y;
+        const float o2 = (v[r][u].z - s[r]) * rstd * g4.z + b4.z, o3 = (v[r][u].w - s[r]) * rstd * g4.w + b4.w;
+        if constexpr (is_half_t<OutT>::value) amax = fmaxf(fmaxf(amax, fabsf(o0)), fmaxf(fmaxf(fabsf(o1), fabsf(o2)), fabsf(o3)));
+        const uint32_t w0 = pack2<OutT>(o0, o1), w1 = pack2<OutT>(o2, o3);
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_base + col_off + rt * 128u + ((chunk ^ (rt & 7u)) << 4)), "r"(w0), "r"(w1)
+                     : "memory");
+      }
+    }
+  }
+  return amax;
+}
+
+template <typename OutT>
+__device__ __forceinline__ float lg_normalise(const LgParams &p, uint32_t a_base, long m0, int warp, int lane) {
+  switch (p.K) {
+    case 96: return lg_normalise_rows<OutT, 8, 3, 2>(p, a_base, m0, warp, lane);
+    case 128: return lg_normalise_rows<OutT, 8, 4, 2>(p, a_base, m0, warp, lane);
+    case 192: return lg_normalise_rows<OutT, 16, 3, 2>(p, a_base, m0, warp, lane);
+    case 256: return lg_normalise_rows<OutT, 16, 4, 2>(p, a_base, m0, warp, lane);
+    case 384: return lg_normalise_rows<OutT, 32, 3, 2>(p, a_base, m0, warp, lane);
+    default: return lg_normalise_rows<OutT, 32, 4, 2>(p, a_base, m0, warp, lane);
+  }
+}
+
+__global__ void __launch_bounds__(LG_THREADS, 1) ln_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const LgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * LG_MAX_STAGES + 5];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t a_base = (raw + 1023u) & ~1023u;                         // resident A: nkb k-blocks of 128 rows x 128 B
+  const uint32_t b_base = a_base + static_cast<uint32_t>(p.nkb) * LG_A_KB_BYTES;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t epi_base = b_base + static_cast<uint32_t>(p.stages) * b_bytes;
+  const uint32_t full0 = smem_u32(&bars[0]);
+  const uint32_t empty0 = smem_u32(&bars[LG_MAX_STAGES]);
+  const uint32_t acc_full0 = smem_u32(&bars[2 * LG_MAX_STAGES]);
+  const uint32_t acc_empty0 = smem_u32(&bars[2 * LG_MAX_STAGES + 2]);
+  const uint32_t a_full = smem_u32(&bars[2 * LG_MAX_STAGES + 4]);
+
+  if (warp == LG_EPI_WARPS && lane == 0) {
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full0 + 8 * s, 1);
+      mbar_init(acc_empty0 + 8 * s, LG_EPI_WARPS);
+    }
+    mbar_init(a_full, LG_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == LG_EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2 * p.acc_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_grid_sync();
+
+  if (warp == LG_EPI_WARPS) {
+    // ------------------------------------------------ TMA producer (weights only) ------------------------------------
+    // (whole warp converged, one elected lane issues: elect_one(), tc_common.cuh)
+    uint32_t s = 0, ph = 0;
+    for (long item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int nt = 0; nt < p.ng; ++nt) {
+        const int n0 = lg_ntile(p, item, nt) * p.BN;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          if (elect_one()) {
+            if (p.debug & 8) {
+              mbar_arrive(full0 + 8 * s);
+            } else {
+              mbar_arrive_expect_tx(full0 + 8 * s, b_bytes);
+              tma_load_2d(b_base + s * b_bytes, &tmB, full0 + 8 * s, kb * LG_BK, n0);
+            }
+          }
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == LG_EPI_WARPS + 1) {
+    // ------------------------------------------------ MMA issuer -----------------------------------------------------
+    uint32_t s = 0, ph = 0, t = 0, wi = 0;
+    for (long item = blockIdx.x; item < p.num_items; item += gridDim.x, ++wi) {
+      mbar_wait(a_full, wi & 1);                          // the item's normalised rows are in shared memory
+      tc_fence_after();
+      for (int nt = 0; nt < p.ng; ++nt, ++t) {
+        const uint32_t slot = t & 1, aph = (t >> 1) & 1;
+        mbar_wait(acc_empty0 + 8 * slot, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + slot * p.acc_cols;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(a_base + kb * LG_A_KB_BYTES);
+          const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s * b_bytes);
+          const bool tail = (kb + 1) * LG_BK > p.K;           // K = 96: the second k-block holds 32 columns
+          if (elect_one()) {
+            if (p.debug & 4) {
+              mbar_arrive(empty0 + 8 * s);
+            } else {
+              umma_bf16(d_tmem, adesc, bdesc, p.idesc, kb > 0 ? 1u : 0u);
+              umma_bf16(d_tmem, adesc + 2, bdesc + 2, p.idesc, 1u);
+              if (!tail) {
+                umma_bf16(d_tmem, adesc + 4, bdesc + 4, p.idesc, 1u);
+                umma_bf16(d_tmem, adesc + 6, bdesc + 6, p.idesc, 1u);
+              }
+              umma_commit(empty0 + 8 * s);
+            }
+          }
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+        }
+        if (elect_one()) umma_commit(acc_full0 + 8 * slot);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------ LayerNorm prologue + epilogue ----------------------------------
+    const uint32_t st_base = epi_base + warp * LG_STAGING;
+    float *bias_s = reinterpret_cast<float *>(smem_raw + (epi_base - raw) + LG_EPI_WARPS * LG_STAGING) + warp * (LG_BIAS / 4);
+    uint32_t t = 0;
+    float amax = 0.0f;
+    for (long item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const long m0 = (item / p.n_groups) * LG_BM;
+      // every MMA that read the previous item's rows has completed: this warp waited for the accumulator of that item's last
+      // N-tile, which tcgen05.commit publishes after all earlier MMAs
+      if (!(p.debug & 1)) amax = fmaxf(amax, p.f16 ? lg_normalise<__half>(p, a_base, m0, warp, lane) : lg_normalise<__nv_bfloat16>(p, a_base, m0, warp, lane));
+      lg_fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+      for (int nt = 0; nt < p.ng; ++nt, ++t) {
+        const uint32_t slot = t & 1, aph = (t >> 1) & 1;
+        const int n0 = lg_ntile(p, item, nt) * p.BN;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = (warp >> 2) * 32 + 32 * LG_EPI_GROUPS * ci + lane;
+          bias_s[ci * 32 + lane] = (p.bias && c < p.BN && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.0f;
+        }
+        __syncwarp();
+        mbar_wait(acc_full0 + 8 * slot, aph);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + slot * p.acc_cols;
+        float a = 0.0f;
+        if (p.debug & 2) {
+        } else if (p.f16) {
+          a = p.act == MUMPY_ACT_GELU ? epilogue16_tile<__half, 1>(p.out, p.ldo, p.M, p.N, p.BN, p.act, LG_EPI_GROUPS, st_base, bias_s, acc, warp, lane, m0, n0)
+                                      : epilogue16_tile<__half, 0>(p.out, p.ldo, p.M, p.N, p.BN, p.act, LG_EPI_GROUPS, st_base, bias_s, acc, warp, lane, m0, n0);
+        } else {
+          a = p.act == MUMPY_ACT_GELU ? epilogue16_tile<__nv_bfloat16, 1>(p.out, p.ldo, p.M, p.N, p.BN, p.act, LG_EPI_GROUPS, st_base, bias_s, acc, warp, lane, m0, n0)
+                                      : epilogue16_tile<__nv_bfloat16, 0>(p.out, p.ldo, p.M, p.N, p.BN, p.act, LG_EPI_GROUPS, st_base, bias_s, acc, warp, lane, m0, n0);
+        }
+        amax = fmaxf(amax, a);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty0 + 8 * slot);
+      }
+    }
+    f16_guard(amax);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == LG_EPI_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * p.acc_cols) : "memory");
+}
+
+static int lg_env(const char *name) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+
+bool ln_linear_supported(int N, int K) {
+  return (K == 96 || K == 128 || K == 192 || K == 256 || K == 384 || K == 512) && (N % 64 == 0 || N % 96 == 0);
+}
+
+// Tile width and N-grouping: minimise  waves x (prologue + ng x max(main loop, epilogue)) + one epilogue  over the divisors of N.
+// Development overrides: MUMPY_LG_BN, MUMPY_LG_GROUPS.
+int ln_linear_16(const float *x, const float *gamma, const float *beta, float eps, const void *W, const float *bias, void *out, long ldo,
+                 long M, int N, int K, int w_dtype, int act, cudaStream_t st) {
+  int rc = resolve_driver_entry_points();
+  if (rc) return rc;
+  MUMPY_REQUIRE(ln_linear_supported(N, K), "ln_linear: unsupported shape N=%d K=%d (K in {96,128,192,256,384,512}, N %% 64 == 0 or N %% 96 == 0)", N, K);
+  MUMPY_REQUIRE(act == MUMPY_ACT_NONE || act == MUMPY_ACT_GELU, "ln_linear: activation must be none or GELU");
+  MUMPY_REQUIRE(ldo % 8 == 0 && M > 0 && M < (1l << 31), "ln_linear: ldo %% 8 == 0 and 0 < M < 2^31 required");
+  MUMPY_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
+                "ln_linear: x, gamma, beta, W, out must be 16-byte aligned");
+  static int dbg_bn = -1, dbg_groups = -1, dbg_stages = -1, dbg_mode = 0;
+  if (dbg_bn < 0) {
+    dbg_mode = lg_env("MUMPY_LG_DEBUG");
+    dbg_bn = lg_env("MUMPY_LG_BN");
+    dbg_groups = lg_env("MUMPY_LG_GROUPS");
+    dbg_stages = lg_env("MUMPY_LG_STAGES");
+  }
+  const int nkb = (K + LG_BK - 1) / LG_BK;
+  const long m_tiles = cdiv(M, LG_BM);
+  const int sms = tc_num_sms();
+  const int fixed = 1024 + nkb * LG_A_KB_BYTES + LG_EPI_WARPS * (LG_STAGING + LG_BIAS);
+  static const int cands[] = {256, 192, 128, 96, 64};
+  int best_bn = 0, best_groups = 1, best_stages = 0;
+  double best_cost = 1e30;
+  const bool gelu = act == MUMPY_ACT_GELU;
+  for (int bn : cands) {
+    if (N % bn) continue;
+    if (dbg_bn > 0 && N % dbg_bn == 0 && bn != dbg_bn) continue;
+    int stages = (LG_SMEM_TOTAL - fixed) / (bn * 128);
+    if (stages > LG_MAX_STAGES) stages = LG_MAX_STAGES;
+    if (stages < 2) continue;
+    const int tiles_n = N / bn;
+    // measured (tools/umma_bench*.cu, tools/ln_gemm_bench.py): an MMA of N columns costs max(N / 2, ~105) clk to issue and run, a
+    // k-block of a 2-stage ring ~0.64 us (latency bound), of a deeper one ~0.5 us at BN = 256; narrow tiles waste the tensor pipe
+    const double per_kb = fmax(bn * 2.0, 420.0) / 1.9 * (stages >= 3 ? 1.0 : 1.25);
+    const double tile = nkb * per_kb;
+    const double epi = ((bn + 32 * LG_EPI_GROUPS - 1) / (32 * LG_EPI_GROUPS)) * (gelu ? 1150.0 : 800.0);
+    const double prologue = K * 20.0;        // 128 rows x K fp32 through 12 warps: ~12 us at K = 512 (cold)
+    for (int groups = 1; groups <= tiles_n; ++groups) {
+      if (tiles_n % groups) continue;
+      if (dbg_groups > 0 && tiles_n % dbg_groups == 0 && groups != dbg_groups) continue;
+      const int ng = tiles_n / groups;
+      const double waves = (double)cdiv(m_tiles * groups, sms);
+      const double cost = waves * (prologue + ng * fmax(tile, epi)) + fmin(tile, epi);
+      if (cost < best_cost * 0.99) {
+        best_cost = cost;
+        best_bn = bn;
+        best_groups = groups;
+        best_stages = stages;
+      }
+    }
+  }
+  MUMPY_REQUIRE(best_bn > 0, "ln_linear: no tile fits (N=%d K=%d)", N, K);
+  if (dbg_stages > 0 && dbg_stages < best_stages) best_stages = dbg_stages;
+  LgParams p = {};
+  p.x = x;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.bias = bias;
+  p.out = static_cast<uint16_t *>(out);
+  p.M = M;
+  p.ldo = ldo;
+  p.N = N;
+  p.K = K;
+  p.BN = best_bn;
+  p.act = act;
+  p.f16 = w_dtype == MUMPY_F16;
+  p.n_groups = best_groups;
+  p.ng = N / best_bn / best_groups;
+  p.num_items = m_tiles * best_groups;
+  p.nkb = nkb;
+  p.eps = eps;
+  p.debug = dbg_mode;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)p.BN) cols <<= 1;
+  p.acc_cols = cols;
+  p.idesc = make_idesc_16_f32(LG_BM, p.BN, p.f16 != 0);
+  const long kb_per_cta = (long)nkb * p.ng * cdiv(p.num_items, sms);
+  if (best_stages > kb_per_cta) best_stages = (int)kb_per_cta;
+  p.stages = best_stages;
+  CUtensorMap tmB;
+  rc = tc_encode_2d_16(&tmB, W, p.f16 != 0, (uint64_t)K, (uint64_t)N, (uint64_t)K, LG_BK, (uint32_t)p.BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ln_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_SMEM_TOTAL);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(ln_gemm_tc_kernel): %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int smem = fixed + p.stages * p.BN * 128;
+  const unsigned grid = (unsigned)(p.num_items < sms ? p.num_items : sms);
+  launch_kernel(ln_gemm_tc_kernel, grid, LG_THREADS, smem, st, tmB, p);
+  return launch_status("ln_gemm_tc_kernel");
+}
+
+}  // namespace mumpy

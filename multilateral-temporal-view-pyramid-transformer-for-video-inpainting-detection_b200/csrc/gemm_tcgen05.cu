@@ -12,9 +12,11 @@
 //               w/4), fused bias / GELU / ReLU / fp32 residual, 16-byte stores, fp32 or bf16 output.
 // Workhorse of the bf16 mode: qkv / proj / fc1 / fc2 / pre / proj_{q,k,v,out} / reduction / globalembedding /
 // global blocks / rgb_decoder linears and every decoder convolution (94% + 11% of the forward's FLOPs).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 namespace mumpy {
 
@@ -224,6 +226,23 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint8_t *stage,
   f16_guard(amax);
 }
 
+// The lean 16-bit epilogue as an out-of-line call (once per warp and tile): inlined next to the twelve fp32 / residual variants it
+// pushed gemm_tc_kernel over its 128-register limit (spills in every instantiation).
+__device__ __noinline__ void epilogue16_call(uint16_t *out, long ldo, long M, int N, int BN, int act, int f16, uint32_t st_base, const float *bias_s,
+                                             uint32_t acc, int warp, int lane, long m0, int n0) {
+  float amax;
+  if (f16) {
+    amax = act == MUMPY_ACT_GELU   ? epilogue16_tile<__half, 1>(out, ldo, M, N, BN, act, TC_EPI_GROUPS, st_base, bias_s, acc, warp, lane, m0, n0)
+           : act == MUMPY_ACT_NONE ? epilogue16_tile<__half, 0>(out, ldo, M, N, BN, act, TC_EPI_GROUPS, st_base, bias_s, acc, warp, lane, m0, n0)
+                                   : epilogue16_tile<__half, 2>(out, ldo, M, N, BN, act, TC_EPI_GROUPS, st_base, bias_s, acc, warp, lane, m0, n0);
+  } else {
+    amax = act == MUMPY_ACT_GELU   ? epilogue16_tile<__nv_bfloat16, 1>(out, ldo, M, N, BN, act, TC_EPI_GROUPS, st_base, bias_s, acc, warp, lane, m0, n0)
+           : act == MUMPY_ACT_NONE ? epilogue16_tile<__nv_bfloat16, 0>(out, ldo, M, N, BN, act, TC_EPI_GROUPS, st_base, bias_s, acc, warp, lane, m0, n0)
+                                   : epilogue16_tile<__nv_bfloat16, 2>(out, ldo, M, N, BN, act, TC_EPI_GROUPS, st_base, bias_s, acc, warp, lane, m0, n0);
+  }
+  f16_guard(amax);
+}
+
 // kPair: the two CTAs of a (2,1,1) cluster (one TPC) work on one 256 x BN tile with tcgen05.mma.cta_group::2: CTA r loads
 // A rows [128 r, 128 r + 128) and B rows [BN/2 r, BN/2 r + BN/2) of the tile, the leader (rank 0) issues the M=256 MMAs,
 // each CTA's TMEM receives its own 128 accumulator rows.  Per CTA and k-block that is (128 + BN/2) x 128 B from L2
@@ -237,6 +256,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   __shared__ uint64_t bars[2 * TC_MAX_STAGES + 4];
   __shared__ uint32_t tmem_slot;
 
+#ifdef GEMM_TIMING
+  const long long gt_entry = clock64();
+#endif
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
@@ -289,8 +311,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
   if (warp == TC_EPI_WARPS) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
-    if (lane == 0) {
-      uint32_t it = 0;
+    // (the whole warp runs the loop converged, one elected lane issues: see elect_one())
+    {
+      uint32_t s = 0, ph = 0;
       const uint32_t full_leader = kPair ? mapa_shared(full0, 0) : full0;      // shared::cluster address on rank 0
       for (long tile_s = group; tile_s < p.num_tiles; tile_s += n_groups) {
         const long tile = kSplit ? tile_s / p.k_splits : tile_s;
@@ -306,40 +329,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           ch = static_cast<int>(r % p.Hout) + p.lower_h;
           cn = static_cast<int>(r / p.Hout);
         }
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const uint32_t s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        int tap = kConv ? kb0 / p.cblocks : 0, cb = kConv ? kb0 - tap * p.cblocks : 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t sa = tiles + s * stage_bytes;
-          if (kPair) {
-            mbar_arrive_expect_tx_cluster(full_leader + 8 * s, stage_bytes);
-            if (kConv) {
-              const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-              tma_load_im2col_4d_pair(sa, &tmA, full_leader + 8 * s, cb * TC_BK, cw, ch, cn, static_cast<uint16_t>(tap % p.kw),
-                                      static_cast<uint16_t>(tap / p.kw));
+          if (elect_one()) {
+            if (kPair) {
+              mbar_arrive_expect_tx_cluster(full_leader + 8 * s, stage_bytes);
+              if (kConv) tma_load_im2col_4d_pair(sa, &tmA, full_leader + 8 * s, cb * TC_BK, cw, ch, cn, static_cast<uint16_t>(tap % p.kw), static_cast<uint16_t>(tap / p.kw));
+              else tma_load_2d_pair(sa, &tmA, full_leader + 8 * s, kb * TC_BK, static_cast<int>(m0));
+              tma_load_2d_pair(sa + a_bytes, &tmB, full_leader + 8 * s, kb * TC_BK, n0);
             } else {
-              tma_load_2d_pair(sa, &tmA, full_leader + 8 * s, kb * TC_BK, static_cast<int>(m0));
+              mbar_arrive_expect_tx(full0 + 8 * s, stage_bytes);
+              if (kConv) tma_load_im2col_4d(sa, &tmA, full0 + 8 * s, cb * TC_BK, cw, ch, cn, static_cast<uint16_t>(tap % p.kw), static_cast<uint16_t>(tap / p.kw));
+              else tma_load_2d(sa, &tmA, full0 + 8 * s, kb * TC_BK, static_cast<int>(m0));
+              tma_load_2d(sa + a_bytes, &tmB, full0 + 8 * s, kb * TC_BK, n0);
             }
-            tma_load_2d_pair(sa + a_bytes, &tmB, full_leader + 8 * s, kb * TC_BK, n0);
-            continue;
           }
-          mbar_arrive_expect_tx(full0 + 8 * s, stage_bytes);
-          if (kConv) {
-            const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-            tma_load_im2col_4d(sa, &tmA, full0 + 8 * s, cb * TC_BK, cw, ch, cn, static_cast<uint16_t>(tap % p.kw),
-                               static_cast<uint16_t>(tap / p.kw));
-          } else {
-            tma_load_2d(sa, &tmA, full0 + 8 * s, kb * TC_BK, static_cast<int>(m0));
-          }
-          tma_load_2d(sa + a_bytes, &tmB, full0 + 8 * s, kb * TC_BK, n0);
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+          if (kConv && ++cb == p.cblocks) { cb = 0; ++tap; }
         }
       }
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ------------------------------------------------ MMA issuer --------------------------------------------------
-    if (lane == 0 && rank == 0) {
-      uint32_t it = 0, t = 0;
+    if (rank == 0) {
+      uint32_t s = 0, ph = 0, t = 0;
+#ifdef GEMM_TIMING
+      const long long gt_ready = clock64();
+      long long gt_tile[8][3];
+#endif
       for (long tile_s = group; tile_s < p.num_tiles; tile_s += n_groups, ++t) {
+#ifdef GEMM_TIMING
+        if (t < 8) gt_tile[t][0] = clock64();
+#endif
         const int ks = kSplit ? static_cast<int>(tile_s % p.k_splits) : 0;
         const int kb0 = kSplit ? static_cast<int>((long)ks * nkb / p.k_splits) : 0;
         const int kb1 = kSplit ? static_cast<int>((long)(ks + 1) * nkb / p.k_splits) : nkb;
@@ -347,24 +371,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         mbar_wait(acc_empty0 + 8 * slot, aph ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + slot * p.acc_cols;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const uint32_t s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+#ifdef GEMM_TIMING
+        if (t < 8) gt_tile[t][1] = clock64();
+#endif
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
           const uint32_t sa = tiles + s * stage_bytes;
           const uint64_t adesc = make_kmajor_sw128_desc(sa);
           const uint64_t bdesc = make_kmajor_sw128_desc(sa + a_bytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr>>4) field
-            if (kPair) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr>>4) field
+              if (kPair) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if (kPair) umma_commit_pair(empty0 + 8 * s); else umma_commit(empty0 + 8 * s);      // frees the smem slot(s) once these MMAs have read them
           }
-          if (kPair) umma_commit_pair(empty0 + 8 * s); else umma_commit(empty0 + 8 * s);      // frees the smem slot(s) once these MMAs have read them
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
         }
-        if (kPair) umma_commit_pair(acc_full0 + 8 * slot); else umma_commit(acc_full0 + 8 * slot);  // accumulator complete
+        if (elect_one()) {
+          if (kPair) umma_commit_pair(acc_full0 + 8 * slot); else umma_commit(acc_full0 + 8 * slot);  // accumulator complete
+        }
+        __syncwarp();
+#ifdef GEMM_TIMING
+        if (t < 8) gt_tile[t][2] = clock64();
+#endif
       }
+#ifdef GEMM_TIMING
+      if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0) {
+        printf("cta %d M=%ld N=%d K=%d BN=%d stages=%d: setup %lld clk, tiles:", blockIdx.x, p.M, p.N, p.K, p.BN, p.stages, gt_ready - gt_entry);
+        for (uint32_t i = 0; i < t && i < 8; ++i) printf(" [wait_acc %lld mainloop %lld | start %lld]", gt_tile[i][1] - gt_tile[i][0], gt_tile[i][2] - gt_tile[i][1], gt_tile[i][0] - gt_entry);
+        printf(" end %lld\n", clock64() - gt_entry);
+      }
+#endif
     }
   } else {
     // ---------------- epilogue ----------------
@@ -372,6 +414,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     float *bias_s = reinterpret_cast<float *>(smem_raw + (tiles - raw) + p.stages * stage_bytes + TC_EPI_WARPS * EPI_STAGE_BYTES) + warp * 128;
     const int mode = (p.act == MUMPY_ACT_GELU ? 1 : (p.act == MUMPY_ACT_NONE ? 0 : 2)) | (p.out_bf16 ? 4 : 0) | (p.residual ? 8 : 0);
     uint32_t t = 0;
+#ifdef GEMM_TIMING
+    long long ge_tile[8][3];
+#endif
     const uint32_t acc_empty_leader = kPair ? mapa_shared(acc_empty0, 0) : acc_empty0;
     for (long tile_s = group; tile_s < p.num_tiles; tile_s += n_groups, ++t) {
       const long tile = kSplit ? tile_s / p.k_splits : tile_s;
@@ -396,16 +441,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.residual + gm * p.ldo + n0), "r"(bytes) : "memory");
         }
       }
+#ifdef GEMM_TIMING
+      if (t < 8) ge_tile[t][0] = clock64();
+#endif
       mbar_wait(acc_full0 + 8 * slot, aph);
       tc_fence_after();
+#ifdef GEMM_TIMING
+      if (t < 8) ge_tile[t][1] = clock64();
+#endif
       const uint32_t acc = tmem_base + slot * p.acc_cols;
       switch (mode) {
         case 0: epilogue_tile<0, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
         case 1: epilogue_tile<1, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
         case 2: epilogue_tile<2, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
-        case 4: epilogue_tile<0, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
-        case 5: epilogue_tile<1, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
-        case 6: epilogue_tile<2, true, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
+        // 16-bit output, no residual (qkv, fc1 + GELU, pre, k/v, operand-precision convolutions): the lean epilogue of tc_epilogue.cuh
+        case 4: case 5: case 6:
+          epilogue16_call(reinterpret_cast<uint16_t *>(p.out) + out_shift, p.ldo, p.M, p.N, p.BN, p.act, p.f16, smem_u32(stage), bias_s, acc, warp, lane, m0, n0);
+          break;
         case 8: epilogue_tile<0, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
         case 9: epilogue_tile<1, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
         case 10: epilogue_tile<2, false, true>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
@@ -419,7 +471,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       if (lane == 0) {
         if (kPair) mbar_arrive_cluster(acc_empty_leader + 8 * slot); else mbar_arrive(acc_empty0 + 8 * slot);
       }
+#ifdef GEMM_TIMING
+      if (t < 8) ge_tile[t][2] = clock64();
+#endif
     }
+#ifdef GEMM_TIMING
+    if (blockIdx.x == 0 && (warp == 0 || warp == 11) && lane == 0) {
+      printf("cta 0 epilogue warp %d:", warp);
+      for (uint32_t i = 0; i < t && i < 8; ++i) printf(" [wait %lld epi %lld | at %lld]", ge_tile[i][1] - ge_tile[i][0], ge_tile[i][2] - ge_tile[i][1], ge_tile[i][1] - gt_entry);
+      printf("\n");
+    }
+#endif
   }
 
   tc_fence_before();
@@ -446,6 +508,13 @@ static int encode_2d_bf16(CUtensorMap *map, const void *ptr, bool f16, uint64_t 
   }
   return MUMPY_OK;
 }
+
+// shared with gemm_ln_tcgen05.cu
+int tc_encode_2d_16(CUtensorMap *map, const void *ptr, bool f16, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                    uint32_t box_inner, uint32_t box_outer) {
+  return encode_2d_bf16(map, ptr, f16, inner, outer, row_stride_elems, box_inner, box_outer);
+}
+int tc_num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 
 // development knobs (environment, read once): MUMPY_TC_BN / MUMPY_TC_STAGES override the tile heuristics,
 // MUMPY_TC_DEBUG=1 skips the epilogue's global stores, =2 also skips its math (timing attribution only).

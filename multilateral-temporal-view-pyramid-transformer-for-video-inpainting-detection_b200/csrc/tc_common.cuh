@@ -115,6 +115,21 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, 
       : "memory");
 }
 
+// One lane of the (converged) warp.  The single-thread instructions of the tensor-core path (tcgen05.mma / commit, TMA loads) are
+// issued inside `if (elect_one())` by a warp that runs its whole loop converged: ptxas then keeps the descriptors / addresses in
+// uniform registers.  Under a `lane == 0` branch it cannot (the region is divergent): every operand goes through R2UR and every
+// issue through an ELECT waterfall loop, which made the old main loops issue-bound (measured with tools/umma_bench.cu: 230-290
+// clk per MMA instead of the 128 clk floor of a 128 x 256 x 16 MMA; with elect.sync the same loop runs at the floor).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

@@ -236,7 +236,9 @@ class Decoder(PackedModule):
                 # 9-channel map can feed the TMA convolution (the padding is never read)
                 cf = ffinfo.shape[1]
                 ldf = (cf + 7) // 8 * 8
-                f_in = torch.empty((B, S // 2, S // 2, ldf), dtype=torch.float32, device=x.device)
+                # (zero-filled: the operand cast below converts the padding channels too, and stale memory there could trip the
+                # fp16 range guard although the convolution never reads them)
+                f_in = torch.zeros((B, S // 2, S // 2, ldf), dtype=torch.float32, device=x.device)
                 ops.nchw_to_nhwc(ffinfo.contiguous().float(), pool2=True, out=f_in, ld_out=ldf)
                 freq0 = self._freq_stage("decoder_frequency_0", f_in, B, S // 2, S // 2, pooled=True, ld_in=ldf)
                 reg.publish("freq0", freq0)

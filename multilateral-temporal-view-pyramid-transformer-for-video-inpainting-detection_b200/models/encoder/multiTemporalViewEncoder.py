@@ -95,8 +95,7 @@ class CrossSwinBlock(PackedModule):
         B, L1, C1 = x1.shape
         TH1 = L1 // W
         x1 = x1.contiguous()
-        xn = ops.layernorm(x1, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        ao = self.attn.canvas_attention(xn, B, TH1, W, self.shift_size, self.attn_mask)
+        ao = self.attn.canvas_attention(x1, B, TH1, W, self.shift_size, self.attn_mask, norm=self.norm1)
         if ops.tensor_cores() and not need_out_fp32:
             if need_out:
                 h, out_op = ops.linear_dual(ao, self.attn._gemm_weight("proj", self.attn.proj.weight), self.attn.proj.bias, x1)
@@ -120,8 +119,7 @@ class CrossSwinBlock(PackedModule):
             y = self.cva.crossattn.canvas_forward(h, x2p, B, TH1, TH2, W, PER_CLIP_PAIRING)
             # h + (window_partition(h) + raw_reshape(y)) added in window-major order, no window_reverse (:138,284-286)
             h = ops.cva_residual(h, y, B, TH1, W, C1, self.window_size)
-        xn = ops.layernorm(h, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        return self.mlp.fused(xn, residual=h)
+        return self.mlp.fused(h, residual=h, norm=self.norm2)
 
     def forward(self, x1, x2):
         """x1 (B,L1,C1), x2 (B,L2,C2) canvases -> (x1', out) with out = the un-summed W-MSA branch (:228-291)."""

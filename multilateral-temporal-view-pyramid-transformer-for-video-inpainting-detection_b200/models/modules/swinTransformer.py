@@ -41,9 +41,16 @@ class Mlp(PackedModule):
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
 
-    def fused(self, xn, residual=None):
-        """xn: normalised input already in operand precision; returns fc2(gelu(fc1(xn))) (+ residual), fp32."""
-        h = ops.linear(xn, self._gemm_weight("fc1", self.fc1.weight), self.fc1.bias, act=ops.ACT_GELU, out_dtype=ops.act_dtype())
+    def fused(self, xn, residual=None, norm=None):
+        """xn: normalised input already in operand precision -- or, with `norm` (the block's LayerNorm), the raw fp32 stream, which
+        is then normalised inside the fc1 kernel where the width fits (mumpy_ln_linear); returns fc2(gelu(fc1(.))) (+ residual), fp32."""
+        w1 = self._gemm_weight("fc1", self.fc1.weight)
+        if norm is not None and ops.ln_linear_fits(w1.shape[0], w1.shape[1]):
+            h = ops.ln_linear(xn, norm.weight, norm.bias, norm.eps, w1, self.fc1.bias, act=ops.ACT_GELU)
+        else:
+            if norm is not None:
+                xn = ops.layernorm(xn, norm.weight, norm.bias, norm.eps)
+            h = ops.linear(xn, w1, self.fc1.bias, act=ops.ACT_GELU, out_dtype=ops.act_dtype())
         return ops.linear(h, self._gemm_weight("fc2", self.fc2.weight), self.fc2.bias, residual=residual)
 
     def forward(self, x):
@@ -88,11 +95,18 @@ class WindowAttention(PackedModule):
         return self._packed("table", [self.relative_position_bias_table],
                             lambda: self.relative_position_bias_table.detach().float().contiguous())
 
-    def canvas_attention(self, xn, B, TH, W, shift, mask, standard_mask=False):
-        """xn (B, TH*W, C) normalised canvas in operand precision -> attention output before `proj`.
+    def canvas_attention(self, xn, B, TH, W, shift, mask, standard_mask=False, norm=None):
+        """xn (B, TH*W, C) normalised canvas in operand precision -> attention output before `proj`.  With `norm` (the block's
+        norm1) xn is the raw fp32 canvas and the LayerNorm runs inside the qkv kernel where the width fits (mumpy_ln_linear).
         standard_mask: `mask` is exactly the Swin shift mask for (TH, W, ws, shift) (lets the kernel recompute it)."""
         C = self.dim
-        qkv = ops.linear(xn, self._gemm_weight("qkv", self.qkv.weight), self.qkv.bias, out_dtype=ops.act_dtype())
+        wq = self._gemm_weight("qkv", self.qkv.weight)
+        if norm is not None and ops.ln_linear_fits(wq.shape[0], wq.shape[1]):
+            qkv = ops.ln_linear(xn, norm.weight, norm.bias, norm.eps, wq, self.qkv.bias)
+        else:
+            if norm is not None:
+                xn = ops.layernorm(xn, norm.weight, norm.bias, norm.eps)
+            qkv = ops.linear(xn, wq, self.qkv.bias, out_dtype=ops.act_dtype())
         return ops.window_attention(qkv, self._bias(), mask, B, TH, W, C, self.num_heads, self.window_size[0], shift,
                                     rel_table=self._table(), standard_mask=standard_mask)
 
@@ -171,11 +185,9 @@ class SwinTransformerBlock(PackedModule):
         assert L % (H * W) == 0, "input feature has wrong size"
         TH = L // W
         x = x.contiguous()
-        xn = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        ao = self.attn.canvas_attention(xn, B, TH, W, self.shift_size, self.attn_mask, self._mask_is_standard(TH, W))
+        ao = self.attn.canvas_attention(x, B, TH, W, self.shift_size, self.attn_mask, self._mask_is_standard(TH, W), norm=self.norm1)
         x = self.attn.project(ao, residual=x)                    # shortcut + W-MSA  (:302)
-        xn = ops.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        return self.mlp.fused(xn, residual=x)                    # x + Mlp(LN2(x))   (:305)
+        return self.mlp.fused(x, residual=x, norm=self.norm2)    # x + Mlp(LN2(x))   (:305)
 
 
 class PatchMerging(PackedModule):

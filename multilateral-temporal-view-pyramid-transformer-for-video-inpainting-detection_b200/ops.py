@@ -162,6 +162,37 @@ def layernorm(x, gamma, beta, eps=1e-5, out_dtype=None):
     return out
 
 
+# LayerNorm inside the consuming GEMM (mumpy_ln_linear).  Opt-in: bit-identical to mumpy_layernorm + mumpy_linear and 108 fewer
+# launches per forward, but measured no faster (round 2, B = 32: 2078-2201 vs 2163-2193 clips/s; the un-overlapped LayerNorm
+# prologue and the 2-stage weight ring at K = 512 cost what the removed kernel saved -- DESIGN.md section 4).
+FUSED_LN = os.environ.get("MUMPY_FUSED_LN", "0") != "0"
+
+
+def set_fused_ln(enabled: bool):
+    global FUSED_LN
+    FUSED_LN = bool(enabled)
+
+
+def ln_linear_fits(N, K) -> bool:
+    """True when ln_linear() can run: a 16-bit operand mode, the switch on, and a width the fused kernel holds on chip."""
+    return FUSED_LN and tensor_cores() and K in (96, 128, 192, 256, 384, 512) and (N % 64 == 0 or N % 96 == 0)
+
+
+def ln_linear(x, gamma, beta, eps, w, bias=None, act=ACT_NONE):
+    """act(LayerNorm(x) @ w.T + bias) in operand precision; x (..., K) fp32, w (N, K) 16-bit.  One kernel: the normalised rows only
+    exist in shared memory (mumpy_ln_linear)."""
+    K = x.shape[-1]
+    N = w.shape[0]
+    M = x.numel() // K
+    if w.shape[1] != K or x.dtype != torch.float32 or w.dtype not in (torch.bfloat16, torch.float16):
+        raise _lib.MumpyError("ln_linear: x%s %s w%s %s" % (tuple(x.shape), x.dtype, tuple(w.shape), w.dtype))
+    out = torch.empty(x.shape[:-1] + (N,), dtype=w.dtype, device=x.device)
+    lib, st = _prep(x, gamma, beta, w, bias, out)
+    _lib.check(lib.mumpy_ln_linear(_p(x), _p(gamma), _p(beta), float(eps), _p(w), _p(bias), _p(out), N, M, N, K, code(w.dtype), act, st),
+               "mumpy_ln_linear")
+    return out
+
+
 def patch_merge_norm(x, gamma, beta, B, TH, W, C, eps=1e-5, out_dtype=None):
     out = torch.empty((B, (TH // 2) * (W // 2), 4 * C), dtype=out_dtype or act_dtype(), device=x.device)
     lib, st = _prep(x, gamma, beta, out)

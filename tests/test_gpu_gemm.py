@@ -82,3 +82,56 @@ def test_linear_dual_outputs(M, N, K, dt):
     assert out.dtype == torch.float32 and aux.dtype == dt
     assert util.maxabs(out, branch + res) < 1e-4 * max(1.0, float(branch.abs().max()))
     assert util.maxabs(aux.float(), branch) < (1e-2 if dt == torch.bfloat16 else 2e-3) * max(1.0, float(branch.abs().max()))
+
+
+LN_SHAPES = [  # (M, N, K): norm1 -> qkv and norm2 -> fc1 of the Swin blocks (stages 0-2 of the three views), ragged M
+    (3136, 288, 96), (3136, 384, 96), (9408, 384, 128), (9408, 512, 128), (784, 576, 192), (784, 768, 192), (2352, 768, 256),
+    (2352, 1024, 256), (196, 1152, 384), (6272, 1536, 384), (588, 1536, 512), (18816, 2048, 512), (130, 64, 128), (1, 192, 96),
+]
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", LN_SHAPES)
+@pytest.mark.parametrize("gelu", [False, True])
+def test_ln_linear_fused(M, N, K, gelu, dt):
+    """mumpy_ln_linear (LayerNorm produced in shared memory as the tcgen05 A operand) against (1) the oracle's fp32
+    layer_norm -> round to operand precision -> linear (-> GELU) on the same seeded tensors, and (2) the unfused kernels
+    (mumpy_layernorm + mumpy_linear), which it must reproduce bit for bit: same statistics arithmetic, same k-block order."""
+    ops = _ops()
+    x = util.seeded_input((M, K), 1) * 3.0 + util.seeded_input((M, 1), 5)
+    g, b = 1.0 + 0.2 * util.seeded_input((K,), 6), 0.1 * util.seeded_input((K,), 7)
+    w = (util.seeded_input((N, K), 2) / K ** 0.5).to(dt)
+    bias = util.seeded_input((N,), 3)
+    xn = orc.layer_norm(x, g, b).to(dt).float()
+    ref = orc.linear(xn, w.float(), bias)
+    if gelu:
+        ref = orc.gelu(ref)
+    act = ops.ACT_GELU if gelu else ops.ACT_NONE
+    xc, gc, bc, wc, biasc = x.cuda(), g.cuda(), b.cuda(), w.cuda(), bias.cuda()
+    out = ops.ln_linear(xc, gc, bc, 1e-5, wc, biasc, act=act)
+    assert out.dtype == dt and tuple(out.shape) == (M, N)
+    tol = 2e-2 if dt == torch.bfloat16 else 3e-3
+    assert util.maxabs(out.float(), ref) < tol * max(1.0, float(ref.abs().max()))
+    unfused = ops.linear(ops.layernorm(xc, gc, bc, 1e-5, out_dtype=dt), wc, biasc, act=act, out_dtype=dt)
+    assert torch.equal(out, unfused)
+
+
+def test_ln_linear_many_items_per_cta():
+    """More work items than SMs (the persistent loop re-normalises into the same shared-memory operand) and no bias."""
+    ops = _ops()
+    M, N, K = 128 * 400 + 17, 384, 128
+    x = util.seeded_input((M, K), 11).cuda()
+    g, b = (1.0 + 0.1 * util.seeded_input((K,), 12)).cuda(), (0.1 * util.seeded_input((K,), 13)).cuda()
+    w = (util.seeded_input((N, K), 14) / K ** 0.5).half().cuda()
+    out = ops.ln_linear(x, g, b, 1e-5, w, None)
+    unfused = ops.linear(ops.layernorm(x, g, b, 1e-5, out_dtype=torch.float16), w, None, out_dtype=torch.float16)
+    assert torch.equal(out, unfused)
+
+
+def test_ln_linear_rejects_unsupported_shapes():
+    import mumpy_b200
+    ops = _ops()
+    x = torch.zeros((64, 768)).cuda()
+    with pytest.raises(mumpy_b200._lib.MumpyError):
+        ops.ln_linear(x, torch.ones(768).cuda(), torch.zeros(768).cuda(), 1e-5, torch.zeros((768, 768), dtype=torch.float16).cuda())
+    assert not ops.ln_linear_fits(768, 768) and ops.ln_linear_fits(1536, 512)
