@@ -61,6 +61,8 @@ constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_EPI_WARPS = 12;
 constexpr int TC_EPI_GROUPS = TC_EPI_WARPS / 4;      // warps per TMEM lane quadrant: each takes every TC_EPI_GROUPS-th 32-column chunk
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_EPI_WARPS_LEAN = 16;
+constexpr int TC_THREADS_LEAN = (TC_EPI_WARPS_LEAN + 2) * 32;
 constexpr int TC_SMEM_BUDGET = 164 * 1024;      // operand ring; + 8 x (4 KB epilogue staging + 512 B bias) + 1 KB alignment slack
 
 struct TcParams {
@@ -249,9 +251,16 @@ __device__ __noinline__ void epilogue16_call(uint16_t *out, long ldo, long M, in
 // instead of (128 + BN) x 128 B -- the main loop of the 1-CTA kernel is bound by exactly that path (42.5 B/clk/SM).
 // kSplit: split-K instantiation (conv only): kept apart so that the plain kernels carry none of its index arithmetic (the
 // epilogue warps are at the register limit: one more live 64-bit value spills)
-template <bool kConv, bool kPair, bool kSplit = false>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+// kLean: 16-bit output without residual (qkv, fc1 + GELU, pre, k/v).  These GEMMs are epilogue-bound (per 128 x 256 tile the GELU
+// epilogue issues ~10 k warp instructions at an IPC of ~1.7: ~7 k clk against a 5 k clk main loop at K = 512, 2.4 k at K = 256), so
+// the variant carries ONLY the lean epilogue (tc_epilogue.cuh), which fits 112 registers, and runs 16 epilogue warps instead of
+// 12: four per TMEM lane quadrant, i.e. exactly two 32-column chunks per warp of a 256-wide tile instead of 3 / 3 / 2.
+template <bool kConv, bool kPair, bool kSplit = false, bool kLean = false>
+__global__ void __launch_bounds__(kLean ? TC_THREADS_LEAN : TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                                         const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  constexpr int EW = kLean ? TC_EPI_WARPS_LEAN : TC_EPI_WARPS;        // epilogue warps; warp EW = TMA producer, EW + 1 = MMA issuer
+  constexpr int EG = EW / 4;
+  constexpr int EST = kLean ? EPI16_STAGING : EPI_STAGE_BYTES;       // per-warp staging tile
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * TC_MAX_STAGES + 4];
   __shared__ uint32_t tmem_slot;
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const uint32_t acc_empty0 = smem_u32(&bars[2 * TC_MAX_STAGES + 2]);
   const int nkb = kConv ? p.K : (p.K + TC_BK - 1) / TC_BK;      // conv: p.K already counts k-blocks (taps x cblocks)
 
-  if (warp == TC_EPI_WARPS && lane == 0) {
+  if (warp == EW && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     // pair mode: `full` and `acc_empty` live on the leader and collect arrivals from both CTAs
@@ -286,11 +295,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full0 + 8 * s, 1);
-      mbar_init(acc_empty0 + 8 * s, kPair ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);
+      mbar_init(acc_empty0 + 8 * s, kPair ? 2 * EW : EW);
     }
     fence_barrier_init();
   }
-  if (warp == TC_EPI_WARPS + 1) {
+  if (warp == EW + 1) {
     if (kPair) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2 * p.acc_cols)
                    : "memory");
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   // stream; from here on global memory written by it is read
   pdl_grid_sync();
 
-  if (warp == TC_EPI_WARPS) {
+  if (warp == EW) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
     // (the whole warp runs the loop converged, one elected lane issues: see elect_one())
     {
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == TC_EPI_WARPS + 1) {
+  } else if (warp == EW + 1) {
     // ------------------------------------------------ MMA issuer --------------------------------------------------
     if (rank == 0) {
       uint32_t s = 0, ph = 0, t = 0;
@@ -410,8 +419,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     }
   } else {
     // ---------------- epilogue ----------------
-    uint8_t *stage = smem_raw + (tiles - raw) + p.stages * stage_bytes + warp * EPI_STAGE_BYTES;
-    float *bias_s = reinterpret_cast<float *>(smem_raw + (tiles - raw) + p.stages * stage_bytes + TC_EPI_WARPS * EPI_STAGE_BYTES) + warp * 128;
+    uint8_t *stage = smem_raw + (tiles - raw) + p.stages * stage_bytes + warp * EST;
+    float *bias_s = reinterpret_cast<float *>(smem_raw + (tiles - raw) + p.stages * stage_bytes + EW * EST) + warp * 128;
     const int mode = (p.act == MUMPY_ACT_GELU ? 1 : (p.act == MUMPY_ACT_NONE ? 0 : 2)) | (p.out_bf16 ? 4 : 0) | (p.residual ? 8 : 0);
     uint32_t t = 0;
 #ifdef GEMM_TIMING
@@ -427,7 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       // bias values of this warp's column chunks -> shared memory while the accumulator is still being produced
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
-        const int c = (warp >> 2) * 32 + 32 * TC_EPI_GROUPS * ci + lane;
+        const int c = (warp >> 2) * 32 + 32 * EG * ci + lane;
         bias_s[ci * 32 + lane] = (p.bias && c < p.BN && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.0f;
       }
       __syncwarp();
@@ -450,6 +459,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       if (t < 8) ge_tile[t][1] = clock64();
 #endif
       const uint32_t acc = tmem_base + slot * p.acc_cols;
+      if constexpr (kLean) {
+        float amax;
+        if (p.f16) {
+          amax = p.act == MUMPY_ACT_GELU ? epilogue16_tile<__half, 1>(reinterpret_cast<uint16_t *>(p.out), p.ldo, p.M, p.N, p.BN, p.act, EG, smem_u32(stage), bias_s, acc, warp, lane, m0, n0)
+                                         : epilogue16_tile<__half, 0>(reinterpret_cast<uint16_t *>(p.out), p.ldo, p.M, p.N, p.BN, p.act, EG, smem_u32(stage), bias_s, acc, warp, lane, m0, n0);
+        } else {
+          amax = p.act == MUMPY_ACT_GELU ? epilogue16_tile<__nv_bfloat16, 1>(reinterpret_cast<uint16_t *>(p.out), p.ldo, p.M, p.N, p.BN, p.act, EG, smem_u32(stage), bias_s, acc, warp, lane, m0, n0)
+                                         : epilogue16_tile<__nv_bfloat16, 0>(reinterpret_cast<uint16_t *>(p.out), p.ldo, p.M, p.N, p.BN, p.act, EG, smem_u32(stage), bias_s, acc, warp, lane, m0, n0);
+        }
+        f16_guard(amax);
+      } else
       switch (mode) {
         case 0: epilogue_tile<0, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
         case 1: epilogue_tile<1, false, false>(p, stage, bias_s, acc, warp, lane, m0, n0, out_shift); break;
@@ -486,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
   tc_fence_before();
   if (kPair) cluster_sync_all(); else __syncthreads();     // nobody leaves while the partner can still touch its barriers / tiles
-  if (warp == TC_EPI_WARPS + 1) {
+  if (warp == EW + 1) {
     if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * p.acc_cols) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * p.acc_cols) : "memory");
   }
@@ -609,7 +629,8 @@ static void launch_pair_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-static bool g_attr_set[5] = {false, false, false, false, false};
+static bool g_attr_set[6] = {false, false, false, false, false, false};
+static int g_dbg_lean = -1;      // MUMPY_TC_LEAN=0 keeps the 12-warp kernel for 16-bit outputs (A/B runs)
 
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p, bool pair, cudaStream_t st) {
   uint32_t cols = 32;
@@ -621,6 +642,8 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   if (p.k_splits < 1) p.k_splits = 1;
   p.num_tiles = cdiv(p.M, bm) * p.tiles_n * p.k_splits;
   if (g_dbg_stages < 0) {
+    const char *lv = getenv("MUMPY_TC_LEAN");
+    g_dbg_lean = lv ? atoi(lv) : 1;
     g_dbg_stages = env_int("MUMPY_TC_STAGES");
     g_dbg_mode = env_int("MUMPY_TC_DEBUG");
   }
@@ -635,8 +658,12 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   if (stages > kb_per_cta) stages = (int)kb_per_cta;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  const int smem = stages * stage_bytes + 1024 + TC_EPI_WARPS * (32 * 128 + 512);
-  const int which = p.k_splits > 1 ? 4 : (p.conv ? 1 : 0) + (pair ? 2 : 0);      // split-K: conv, single-CTA tiles only
+  // lean variant: plain linear, 16-bit output, no residual / side output, activation none or GELU
+  const bool lean = !p.conv && !pair && p.k_splits == 1 && p.out_bf16 && !p.residual && !p.aux && (p.act == MUMPY_ACT_NONE || p.act == MUMPY_ACT_GELU) &&
+                    g_dbg_lean != 0;
+  const int epi_smem = lean ? TC_EPI_WARPS_LEAN * (EPI16_STAGING + 512) : TC_EPI_WARPS * (32 * 128 + 512);
+  const int smem = stages * stage_bytes + 1024 + epi_smem;
+  const int which = lean ? 5 : p.k_splits > 1 ? 4 : (p.conv ? 1 : 0) + (pair ? 2 : 0);      // split-K: conv, single-CTA tiles only
   if (!g_attr_set[which]) {
     const int max_smem = TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * (32 * 128 + 512);
     cudaError_t e;
@@ -645,7 +672,8 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
       case 1: e = cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
       case 2: e = cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
       case 3: e = cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
-      default: e = cudaFuncSetAttribute(gemm_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+      case 4: e = cudaFuncSetAttribute(gemm_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+      default: e = cudaFuncSetAttribute(gemm_tc_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
     }
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
@@ -659,7 +687,8 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
     case 1: launch_kernel(gemm_tc_kernel<true, false>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
     case 2: launch_pair_kernel(gemm_tc_kernel<false, true>, 2 * groups, TC_THREADS, smem, st, tmA, tmB, p); break;
     case 3: launch_pair_kernel(gemm_tc_kernel<true, true>, 2 * groups, TC_THREADS, smem, st, tmA, tmB, p); break;
-    default: launch_kernel(gemm_tc_kernel<true, false, true>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
+    case 4: launch_kernel(gemm_tc_kernel<true, false, true>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
+    default: launch_kernel(gemm_tc_kernel<false, false, false, true>, groups, TC_THREADS_LEAN, smem, st, tmA, tmB, p); break;
   }
   return launch_status("gemm_tc_kernel");
 }

@@ -134,4 +134,32 @@ def test_ln_linear_rejects_unsupported_shapes():
     x = torch.zeros((64, 768)).cuda()
     with pytest.raises(mumpy_b200._lib.MumpyError):
         ops.ln_linear(x, torch.ones(768).cuda(), torch.zeros(768).cuda(), 1e-5, torch.zeros((768, 768), dtype=torch.float16).cuda())
-    assert not ops.ln_linear_fits(768, 768) and ops.ln_linear_fits(1536, 512)
+    was = ops.FUSED_LN
+    try:
+        ops.set_fused_ln(True)
+        assert not ops.ln_linear_fits(768, 768) and ops.ln_linear_fits(1536, 512)
+        ops.set_fused_ln(False)                                    # the switch is opt-in: off -> the mirrors never take the fused path
+        assert not ops.ln_linear_fits(1536, 512)
+    finally:
+        ops.set_fused_ln(was)
+
+
+def test_fused_ln_forward_is_bit_identical():
+    """A Swin block and a CrossSwin block with the LayerNorms fused into qkv / fc1 (mumpy_ln_linear) equal the unfused kernels bit
+    for bit (same statistics arithmetic, same k-block order)."""
+    from mumpy_b200.models.modules.swinTransformer import SwinTransformerBlock
+    ops = _ops()
+    blk = SwinTransformerBlock(128, (14, 14), 4, window_size=7, shift_size=3, temporal_dim=3).eval()
+    util.load_seeded(blk)
+    blk = blk.cuda()
+    x = util.seeded_input((2, 3 * 14 * 14, 128), 7).cuda()
+    was = ops.FUSED_LN
+    try:
+        with torch.no_grad():
+            ops.set_fused_ln(False)
+            ref = blk(x).clone()
+            ops.set_fused_ln(True)
+            out = blk(x)
+        assert torch.equal(out, ref)
+    finally:
+        ops.set_fused_ln(was)
