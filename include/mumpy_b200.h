@@ -89,6 +89,9 @@ int mumpy_linear(const void *A, long lda, const void *W, const float *bias, cons
  * Shapes: K in {96,128,192,256,384,512} and N a multiple of 64 or 96 (mumpy_ln_linear_supported returns 1); anything else is an error --
  * the caller then runs mumpy_layernorm + mumpy_linear.  Statistics are exact two-pass fp32, bit-identical to mumpy_layernorm. */
 int mumpy_ln_linear_supported(int N, int K);
+/* CTA-pair policy of mumpy_ln_linear (two adjacent 128-row tiles on a (2,1,1) cluster, tcgen05 cta_group::2, each CTA streaming half of
+ * every weight tile): 0 never, 1 the cost model decides (default), 2 whenever the shape allows.  Environment: MUMPY_LG_PAIR. */
+int mumpy_set_ln_linear_pair_mode(int mode);
 int mumpy_ln_linear(const float *x, const float *gamma, const float *beta, float eps, const void *W, const float *bias, void *out,
                     long ldo, long M, int N, int K, int w_dtype, int act, void *stream);
 /* Same GEMM on bf16 operands with two results: out = act(A . W^T + bias) + residual (fp32) and

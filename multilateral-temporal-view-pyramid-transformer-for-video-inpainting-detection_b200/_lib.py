@@ -26,6 +26,7 @@ SIGNATURES = {
     "mumpy_linear_dual": [vp, cl, vp, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, vp],
     "mumpy_layernorm": [vp, vp, vp, vp, ci, cl, ci, cf, vp],
     "mumpy_ln_linear_supported": [ci, ci],
+    "mumpy_set_ln_linear_pair_mode": [ci],
     "mumpy_ln_linear": [vp, vp, vp, cf, vp, vp, vp, cl, cl, ci, ci, ci, ci, vp],
     "mumpy_patch_merge_norm": [vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
     "mumpy_window_attention": [vp, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],

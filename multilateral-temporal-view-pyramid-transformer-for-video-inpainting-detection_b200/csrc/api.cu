@@ -44,6 +44,7 @@ int linear_bf16(const void *A, long lda, const void *W, const float *bias, const
                 long M, int N, int K, int ab_dtype, int out_dtype, int act, cudaStream_t st);
 
 bool ln_linear_supported(int N, int K);
+void set_ln_linear_pair_mode(int mode);
 int ln_linear_16(const float *x, const float *gamma, const float *beta, float eps, const void *W, const float *bias, void *out, long ldo,
                  long M, int N, int K, int w_dtype, int act, cudaStream_t st);
 
@@ -166,6 +167,11 @@ extern "C" int mumpy_linear(const void *A, long lda, const void *W, const float 
   if (is_16bit(ab_dtype)) return linear_bf16(A, lda, W, bias, residual, out, nullptr, ldo, M, N, K, ab_dtype, out_dtype, act, as_stream(stream));
   set_error("linear: unknown dtype %d", ab_dtype);
   return MUMPY_ERR_ARG;
+}
+
+extern "C" int mumpy_set_ln_linear_pair_mode(int mode) {
+  set_ln_linear_pair_mode(mode);
+  return MUMPY_OK;
 }
 
 extern "C" int mumpy_ln_linear_supported(int N, int K) { return ln_linear_supported(N, K) ? 1 : 0; }

@@ -173,6 +173,11 @@ def set_fused_ln(enabled: bool):
     FUSED_LN = bool(enabled)
 
 
+def set_ln_linear_pair_mode(mode: int):
+    """CTA-pair policy of ln_linear: 0 never, 1 the cost model decides (default), 2 whenever the shape allows."""
+    _lib.check(_lib.load().mumpy_set_ln_linear_pair_mode(int(mode)), "mumpy_set_ln_linear_pair_mode")
+
+
 def ln_linear_fits(N, K) -> bool:
     """True when ln_linear() can run: a 16-bit operand mode, the switch on, and a width the fused kernel holds on chip."""
     return FUSED_LN and tensor_cores() and K in (96, 128, 192, 256, 384, 512) and (N % 64 == 0 or N % 96 == 0)

@@ -90,10 +90,20 @@ LN_SHAPES = [  # (M, N, K): norm1 -> qkv and norm2 -> fc1 of the Swin blocks (st
 ]
 
 
+@pytest.fixture
+def ln_pair_mode(request):
+    """CTA-pair policy of mumpy_ln_linear for one test (0 = 1-CTA tiles, 2 = cta_group::2 pairs whenever legal)."""
+    ops = _ops()
+    ops.set_ln_linear_pair_mode(request.param)
+    yield request.param
+    ops.set_ln_linear_pair_mode(1)
+
+
+@pytest.mark.parametrize("ln_pair_mode", [0, 2], indirect=True)
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("M,N,K", LN_SHAPES)
 @pytest.mark.parametrize("gelu", [False, True])
-def test_ln_linear_fused(M, N, K, gelu, dt):
+def test_ln_linear_fused(M, N, K, gelu, dt, ln_pair_mode):
     """mumpy_ln_linear (LayerNorm produced in shared memory as the tcgen05 A operand) against (1) the oracle's fp32
     layer_norm -> round to operand precision -> linear (-> GELU) on the same seeded tensors, and (2) the unfused kernels
     (mumpy_layernorm + mumpy_linear), which it must reproduce bit for bit: same statistics arithmetic, same k-block order."""
@@ -116,7 +126,8 @@ def test_ln_linear_fused(M, N, K, gelu, dt):
     assert torch.equal(out, unfused)
 
 
-def test_ln_linear_many_items_per_cta():
+@pytest.mark.parametrize("ln_pair_mode", [0, 2], indirect=True)
+def test_ln_linear_many_items_per_cta(ln_pair_mode):
     """More work items than SMs (the persistent loop re-normalises into the same shared-memory operand) and no bias."""
     ops = _ops()
     M, N, K = 128 * 400 + 17, 384, 128
