@@ -137,8 +137,9 @@ int mumpy_faf(const float *x, const float *dct, float *ws, float *out, int B, in
 
 /* The same transform on the tensor cores (16-bit modes): the four DCT passes run as tcgen05 GEMMs over split operands
  * (a = a_hi + a_lo in `dtype`, three partial products accumulated in fp32: error 2.9e-5 (bf16) / 2.5e-6 (f16) on outputs ~3),
- * with a repack kernel (per-image transpose, band masks, hi/lo split) between them.  dcat / dtcat (S, 3S) of `dtype` =
- * [D_hi | D_lo | D_hi] for D and for D^T; ws16: 9*B*S x 3S 16-bit values; ws32: 9*B*S*S floats. */
+ * whose epilogues write each result already transposed per image, band masked and split -- the operand of the next pass (one
+ * split kernel for the input frame, no repack kernels in between).  dcat / dtcat (S, 3S) of `dtype` = [D_hi | D_lo | D_hi] for D
+ * and for D^T; ws16: 2 x (9*B*S x 3S) 16-bit values (the passes ping-pong between the halves); ws32: unused, may be NULL. */
 int mumpy_faf16(const float *x, const void *dcat, const void *dtcat, void *ws16, float *ws32, float *out, int B, int T,
                 int frame, int S, const int *band_lo_hi6, int dtype, void *stream);
 

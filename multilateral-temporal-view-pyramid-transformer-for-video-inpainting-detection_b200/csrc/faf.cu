@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(256) faf_repack_kernel(const RepackParams p) {
   }
 }
 
-int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, void *aux, long ldo,
-                long M, int N, int K, int ab_dtype, int out_dtype, int act, cudaStream_t st);
+int linear_faf_pass(const void *A, const void *W, void *out, long M, int K, int S, int imgs_per_band, int bands, const int *lo_hi6, int final_pass,
+                    int ab_dtype, cudaStream_t st);
 
 static int faf_repack(const RepackParams &p, int n_img, int dtype, cudaStream_t st) {
   dim3 grid(1, (unsigned)cdiv(p.R, 32), (unsigned)n_img);
@@ -166,10 +166,10 @@ extern "C" int mumpy_faf(const float *x, const float *dct, float *ws, float *out
 }
 
 // Tensor-core FAF.  dcat (S, 3S) = [D_hi | D_lo | D_hi], dtcat (S, 3S) = the same for D^T, both of `dtype`;
-// ws16: 9*B*S rows x 3S 16-bit values; ws32: 9*B*S*S floats.
+// ws16: 2 x (9*B*S rows x 3S) 16-bit values (the passes ping-pong between the halves); ws32 is no longer used (may be NULL).
 extern "C" int mumpy_faf16(const float *x, const void *dcat, const void *dtcat, void *ws16, float *ws32, float *out, int B, int T,
                            int frame, int S, const int *band_lo_hi6, int dtype, void *stream) {
-  MUMPY_REQUIRE(x && dcat && dtcat && ws16 && ws32 && out && band_lo_hi6 && B > 0 && frame >= 0 && frame < T, "faf16: bad arguments");
+  MUMPY_REQUIRE(x && dcat && dtcat && ws16 && out && band_lo_hi6 && B > 0 && frame >= 0 && frame < T, "faf16: bad arguments");
   MUMPY_REQUIRE(is_16bit(dtype) && S % 8 == 0, "faf16: 16-bit operand type and S %% 8 == 0 required");
   cudaStream_t st = as_stream(stream);
   const int n_img = B * 3;
@@ -188,41 +188,22 @@ extern "C" int mumpy_faf16(const float *x, const void *dcat, const void *dtcat, 
   p.n_bands = 1;
   int rc = faf_repack(p, n_img, dtype, st);
   if (rc) return rc;
-  // G1: T1[(img,i), k] = sum_j x[i,j] D[k,j]
-  rc = linear_bf16(ws16, 3 * S, dcat, nullptr, nullptr, ws32, nullptr, S, (long)n_img * S, S, 3 * S, dtype, MUMPY_F32, MUMPY_ACT_NONE, st);
+  // The four GEMMs write their results already transposed per image, band masked and split (faf_ts_epilogue, gemm_tcgen05.cu)
+  // into the other half of ws16, so no repack kernel runs between them.
+  char *ws_a = static_cast<char *>(ws16);
+  char *ws_b = ws_a + (size_t)9 * B * S * 3 * S * 2;
+  int lohi[6];
+  for (int i = 0; i < 6; ++i) lohi[i] = band_lo_hi6[i];
+  for (int b = 0; b < 3; ++b) MUMPY_REQUIRE(lohi[2 * b] >= 0 && lohi[2 * b + 1] < 65536, "faf16: band limits out of range");
+  // G1: T1[(img,i), k] = sum_j x[i,j] D[k,j]                      -> rows (img, k), columns i
+  rc = linear_faf_pass(ws_a, dcat, ws_b, (long)n_img * S, 3 * S, S, n_img, 1, nullptr, 0, dtype, st);
   if (rc) return rc;
-  // P1: transpose -> rows (img, k), columns i
-  p.in = ws32;
-  p.group = 1;
-  p.group_stride = SS;
-  p.transpose = 1;
-  rc = faf_repack(p, n_img, dtype, st);
+  // G2: Xf^T[(img,k), k'] = sum_i T1[i,k] D[k',i]                 -> rows (band, img, k'), columns k of F_band o Xf
+  rc = linear_faf_pass(ws_b, dcat, ws_a, (long)n_img * S, 3 * S, S, n_img, 3, lohi, 0, dtype, st);
   if (rc) return rc;
-  // G2: Xf^T[(img,k), k'] = sum_i T1[i,k] D[k',i]
-  rc = linear_bf16(ws16, 3 * S, dcat, nullptr, nullptr, ws32, nullptr, S, (long)n_img * S, S, 3 * S, dtype, MUMPY_F32, MUMPY_ACT_NONE, st);
+  // G3: U[(band,img,k'), j] = sum_k (F o Xf)[k',k] D[k,j]          -> rows (band, img, j), columns k'
+  rc = linear_faf_pass(ws_a, dtcat, ws_b, 3l * n_img * S, 3 * S, S, 3 * n_img, 1, nullptr, 0, dtype, st);
   if (rc) return rc;
-  // P2: transpose + band masks -> rows (band, img, k'), columns k of F_band o Xf
-  p.n_bands = 3;
-  for (int b = 0; b < 3; ++b) {
-    p.lo[b] = band_lo_hi6[2 * b];
-    p.hi[b] = band_lo_hi6[2 * b + 1];
-  }
-  rc = faf_repack(p, n_img, dtype, st);
-  if (rc) return rc;
-  // G3: U[(band,img,k'), j] = sum_k (F o Xf)[k',k] D[k,j]
-  rc = linear_bf16(ws16, 3 * S, dtcat, nullptr, nullptr, ws32, nullptr, S, 3l * n_img * S, S, 3 * S, dtype, MUMPY_F32, MUMPY_ACT_NONE, st);
-  if (rc) return rc;
-  // P3: transpose -> rows (band, img, j), columns k'
-  p.n_bands = 1;
-  p.n_img = 3 * n_img;
-  rc = faf_repack(p, 3 * n_img, dtype, st);
-  if (rc) return rc;
-  // G4: Y^T[(band,img,j), i] = sum_k' U[k',j] D[k',i]
-  rc = linear_bf16(ws16, 3 * S, dtcat, nullptr, nullptr, ws32, nullptr, S, 3l * n_img * S, S, 3 * S, dtype, MUMPY_F32, MUMPY_ACT_NONE, st);
-  if (rc) return rc;
-  // P4: transpose into out (B, 9, S, S), channel = band*3 + rgb
-  p.out16 = nullptr;
-  p.out32 = out;
-  p.final_imgs = n_img;
-  return faf_repack(p, 3 * n_img, dtype, st);
+  // G4: Y^T[(band,img,j), i] = sum_k' U[k',j] D[k',i]              -> out (B, 9, S, S), channel = band*3 + rgb, element (i, j)
+  return linear_faf_pass(ws_b, dtcat, out, 3l * n_img * S, 3 * S, S, n_img, 1, nullptr, 1, dtype, st);
 }

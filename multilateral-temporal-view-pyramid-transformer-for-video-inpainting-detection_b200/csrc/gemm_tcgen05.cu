@@ -245,6 +245,62 @@ __device__ __noinline__ void epilogue16_call(uint16_t *out, long ldo, long M, in
   f16_guard(amax);
 }
 
+// FAF pass epilogue (kTS kernels): the DCT branch chains four GEMMs whose outputs are consumed TRANSPOSED per S x S image, band
+// masked and split into [hi | hi | lo] 16-bit operands (faf.cu).  Thread <-> accumulator row m = (image, r): for a fixed column n
+// the 32 lanes of a warp hold 32 consecutive r, so writing element (r, n) at transposed position (n, r) is a coalesced 64-byte
+// store straight from registers -- the five repack kernels between the GEMMs become three 2-byte stores per element here.
+// Geometry travels in the convolution fields of TcParams (unused by a plain linear; the struct must not grow): Wout = S,
+// Hout = images per band, kw = bands written (1 or 3), lower_w / lower_h / cblocks = lo | hi << 16 of the three bands,
+// act = MUMPY_FAF_FINAL for the last pass (fp32 result straight into the (B, 9, S, S) output).
+constexpr int MUMPY_FAF_FINAL = 100;
+template <typename T16>
+__device__ __forceinline__ void faf_ts_epilogue(const TcParams &p, uint32_t acc, int warp, int lane, long m0, int n0, int groups) {
+  const int quad = warp & 3, grp = warp >> 2;
+  const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
+  const long m = m0 + quad * 32 + lane;
+  const int S = p.Wout, n_img = p.Hout, bands = p.kw;
+  const bool valid = m < p.M;
+  const int img = valid ? static_cast<int>(m / S) : 0;
+  const int r = valid ? static_cast<int>(m - (long)img * S) : 0;
+  const bool final_pass = p.act == MUMPY_FAF_FINAL;
+  float amax = 0.0f;
+  // final pass: image (band, b, c) -> channel band * 3 + c of clip b
+  const int f_band = img / n_img, f_im = img - f_band * n_img;
+  float *out32 = reinterpret_cast<float *>(p.out) + (((long)(f_im / 3) * 9 + f_band * 3 + f_im % 3) * S) * S + r;
+  T16 *out16 = reinterpret_cast<T16 *>(p.out) + ((long)img * S) * 3 * S + r;
+  const long band_stride = (long)n_img * S * 3 * S;
+  const int lo[3] = {p.lower_w & 0xffff, p.lower_h & 0xffff, p.cblocks & 0xffff};
+  const int hi[3] = {p.lower_w >> 16, p.lower_h >> 16, p.cblocks >> 16};
+  for (int c0 = grp * 32; c0 < p.BN; c0 += 32 * groups) {
+    uint32_t v[32];
+    tmem_ld32(lane_addr + c0, v);
+    if (!valid) continue;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = n0 + c0 + j;
+      if (c0 + j >= p.BN || n >= p.N) break;
+      const float val = __uint_as_float(v[j]);
+      if (final_pass) {
+        out32[(long)n * S] = val;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (q >= bands) break;
+          const float mv = (bands > 1 && (r + n < lo[q] || r + n > hi[q])) ? 0.0f : val;
+          if (is_half_t<T16>::value) amax = fmaxf(amax, fabsf(mv));
+          const T16 h = from_f32<T16>(mv);
+          const T16 l = from_f32<T16>(mv - to_f32(h));
+          T16 *row = out16 + q * band_stride + (long)n * 3 * S;
+          row[0] = h;
+          row[S] = h;
+          row[2 * S] = l;
+        }
+      }
+    }
+  }
+  if (is_half_t<T16>::value) f16_guard(amax);
+}
+
 // kPair: the two CTAs of a (2,1,1) cluster (one TPC) work on one 256 x BN tile with tcgen05.mma.cta_group::2: CTA r loads
 // A rows [128 r, 128 r + 128) and B rows [BN/2 r, BN/2 r + BN/2) of the tile, the leader (rank 0) issues the M=256 MMAs,
 // each CTA's TMEM receives its own 128 accumulator rows.  Per CTA and k-block that is (128 + BN/2) x 128 B from L2
@@ -255,7 +311,7 @@ __device__ __noinline__ void epilogue16_call(uint16_t *out, long ldo, long M, in
 // epilogue issues ~10 k warp instructions at an IPC of ~1.7: ~7 k clk against a 5 k clk main loop at K = 512, 2.4 k at K = 256), so
 // the variant carries ONLY the lean epilogue (tc_epilogue.cuh), which fits 112 registers, and runs 16 epilogue warps instead of
 // 12: four per TMEM lane quadrant, i.e. exactly two 32-column chunks per warp of a 256-wide tile instead of 3 / 3 / 2.
-template <bool kConv, bool kPair, bool kSplit = false, bool kLean = false>
+template <bool kConv, bool kPair, bool kSplit = false, bool kLean = false, bool kTS = false>
 __global__ void __launch_bounds__(kLean ? TC_THREADS_LEAN : TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                                          const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   constexpr int EW = kLean ? TC_EPI_WARPS_LEAN : TC_EPI_WARPS;        // epilogue warps; warp EW = TMA producer, EW + 1 = MMA issuer
@@ -459,7 +515,10 @@ __global__ void __launch_bounds__(kLean ? TC_THREADS_LEAN : TC_THREADS, 1) gemm_
       if (t < 8) ge_tile[t][1] = clock64();
 #endif
       const uint32_t acc = tmem_base + slot * p.acc_cols;
-      if constexpr (kLean) {
+      if constexpr (kTS) {
+        if (p.f16) faf_ts_epilogue<__half>(p, acc, warp, lane, m0, n0, EG);
+        else faf_ts_epilogue<__nv_bfloat16>(p, acc, warp, lane, m0, n0, EG);
+      } else if constexpr (kLean) {
         float amax;
         if (p.f16) {
           amax = p.act == MUMPY_ACT_GELU ? epilogue16_tile<__half, 1>(reinterpret_cast<uint16_t *>(p.out), p.ldo, p.M, p.N, p.BN, p.act, EG, smem_u32(stage), bias_s, acc, warp, lane, m0, n0)
@@ -629,7 +688,7 @@ static void launch_pair_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-static bool g_attr_set[6] = {false, false, false, false, false, false};
+static bool g_attr_set[7] = {false, false, false, false, false, false, false};
 static int g_dbg_lean = -1;      // MUMPY_TC_LEAN=0 keeps the 12-warp kernel for 16-bit outputs (A/B runs)
 
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p, bool pair, cudaStream_t st) {
@@ -659,11 +718,12 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   if (stages < 1) stages = 1;
   p.stages = stages;
   // lean variant: plain linear, 16-bit output, no residual / side output, activation none or GELU
-  const bool lean = !p.conv && !pair && p.k_splits == 1 && p.out_bf16 && !p.residual && !p.aux && (p.act == MUMPY_ACT_NONE || p.act == MUMPY_ACT_GELU) &&
+  const bool lean = !p.conv && p.Wout == 0 && !pair && p.k_splits == 1 && p.out_bf16 && !p.residual && !p.aux && (p.act == MUMPY_ACT_NONE || p.act == MUMPY_ACT_GELU) &&
                     g_dbg_lean != 0;
   const int epi_smem = lean ? TC_EPI_WARPS_LEAN * (EPI16_STAGING + 512) : TC_EPI_WARPS * (32 * 128 + 512);
   const int smem = stages * stage_bytes + 1024 + epi_smem;
-  const int which = lean ? 5 : p.k_splits > 1 ? 4 : (p.conv ? 1 : 0) + (pair ? 2 : 0);      // split-K: conv, single-CTA tiles only
+  const bool ts = !p.conv && p.Wout > 0;      // FAF pass: transposed / split store (geometry in the convolution fields)
+  const int which = ts ? 6 : lean ? 5 : p.k_splits > 1 ? 4 : (p.conv ? 1 : 0) + (pair ? 2 : 0);      // split-K: conv, single-CTA tiles only
   if (!g_attr_set[which]) {
     const int max_smem = TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * (32 * 128 + 512);
     cudaError_t e;
@@ -673,7 +733,8 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
       case 2: e = cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
       case 3: e = cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
       case 4: e = cudaFuncSetAttribute(gemm_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
-      default: e = cudaFuncSetAttribute(gemm_tc_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+      case 5: e = cudaFuncSetAttribute(gemm_tc_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+      default: e = cudaFuncSetAttribute(gemm_tc_kernel<false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
     }
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
@@ -688,7 +749,8 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
     case 2: launch_pair_kernel(gemm_tc_kernel<false, true>, 2 * groups, TC_THREADS, smem, st, tmA, tmB, p); break;
     case 3: launch_pair_kernel(gemm_tc_kernel<true, true>, 2 * groups, TC_THREADS, smem, st, tmA, tmB, p); break;
     case 4: launch_kernel(gemm_tc_kernel<true, false, true>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
-    default: launch_kernel(gemm_tc_kernel<false, false, false, true>, groups, TC_THREADS_LEAN, smem, st, tmA, tmB, p); break;
+    case 5: launch_kernel(gemm_tc_kernel<false, false, false, true>, groups, TC_THREADS_LEAN, smem, st, tmA, tmB, p); break;
+    default: launch_kernel(gemm_tc_kernel<false, false, false, false, true>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
   }
   return launch_status("gemm_tc_kernel");
 }
@@ -727,6 +789,38 @@ int linear_bf16(const void *A, long lda, const void *W, const float *bias, const
   rc = encode_2d_bf16(&tmB, W, p.f16 != 0, (uint64_t)K, (uint64_t)N, (uint64_t)K, TC_BK, (uint32_t)(tc.pair ? p.BN / 2 : p.BN));
   if (rc) return rc;
   return launch_tc(tmA, tmB, p, tc.pair, st);
+}
+
+// One pass of the tensor-core FAF (faf.cu): out(transposed per S x S image, band masked, split) = A . W^T.
+// A (M = images * S, K) and W (S, K) 16-bit K-major.  final_pass: fp32 result into the (B, 9, S, S) output instead.
+int linear_faf_pass(const void *A, const void *W, void *out, long M, int K, int S, int imgs_per_band, int bands, const int *lo_hi6, int final_pass,
+                    int ab_dtype, cudaStream_t st) {
+  int rc = resolve_driver_entry_points();
+  if (rc) return rc;
+  MUMPY_REQUIRE(S % 8 == 0 && K % 8 == 0 && S < 65536 && M % S == 0, "faf pass: S, K multiples of 8 and M a multiple of S required");
+  TcParams p = {};
+  p.out = out;
+  p.f16 = ab_dtype == MUMPY_F16;
+  p.ldo = S;
+  p.M = M;
+  p.N = S;
+  p.K = K;
+  const TileChoice tc = pick_tile(M, S, (K + TC_BK - 1) / TC_BK, false, false);
+  p.BN = tc.bn;
+  p.act = final_pass ? MUMPY_FAF_FINAL : MUMPY_ACT_NONE;
+  p.out_bf16 = final_pass ? 0 : 1;
+  p.Wout = S;
+  p.Hout = imgs_per_band;
+  p.kw = bands;
+  p.lower_w = lo_hi6 ? (lo_hi6[0] | (lo_hi6[1] << 16)) : 0;
+  p.lower_h = lo_hi6 ? (lo_hi6[2] | (lo_hi6[3] << 16)) : 0;
+  p.cblocks = lo_hi6 ? (lo_hi6[4] | (lo_hi6[5] << 16)) : 0;
+  CUtensorMap tmA, tmB;
+  rc = encode_2d_bf16(&tmA, A, p.f16 != 0, (uint64_t)K, (uint64_t)M, (uint64_t)K, TC_BK, TC_BM);
+  if (rc) return rc;
+  rc = encode_2d_bf16(&tmB, W, p.f16 != 0, (uint64_t)K, (uint64_t)S, (uint64_t)K, TC_BK, (uint32_t)p.BN);
+  if (rc) return rc;
+  return launch_tc(tmA, tmB, p, false, st);
 }
 
 // Second half of a split-K GEMM: out = act(sum_s partial[s] + bias) (+ residual), four columns per thread.  The partial

@@ -249,14 +249,13 @@ def faf(x, dct, bands, frame=1):
 def faf16(x, dcat, dtcat, bands, frame=1):
     """Tensor-core FAF (16-bit modes): dcat / dtcat (S, 3S) = [D_hi | D_lo | D_hi] for D and D^T in the operand type."""
     B, T, _, S, _ = x.shape
-    ws16 = torch.empty((9 * B * S, 3 * S), dtype=dcat.dtype, device=x.device)
-    ws32 = torch.empty((9 * B * S * S,), dtype=torch.float32, device=x.device)
+    ws16 = torch.empty((2, 9 * B * S, 3 * S), dtype=dcat.dtype, device=x.device)      # the four passes ping-pong between the halves
     out = torch.empty((B, 9, S, S), dtype=torch.float32, device=x.device)
-    lib, st = _prep(x, dcat, dtcat, ws16, ws32, out)
+    lib, st = _prep(x, dcat, dtcat, ws16, out)
     arr = (ctypes.c_int * 6)(*[int(v) for lohi in bands for v in lohi])
     global launch_count
-    launch_count += 8            # five repacks + four GEMMs per call
-    _lib.check(lib.mumpy_faf16(_p(x), _p(dcat), _p(dtcat), _p(ws16), _p(ws32), _p(out), B, T, frame, S, arr, code(dcat.dtype), st),
+    launch_count += 4            # the input split + four GEMMs per call (transposes / band masks / splits live in their epilogues)
+    _lib.check(lib.mumpy_faf16(_p(x), _p(dcat), _p(dtcat), _p(ws16), None, _p(out), B, T, frame, S, arr, code(dcat.dtype), st),
                "mumpy_faf16")
     return out
 
