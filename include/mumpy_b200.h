@@ -128,6 +128,12 @@ int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, int N, int C
 int mumpy_tokenize(const float *x, const float *w_kc, const float *bias, const float *gamma, const float *beta,
                    float *out, int B, int T, int S, int kt, int C, float eps, void *stream);
 
+/* The same layer on the tensor cores (16-bit modes), step 1: the patches as a GEMM operand.  x (B,T,3,S,S) fp32 ->
+ * out (B*To*(S/4)^2, 3K) of `out_dtype`, K = 3*kt*16 in Conv3d's weight.reshape(C,-1) order, each row = [hi | hi | lo] with
+ * value = hi + lo; mumpy_linear against the weight rows [w_hi | w_lo | w_hi] (fp32 out, + bias) and mumpy_layernorm (fp32 out)
+ * complete multiTemporalViewEncoder.py:605-618 at fp32 accuracy. */
+int mumpy_patchify16(const float *x, void *out, int out_dtype, int B, int T, int S, int kt, void *stream);
+
 /* FAF on the middle frame (dct.py:71-79; multiTemporalViewEncoder.py:734).  x (B,T,3,S,S) fp32, frame index
  * `frame`; dct (S,S) fp32 DCT-II matrix; ws fp32 workspace of 5*B*3*S*S floats; out (B,9,S,S) fp32,
  * channel = band*3 + rgb; band k keeps lo_k <= i+j <= hi_k, band_lo_hi6 = HOST array {lo0,hi0,lo1,hi1,lo2,hi2}

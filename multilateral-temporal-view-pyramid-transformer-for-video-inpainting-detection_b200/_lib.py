@@ -32,6 +32,7 @@ SIGNATURES = {
     "mumpy_window_attention": [vp, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_mha_short": [vp, vp, ci, cl, ci, ci, ci, vp],
     "mumpy_tokenize": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
+    "mumpy_patchify16": [vp, vp, ci, ci, ci, ci, ci, vp],
     "mumpy_faf": [vp, vp, vp, vp, ci, ci, ci, ci, ctypes.POINTER(ci), vp],
     "mumpy_faf16": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ctypes.POINTER(ci), ci, vp],
     "mumpy_cva_offsets": [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],

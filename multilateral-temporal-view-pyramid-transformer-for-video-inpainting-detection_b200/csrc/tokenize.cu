@@ -118,9 +118,79 @@ __global__ void __launch_bounds__(512) tokenize_kernel(const float *__restrict__
   }
 }
 
+// Tensor-core tokenizer, step 1: the patches of one view as a GEMM operand.  x (B,T,3,S,S) fp32 -> P (B*To*(S/4)^2, 3K) in the
+// 16-bit operand type, K = 3*kt*16 in the order (c, dt, dy, dx) of Conv3d's weight.reshape(C, -1), each row = [hi | hi | lo]
+// with v = hi + lo (the split of the FAF passes: against a weight row [w_hi | w_lo | w_hi] the three partial products give
+// ~22 mantissa bits, so the tokens that seed the fp32 residual stream keep fp32 accuracy).  One CTA per row of S/4 patches:
+// the 3*kt*4 image rows it covers are staged with coalesced 16-byte reads (row pitch S + 4 floats: conflict-free 16-byte reads
+// across filter rows), then written token by token, 8 contiguous bytes per thread.
+template <typename T16>
+__global__ void __launch_bounds__(256) patchify16_kernel(const float *__restrict__ x, T16 *__restrict__ out, int T, int S, int kt, long n_rows) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) float rows[];      // [3*kt*4][S + 4]
+  const int G = 3 * kt * 4;                          // image rows (c, dt, dy) = groups of 4 consecutive K entries
+  const int K = G * 4;
+  const int Hp = S / 4, To = T / kt, pitch = S + 4, S4 = S >> 2;
+  float amax = 0.0f;
+  for (long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int hp = static_cast<int>(row % Hp);
+    const long t2 = row / Hp;
+    const int to = static_cast<int>(t2 % To);
+    const long b = t2 / To;
+    __syncthreads();
+    for (int i = threadIdx.x; i < G * S4; i += blockDim.x) {
+      const int g = i / S4, c4 = i - g * S4;
+      const int c = g / (kt * 4), dt = (g / 4) % kt, dy = g & 3;
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(x + (((b * T + to * kt + dt) * 3 + c) * S + 4 * hp + dy) * (long)S) + c4);
+      *reinterpret_cast<float4 *>(rows + g * pitch + 4 * c4) = v;
+    }
+    __syncthreads();
+    T16 *o = out + row * Hp * 3 * K;
+    for (int i = threadIdx.x; i < Hp * G; i += blockDim.x) {
+      const int pw = i / G, g = i - pw * G;
+      const float4 v = *reinterpret_cast<const float4 *>(rows + g * pitch + 4 * pw);
+      if (is_half_t<T16>::value) amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fmaxf(fabsf(v.y), fabsf(v.z)), fabsf(v.w)));
+      const T16 h0 = from_f32<T16>(v.x), h1 = from_f32<T16>(v.y), h2 = from_f32<T16>(v.z), h3 = from_f32<T16>(v.w);
+      uint2 hi, lo;
+      hi.x = pack2<T16>(to_f32(h0), to_f32(h1));
+      hi.y = pack2<T16>(to_f32(h2), to_f32(h3));
+      lo.x = pack2<T16>(v.x - to_f32(h0), v.y - to_f32(h1));
+      lo.y = pack2<T16>(v.z - to_f32(h2), v.w - to_f32(h3));
+      T16 *t = o + (long)pw * 3 * K + 4 * g;
+      *reinterpret_cast<uint2 *>(t) = hi;
+      *reinterpret_cast<uint2 *>(t + K) = hi;
+      *reinterpret_cast<uint2 *>(t + 2 * K) = lo;
+    }
+  }
+  if (is_half_t<T16>::value) f16_guard(amax);
+}
+
 }  // namespace mumpy
 
 using namespace mumpy;
+
+extern "C" int mumpy_patchify16(const float *x, void *out, int out_dtype, int B, int T, int S, int kt, void *stream) {
+  MUMPY_REQUIRE(x && out && B > 0 && S % 4 == 0 && kt >= 1 && kt <= T && is_16bit(out_dtype), "patchify16: bad arguments (S must be a multiple of 4)");
+  MUMPY_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "patchify16: buffers must be 16-byte aligned");
+  const int Hp = S / 4, To = T / kt, G = 3 * kt * 4;
+  const size_t smem = (size_t)G * (S + 4) * sizeof(float);
+  MUMPY_REQUIRE(smem <= 200 * 1024, "patchify16: S=%d too large", S);
+  static bool granted[2] = {false, false};
+  const int gi = out_dtype == MUMPY_F16 ? 0 : 1;
+  if (smem > 48 * 1024 && !granted[gi]) {
+    cudaError_t e = gi == 0 ? cudaFuncSetAttribute(patchify16_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                            : cudaFuncSetAttribute(patchify16_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      set_error("patchify16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+    granted[gi] = true;
+  }
+  const long n_rows = (long)B * To * Hp;
+  const long ctas = n_rows < 148l * 8 ? n_rows : 148l * 8;
+  MUMPY_WITH_16(out_dtype, T16, launch_kernel(patchify16_kernel<T16>, (unsigned)ctas, 256, smem, as_stream(stream), x, static_cast<T16 *>(out), T, S, kt, n_rows));
+  return launch_status("patchify16");
+}
 
 extern "C" int mumpy_tokenize(const float *x, const float *w_kc, const float *bias, const float *gamma, const float *beta,
                               float *out, int B, int T, int S, int kt, int C, float eps, void *stream) {

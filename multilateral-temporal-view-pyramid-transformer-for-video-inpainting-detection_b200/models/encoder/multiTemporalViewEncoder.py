@@ -250,6 +250,9 @@ class CreateStages(nn.Module):
         return x, out
 
 
+TENSOR_CORE_TOKENIZER = True      # 16-bit modes: tokenizer convolution as split-operand tcgen05 GEMMs (False: the fp32 FMA kernel)
+
+
 class CrossThreeViewTokenize(PackedModule):
     def __init__(self, view_configs):
         super().__init__()
@@ -274,9 +277,21 @@ class CrossThreeViewTokenize(PackedModule):
                 if proj.kernel_size[1:] != (4, 4):
                     raise NotImplementedError("tokenizer kernel supports 4x4 spatial patches")
                 C = proj.out_channels
-                w_kc = self._packed("w%d" % i, [proj.weight], lambda p=proj, c=C: p.weight.detach().reshape(c, -1).t().contiguous())
                 with reg.lane(i):
-                    tok = ops.tokenize(x, w_kc, proj.bias, norm.weight, norm.bias, kt, norm.eps)
+                    if ops.tensor_cores() and TENSOR_CORE_TOKENIZER:
+                        # patches [hi | hi | lo] x weight rows [w_hi | w_lo | w_hi] on the tensor cores (fp32 accuracy: the tokens seed
+                        # the fp32 residual stream), + bias, then LayerNorm in fp32
+                        def split_w(p=proj, c=C):
+                            w = p.weight.detach().reshape(c, -1).contiguous()
+                            hi = w.to(ops.act_dtype())
+                            lo = (w - hi.float()).to(ops.act_dtype())
+                            return torch.cat([hi, lo, hi], dim=1).contiguous()
+                        w3 = self._packed("w3_%d" % i, [proj.weight], split_w)
+                        tok = ops.linear(ops.patchify16(x, kt), w3, proj.bias)
+                        tok = ops.layernorm(tok, norm.weight, norm.bias, norm.eps, out_dtype=torch.float32)
+                    else:
+                        w_kc = self._packed("w%d" % i, [proj.weight], lambda p=proj, c=C: p.weight.detach().reshape(c, -1).t().contiguous())
+                        tok = ops.tokenize(x, w_kc, proj.bias, norm.weight, norm.bias, kt, norm.eps)
                 out.append(tok.view(B, T // kt, (S // 4) ** 2, C))
         return out
 

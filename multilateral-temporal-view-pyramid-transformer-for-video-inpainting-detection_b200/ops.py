@@ -234,6 +234,17 @@ def tokenize(x, w_kc, bias, gamma, beta, kt, eps=1e-5):
     return out
 
 
+def patchify16(x, kt, dtype=None):
+    """Patches of Conv3d(k=s=(kt,4,4)) as a split GEMM operand: (B,T,3,S,S) fp32 -> (B*To*(S/4)^2, 3*K) [hi | hi | lo], K = 3*kt*16."""
+    B, T, _, S, _ = x.shape
+    dtype = dtype or act_dtype()
+    K = 3 * kt * 16
+    out = torch.empty((B * (T // kt) * (S // 4) ** 2, 3 * K), dtype=dtype, device=x.device)
+    lib, st = _prep(x, out)
+    _lib.check(lib.mumpy_patchify16(_p(x), _p(out), code(dtype), B, T, S, kt, st), "mumpy_patchify16")
+    return out
+
+
 def faf(x, dct, bands, frame=1):
     B, T, _, S, _ = x.shape
     ws = torch.empty((5 * B * 3 * S * S,), dtype=torch.float32, device=x.device)

@@ -103,6 +103,54 @@ def test_tokenize(mods):
         assert util.maxabs(out[i].reshape(2, -1, out[i].shape[-1]), f["outputs"]["v%d" % i]) < TOL
 
 
+@pytest.mark.parametrize("mode,tol", [("fp16", 2e-5), ("bf16", 3e-4)])
+def test_tokenize_tensor_core_path(mods, mode, tol):
+    """16-bit modes: the tokenizer convolution as split-operand tcgen05 GEMMs (patches [hi|hi|lo] x weights [hi|lo|hi], ~22 / ~16
+    mantissa bits) + fp32 LayerNorm, against the reference capture; and the fp32 FMA kernel it replaces gives the same tokens."""
+    import mumpy_b200
+    from mumpy_b200.models.encoder import multiTemporalViewEncoder as mtv
+    from mumpy_b200.models.factory.modelFactory import default_view_configs
+    f = mods["tokenize"]
+    m = mtv.CrossThreeViewTokenize(default_view_configs()).eval()
+    util.load_seeded(m)
+    m = m.cuda()
+    x = util.seeded_input(f["input_shape"], f["input_seed"]).cuda()
+    mumpy_b200.set_precision(mode)
+    try:
+        out = m(x)
+        mtv.TENSOR_CORE_TOKENIZER = False
+        fma = m(x)
+    finally:
+        mtv.TENSOR_CORE_TOKENIZER = True
+        mumpy_b200.set_precision(mumpy_b200.ops.DEFAULT_PRECISION)
+    for i in range(3):
+        assert out[i].dtype == torch.float32 and out[i].shape == fma[i].shape
+        assert util.maxabs(out[i].reshape(2, -1, out[i].shape[-1]), f["outputs"]["v%d" % i]) < tol
+        assert util.maxabs(out[i], fma[i]) < tol
+
+
+def test_decoder_feats_view_equals_transposed_copy():
+    """Decoder.forward hands x_feats back as a channels-last view with the reference's shape; NCHW_FEATS = True restores the
+    explicit transposition: identical values."""
+    import mumpy_b200
+    from mumpy_b200.models.decoder.decoder import Decoder
+    dec = Decoder().eval()
+    util.load_seeded(dec)
+    dec = dec.cuda()
+    B = 1
+    final_x, view_x, ff = util.decoder_inputs(B)
+    x, view_x, ff = final_x.cuda(), [[t.cuda() for t in st] for st in view_x], ff.cuda()
+    with torch.no_grad():
+        m0, f0 = dec(x, view_x, ff)
+        Decoder.NCHW_FEATS = True
+        try:
+            m1, f1 = dec(x, view_x, ff)
+        finally:
+            Decoder.NCHW_FEATS = False
+    assert f0.shape == f1.shape == (B, 32, 224, 224) and f1.is_contiguous() and not f0.is_contiguous()
+    assert torch.equal(f0, f1) and torch.equal(m0, m1)
+
+
 def test_window_attention_with_mask_api():
     """WindowAttention.forward(x_windows, mask) keeps the reference call form (swinTransformer.py:134-166)."""
     from mumpy_b200.models.modules.swinTransformer import WindowAttention
