@@ -119,9 +119,49 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
   const int half = tid >> 6, p = tid & 63;
 
   for (int i = tid; i < WTC_TILE_BYTES / 16; i += WTC_THREADS) reinterpret_cast<uint4 *>(gen)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < TBL * heads; i += WTC_THREADS) {
-    const int hh = i / TBL, e = i - hh * TBL;
-    tbl_all[i] = __ldg(rel_table + (long)e * heads + hh) * kLog2e;
+  // bias table (TBL, heads) -> shared [heads][TBL] x log2(e).  Coalesced 16-byte reads, four in flight per thread: the former
+  // transposing loop issued one dependent 4-byte load per iteration (21 L2 round trips, ~8 us before a CTA's first tile)
+  if ((heads & 3) == 0) {
+    const int n4 = TBL * heads / 4;
+    const float4 *t4 = reinterpret_cast<const float4 *>(rel_table);
+    for (int base = tid; base < n4; base += 4 * WTC_THREADS) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * WTC_THREADS;
+        v[u] = i < n4 ? __ldg(t4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * WTC_THREADS;
+        if (i < n4) {
+          const int e = (4 * i) / heads, hh = 4 * i - e * heads;          // four consecutive heads of table entry e
+          float *d = tbl_all + hh * TBL + e;
+          d[0] = v[u].x * kLog2e;
+          d[TBL] = v[u].y * kLog2e;
+          d[2 * TBL] = v[u].z * kLog2e;
+          d[3 * TBL] = v[u].w * kLog2e;
+        }
+      }
+    }
+  } else {
+    const int n = TBL * heads;
+    for (int base = tid; base < n; base += 4 * WTC_THREADS) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * WTC_THREADS;
+        v[u] = i < n ? __ldg(rel_table + i) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * WTC_THREADS;
+        if (i < n) {
+          const int e = i / heads, hh = i - e * heads;
+          tbl_all[hh * TBL + e] = v[u] * kLog2e;
+        }
+      }
+    }
   }
   const uint32_t bar_s = smem_u32(&bars[0]), bar_o = smem_u32(&bars[1]);
   if (tid == 0) {
@@ -240,15 +280,17 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     __syncthreads();
     WTC_T(1);
     // ---- S = Q K^T
-    if (tid == 0) {
+    if (warp == 0) {              // converged warp, one elected lane issues (tc_common.cuh elect_one: descriptors stay in uniform registers)
       tc_fence_after();
-#pragma unroll
-      for (int w2 = 0; w2 < 2; ++w2) {
-        const uint64_t dK = make_sw64_desc(sK + w2 * WTC_K_BYTES);
-#pragma unroll
-        for (int k = 0; k < 2; ++k) umma_bf16(tmem + w2 * 64, dQ + 2 * k, dK + 2 * k, idesc_s, k);
+      const uint64_t dK0 = make_sw64_desc(sK), dK1 = make_sw64_desc(sK + WTC_K_BYTES);
+      if (elect_one()) {
+        umma_bf16(tmem, dQ, dK0, idesc_s, 0u);
+        umma_bf16(tmem, dQ + 2, dK0 + 2, idesc_s, 1u);
+        umma_bf16(tmem + 64, dQ, dK1, idesc_s, 0u);
+        umma_bf16(tmem + 64, dQ + 2, dK1 + 2, idesc_s, 1u);
+        umma_commit(bar_s);
       }
-      umma_commit(bar_s);
+      __syncwarp();
     }
     mbar_wait(bar_s, phase);
     tc_fence_after();
@@ -296,16 +338,19 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     __syncthreads();
     WTC_T(5);
     // ---- O = P V
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-#pragma unroll
-      for (int w2 = 0; w2 < 2; ++w2) {
-        const uint64_t dV = make_sw64_desc(sV + w2 * WTC_V_BYTES);
+      const uint64_t dV0 = make_sw64_desc(sV), dV1 = make_sw64_desc(sV + WTC_V_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)      // per k-step: 16 keys = 8 packed columns of P, 1024 B of V
-          umma_bf16_tmem_a(tmem + w2 * 32, tmem + WTC_P_COL + 8 * k, dV + (16 * 64 / 16) * k, idesc_o, k);
+          umma_bf16_tmem_a(tmem, tmem + WTC_P_COL + 8 * k, dV0 + (16 * 64 / 16) * k, idesc_o, k);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_tmem_a(tmem + 32, tmem + WTC_P_COL + 8 * k, dV1 + (16 * 64 / 16) * k, idesc_o, k);
+        umma_commit(bar_o);
       }
-      umma_commit(bar_o);
+      __syncwarp();
     }
     mbar_wait(bar_o, phase);
     tc_fence_after();
