@@ -89,6 +89,15 @@ int mumpy_linear(const void *A, long lda, const void *W, const float *bias, cons
  * Shapes: K in {96,128,192,256,384,512} and N a multiple of 64 or 96 (mumpy_ln_linear_supported returns 1); anything else is an error --
  * the caller then runs mumpy_layernorm + mumpy_linear.  Statistics are exact two-pass fp32, bit-identical to mumpy_layernorm. */
 int mumpy_ln_linear_supported(int N, int K);
+/* Fused Swin MLP for the narrow stages (16-bit operand modes):  out = x + fc2( GELU( fc1( LayerNorm(x) ) ) )
+ * replaces `x = x + self.drop_path(self.mlp(self.norm2(x)))` (swinTransformer.py:305 with Mlp.forward :45-51;
+ * multiTemporalViewEncoder.py:289) in ONE kernel: the normalised rows and the 4C-wide hidden activations only exist in shared /
+ * tensor memory.  x, out (M,C) fp32 row-major (the residual stream; out may not alias x), gamma/beta (C) fp32, W1 (4C,C) and
+ * W2 (C,4C) row-major of `w_dtype`, b1 (4C), b2 (C) fp32.  C in {96,128,192,256} (mumpy_mlp_fused_supported returns 1); wider
+ * blocks run mumpy_layernorm / mumpy_ln_linear + mumpy_linear.  Bit-identical to the unfused kernels. */
+int mumpy_mlp_fused_supported(int C);
+int mumpy_mlp_fused(const float *x, const float *gamma, const float *beta, float eps, const void *W1, const float *b1, const void *W2,
+                    const float *b2, float *out, long M, int C, int w_dtype, void *stream);
 /* CTA-pair policy of mumpy_ln_linear (two adjacent 128-row tiles on a (2,1,1) cluster, tcgen05 cta_group::2, each CTA streaming half of
  * every weight tile): 0 never, 1 the cost model decides (default), 2 whenever the shape allows.  Environment: MUMPY_LG_PAIR. */
 int mumpy_set_ln_linear_pair_mode(int mode);

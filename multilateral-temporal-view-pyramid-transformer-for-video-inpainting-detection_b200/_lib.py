@@ -25,6 +25,8 @@ SIGNATURES = {
     "mumpy_linear": [vp, cl, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, ci, vp],
     "mumpy_linear_dual": [vp, cl, vp, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, vp],
     "mumpy_layernorm": [vp, vp, vp, vp, ci, cl, ci, cf, vp],
+    "mumpy_mlp_fused_supported": [ci],
+    "mumpy_mlp_fused": [vp, vp, vp, cf, vp, vp, vp, vp, vp, cl, ci, ci, vp],
     "mumpy_ln_linear_supported": [ci, ci],
     "mumpy_set_ln_linear_pair_mode": [ci],
     "mumpy_ln_linear": [vp, vp, vp, cf, vp, vp, vp, cl, cl, ci, ci, ci, ci, vp],

@@ -43,6 +43,9 @@ int linear_f32(const float *A, long lda, const float *W, const float *bias, cons
 int linear_bf16(const void *A, long lda, const void *W, const float *bias, const float *residual, void *out, void *aux, long ldo,
                 long M, int N, int K, int ab_dtype, int out_dtype, int act, cudaStream_t st);
 
+bool mlp_fused_supported(int C);
+int mlp_fused_16(const float *x, const float *gamma, const float *beta, float eps, const void *W1, const float *b1, const void *W2, const float *b2,
+                 float *out, long M, int C, int w_dtype, cudaStream_t st);
 bool ln_linear_supported(int N, int K);
 void set_ln_linear_pair_mode(int mode);
 int ln_linear_16(const float *x, const float *gamma, const float *beta, float eps, const void *W, const float *bias, void *out, long ldo,
@@ -167,6 +170,14 @@ extern "C" int mumpy_linear(const void *A, long lda, const void *W, const float 
   if (is_16bit(ab_dtype)) return linear_bf16(A, lda, W, bias, residual, out, nullptr, ldo, M, N, K, ab_dtype, out_dtype, act, as_stream(stream));
   set_error("linear: unknown dtype %d", ab_dtype);
   return MUMPY_ERR_ARG;
+}
+
+extern "C" int mumpy_mlp_fused_supported(int C) { return mlp_fused_supported(C) ? 1 : 0; }
+
+extern "C" int mumpy_mlp_fused(const float *x, const float *gamma, const float *beta, float eps, const void *W1, const float *b1, const void *W2,
+                               const float *b2, float *out, long M, int C, int w_dtype, void *stream) {
+  MUMPY_REQUIRE(x && gamma && beta && W1 && b1 && W2 && b2 && out && M > 0 && C > 0 && is_16bit(w_dtype), "mlp_fused: bad arguments (M=%ld C=%d)", M, C);
+  return mlp_fused_16(x, gamma, beta, eps, W1, b1, W2, b2, out, M, C, w_dtype, as_stream(stream));
 }
 
 extern "C" int mumpy_set_ln_linear_pair_mode(int mode) {

@@ -1,0 +1,450 @@
+// Fused Swin MLP for the narrow (HBM-bound) stages, C <= 256 (swinTransformer.py:305 + 45-51):
+//   out = x + fc2( GELU( fc1( LayerNorm(x) ) ) )            x, out (M, C) fp32 residual stream; W1 (4C, C), W2 (C, 4C) 16-bit
+// One kernel per block instead of LayerNorm + fc1 + fc2: neither the normalised rows nor the 4C-wide hidden activations ever
+// reach global memory (at stage 0 of view 3, batch 32, the hidden matrix alone is 308 MB written and 308 MB read back per block).
+//
+// Per 128-row tile (persistent CTAs, one per SM):
+//   prologue    the 16 epilogue warps normalise the tile's rows into a resident 16-bit K-major SWIZZLE_128B A operand
+//               (lg_normalise_rows' arithmetic = layernorm_vec_kernel's: bit-identical operand);
+//   hidden chunk j (128 of the 4C columns):
+//     MMA1      acc1[j&1] (TMEM, 128 columns) = A . W1[128 j : 128 j + 128, :]^T          K = C
+//     epi1      + b1, GELU, pack to 16 bits, written by the row's own thread straight into the K-major SWIZZLE_128B operand
+//               H[j&1] in shared memory (two k-blocks of 128 rows x 128 B) -- the hidden tile never leaves the SM
+//     MMA2      acc2 (TMEM, C columns) += H[j&1] . W2[:, 128 j : 128 j + 128]^T              K = 128
+//   epi2        acc2 + b2 + x (fp32 residual re-read, coalesced) -> out.
+// The MMA warp issues MMA1(j+1) before MMA2(j), so the tensor pipe works on the next chunk while the epilogue warps run the
+// GELU of this one; weight tiles of both matrices stream through one TMA ring in exactly that consumption order.
+// Accumulation order equals the unfused kernels' (k-blocks in ascending order), so the result is bit-identical to
+// mumpy_layernorm + mumpy_linear(GELU, 16-bit) + mumpy_linear(residual).
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace mumpy {
+
+int resolve_driver_entry_points();
+int tc_encode_2d_16(CUtensorMap *map, const void *ptr, bool f16, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                    uint32_t box_inner, uint32_t box_outer);
+int tc_num_sms();
+
+constexpr int ML_BM = 128;
+constexpr int ML_HC = 128;                         // hidden columns per chunk
+constexpr int ML_EPI_WARPS = 16;             // four per TMEM lane quadrant: the 16 (quadrant, 32-column) units of a hidden chunk map one to one
+constexpr int ML_EPI_GROUPS = ML_EPI_WARPS / 4;
+constexpr int ML_THREADS = (ML_EPI_WARPS + 2) * 32;
+constexpr int ML_MAX_STAGES = 6;
+constexpr int ML_KB_BYTES = ML_BM * 128;           // one 64-column k-block of a 128-row operand
+constexpr int ML_H_BYTES = 2 * ML_KB_BYTES;        // one hidden chunk: 128 rows x 128 columns x 16 bit
+constexpr int ML_SMEM_TOTAL = 226 * 1024;
+
+struct MlpParams {
+  const float *x;
+  const float *gamma;
+  const float *beta;
+  const float *b1;
+  const float *b2;
+  float *out;
+  long M;
+  long num_tiles;
+  int C;              // width (K of fc1, N of fc2)
+  int nkb;            // 64-column k-blocks of the A operand (C = 96: the second holds 32 columns)
+  int n_chunks;       // 4C / 128
+  int stages;
+  int f16;
+  uint32_t stage_bytes;
+  uint32_t idesc1, idesc2;
+  float eps;
+};
+
+__device__ __forceinline__ void ml_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// LayerNorm of rows [m0, m0 + 128) into the resident A operand (same scheme as gemm_ln_tcgen05.cu / norm.cu)
+template <typename OutT, int LPR, int NV, int RI>
+__device__ __forceinline__ float ml_normalise_rows(const MlpParams &p, uint32_t a_base, long m0, int warp, int lane) {
+  constexpr int G = 32 / LPR;
+  constexpr int RPW = G * RI;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const int C = p.C;
+  float amax = 0.0f;
+  for (int r0 = warp * RPW; r0 < ML_BM; r0 += ML_EPI_WARPS * RPW) {
+    float4 v[RI][NV];
+    float s[RI], q[RI];
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      const long row = m0 + r0 + r * G + grp;
+#pragma unroll
+      for (int u = 0; u < NV; ++u)
+        v[r][u] = row < p.M ? *(reinterpret_cast<const float4 *>(p.x + row * C) + sub + LPR * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      s[r] = 0.0f;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) s[r] += (v[r][u].x + v[r][u].y) + (v[r][u].z + v[r][u].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < RI; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      s[r] = s[r] / C;
+      q[r] = 0.0f;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const float a = v[r][u].x - s[r], b = v[r][u].y - s[r], c = v[r][u].z - s[r], d = v[r][u].w - s[r];
+        q[r] += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < RI; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+#pragma unroll
+    for (int r = 0; r < RI; ++r) q[r] = 1.0f / sqrtf(q[r] / C + p.eps);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int i = sub + LPR * u;
+      const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma) + i), b4 = __ldg(reinterpret_cast<const float4 *>(p.beta) + i);
+      const uint32_t col_off = static_cast<uint32_t>(i >> 4) * ML_KB_BYTES + static_cast<uint32_t>(i & 1) * 8u;
+      const uint32_t chunk = static_cast<uint32_t>(i & 15) >> 1;
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        const uint32_t rt = static_cast<uint32_t>(r0 + r * G + grp);
+        const float rstd = q[r];
+        const float o0 = (v[r][u].x - s[r]) * rstd * g4.x + b4.x, o1 = (v[r][u].y - s[r]) * rstd * g4.y + b4.y;
+        const float o2 = (v[r][u].z - s[r]) * rstd * g4.z + b4.z, o3 = (v[r][u].w - s[r]) * rstd * g4.w + b4.w;
+        if constexpr (is_half_t<OutT>::value) amax = fmaxf(fmaxf(amax, fabsf(o0)), fmaxf(fmaxf(fabsf(o1), fabsf(o2)), fabsf(o3)));
+        const uint32_t w0 = pack2<OutT>(o0, o1), w1 = pack2<OutT>(o2, o3);
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_base + col_off + rt * 128u + ((chunk ^ (rt & 7u)) << 4)), "r"(w0), "r"(w1)
+                     : "memory");
+      }
+    }
+  }
+  return amax;
+}
+
+// (out of line, like the output epilogue below: both run once per tile, and inlined next to the hidden epilogue they make it spill)
+template <typename OutT>
+__device__ __noinline__ float ml_normalise(const MlpParams &p, uint32_t a_base, long m0, int warp, int lane) {
+  switch (p.C) {
+    case 96: return ml_normalise_rows<OutT, 8, 3, 2>(p, a_base, m0, warp, lane);
+    case 128: return ml_normalise_rows<OutT, 8, 4, 2>(p, a_base, m0, warp, lane);
+    case 192: return ml_normalise_rows<OutT, 16, 3, 2>(p, a_base, m0, warp, lane);
+    default: return ml_normalise_rows<OutT, 16, 4, 2>(p, a_base, m0, warp, lane);
+  }
+}
+
+// epi1: one warp's share of a 128 x 128 fc1 accumulator (lane quadrant warp&3, 32-column chunks warp>>2, +3): + b1, GELU, pack,
+// written as the K-major SWIZZLE_128B A operand of fc2 (row = this thread's accumulator row: no transposition needed)
+template <typename OutT>
+__device__ __forceinline__ float ml_hidden_epilogue(const float *__restrict__ b1, uint32_t h_base, uint32_t acc, int warp, int lane) {
+  const int quad = warp & 3, grp = warp >> 2;
+  const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
+  const uint32_t row = static_cast<uint32_t>(quad * 32 + lane);
+  float amax = 0.0f;
+  for (int c0 = grp * 32; c0 < ML_HC; c0 += 32 * ML_EPI_GROUPS) {
+    uint32_t v[32];
+    tmem_ld32(lane_addr + c0, v);
+    const uint32_t kb_base = h_base + static_cast<uint32_t>(c0 >> 6) * ML_KB_BYTES + row * 128u;
+    const uint32_t chunk0 = static_cast<uint32_t>(c0 & 63) >> 3;                 // first 16-byte chunk of these 32 columns in the 128-byte row
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float2 f[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float2 b = __ldg(reinterpret_cast<const float2 *>(b1 + c0 + 8 * g + 2 * h));
+        f[h] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2 * h]), __uint_as_float(v[8 * g + 2 * h + 1])), b));
+        if constexpr (is_half_t<OutT>::value) amax = fmaxf(amax, fmaxf(fabsf(f[h].x), fabsf(f[h].y)));
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(kb_base + (((chunk0 + g) ^ (row & 7u)) << 4)), "r"(pack2<OutT>(f[0].x, f[0].y)),
+                   "r"(pack2<OutT>(f[1].x, f[1].y)), "r"(pack2<OutT>(f[2].x, f[2].y)), "r"(pack2<OutT>(f[3].x, f[3].y))
+                   : "memory");
+    }
+  }
+  return amax;
+}
+
+// epi2: one warp's share of the 128 x C fc2 accumulator: + b2 + residual -> fp32 out, through a 4 KB swizzled staging tile so
+// that residual loads and output stores are full 128-byte row segments
+__device__ __noinline__ void ml_output_epilogue(const MlpParams &p, uint32_t st_base, uint32_t acc, int warp, int lane, long m0) {
+  const int quad = warp & 3, grp = warp >> 2;
+  const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
+  const long row0 = m0 + quad * 32;
+  const int c4 = lane & 7;
+  for (int c0 = grp * 32; c0 < p.C; c0 += 32 * ML_EPI_GROUPS) {
+    const int col = c0 + c4 * 4;
+    float4 res[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long gm = row0 + i * 4 + (lane >> 3);
+      res[i] = gm < p.M ? *reinterpret_cast<const float4 *>(p.x + gm * p.C + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t v[32];
+    tmem_ld32(lane_addr + c0, v);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(p.b2 + c0 + 4 * g));
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + lane * 128 + ((g ^ (lane & 7)) << 4)), "f"(__uint_as_float(v[4 * g]) + b.x),
+                   "f"(__uint_as_float(v[4 * g + 1]) + b.y), "f"(__uint_as_float(v[4 * g + 2]) + b.z), "f"(__uint_as_float(v[4 * g + 3]) + b.w)
+                   : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      const long gm = row0 + r;
+      float4 o;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(st_base + r * 128 + ((c4 ^ (r & 7)) << 4)));
+      if (gm < p.M) {
+        o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w;
+        *reinterpret_cast<float4 *>(p.out + gm * p.C + col) = o;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                                                                    const MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * ML_MAX_STAGES + 11];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t a_base = (raw + 1023u) & ~1023u;
+  const uint32_t h_base = a_base + static_cast<uint32_t>(p.nkb) * ML_KB_BYTES;          // two hidden-chunk operands (also the epi2 staging)
+  const uint32_t ring = h_base + 2 * ML_H_BYTES;
+  const uint32_t w_full0 = smem_u32(&bars[0]);
+  const uint32_t w_empty0 = smem_u32(&bars[ML_MAX_STAGES]);
+  const uint32_t a_full = smem_u32(&bars[2 * ML_MAX_STAGES]);
+  const uint32_t acc1_full0 = smem_u32(&bars[2 * ML_MAX_STAGES + 1]);       // [2]
+  const uint32_t acc1_empty0 = smem_u32(&bars[2 * ML_MAX_STAGES + 3]);      // [2]
+  const uint32_t h_full0 = smem_u32(&bars[2 * ML_MAX_STAGES + 5]);          // [2]
+  const uint32_t h_empty0 = smem_u32(&bars[2 * ML_MAX_STAGES + 7]);         // [2]
+  const uint32_t acc2_full = smem_u32(&bars[2 * ML_MAX_STAGES + 9]);
+  const uint32_t acc2_empty = smem_u32(&bars[2 * ML_MAX_STAGES + 10]);
+
+  if (warp == ML_EPI_WARPS && lane == 0) {
+    prefetch_tensormap(&tmW1);
+    prefetch_tensormap(&tmW2);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(w_full0 + 8 * s, 1);
+      mbar_init(w_empty0 + 8 * s, 1);
+    }
+    mbar_init(a_full, ML_EPI_WARPS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc1_full0 + 8 * s, 1);
+      mbar_init(acc1_empty0 + 8 * s, ML_EPI_WARPS);
+      mbar_init(h_full0 + 8 * s, ML_EPI_WARPS);
+      mbar_init(h_empty0 + 8 * s, 1);
+    }
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, ML_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == ML_EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t acc2 = tmem_base + 2 * ML_HC;                   // acc1[0] | acc1[1] | acc2 (C <= 256 columns)
+  pdl_grid_sync();
+
+  const int n = p.n_chunks;
+  if (warp == ML_EPI_WARPS) {
+    // ------------------------------------------------ TMA producer: weight tiles in the MMA warp's consumption order ----
+    uint32_t s = 0, ph = 0;
+    const uint32_t w1_bytes = ML_HC * 128u, w2_bytes = static_cast<uint32_t>(p.C) * 128u;
+    auto load = [&](const CUtensorMap *map, uint32_t bytes, int kx, int ry) {
+      mbar_wait(w_empty0 + 8 * s, ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(w_full0 + 8 * s, bytes);
+        tma_load_2d(ring + s * p.stage_bytes, map, w_full0 + 8 * s, kx, ry);
+      }
+      __syncwarp();
+      if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+    };
+    for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.nkb; ++kb) load(&tmW1, w1_bytes, kb * 64, 0);                                   // MMA1(0)
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n)
+          for (int kb = 0; kb < p.nkb; ++kb) load(&tmW1, w1_bytes, kb * 64, (j + 1) * ML_HC);                // MMA1(j+1)
+        for (int kb = 0; kb < 2; ++kb) load(&tmW2, w2_bytes, j * ML_HC + kb * 64, 0);                         // MMA2(j)
+      }
+    }
+  } else if (warp == ML_EPI_WARPS + 1) {
+    // ------------------------------------------------ MMA issuer ---------------------------------------------------------
+    uint32_t s = 0, ph = 0;
+    uint32_t c1 = 0;          // fc1 chunks issued so far (acc1 slot = c1 & 1, phase (c1 >> 1) & 1)
+    uint32_t c2 = 0;          // fc2 chunks issued so far (H slot = c2 & 1)
+    uint32_t ti = 0;
+    auto mma1 = [&]() {
+      const uint32_t slot = c1 & 1, aph = (c1 >> 1) & 1;
+      mbar_wait(acc1_empty0 + 8 * slot, aph ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + slot * ML_HC;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(w_full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint64_t adesc = make_kmajor_sw128_desc(a_base + kb * ML_KB_BYTES);
+        const uint64_t bdesc = make_kmajor_sw128_desc(ring + s * p.stage_bytes);
+        const bool tail = (kb + 1) * 64 > p.C;
+        if (elect_one()) {
+          umma_bf16(d, adesc, bdesc, p.idesc1, kb > 0 ? 1u : 0u);
+          umma_bf16(d, adesc + 2, bdesc + 2, p.idesc1, 1u);
+          if (!tail) {
+            umma_bf16(d, adesc + 4, bdesc + 4, p.idesc1, 1u);
+            umma_bf16(d, adesc + 6, bdesc + 6, p.idesc1, 1u);
+          }
+          umma_commit(w_empty0 + 8 * s);
+        }
+        __syncwarp();
+        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+      }
+      if (elect_one()) umma_commit(acc1_full0 + 8 * slot);
+      __syncwarp();
+      ++c1;
+    };
+    for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+      mbar_wait(a_full, ti & 1);
+      tc_fence_after();
+      mma1();
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) mma1();
+        const uint32_t hs = c2 & 1, hph = (c2 >> 1) & 1;
+        mbar_wait(h_full0 + 8 * hs, hph);                         // GELU(fc1 chunk j) is in shared memory
+        tc_fence_after();
+        if (j == 0) {
+          mbar_wait(acc2_empty, (ti & 1) ^ 1);                    // the previous tile's output has left the accumulator
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait(w_full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(h_base + hs * ML_H_BYTES + kb * ML_KB_BYTES);
+          const uint64_t bdesc = make_kmajor_sw128_desc(ring + s * p.stage_bytes);
+          if (elect_one()) {
+            umma_bf16(acc2, adesc, bdesc, p.idesc2, (j > 0 || kb > 0) ? 1u : 0u);
+            umma_bf16(acc2, adesc + 2, bdesc + 2, p.idesc2, 1u);
+            umma_bf16(acc2, adesc + 4, bdesc + 4, p.idesc2, 1u);
+            umma_bf16(acc2, adesc + 6, bdesc + 6, p.idesc2, 1u);
+            umma_commit(w_empty0 + 8 * s);
+          }
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+        }
+        if (elect_one()) {
+          umma_commit(h_empty0 + 8 * hs);                         // H[hs] may be overwritten once these MMAs have read it
+          if (j == n - 1) umma_commit(acc2_full);
+        }
+        __syncwarp();
+        ++c2;
+      }
+    }
+  } else {
+    // ------------------------------------------------ LayerNorm prologue, hidden epilogue, output epilogue ---------------
+    uint32_t c = 0, ti = 0;        // hidden chunks processed so far
+    float amax = 0.0f;
+    const uint32_t st_base = h_base + warp * 4096;             // epi2 staging lives in the hidden-chunk buffers (idle by then)
+    for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+      const long m0 = tile * ML_BM;
+      // (every fc1 MMA of the previous tile has completed: this warp waited for its last acc1_full)
+      amax = fmaxf(amax, p.f16 ? ml_normalise<__half>(p, a_base, m0, warp, lane) : ml_normalise<__nv_bfloat16>(p, a_base, m0, warp, lane));
+      ml_fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+      for (int j = 0; j < n; ++j, ++c) {
+        const uint32_t slot = c & 1, cph = (c >> 1) & 1;
+        mbar_wait(acc1_full0 + 8 * slot, cph);
+        mbar_wait(h_empty0 + 8 * slot, cph ^ 1);                 // fc2 of the chunk two back has read H[slot]
+        tc_fence_after();
+        const uint32_t acc1 = tmem_base + slot * ML_HC;
+        const float a = p.f16 ? ml_hidden_epilogue<__half>(p.b1 + j * ML_HC, h_base + slot * ML_H_BYTES, acc1, warp, lane)
+                              : ml_hidden_epilogue<__nv_bfloat16>(p.b1 + j * ML_HC, h_base + slot * ML_H_BYTES, acc1, warp, lane);
+        amax = fmaxf(amax, a);
+        tc_fence_before();
+        ml_fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(acc1_empty0 + 8 * slot);
+          mbar_arrive(h_full0 + 8 * slot);
+        }
+      }
+      mbar_wait(acc2_full, ti & 1);                               // all fc2 MMAs done: H buffers are free for the staging tiles
+      tc_fence_after();
+      ml_output_epilogue(p, st_base, acc2, warp, lane, m0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_empty);
+    }
+    f16_guard(amax);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == ML_EPI_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+bool mlp_fused_supported(int C) { return C == 96 || C == 128 || C == 192 || C == 256; }
+
+int mlp_fused_16(const float *x, const float *gamma, const float *beta, float eps, const void *W1, const float *b1, const void *W2, const float *b2,
+                 float *out, long M, int C, int w_dtype, cudaStream_t st) {
+  int rc = resolve_driver_entry_points();
+  if (rc) return rc;
+  MUMPY_REQUIRE(mlp_fused_supported(C), "mlp_fused: unsupported width C=%d (96, 128, 192, 256)", C);
+  MUMPY_REQUIRE(M > 0 && M < (1l << 31), "mlp_fused: 0 < M < 2^31 required");
+  MUMPY_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(W1) |
+                  reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(W2) | reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "mlp_fused: all buffers must be 16-byte aligned");
+  MlpParams p = {};
+  p.x = x;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.b1 = b1;
+  p.b2 = b2;
+  p.out = out;
+  p.M = M;
+  p.num_tiles = cdiv(M, ML_BM);
+  p.C = C;
+  p.nkb = (C + 63) / 64;
+  p.n_chunks = 4 * C / ML_HC;
+  p.f16 = w_dtype == MUMPY_F16;
+  p.eps = eps;
+  p.idesc1 = make_idesc_16_f32(ML_BM, ML_HC, p.f16 != 0);
+  p.idesc2 = make_idesc_16_f32(ML_BM, C, p.f16 != 0);
+  const int w2_bytes = C * 128;
+  p.stage_bytes = (uint32_t)(w2_bytes > ML_HC * 128 ? w2_bytes : ML_HC * 128);
+  p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
+  const int fixed = 1024 + p.nkb * ML_KB_BYTES + 2 * ML_H_BYTES;
+  int stages = (ML_SMEM_TOTAL - fixed) / (int)p.stage_bytes;
+  if (stages > ML_MAX_STAGES) stages = ML_MAX_STAGES;
+  MUMPY_REQUIRE(stages >= 2, "mlp_fused: shared memory budget (C=%d)", C);
+  p.stages = stages;
+  CUtensorMap tmW1, tmW2;
+  rc = tc_encode_2d_16(&tmW1, W1, p.f16 != 0, (uint64_t)C, (uint64_t)4 * C, (uint64_t)C, 64, ML_HC);
+  if (rc) return rc;
+  rc = tc_encode_2d_16(&tmW2, W2, p.f16 != 0, (uint64_t)4 * C, (uint64_t)C, (uint64_t)4 * C, 64, (uint32_t)C);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM_TOTAL);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(mlp_fused_tc_kernel): %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int sms = tc_num_sms();
+  const int smem = fixed + p.stages * (int)p.stage_bytes;
+  const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
+  launch_kernel(mlp_fused_tc_kernel, grid, ML_THREADS, smem, st, tmW1, tmW2, p);
+  return launch_status("mlp_fused_tc_kernel");
+}
+
+}  // namespace mumpy

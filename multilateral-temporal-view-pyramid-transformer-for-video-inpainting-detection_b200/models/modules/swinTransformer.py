@@ -45,6 +45,10 @@ class Mlp(PackedModule):
         """xn: normalised input already in operand precision -- or, with `norm` (the block's LayerNorm), the raw fp32 stream, which
         is then normalised inside the fc1 kernel where the width fits (mumpy_ln_linear); returns fc2(gelu(fc1(.))) (+ residual), fp32."""
         w1 = self._gemm_weight("fc1", self.fc1.weight)
+        if (norm is not None and residual is xn and ops.mlp_fused_fits(w1.shape[1]) and w1.shape[0] == 4 * w1.shape[1]
+                and self.fc1.bias is not None and self.fc2.bias is not None and tuple(self.fc2.weight.shape) == (w1.shape[1], w1.shape[0])):
+            # narrow (HBM-bound) stages: the whole `x + Mlp(LN(x))` in one kernel, hidden activations never leave the SM
+            return ops.mlp_fused(xn, norm.weight, norm.bias, norm.eps, w1, self.fc1.bias, self._gemm_weight("fc2", self.fc2.weight), self.fc2.bias)
         if norm is not None and ops.ln_linear_fits(w1.shape[0], w1.shape[1]):
             h = ops.ln_linear(xn, norm.weight, norm.bias, norm.eps, w1, self.fc1.bias, act=ops.ACT_GELU)
         else:

@@ -198,6 +198,31 @@ def ln_linear(x, gamma, beta, eps, w, bias=None, act=ACT_NONE):
     return out
 
 
+FUSED_MLP = os.environ.get("MUMPY_FUSED_MLP", "1") != "0"      # LayerNorm + fc1 + GELU + fc2 + residual in one kernel for C <= 256
+
+
+def set_fused_mlp(enabled: bool):
+    global FUSED_MLP
+    FUSED_MLP = bool(enabled)
+
+
+def mlp_fused_fits(C) -> bool:
+    return FUSED_MLP and tensor_cores() and C in (96, 128, 192, 256)
+
+
+def mlp_fused(x, gamma, beta, eps, w1, b1, w2, b2):
+    """x + fc2(gelu(fc1(LayerNorm(x)))) in one kernel (mumpy_mlp_fused); x (..., C) fp32, w1 (4C, C), w2 (C, 4C) 16-bit."""
+    C = x.shape[-1]
+    M = x.numel() // C
+    if tuple(w1.shape) != (4 * C, C) or tuple(w2.shape) != (C, 4 * C) or x.dtype != torch.float32 or w1.dtype != w2.dtype:
+        raise _lib.MumpyError("mlp_fused: x%s w1%s w2%s" % (tuple(x.shape), tuple(w1.shape), tuple(w2.shape)))
+    out = torch.empty_like(x)
+    lib, st = _prep(x, gamma, beta, w1, b1, w2, b2, out)
+    _lib.check(lib.mumpy_mlp_fused(_p(x), _p(gamma), _p(beta), float(eps), _p(w1), _p(b1), _p(w2), _p(b2), _p(out), M, C, code(w1.dtype), st),
+               "mumpy_mlp_fused")
+    return out
+
+
 def patch_merge_norm(x, gamma, beta, B, TH, W, C, eps=1e-5, out_dtype=None):
     out = torch.empty((B, (TH // 2) * (W // 2), 4 * C), dtype=out_dtype or act_dtype(), device=x.device)
     lib, st = _prep(x, gamma, beta, out)

@@ -174,3 +174,48 @@ def test_fused_ln_forward_is_bit_identical():
         assert torch.equal(out, ref)
     finally:
         ops.set_fused_ln(was)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,C", [(3136, 96), (9408 + 17, 128), (784, 192), (2352, 256), (130, 128), (1, 96), (128 * 300 + 5, 128), (128 * 160, 256)])
+def test_mlp_fused(M, C, dt):
+    """mumpy_mlp_fused (LayerNorm -> fc1 -> GELU -> fc2 -> + x in one kernel, hidden activations in shared / tensor memory only)
+    against (1) the oracle's fp32 arithmetic on operands rounded where the kernel rounds them and (2) the three unfused kernels,
+    which it must reproduce bit for bit (same statistics arithmetic, same k-block order in both GEMMs)."""
+    ops = _ops()
+    x = util.seeded_input((M, C), 1) * 2.0 + util.seeded_input((M, 1), 5)
+    g, b = 1.0 + 0.2 * util.seeded_input((C,), 6), 0.1 * util.seeded_input((C,), 7)
+    w1 = (util.seeded_input((4 * C, C), 2) / C ** 0.5).to(dt)
+    w2 = (util.seeded_input((C, 4 * C), 3) / (4 * C) ** 0.5).to(dt)
+    b1, b2 = util.seeded_input((4 * C,), 8), util.seeded_input((C,), 9)
+    xn = orc.layer_norm(x, g, b).to(dt).float()
+    h = orc.gelu(orc.linear(xn, w1.float(), b1)).to(dt).float()
+    ref = x + orc.linear(h, w2.float(), b2)
+    xc, gc, bc, w1c, w2c, b1c, b2c = x.cuda(), g.cuda(), b.cuda(), w1.cuda(), w2.cuda(), b1.cuda(), b2.cuda()
+    out = ops.mlp_fused(xc, gc, bc, 1e-5, w1c, b1c, w2c, b2c)
+    assert out.dtype == torch.float32 and tuple(out.shape) == (M, C)
+    tol = 3e-2 if dt == torch.bfloat16 else 4e-3          # one operand-precision rounding of h feeds a K = 4C reduction
+    assert util.maxabs(out, ref) < tol * max(1.0, float(ref.abs().max()))
+    hid = ops.linear(ops.layernorm(xc, gc, bc, 1e-5, out_dtype=dt), w1c, b1c, act=ops.ACT_GELU, out_dtype=dt)
+    unfused = ops.linear(hid, w2c, b2c, residual=xc)
+    assert torch.equal(out, unfused)
+
+
+def test_fused_mlp_block_is_bit_identical():
+    """A stage-0 Swin block with the fused MLP kernel equals the three-kernel path bit for bit."""
+    from mumpy_b200.models.modules.swinTransformer import SwinTransformerBlock
+    ops = _ops()
+    blk = SwinTransformerBlock(128, (14, 14), 4, window_size=7, shift_size=3, temporal_dim=3).eval()
+    util.load_seeded(blk)
+    blk = blk.cuda()
+    x = util.seeded_input((2, 3 * 14 * 14, 128), 7).cuda()
+    was = ops.FUSED_MLP
+    try:
+        with torch.no_grad():
+            ops.set_fused_mlp(False)
+            ref = blk(x).clone()
+            ops.set_fused_mlp(True)
+            out = blk(x)
+        assert torch.equal(out, ref)
+    finally:
+        ops.set_fused_mlp(was)
