@@ -209,11 +209,14 @@ int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int out_dtype, int
  * PixelShuffle(2) -> AvgPool2d(2), which commutes with the bilinear upsample that follows) -- ld_out / out_col then count those. */
 int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *stats_ws, float *out,
                          long ld_out, int out_col, int B, int HW, int C, int groups, float eps, int act, int quad_mean, void *stream);
-/* out[..., col:col+Cout] = resample(in) (* mul) (+ add); mul/add are (B,Ho,Wo,Cout) contiguous or NULL. */
-int mumpy_resample_nhwc(const float *in, const float *mul, const float *add, float *out, long ld_out, int out_col,
+/* out[..., col:col+Cout] = resample(in) (* mul) (+ add); mul/add are (B,Ho,Wo,Cout) fp32 contiguous or NULL.  out is fp32
+ * (out_dtype MUMPY_F32) or, when the only consumer is a tensor-core convolution, directly its 16-bit operand (MUMPY_BF16 / MUMPY_F16:
+ * same rounding as mumpy_cast16, one pass over the map less; needs C, ld_out, out_col multiples of 4 and a mode other than pixel
+ * shuffle).  ld_out / out_col count elements of out. */
+int mumpy_resample_nhwc(const float *in, const float *mul, const float *add, void *out, int out_dtype, long ld_out, int out_col,
                         int B, int H, int W, int C, int mode, int scale, void *stream);
-/* out = a * b (+ c) elementwise over n floats (c may be NULL). */
-int mumpy_mul_add(const float *a, const float *b, const float *c, float *out, long n, void *stream);
+/* out = a * b (+ c), elementwise over n fp32 values (decoder.py:204-221 gates and skips); out fp32 or a 16-bit operand type. */
+int mumpy_mul_add(const float *a, const float *b, const float *c, void *out, int out_dtype, long n, void *stream);
 /* out = a + b elementwise over n floats (the `shortcut + attn` of CrossSwinBlock, whose un-summed attention
  * branch is also an output: multiTemporalViewEncoder.py:275-276). */
 int mumpy_add(const float *a, const float *b, float *out, long n, void *stream);

@@ -47,8 +47,8 @@ SIGNATURES = {
     "mumpy_conv2d_nhwc_cout1": [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_im2col_nhwc": [vp, cl, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_groupnorm_nhwc": [vp, vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, cf, ci, ci, vp],
-    "mumpy_resample_nhwc": [vp, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, vp],
-    "mumpy_mul_add": [vp, vp, vp, vp, cl, vp],
+    "mumpy_resample_nhwc": [vp, vp, vp, vp, ci, cl, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_mul_add": [vp, vp, vp, vp, ci, cl, vp],
     "mumpy_add": [vp, vp, vp, cl, vp],
     "mumpy_nchw_to_nhwc": [vp, vp, cl, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_nhwc_to_nchw": [vp, cl, vp, ci, ci, ci, ci, vp],

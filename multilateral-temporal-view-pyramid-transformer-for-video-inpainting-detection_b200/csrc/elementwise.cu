@@ -150,11 +150,14 @@ __global__ void __launch_bounds__(256) resample_kernel(const float *__restrict__
 // 4 channels per thread for every mode but pixel-shuffle (C, ld_out, out_col multiples of 4).  Idx = uint32_t whenever the
 // element count allows: the index decomposition is three divisions by run-time values per element, and 64-bit ones cost
 // ~100 instructions each (the kernel was instruction-bound at a third of HBM bandwidth).
-template <typename Idx>
+// OutT = float, or the 16-bit operand type when the only consumer is a tensor-core convolution (the separate cast pass -- one
+// more read and write of the map -- disappears; same rounding as mumpy_cast16).
+template <typename Idx, typename OutT>
 __global__ void __launch_bounds__(256) resample_vec_kernel(const float *__restrict__ in, const float *__restrict__ mul,
-                                                           const float *__restrict__ add, float *__restrict__ out, long ld_out, int out_col,
+                                                           const float *__restrict__ add, OutT *__restrict__ out, long ld_out, int out_col,
                                                            long total4, int H, int W, int C4, int Ho, int Wo, int mode, int scale) {
   pdl_grid_sync();
+  [[maybe_unused]] float amax = 0.0f;
   Idx i = (Idx)blockIdx.x * blockDim.x + threadIdx.x;
   const Idx stride = (Idx)gridDim.x * blockDim.x;
   const float4 *in4 = reinterpret_cast<const float4 *>(in);
@@ -197,15 +200,26 @@ __global__ void __launch_bounds__(256) resample_vec_kernel(const float *__restri
       const float4 m = __ldg(reinterpret_cast<const float4 *>(add) + i);
       v.x += m.x; v.y += m.y; v.z += m.z; v.w += m.w;
     }
-    *reinterpret_cast<float4 *>(out + (long)pixel * ld_out + out_col + 4 * c4) = v;
+    if constexpr (sizeof(OutT) == 4) {
+      *reinterpret_cast<float4 *>(out + (long)pixel * ld_out + out_col + 4 * c4) = v;
+    } else {
+      if constexpr (is_half_t<OutT>::value) amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fmaxf(fabsf(v.y), fabsf(v.z)), fabsf(v.w)));
+      uint2 pk;
+      pk.x = pack2<OutT>(v.x, v.y);
+      pk.y = pack2<OutT>(v.z, v.w);
+      *reinterpret_cast<uint2 *>(out + (long)pixel * ld_out + out_col + 4 * c4) = pk;
+    }
   }
+  if constexpr (is_half_t<OutT>::value) f16_guard(amax);
 }
 
+template <typename OutT>
 __global__ void __launch_bounds__(256) mul_add_vec_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, const float4 *__restrict__ c,
-                                                          float4 *__restrict__ out, long n4) {
+                                                          OutT *__restrict__ out, long n4) {
   pdl_grid_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
+  [[maybe_unused]] float amax = 0.0f;
   for (; i < n4; i += stride) {
     const float4 x = __ldg(a + i), y = b ? __ldg(b + i) : make_float4(1.f, 1.f, 1.f, 1.f);
     float4 v = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
@@ -213,8 +227,17 @@ __global__ void __launch_bounds__(256) mul_add_vec_kernel(const float4 *__restri
       const float4 z = __ldg(c + i);
       v.x += z.x; v.y += z.y; v.z += z.z; v.w += z.w;
     }
-    out[i] = v;
+    if constexpr (sizeof(OutT) == 4) {
+      reinterpret_cast<float4 *>(out)[i] = v;
+    } else {
+      if constexpr (is_half_t<OutT>::value) amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fmaxf(fabsf(v.y), fabsf(v.z)), fabsf(v.w)));
+      uint2 pk;
+      pk.x = pack2<OutT>(v.x, v.y);
+      pk.y = pack2<OutT>(v.z, v.w);
+      reinterpret_cast<uint2 *>(out)[i] = pk;
+    }
   }
+  if constexpr (is_half_t<OutT>::value) f16_guard(amax);
 }
 
 __global__ void __launch_bounds__(256) mul_add_kernel(const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ c,
@@ -526,7 +549,16 @@ extern "C" int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int out
   return launch_status("im2col_nhwc");
 }
 
-extern "C" int mumpy_resample_nhwc(const float *in, const float *mul, const float *add, float *out, long ld_out, int out_col,
+template <typename OutT>
+static void launch_resample_vec(const float *in, const float *mul, const float *add, void *out, long ld_out, int out_col, long total4, int H, int W, int C4,
+                                int Ho, int Wo, int mode, int scale, cudaStream_t st) {
+  if (total4 < (1l << 31) - (1l << 24))
+    launch_kernel(resample_vec_kernel<uint32_t, OutT>, flat_blocks(total4), 256, 0, st, in, mul, add, static_cast<OutT *>(out), ld_out, out_col, total4, H, W, C4, Ho, Wo, mode, scale);
+  else
+    launch_kernel(resample_vec_kernel<long, OutT>, flat_blocks(total4), 256, 0, st, in, mul, add, static_cast<OutT *>(out), ld_out, out_col, total4, H, W, C4, Ho, Wo, mode, scale);
+}
+
+extern "C" int mumpy_resample_nhwc(const float *in, const float *mul, const float *add, void *out, int out_dtype, long ld_out, int out_col,
                                    int B, int H, int W, int C, int mode, int scale, void *stream) {
   MUMPY_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0, "resample_nhwc: bad arguments");
   int Ho = H, Wo = W, Co = C;
@@ -547,24 +579,27 @@ extern "C" int mumpy_resample_nhwc(const float *in, const float *mul, const floa
   const long total = (long)B * Ho * Wo * Co;
   if (mode != MUMPY_RS_PIXEL_SHUFFLE2 && C % 4 == 0 && ld_out % 4 == 0 && out_col % 4 == 0 &&
       ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mul) | reinterpret_cast<uintptr_t>(add)) & 15) == 0) {
-    if (total / 4 < (1l << 31) - (1l << 24))
-      launch_kernel(resample_vec_kernel<uint32_t>, flat_blocks(total / 4), 256, 0, as_stream(stream), in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale);
-    else
-      launch_kernel(resample_vec_kernel<long>, flat_blocks(total / 4), 256, 0, as_stream(stream), in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale);
+    if (out_dtype == MUMPY_F32) launch_resample_vec<float>(in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale, as_stream(stream));
+    else if (out_dtype == MUMPY_F16) launch_resample_vec<__half>(in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale, as_stream(stream));
+    else launch_resample_vec<__nv_bfloat16>(in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale, as_stream(stream));
     return launch_status("resample_vec");
   }
-  launch_kernel(resample_kernel, flat_blocks(total), 256, 0, as_stream(stream), in, mul, add, out, ld_out, out_col, total, H, W, C, Ho, Wo, Co, mode, scale);
+  MUMPY_REQUIRE(out_dtype == MUMPY_F32, "resample_nhwc: 16-bit output needs C, ld_out, out_col multiples of 4, 16-byte aligned buffers and a mode other than pixel shuffle");
+  launch_kernel(resample_kernel, flat_blocks(total), 256, 0, as_stream(stream), in, mul, add, static_cast<float *>(out), ld_out, out_col, total, H, W, C, Ho, Wo, Co, mode, scale);
   return launch_status("resample_nhwc");
 }
 
-extern "C" int mumpy_mul_add(const float *a, const float *b, const float *c, float *out, long n, void *stream) {
+extern "C" int mumpy_mul_add(const float *a, const float *b, const float *c, void *out, int out_dtype, long n, void *stream) {
   MUMPY_REQUIRE(a && b && out && n > 0, "mul_add: bad arguments");
   if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
-    launch_kernel(mul_add_vec_kernel, flat_blocks(n / 4), 256, 0, as_stream(stream), reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(b),
-                                                                        reinterpret_cast<const float4 *>(c), reinterpret_cast<float4 *>(out), n / 4);
+    const float4 *a4 = reinterpret_cast<const float4 *>(a), *b4 = reinterpret_cast<const float4 *>(b), *c4 = reinterpret_cast<const float4 *>(c);
+    if (out_dtype == MUMPY_F32) launch_kernel(mul_add_vec_kernel<float>, flat_blocks(n / 4), 256, 0, as_stream(stream), a4, b4, c4, static_cast<float *>(out), n / 4);
+    else if (out_dtype == MUMPY_F16) launch_kernel(mul_add_vec_kernel<__half>, flat_blocks(n / 4), 256, 0, as_stream(stream), a4, b4, c4, static_cast<__half *>(out), n / 4);
+    else launch_kernel(mul_add_vec_kernel<__nv_bfloat16>, flat_blocks(n / 4), 256, 0, as_stream(stream), a4, b4, c4, static_cast<__nv_bfloat16 *>(out), n / 4);
     return launch_status("mul_add_vec");
   }
-  launch_kernel(mul_add_kernel, flat_blocks(n), 256, 0, as_stream(stream), a, b, c, out, n);
+  MUMPY_REQUIRE(out_dtype == MUMPY_F32, "mul_add: 16-bit output needs n %% 4 == 0 and 16-byte aligned buffers");
+  launch_kernel(mul_add_kernel, flat_blocks(n), 256, 0, as_stream(stream), a, b, c, static_cast<float *>(out), n);
   return launch_status("mul_add");
 }
 
@@ -572,8 +607,8 @@ extern "C" int mumpy_add(const float *a, const float *b, float *out, long n, voi
   MUMPY_REQUIRE(a && b && out && n > 0, "add: bad arguments");
   if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     // out = a * 1 + b through the fused kernel (b slot = nullptr means multiply by one)
-    launch_kernel(mul_add_vec_kernel, flat_blocks(n / 4), 256, 0, as_stream(stream), reinterpret_cast<const float4 *>(a), nullptr, reinterpret_cast<const float4 *>(b),
-                                                                        reinterpret_cast<float4 *>(out), n / 4);
+    launch_kernel(mul_add_vec_kernel<float>, flat_blocks(n / 4), 256, 0, as_stream(stream), reinterpret_cast<const float4 *>(a), nullptr, reinterpret_cast<const float4 *>(b),
+                                                                        out, n / 4);
     return launch_status("add_vec");
   }
   launch_kernel(add_kernel, flat_blocks(n), 256, 0, as_stream(stream), a, b, out, n);

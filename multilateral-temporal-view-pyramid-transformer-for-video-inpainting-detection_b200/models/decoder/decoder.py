@@ -52,16 +52,22 @@ def _conv(owner, name, conv, x, B, H, W, ld_in=None, out16=False, residual=None)
     return y if residual is None else ops.add(y, residual)
 
 
+def _conv_in_dtype():
+    """dtype of a map whose only consumer is a convolution: the GEMM operand type in the tensor-core modes (the producer writes
+    it directly, no separate cast pass), fp32 otherwise."""
+    return ops.act_dtype() if ops.tensor_cores() else torch.float32
+
+
 class SEB(PackedModule):
     def __init__(self, in_channels, out_channels):
         super().__init__()
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
         self.upsample = nn.Upsample(scale_factor=2, mode="bilinear")
 
-    def nhwc(self, x1, x2, B, H2, W2):
+    def nhwc(self, x1, x2, B, H2, W2, out_dtype=torch.float32):
         """x1 (B,2H2,2W2,Co), x2 (B,H2,W2,Ci) NHWC -> x1 * up2(conv(x2)), half-pixel bilinear (:12-14)."""
         c = _conv(self, "conv", self.conv, x2, B, H2, W2)
-        return ops.resample_nhwc(c, B, H2, W2, c.shape[-1], ops.RS_UP_HALFPIX, 2, mul=x1)
+        return ops.resample_nhwc(c, B, H2, W2, c.shape[-1], ops.RS_UP_HALFPIX, 2, mul=x1, out_dtype=out_dtype)
 
     def forward(self, x):
         require_inference(self)
@@ -199,12 +205,12 @@ class Decoder(PackedModule):
         """AvgPool2 -> Conv3x3 -> GroupNorm -> Sigmoid (:147-181). x NHWC (B,H,W,C) (already pooled if `pooled`)."""
         seq = getattr(self, name)
         if not pooled:
-            x = ops.resample_nhwc(x, B, H, W, x.shape[-1], ops.RS_AVGPOOL2)
+            x = ops.resample_nhwc(x, B, H, W, x.shape[-1], ops.RS_AVGPOOL2, out_dtype=_conv_in_dtype())
             H, W = H // 2, W // 2
         c = _conv(self, name, seq[1], x, B, H, W, ld_in=ld_in)
         return ops.groupnorm_nhwc(c, seq[2].weight, seq[2].bias, B, H * W, c.shape[-1], seq[2].num_groups, ops.ACT_SIGMOID, seq[2].eps)
 
-    def _dec_stage(self, name, x, B, H, W, dap=False, gate=None):
+    def _dec_stage(self, name, x, B, H, W, dap=False, gate=None, out_dtype=torch.float32):
         """Conv3x3 -> GroupNorm(8) -> ReLU -> Upsample x2 align_corners=True (:67-95); with dap=True the DAP channel-group
         mean (:140-143) is taken before the upsample (they commute)."""
         seq = getattr(self, name)
@@ -219,7 +225,7 @@ class Decoder(PackedModule):
             C //= k
         # gate: the next stage's input is this stage's output times a frequency map (decoder.py:221 `x * freq0`): multiplied inside
         # the upsample kernel instead of a separate pass over the (B, 2H, 2W, C) map
-        return ops.resample_nhwc(g, B, H, W, C, ops.RS_UP_ALIGNED, 2, mul=gate)
+        return ops.resample_nhwc(g, B, H, W, C, ops.RS_UP_ALIGNED, 2, mul=gate, out_dtype=out_dtype)
 
     def forward(self, x, view_x, ffinfo):
         """x (B,2304,n,n), view_x [4][3] of (B,1,L,C), ffinfo (B,9,S,S) -> (binary_mask (B,1,S,S), x_feats (B,32,S,S))."""
@@ -269,13 +275,13 @@ class Decoder(PackedModule):
 
             with reg.lane(1):
                 reg.need("rgb4")
-                seb1 = self.seb1.nhwc(rgb3, rgb4, B, s3, s3)
+                seb1 = self.seb1.nhwc(rgb3, rgb4, B, s3, s3, out_dtype=_conv_in_dtype())
                 gcn1 = self.gcm2.nhwc(seb1, B, s2, s2)
                 reg.publish("gcn1", gcn1)
-                cat2 = torch.empty((B, s2, s2, c3 + c4), dtype=torch.float32, device=x.device)  # cat[rgb3, up2(rgb4)] (:210)
+                cat2 = torch.empty((B, s2, s2, c3 + c4), dtype=_conv_in_dtype(), device=x.device)  # cat[rgb3, up2(rgb4)] (:210)
                 ops.resample_nhwc(rgb3, B, s2, s2, c3, ops.RS_IDENTITY, out=cat2, ld_out=c3 + c4, out_col=0)
                 ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_UP_HALFPIX, 2, out=cat2, ld_out=c3 + c4, out_col=c3)
-                seb2 = self.seb2.nhwc(rgb2, cat2, B, s2, s2)
+                seb2 = self.seb2.nhwc(rgb2, cat2, B, s2, s2, out_dtype=_conv_in_dtype())
                 gcn2 = self.gcm3.nhwc(seb2, B, s1, s1)
                 reg.publish("gcn2", gcn2)
             with reg.lane(0):
@@ -284,17 +290,17 @@ class Decoder(PackedModule):
                 reg.need("rgb2")
                 reg.need("rgb3")
                 ct = c2 + c3 + c4
-                cat3 = torch.empty((B, s1, s1, ct), dtype=torch.float32, device=x.device)     # cat[rgb2, up2(rgb3), up4(rgb4)] (:213)
+                cat3 = torch.empty((B, s1, s1, ct), dtype=_conv_in_dtype(), device=x.device)     # cat[rgb2, up2(rgb3), up4(rgb4)] (:213)
                 ops.resample_nhwc(rgb2, B, s1, s1, c2, ops.RS_IDENTITY, out=cat3, ld_out=ct, out_col=0)
                 ops.resample_nhwc(rgb3, B, s2, s2, c3, ops.RS_UP_HALFPIX, 2, out=cat3, ld_out=ct, out_col=c2)
                 ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_UP_HALFPIX, 4, out=cat3, ld_out=ct, out_col=c2 + c3)
-                seb3 = self.seb3.nhwc(rgb1, cat3, B, s1, s1)
+                seb3 = self.seb3.nhwc(rgb1, cat3, B, s1, s1, out_dtype=_conv_in_dtype())
                 gcn3 = self.gcm4.nhwc(seb3, B, s0, s0)
 
                 # the only part that needs the encoder's final tokens (produced on the caller's stream)
                 reg.need_main()
                 cin = c4 + xh.shape[-1]
-                cat0 = torch.empty((B, s3, s3, cin), dtype=torch.float32, device=x.device)    # cat[rgb4, x] (:204)
+                cat0 = torch.empty((B, s3, s3, cin), dtype=_conv_in_dtype(), device=x.device)    # cat[rgb4, x] (:204)
                 ops.resample_nhwc(rgb4, B, s3, s3, c4, ops.RS_IDENTITY, out=cat0, ld_out=cin, out_col=0)
                 ops.resample_nhwc(xh, B, s3, s3, xh.shape[-1], ops.RS_IDENTITY, out=cat0, ld_out=cin, out_col=c4)
                 gcn0 = self.gcm1.nhwc(cat0, B, s3, s3)
@@ -304,13 +310,13 @@ class Decoder(PackedModule):
 
                 reg.need("gcn1")
                 reg.need("freq3")
-                d = self._dec_stage("decoder_2", ops.mul_add(gcn1, freq3, out1), B, s2, s2)        # (:218)
+                d = self._dec_stage("decoder_2", ops.mul_add(gcn1, freq3, out1, out_dtype=_conv_in_dtype()), B, s2, s2)        # (:218)
                 reg.need("gcn2")
                 reg.need("freq2")
-                d = self._dec_stage("decoder_3", ops.mul_add(gcn2, freq2, d), B, s1, s1)           # (:219)
+                d = self._dec_stage("decoder_3", ops.mul_add(gcn2, freq2, d, out_dtype=_conv_in_dtype()), B, s1, s1)           # (:219)
                 reg.need("freq1")
                 reg.need("freq0")
-                d = self._dec_stage("decoder_4", ops.mul_add(gcn3, freq1, d), B, s0, s0, gate=freq0)   # (:220) and the `* freq0` of (:221)
+                d = self._dec_stage("decoder_4", ops.mul_add(gcn3, freq1, d, out_dtype=_conv_in_dtype()), B, s0, s0, gate=freq0, out_dtype=_conv_in_dtype())   # (:220) and the `* freq0` of (:221)
                 feats = self._dec_stage("decoder_5", d, B, 2 * s0, 2 * s0, dap=True)                    # (:221-222) (B,S,S,32)
             reg.wait_lanes()          # hand the result back to the caller's stream (the lanes stay forked in a nested region)
         Sf = 4 * s0

@@ -407,7 +407,8 @@ def groupnorm_nhwc(x, gamma, beta, B, HW, C, groups, act, eps=1e-5, out=None, ld
     return out
 
 
-def resample_nhwc(x, B, H, W, C, mode, scale=2, mul=None, add=None, out=None, ld_out=None, out_col=0):
+def resample_nhwc(x, B, H, W, C, mode, scale=2, mul=None, add=None, out=None, ld_out=None, out_col=0, out_dtype=torch.float32):
+    """out_dtype: torch.float32, or the operand type when the result only feeds a tensor-core convolution (no separate cast pass)."""
     Ho, Wo, Co = H, W, C
     if mode in (RS_UP_ALIGNED, RS_UP_HALFPIX):
         Ho, Wo = H * scale, W * scale
@@ -416,17 +417,17 @@ def resample_nhwc(x, B, H, W, C, mode, scale=2, mul=None, add=None, out=None, ld
     elif mode == RS_PIXEL_SHUFFLE2:
         Ho, Wo, Co = 2 * H, 2 * W, C // 4
     if out is None:
-        out = torch.empty((B, Ho, Wo, Co), dtype=torch.float32, device=x.device)
+        out = torch.empty((B, Ho, Wo, Co), dtype=out_dtype, device=x.device)
     lib, st = _prep(x, mul, add, out)
-    _lib.check(lib.mumpy_resample_nhwc(_p(x), _p(mul), _p(add), _p(out), ld_out or Co, out_col, B, H, W, C, mode, scale, st),
+    _lib.check(lib.mumpy_resample_nhwc(_p(x), _p(mul), _p(add), _p(out), code(out.dtype), ld_out or Co, out_col, B, H, W, C, mode, scale, st),
                "mumpy_resample_nhwc")
     return out
 
 
-def mul_add(a, b, c=None):
-    out = torch.empty_like(a)
+def mul_add(a, b, c=None, out_dtype=torch.float32):
+    out = torch.empty(a.shape, dtype=out_dtype, device=a.device)
     lib, st = _prep(a, b, c, out)
-    _lib.check(lib.mumpy_mul_add(_p(a), _p(b), _p(c), _p(out), a.numel(), st), "mumpy_mul_add")
+    _lib.check(lib.mumpy_mul_add(_p(a), _p(b), _p(c), _p(out), code(out.dtype), a.numel(), st), "mumpy_mul_add")
     return out
 
 

@@ -217,3 +217,27 @@ def test_gather_rows_view_merge(dt):
     ops.gather_rows(v3.cuda(), 128, merged, 224, 96, B, n * T, n * T, div=T, mul_hi=1, mul_lo=n)
     ref = torch.cat([v1.unsqueeze(2).expand(B, n, T, 96), v3.view(B, T, n, 128).permute(0, 2, 1, 3)], -1).reshape(B * n * T, 224)
     assert torch.equal(merged.float().cpu(), ref.to(dt).float())
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_resample_and_mul_add_write_operands_directly(dt):
+    """16-bit outputs of resample_vec_kernel (all vector modes, strided into a concat buffer, with gate and skip) and of
+    mul_add_vec_kernel equal the fp32 result passed through mumpy_cast16, bit for bit: the decoder writes convolution operands
+    straight from the producing kernel."""
+    import mumpy_b200
+    ops = mumpy_b200.ops
+    B, H, W, C = 2, 14, 10, 32
+    x = util.seeded_input((B, H, W, C), 1).cuda()
+    for mode, scale, Ho, Wo in ((ops.RS_IDENTITY, 1, H, W), (ops.RS_UP_ALIGNED, 2, 2 * H, 2 * W), (ops.RS_UP_HALFPIX, 2, 2 * H, 2 * W),
+                                (ops.RS_UP_HALFPIX, 4, 4 * H, 4 * W), (ops.RS_AVGPOOL2, 2, H // 2, W // 2)):
+        mul = util.seeded_input((B, Ho, Wo, C), 2).cuda()
+        add = util.seeded_input((B, Ho, Wo, C), 3).cuda()
+        ref = ops.cast16(ops.resample_nhwc(x, B, H, W, C, mode, scale, mul=mul, add=add), dt)
+        out = ops.resample_nhwc(x, B, H, W, C, mode, scale, mul=mul, add=add, out_dtype=dt)
+        assert out.dtype == dt and torch.equal(out, ref)
+        cat = torch.zeros((B, Ho, Wo, C + 8), dtype=dt, device=x.device)
+        ops.resample_nhwc(x, B, H, W, C, mode, scale, out=cat, ld_out=C + 8, out_col=8)
+        assert torch.equal(cat[..., 8:], ops.cast16(ops.resample_nhwc(x, B, H, W, C, mode, scale), dt)) and float(cat[..., :8].float().abs().max()) == 0.0
+    a, b, c = (util.seeded_input((B, H, W, C), s).cuda() for s in (4, 5, 6))
+    assert torch.equal(ops.mul_add(a, b, c, out_dtype=dt), ops.cast16(ops.mul_add(a, b, c), dt))
+    assert torch.equal(ops.mul_add(a, b, out_dtype=dt), ops.cast16(ops.mul_add(a, b), dt))
