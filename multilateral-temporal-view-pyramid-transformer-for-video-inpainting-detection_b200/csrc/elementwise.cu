@@ -213,6 +213,71 @@ __global__ void __launch_bounds__(256) resample_vec_kernel(const float *__restri
   if constexpr (is_half_t<OutT>::value) f16_guard(amax);
 }
 
+// The same operation for C/4 dividing 256 (every decoder map): a CTA owns one output row, a thread one channel quad, and walks
+// the row's pixels -- no index decomposition per element, the vertical weights once per CTA (the flat kernel above spends ~70
+// instructions per float4 and is issue bound below 3 TB/s).
+template <typename OutT>
+__global__ void __launch_bounds__(256) resample_rows_kernel(const float *__restrict__ in, const float *__restrict__ mul, const float *__restrict__ add,
+                                                            OutT *__restrict__ out, long ld_out, int out_col, int H, int W, int C4, int Ho, int Wo,
+                                                            int mode, int scale) {
+  pdl_grid_sync();
+  const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
+  const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, lanes_p = 256 / C4;
+  const float4 *img = reinterpret_cast<const float4 *>(in) + (long)b * H * W * C4 + c4;
+  const long orow = ((long)b * Ho + ho) * Wo;
+  const bool aligned = mode == MUMPY_RS_UP_ALIGNED;
+  int y0 = ho, y1 = ho;
+  float wy = 0.0f;
+  if (mode == MUMPY_RS_UP_ALIGNED || mode == MUMPY_RS_UP_HALFPIX) bilinear_axis(ho, H, Ho, scale, aligned, y0, y1, wy);
+  const float uy = 1.0f - wy;
+  const float4 *r0 = img + (long)(mode == MUMPY_RS_AVGPOOL2 ? 2 * ho : y0) * W * C4;
+  const float4 *r1 = img + (long)(mode == MUMPY_RS_AVGPOOL2 ? 2 * ho + 1 : y1) * W * C4;
+  [[maybe_unused]] float amax = 0.0f;
+#pragma unroll 2
+  for (int wo = pl; wo < Wo; wo += lanes_p) {
+    float4 v;
+    if (mode == MUMPY_RS_IDENTITY) {
+      v = __ldg(r0 + (long)wo * C4);
+    } else if (mode == MUMPY_RS_AVGPOOL2) {
+      const float4 a = __ldg(r0 + (long)(2 * wo) * C4), bb = __ldg(r0 + (long)(2 * wo + 1) * C4);
+      const float4 c = __ldg(r1 + (long)(2 * wo) * C4), d = __ldg(r1 + (long)(2 * wo + 1) * C4);
+      v.x = (a.x + bb.x + c.x + d.x) * 0.25f; v.y = (a.y + bb.y + c.y + d.y) * 0.25f;
+      v.z = (a.z + bb.z + c.z + d.z) * 0.25f; v.w = (a.w + bb.w + c.w + d.w) * 0.25f;
+    } else {
+      int x0, x1;
+      float wx;
+      bilinear_axis(wo, W, Wo, scale, aligned, x0, x1, wx);
+      const float4 v00 = __ldg(r0 + (long)x0 * C4), v01 = __ldg(r0 + (long)x1 * C4);
+      const float4 v10 = __ldg(r1 + (long)x0 * C4), v11 = __ldg(r1 + (long)x1 * C4);
+      const float ux = 1.0f - wx;
+      v.x = uy * (ux * v00.x + wx * v01.x) + wy * (ux * v10.x + wx * v11.x);
+      v.y = uy * (ux * v00.y + wx * v01.y) + wy * (ux * v10.y + wx * v11.y);
+      v.z = uy * (ux * v00.z + wx * v01.z) + wy * (ux * v10.z + wx * v11.z);
+      v.w = uy * (ux * v00.w + wx * v01.w) + wy * (ux * v10.w + wx * v11.w);
+    }
+    const long i = (orow + wo) * C4 + c4;
+    if (mul) {
+      const float4 m = __ldg(reinterpret_cast<const float4 *>(mul) + i);
+      v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+    }
+    if (add) {
+      const float4 m = __ldg(reinterpret_cast<const float4 *>(add) + i);
+      v.x += m.x; v.y += m.y; v.z += m.z; v.w += m.w;
+    }
+    OutT *o = out + (orow + wo) * ld_out + out_col + 4 * c4;
+    if constexpr (sizeof(OutT) == 4) {
+      *reinterpret_cast<float4 *>(o) = v;
+    } else {
+      if constexpr (is_half_t<OutT>::value) amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fmaxf(fabsf(v.y), fabsf(v.z)), fabsf(v.w)));
+      uint2 pk;
+      pk.x = pack2<OutT>(v.x, v.y);
+      pk.y = pack2<OutT>(v.z, v.w);
+      *reinterpret_cast<uint2 *>(o) = pk;
+    }
+  }
+  if constexpr (is_half_t<OutT>::value) f16_guard(amax);
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(256) mul_add_vec_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, const float4 *__restrict__ c,
                                                           OutT *__restrict__ out, long n4) {
@@ -392,19 +457,21 @@ __global__ void __launch_bounds__(256) conv_cout1_vec_kernel(const float *__rest
 // one thread per (pixel, quad).  Four neighbouring columns per LPP = 8 warp: 512 contiguous bytes per load instruction.
 constexpr int COUT1_ROWS = 4;
 template <int LPP>
-__global__ void __launch_bounds__(256) conv_cout1_rows_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
+__global__ void __launch_bounds__(256, 4) conv_cout1_rows_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
                                                               float *__restrict__ out, long units, int H, int W) {
   pdl_grid_sync();
-  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long u = gid / LPP;                      // unit = (image, row tile, column)
+  // 32-bit index decomposition (the host checks units * LPP < 2^31): five 64-bit divisions by run-time values were ~500 of the
+  // ~740 instructions a thread executed (ncu: 74 M warp instructions for 14 M warp FMAs)
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned u = gid / LPP;                  // unit = (image, row tile, column)
   const int sub = (int)(gid % LPP);
-  const bool live = u < units;
-  const long uu = live ? u : 0;
-  const int x = (int)(uu % W);
-  const long r = uu / W;
-  const int tiles = (H + COUT1_ROWS - 1) / COUT1_ROWS;
-  const int y0 = (int)(r % tiles) * COUT1_ROWS;
+  const bool live = u < (unsigned)units;
+  const unsigned uu = live ? u : 0u;
+  const unsigned r = uu / (unsigned)W;
+  const int x = (int)(uu - r * (unsigned)W);
+  const unsigned tiles = (unsigned)(H + COUT1_ROWS - 1) / COUT1_ROWS;
   const long b = r / tiles;
+  const int y0 = (int)(r - (unsigned)b * tiles) * COUT1_ROWS;
   const float4 *in4 = reinterpret_cast<const float4 *>(in);
   float4 wt[9];
 #pragma unroll
@@ -412,16 +479,18 @@ __global__ void __launch_bounds__(256) conv_cout1_rows_kernel(const float *__res
   float acc[COUT1_ROWS];
 #pragma unroll
   for (int i = 0; i < COUT1_ROWS; ++i) acc[i] = 0.0f;
+  // (rows outside the image are predicated loads, not branches: the compiler batches the loads of several rows -- the kernel was
+  // latency-bound at 34 % occupancy with one row's loads in flight per thread, ncu: 72 % of the stall samples on long scoreboard)
 #pragma unroll
   for (int ry = 0; ry < COUT1_ROWS + 2; ++ry) {
     const int yy = y0 + ry - 1;
-    if (yy < 0 || yy >= H) continue;
-    const float4 *row = in4 + ((b * H + yy) * W) * LPP + sub;
+    const bool in_y = yy >= 0 && yy < H;
+    const float4 *row = in4 + ((b * H + (in_y ? yy : 0)) * W) * LPP + sub;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 v[3];
-    v[0] = x > 0 ? __ldg(row + (long)(x - 1) * LPP) : zero;
-    v[1] = __ldg(row + (long)x * LPP);
-    v[2] = x + 1 < W ? __ldg(row + (long)(x + 1) * LPP) : zero;
+    v[0] = (in_y && x > 0) ? __ldg(row + (long)(x - 1) * LPP) : zero;
+    v[1] = in_y ? __ldg(row + (long)x * LPP) : zero;
+    v[2] = (in_y && x + 1 < W) ? __ldg(row + (long)(x + 1) * LPP) : zero;
 #pragma unroll
     for (int i = 0; i < COUT1_ROWS; ++i) {
       const int ky = ry - i;                     // input row ry feeds output row i through filter row ky
@@ -579,6 +648,14 @@ extern "C" int mumpy_resample_nhwc(const float *in, const float *mul, const floa
   const long total = (long)B * Ho * Wo * Co;
   if (mode != MUMPY_RS_PIXEL_SHUFFLE2 && C % 4 == 0 && ld_out % 4 == 0 && out_col % 4 == 0 &&
       ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mul) | reinterpret_cast<uintptr_t>(add)) & 15) == 0) {
+    const int C4 = C / 4;
+    if (C4 <= 256 && 256 % C4 == 0 && (long)B * Ho < (1l << 31)) {
+      const unsigned rgrid = (unsigned)((long)B * Ho);
+      if (out_dtype == MUMPY_F32) launch_kernel(resample_rows_kernel<float>, rgrid, 256, 0, as_stream(stream), in, mul, add, static_cast<float *>(out), ld_out, out_col, H, W, C4, Ho, Wo, mode, scale);
+      else if (out_dtype == MUMPY_F16) launch_kernel(resample_rows_kernel<__half>, rgrid, 256, 0, as_stream(stream), in, mul, add, static_cast<__half *>(out), ld_out, out_col, H, W, C4, Ho, Wo, mode, scale);
+      else launch_kernel(resample_rows_kernel<__nv_bfloat16>, rgrid, 256, 0, as_stream(stream), in, mul, add, static_cast<__nv_bfloat16 *>(out), ld_out, out_col, H, W, C4, Ho, Wo, mode, scale);
+      return launch_status("resample_rows");
+    }
     if (out_dtype == MUMPY_F32) launch_resample_vec<float>(in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale, as_stream(stream));
     else if (out_dtype == MUMPY_F16) launch_resample_vec<__half>(in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale, as_stream(stream));
     else launch_resample_vec<__nv_bfloat16>(in, mul, add, out, ld_out, out_col, total / 4, H, W, C / 4, Ho, Wo, mode, scale, as_stream(stream));
@@ -653,8 +730,9 @@ extern "C" int mumpy_conv2d_nhwc_cout1(const float *in, const float *w, const fl
   if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w)) & 15) == 0 && (Cin == 32 || Cin == 64 || Cin == 128 || Cin == 16)) {
     cudaStream_t st = as_stream(stream);
     const int lpp = Cin / 4;
-    if (kh == 3 && kw == 3 && ph == 1 && pw == 1 && (lpp == 8 || lpp == 4)) {
-      const long units = (long)B * ((H + COUT1_ROWS - 1) / COUT1_ROWS) * W;
+    const long units_chk = (long)B * ((H + COUT1_ROWS - 1) / COUT1_ROWS) * W;
+    if (kh == 3 && kw == 3 && ph == 1 && pw == 1 && (lpp == 8 || lpp == 4) && units_chk * lpp + 256 < (1l << 31)) {
+      const long units = units_chk;
       const unsigned rgrid = (unsigned)cdiv(units * lpp, 256);
       if (lpp == 8) launch_kernel(conv_cout1_rows_kernel<8>, rgrid, 256, 0, st, in, w, bias, out, units, H, W);
       else launch_kernel(conv_cout1_rows_kernel<4>, rgrid, 256, 0, st, in, w, bias, out, units, H, W);

@@ -353,6 +353,55 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float *__res
   }
 }
 
+// The same pass for C/4 dividing 256 (C = 32 ... 1024, powers of two -- every GroupNorm of the decoder): a thread keeps ONE
+// channel quad (its gamma / beta / group statistics are loaded once) and walks the pixels of a contiguous range of one image.
+// The flat kernel above spends ~40 instructions per float4 on index decomposition and per-element parameter loads (ncu: issue
+// bound at 3.3 TB/s); here the loop body is load, 4 FMA-pairs, activation, store.
+template <int ACT, bool QUAD>
+__global__ void __launch_bounds__(256) groupnorm_apply_rows_kernel(const float *__restrict__ x, const float *__restrict__ stats,
+                                                                   const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                   float *__restrict__ out, long ld_out, int out_col, int HW, int C4, int cqg,
+                                                                   int groups, int chunks, int pix_per_cta) {
+  pdl_grid_sync();
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x - b * chunks;
+  const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, lanes_p = 256 / C4;
+  const int p1 = min(HW, (chunk + 1) * pix_per_cta);
+  const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + c4), bt = __ldg(reinterpret_cast<const float4 *>(beta) + c4);
+  const float *st = stats + 2 * ((long)b * groups + c4 / cqg);
+  const float mean = st[0], rstd = st[1];
+  const float4 *x4 = reinterpret_cast<const float4 *>(x) + (long)b * HW * C4 + c4;
+  float *o = out + (long)b * HW * ld_out + out_col + (QUAD ? c4 : 4 * c4);
+#pragma unroll 4
+  for (int p = chunk * pix_per_cta + pl; p < p1; p += lanes_p) {
+    const float4 v = x4[(long)p * C4];
+    float4 r;
+    r.x = (v.x - mean) * rstd * g.x + bt.x;
+    r.y = (v.y - mean) * rstd * g.y + bt.y;
+    r.z = (v.z - mean) * rstd * g.z + bt.z;
+    r.w = (v.w - mean) * rstd * g.w + bt.w;
+    if (ACT == MUMPY_ACT_RELU) {
+      r.x = fmaxf(r.x, 0.0f); r.y = fmaxf(r.y, 0.0f); r.z = fmaxf(r.z, 0.0f); r.w = fmaxf(r.w, 0.0f);
+    } else if (ACT != MUMPY_ACT_NONE) {
+      r.x = apply_act(r.x, ACT); r.y = apply_act(r.y, ACT); r.z = apply_act(r.z, ACT); r.w = apply_act(r.w, ACT);
+    }
+    if (QUAD) o[(long)p * ld_out] = (r.x + r.y + r.z + r.w) * 0.25f;      // DAP: mean of 4 consecutive channels
+    else *reinterpret_cast<float4 *>(o + (long)p * ld_out) = r;
+  }
+}
+
+template <int ACT>
+static void launch_gn_apply_rows(const float *x, const float *stats, const float *gamma, const float *beta, float *out, long ld_out, int out_col, int B,
+                                 int HW, int C, int groups, int quad_mean, cudaStream_t st) {
+  const int C4 = C / 4, cqg = C / groups / 4;
+  int pix = 128;
+  while (pix > 16 && (long)B * cdiv(HW, pix) < 148 * 8) pix >>= 1;
+  const int chunks = (int)cdiv(HW, pix);
+  if (quad_mean)
+    launch_kernel(groupnorm_apply_rows_kernel<ACT, true>, (unsigned)(B * chunks), 256, 0, st, x, stats, gamma, beta, out, ld_out, out_col, HW, C4, cqg, groups, chunks, pix);
+  else
+    launch_kernel(groupnorm_apply_rows_kernel<ACT, false>, (unsigned)(B * chunks), 256, 0, st, x, stats, gamma, beta, out, ld_out, out_col, HW, C4, cqg, groups, chunks, pix);
+}
+
 }  // namespace mumpy
 
 using namespace mumpy;
@@ -416,6 +465,15 @@ extern "C" int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const fl
   launch_kernel(gn_finalize_kernel, (unsigned)cdiv(B * groups, 8), 256, 0, st, partial, stats, B * groups, HW, C / groups, pix, nchunks, eps);
   rc = launch_status("gn_finalize");
   if (rc) return rc;
+  if (C4 <= 256 && 256 % C4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
+    switch (act) {
+      case MUMPY_ACT_NONE: launch_gn_apply_rows<MUMPY_ACT_NONE>(x, stats, gamma, beta, out, ld_out, out_col, B, HW, C, groups, quad_mean, st); break;
+      case MUMPY_ACT_RELU: launch_gn_apply_rows<MUMPY_ACT_RELU>(x, stats, gamma, beta, out, ld_out, out_col, B, HW, C, groups, quad_mean, st); break;
+      case MUMPY_ACT_SIGMOID: launch_gn_apply_rows<MUMPY_ACT_SIGMOID>(x, stats, gamma, beta, out, ld_out, out_col, B, HW, C, groups, quad_mean, st); break;
+      default: launch_gn_apply_rows<MUMPY_ACT_GELU>(x, stats, gamma, beta, out, ld_out, out_col, B, HW, C, groups, quad_mean, st); break;
+    }
+    return launch_status("groupnorm_apply_rows");
+  }
   const long total4 = (long)B * HW * C / 4;
   const int blocks = (int)(cdiv(total4, 256) < 148 * 16 ? cdiv(total4, 256) : 148 * 16);
   launch_kernel(groupnorm_apply_kernel, blocks, 256, 0, st, x, stats, gamma, beta, out, ld_out, out_col, total4, HW, C, groups, act, quad_mean);
