@@ -1,5 +1,7 @@
 // LayerNorm (plain rows and the PatchMerging 2x2 gather) and NHWC GroupNorm + activation.
 // Statistics are always fp32 two-pass (mean, then centred variance), like the reference's ATen kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mumpy {
@@ -389,6 +391,60 @@ __global__ void __launch_bounds__(256) groupnorm_apply_rows_kernel(const float *
   }
 }
 
+// Small maps (HW * C/groups <= 16 K values: the 7x7 ... 28x28 levels of the decoder pyramids): statistics and normalisation in ONE
+// kernel, one CTA per (image, group) holding its slice in shared memory -- exact two-pass mean / variance over the whole slice,
+// one read of the map instead of two and one launch instead of three on chains that are launch-latency bound.
+constexpr int GN_SMALL_FLOATS = 16 * 1024;
+__device__ __forceinline__ float gn_block_sum(float v, float *red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();                       // (red may still be read from the previous reduction)
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = lane < 8 ? red[lane] : 0.0f;
+  t = warp_sum(t);
+  return t;                              // every thread holds the CTA total (256 threads = 8 warps)
+}
+__global__ void __launch_bounds__(256) gn_small_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                       float *__restrict__ out, long ld_out, int out_col, int HW, int C, int groups, float eps, int act,
+                                                       int quad_mean) {
+  pdl_grid_sync();
+  extern __shared__ float4 gtile[];      // [HW][cg / 4]
+  __shared__ float red[8];
+  const int b = blockIdx.x / groups, g = blockIdx.x - b * groups;
+  const int cg = C / groups, cq = cg >> 2;
+  const int n4 = HW * cq;
+  const float *src = x + (long)b * HW * C + g * cg;
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const int p = i / cq, q = i - p * cq;
+    const float4 v = *reinterpret_cast<const float4 *>(src + (long)p * C + 4 * q);
+    gtile[i] = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = gn_block_sum(s, red) / (float)(n4 * 4);
+  float m2 = 0.0f;
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 v = gtile[i];
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    m2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  const float rstd = 1.0f / sqrtf(gn_block_sum(m2, red) / (float)(n4 * 4) + eps);
+  float *dst = out + (long)b * HW * ld_out + out_col + (quad_mean ? g * cq : g * cg);
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const int p = i / cq, q = i - p * cq;
+    const float4 v = gtile[i];
+    const float4 gm = __ldg(reinterpret_cast<const float4 *>(gamma + g * cg) + q), bt = __ldg(reinterpret_cast<const float4 *>(beta + g * cg) + q);
+    float4 r;
+    r.x = apply_act((v.x - mean) * rstd * gm.x + bt.x, act);
+    r.y = apply_act((v.y - mean) * rstd * gm.y + bt.y, act);
+    r.z = apply_act((v.z - mean) * rstd * gm.z + bt.z, act);
+    r.w = apply_act((v.w - mean) * rstd * gm.w + bt.w, act);
+    if (quad_mean) dst[(long)p * ld_out + q] = (r.x + r.y + r.z + r.w) * 0.25f;
+    else *reinterpret_cast<float4 *>(dst + (long)p * ld_out + 4 * q) = r;
+  }
+}
+
 template <int ACT>
 static void launch_gn_apply_rows(const float *x, const float *stats, const float *gamma, const float *beta, float *out, long ld_out, int out_col, int B,
                                  int HW, int C, int groups, int quad_mean, cudaStream_t st) {
@@ -444,6 +500,22 @@ extern "C" int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const fl
                 "groupnorm_nhwc: channels per group, ld_out, out_col must be multiples of 4");
   MUMPY_REQUIRE(C <= GN_SMEM_FLOATS, "groupnorm_nhwc: C too large");
   cudaStream_t st = as_stream(stream);
+  static int gn_small = -1;
+  if (gn_small < 0) {
+    const char *v = getenv("MUMPY_GN_SMALL");
+    gn_small = (v && v[0] == '0') ? 0 : 1;
+  }
+  if (gn_small && (long)HW * (C / groups) <= GN_SMALL_FLOATS && C % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
+    static bool small_attr = false;
+    if (!small_attr) {
+      cudaFuncSetAttribute(gn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_SMALL_FLOATS * (int)sizeof(float));
+      small_attr = true;
+    }
+    launch_kernel(gn_small_kernel, (unsigned)(B * groups), 256, (size_t)HW * (C / groups) * sizeof(float), st, x, gamma, beta, out, ld_out, out_col, HW, C,
+                  groups, eps, act, quad_mean);
+    return launch_status("gn_small");
+  }
   int pix = GN_SMEM_FLOATS / C;
   if (pix > 64) pix = 64;
   if (pix > HW) pix = HW;

@@ -162,15 +162,21 @@ def layernorm(x, gamma, beta, eps=1e-5, out_dtype=None):
     return out
 
 
-# LayerNorm inside the consuming GEMM (mumpy_ln_linear).  Opt-in: bit-identical to mumpy_layernorm + mumpy_linear and 108 fewer
-# launches per forward, but measured no faster (round 2, B = 32: 2078-2201 vs 2163-2193 clips/s; the un-overlapped LayerNorm
-# prologue and the 2-stage weight ring at K = 512 cost what the removed kernel saved -- DESIGN.md section 4).
-FUSED_LN = os.environ.get("MUMPY_FUSED_LN", "0") != "0"
+# LayerNorm inside the consuming GEMM (mumpy_ln_linear): bit-identical to mumpy_layernorm + mumpy_linear.  On for the K = 512 blocks
+# (stage 2 of view 3: one CTA pair per pair of row tiles, the weight ring at the tensor floor; 2361-2380 vs 2355 clips/s on one box
+# and 36 LayerNorm launches fewer per forward); the narrower widths measured slower (K = 384: 2322 clips/s -- the un-overlapped
+# LayerNorm prologue costs more than the removed kernel) and stay on the unfused kernels unless listed in
+# MUMPY_FUSED_LN_WIDTHS.
+FUSED_LN = os.environ.get("MUMPY_FUSED_LN", "1") != "0"
+FUSED_LN_WIDTHS = tuple(int(v) for v in os.environ.get("MUMPY_FUSED_LN_WIDTHS", "512").split(",") if v)
 
 
-def set_fused_ln(enabled: bool):
-    global FUSED_LN
+def set_fused_ln(enabled: bool, widths=None):
+    """Switches the fused LayerNorm + GEMM path; `widths` (optional) replaces the set of K it applies to."""
+    global FUSED_LN, FUSED_LN_WIDTHS
     FUSED_LN = bool(enabled)
+    if widths is not None:
+        FUSED_LN_WIDTHS = tuple(int(w) for w in widths)
 
 
 def set_ln_linear_pair_mode(mode: int):
@@ -180,7 +186,7 @@ def set_ln_linear_pair_mode(mode: int):
 
 def ln_linear_fits(N, K) -> bool:
     """True when ln_linear() can run: a 16-bit operand mode, the switch on, and a width the fused kernel holds on chip."""
-    return FUSED_LN and tensor_cores() and K in (96, 128, 192, 256, 384, 512) and (N % 64 == 0 or N % 96 == 0)
+    return FUSED_LN and tensor_cores() and K in (96, 128, 192, 256, 384, 512) and K in FUSED_LN_WIDTHS and (N % 64 == 0 or N % 96 == 0)
 
 
 def ln_linear(x, gamma, beta, eps, w, bias=None, act=ACT_NONE):

@@ -145,14 +145,16 @@ def test_ln_linear_rejects_unsupported_shapes():
     x = torch.zeros((64, 768)).cuda()
     with pytest.raises(mumpy_b200._lib.MumpyError):
         ops.ln_linear(x, torch.ones(768).cuda(), torch.zeros(768).cuda(), 1e-5, torch.zeros((768, 768), dtype=torch.float16).cuda())
-    was = ops.FUSED_LN
+    was, was_w = ops.FUSED_LN, ops.FUSED_LN_WIDTHS
     try:
-        ops.set_fused_ln(True)
-        assert not ops.ln_linear_fits(768, 768) and ops.ln_linear_fits(1536, 512)
-        ops.set_fused_ln(False)                                    # the switch is opt-in: off -> the mirrors never take the fused path
+        ops.set_fused_ln(True, widths=(96, 128, 192, 256, 384, 512))
+        assert not ops.ln_linear_fits(768, 768) and ops.ln_linear_fits(1536, 512) and ops.ln_linear_fits(384, 128)
+        ops.set_fused_ln(True, widths=(512,))                      # the default: only the K = 512 blocks
+        assert ops.ln_linear_fits(1536, 512) and not ops.ln_linear_fits(384, 128)
+        ops.set_fused_ln(False)
         assert not ops.ln_linear_fits(1536, 512)
     finally:
-        ops.set_fused_ln(was)
+        ops.set_fused_ln(was, widths=was_w)
 
 
 def test_fused_ln_forward_is_bit_identical():
@@ -164,16 +166,16 @@ def test_fused_ln_forward_is_bit_identical():
     util.load_seeded(blk)
     blk = blk.cuda()
     x = util.seeded_input((2, 3 * 14 * 14, 128), 7).cuda()
-    was = ops.FUSED_LN
+    was, was_w = ops.FUSED_LN, ops.FUSED_LN_WIDTHS
     try:
         with torch.no_grad():
             ops.set_fused_ln(False)
             ref = blk(x).clone()
-            ops.set_fused_ln(True)
+            ops.set_fused_ln(True, widths=(128,))
             out = blk(x)
         assert torch.equal(out, ref)
     finally:
-        ops.set_fused_ln(was)
+        ops.set_fused_ln(was, widths=was_w)
 
 
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])

@@ -68,8 +68,8 @@ def test_no_kernel_writes_outside_its_buffers(mode, fused):
     enc, dec = enc.cuda(), dec.cuda()
     x = util.seeded_input((2, 3, 3, 224, 224), 3).cuda()
     mumpy_b200.set_precision(mode)
-    was = ops.FUSED_LN
-    ops.set_fused_ln(fused)
+    was, was_w = ops.FUSED_LN, ops.FUSED_LN_WIDTHS
+    ops.set_fused_ln(fused, widths=(96, 128, 192, 256, 384, 512))
     guarded = _GuardedTorch()
     patched = [(m, m.torch) for m in (ops, dec_mod, enc_mod)]
     try:
@@ -82,7 +82,7 @@ def test_no_kernel_writes_outside_its_buffers(mode, fused):
     finally:
         for m, orig in patched:
             m.torch = orig
-        ops.set_fused_ln(was)
+        ops.set_fused_ln(was, widths=was_w)
         mumpy_b200.set_precision(ops.DEFAULT_PRECISION)
     assert len(guarded.blocks) > 300, "the guard hook saw only %d allocations" % len(guarded.blocks)
     assert guarded.check() == 0, "a kernel wrote outside one of the library's buffers"
