@@ -280,7 +280,7 @@ def kernel_section(peaks, device, dt=None):
     return out
 
 
-OPS_TIMED = ["linear", "linear_dual", "linear_into", "ln_linear", "layernorm", "patch_merge_norm", "window_attention", "mha_short", "tokenize", "faf", "faf16", "assemble_clips",
+OPS_TIMED = ["linear", "linear_dual", "linear_into", "ln_linear", "mlp_fused", "patchify16", "layernorm", "patch_merge_norm", "window_attention", "mha_short", "tokenize", "faf", "faf16", "assemble_clips",
              "cva_offsets", "cva_sample", "cva_attention", "cva_residual", "gather_rows", "conv2d_nhwc", "conv2d_nhwc_bf16",
              "conv2d_nhwc_cout1", "im2col_nhwc", "groupnorm_nhwc", "resample_nhwc", "mul_add", "add", "nchw_to_nhwc", "nhwc_to_nchw",
              "channel_group_mean", "mask_counts", "cast16"]
@@ -298,6 +298,9 @@ def timed_serial_step(enc, dec, x, gt):
         if name in ("linear", "linear_dual") and a[0].dtype != torch.float32:
             K_ = a[0].shape[-1]
             return 2.0 * (a[0].numel() // K_) * a[1].shape[0] * K_
+        if name == "mlp_fused":                  # (x, gamma, beta, eps, w1, b1, w2, b2): LayerNorm + fc1 + GELU + fc2 + residual in one kernel
+            C_ = a[0].shape[-1]
+            return 2.0 * (a[0].numel() // C_) * C_ * 4 * C_ * 2
         if name == "ln_linear":                  # (x, gamma, beta, eps, w, ...): LayerNorm fused into the consuming GEMM
             K_ = a[0].shape[-1]
             return 2.0 * (a[0].numel() // K_) * a[4].shape[0] * K_
@@ -705,7 +708,7 @@ def main():
     if live is not None:
         # the contract's per-kernel roofline: dominant kernel, algorithmic flops per launch / live CUDA-event launch time
         line["roofline"].update({
-            "kernel": "gemm_tc_kernel (TMA + tcgen05 GEMM / implicit-GEMM conv), all %d launches of one step" % live["launches_per_step"],
+            "kernel": "tcgen05 GEMM family (gemm_tc_kernel incl. its lean / conv variants, ln_gemm_tc_kernel, mlp_fused_tc_kernel), all %d launches of one step" % live["launches_per_step"],
             "achieved": live["achieved"], "frac": live["achieved"] / peaks["bf16_tflops_sustained"],
             "avg_launch_us": live["avg_launch_us"], "flops_per_launch_avg": live["flops_per_step"] / live["launches_per_step"],
             "share_of_kernel_time": live["share_of_kernel_time"], "serial_kernel_time_ms": live["kernel_time_ms"],
