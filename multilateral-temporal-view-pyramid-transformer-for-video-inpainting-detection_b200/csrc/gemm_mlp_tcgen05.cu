@@ -16,6 +16,7 @@
 // GELU of this one; weight tiles of both matrices stream through one TMA ring in exactly that consumption order.
 // Accumulation order equals the unfused kernels' (k-blocks in ascending order), so the result is bit-identical to
 // mumpy_layernorm + mumpy_linear(GELU, 16-bit) + mumpy_linear(residual).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -135,32 +136,35 @@ __device__ __noinline__ float ml_normalise(const MlpParams &p, uint32_t a_base, 
   }
 }
 
-// epi1: one warp's share of a 128 x 128 fc1 accumulator (lane quadrant warp&3, 32-column chunks warp>>2, +3): + b1, GELU, pack,
-// written as the K-major SWIZZLE_128B A operand of fc2 (row = this thread's accumulator row: no transposition needed)
+// epi1: one warp's unit of a 128 x 128 fc1 accumulator (lane quadrant warp&3, 32-column chunk warp>>2; 16 warps = 16 units): + b1,
+// GELU, pack, written as the K-major SWIZZLE_128B A operand of fc2 (row = this thread's accumulator row: no transposition needed).
+// `bias` = the unit's 32 bias values, loaded by the caller BEFORE it waits for the accumulator (ncu: the FADD2 consuming a bias
+// loaded after the wait was the top non-barrier stall of the kernel).
 template <typename OutT>
-__device__ __forceinline__ float ml_hidden_epilogue(const float *__restrict__ b1, uint32_t h_base, uint32_t acc, int warp, int lane) {
-  const int quad = warp & 3, grp = warp >> 2;
+__device__ __forceinline__ float ml_hidden_epilogue(const float4 (&bias)[8], uint32_t h_base, uint32_t acc, int warp, int lane) {
+  static_assert(ML_EPI_GROUPS * 32 == ML_HC, "one 32-column unit per warp");
+  const int quad = warp & 3, c0 = (warp >> 2) * 32;
   const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
   const uint32_t row = static_cast<uint32_t>(quad * 32 + lane);
   float amax = 0.0f;
-  for (int c0 = grp * 32; c0 < ML_HC; c0 += 32 * ML_EPI_GROUPS) {
-    uint32_t v[32];
-    tmem_ld32(lane_addr + c0, v);
-    const uint32_t kb_base = h_base + static_cast<uint32_t>(c0 >> 6) * ML_KB_BYTES + row * 128u;
-    const uint32_t chunk0 = static_cast<uint32_t>(c0 & 63) >> 3;                 // first 16-byte chunk of these 32 columns in the 128-byte row
+  uint32_t v[32];
+  tmem_ld32(lane_addr + c0, v);
+  const uint32_t kb_base = h_base + static_cast<uint32_t>(c0 >> 6) * ML_KB_BYTES + row * 128u;
+  const uint32_t chunk0 = static_cast<uint32_t>(c0 & 63) >> 3;                 // first 16-byte chunk of these 32 columns in the 128-byte row
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float2 f[4];
+  for (int g = 0; g < 4; ++g) {
+    float2 f[4];
+    f[0] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(bias[2 * g].x, bias[2 * g].y)));
+    f[1] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(bias[2 * g].z, bias[2 * g].w)));
+    f[2] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bias[2 * g + 1].x, bias[2 * g + 1].y)));
+    f[3] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bias[2 * g + 1].z, bias[2 * g + 1].w)));
+    if constexpr (is_half_t<OutT>::value) {
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const float2 b = __ldg(reinterpret_cast<const float2 *>(b1 + c0 + 8 * g + 2 * h));
-        f[h] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2 * h]), __uint_as_float(v[8 * g + 2 * h + 1])), b));
-        if constexpr (is_half_t<OutT>::value) amax = fmaxf(amax, fmaxf(fabsf(f[h].x), fabsf(f[h].y)));
-      }
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(kb_base + (((chunk0 + g) ^ (row & 7u)) << 4)), "r"(pack2<OutT>(f[0].x, f[0].y)),
-                   "r"(pack2<OutT>(f[1].x, f[1].y)), "r"(pack2<OutT>(f[2].x, f[2].y)), "r"(pack2<OutT>(f[3].x, f[3].y))
-                   : "memory");
+      for (int h = 0; h < 4; ++h) amax = fmaxf(amax, fmaxf(fabsf(f[h].x), fabsf(f[h].y)));
     }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(kb_base + (((chunk0 + g) ^ (row & 7u)) << 4)), "r"(pack2<OutT>(f[0].x, f[0].y)),
+                 "r"(pack2<OutT>(f[1].x, f[1].y)), "r"(pack2<OutT>(f[2].x, f[2].y)), "r"(pack2<OutT>(f[3].x, f[3].y))
+                 : "memory");
   }
   return amax;
 }
@@ -352,21 +356,36 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __gri
     uint32_t c = 0, ti = 0;        // hidden chunks processed so far
     float amax = 0.0f;
     const uint32_t st_base = h_base + warp * 4096;             // epi2 staging lives in the hidden-chunk buffers (idle by then)
+#ifdef ML_TIMING
+    long long mt[16];
+#endif
     for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
       const long m0 = tile * ML_BM;
+#ifdef ML_TIMING
+      mt[0] = clock64();
+#endif
       // (every fc1 MMA of the previous tile has completed: this warp waited for its last acc1_full)
       amax = fmaxf(amax, p.f16 ? ml_normalise<__half>(p, a_base, m0, warp, lane) : ml_normalise<__nv_bfloat16>(p, a_base, m0, warp, lane));
       ml_fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
+#ifdef ML_TIMING
+      mt[1] = clock64();
+#endif
       for (int j = 0; j < n; ++j, ++c) {
         const uint32_t slot = c & 1, cph = (c >> 1) & 1;
+        float4 bias[8];                                          // this warp's 32 fc1 bias values of chunk j: in flight during the wait
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bias[i] = __ldg(reinterpret_cast<const float4 *>(p.b1 + j * ML_HC + (warp >> 2) * 32) + i);
         mbar_wait(acc1_full0 + 8 * slot, cph);
         mbar_wait(h_empty0 + 8 * slot, cph ^ 1);                 // fc2 of the chunk two back has read H[slot]
         tc_fence_after();
+#ifdef ML_TIMING
+        if (j < 4) mt[2 + 2 * j] = clock64();
+#endif
         const uint32_t acc1 = tmem_base + slot * ML_HC;
-        const float a = p.f16 ? ml_hidden_epilogue<__half>(p.b1 + j * ML_HC, h_base + slot * ML_H_BYTES, acc1, warp, lane)
-                              : ml_hidden_epilogue<__nv_bfloat16>(p.b1 + j * ML_HC, h_base + slot * ML_H_BYTES, acc1, warp, lane);
+        const float a = p.f16 ? ml_hidden_epilogue<__half>(bias, h_base + slot * ML_H_BYTES, acc1, warp, lane)
+                              : ml_hidden_epilogue<__nv_bfloat16>(bias, h_base + slot * ML_H_BYTES, acc1, warp, lane);
         amax = fmaxf(amax, a);
         tc_fence_before();
         ml_fence_proxy_async();
@@ -375,10 +394,23 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __gri
           mbar_arrive(acc1_empty0 + 8 * slot);
           mbar_arrive(h_full0 + 8 * slot);
         }
+#ifdef ML_TIMING
+        if (j < 4) mt[3 + 2 * j] = clock64();
+#endif
       }
       mbar_wait(acc2_full, ti & 1);                               // all fc2 MMAs done: H buffers are free for the staging tiles
       tc_fence_after();
+#ifdef ML_TIMING
+      mt[10] = clock64();
+#endif
       ml_output_epilogue(p, st_base, acc2, warp, lane, m0);
+#ifdef ML_TIMING
+      mt[11] = clock64();
+      if (blockIdx.x == 0 && (warp == 0 || warp == 15) && lane == 0 && ti >= 1 && ti < 4)
+        printf("tile %u warp %d: prologue %lld | c0 wait %lld work %lld | c1 wait %lld work %lld | c2 wait %lld work %lld | c3 wait %lld work %lld | wait acc2 %lld | epi2 %lld | total %lld\n",
+               ti, warp, mt[1] - mt[0], mt[2] - mt[1], mt[3] - mt[2], mt[4] - mt[3], mt[5] - mt[4], mt[6] - mt[5], mt[7] - mt[6], mt[8] - mt[7], mt[9] - mt[8],
+               mt[10] - mt[9], mt[11] - mt[10], mt[11] - mt[0]);
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty);
