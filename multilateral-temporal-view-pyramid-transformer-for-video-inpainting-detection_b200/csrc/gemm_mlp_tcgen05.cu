@@ -29,14 +29,18 @@ int tc_encode_2d_16(CUtensorMap *map, const void *ptr, bool f16, uint64_t inner,
 int tc_num_sms();
 
 constexpr int ML_BM = 128;
-constexpr int ML_HC = 128;                         // hidden columns per chunk
-constexpr int ML_EPI_WARPS = 16;             // four per TMEM lane quadrant: the 16 (quadrant, 32-column) units of a hidden chunk map one to one
-constexpr int ML_EPI_GROUPS = ML_EPI_WARPS / 4;
-constexpr int ML_THREADS = (ML_EPI_WARPS + 2) * 32;
 constexpr int ML_MAX_STAGES = 6;
 constexpr int ML_KB_BYTES = ML_BM * 128;           // one 64-column k-block of a 128-row operand
-constexpr int ML_H_BYTES = 2 * ML_KB_BYTES;        // one hidden chunk: 128 rows x 128 columns x 16 bit
 constexpr int ML_SMEM_TOTAL = 226 * 1024;
+// Two shapes of the same kernel (template parameters HC = hidden columns per chunk, EW = epilogue warps, four per TMEM lane
+// quadrant: the EW (quadrant, 32-column) units of a hidden chunk map one to one onto the warps):
+//   <128, 16, 1>  one CTA per SM, 128-column chunks, 512 TMEM columns, up to 6 ring stages                       (C = 192, 256)
+//   < 64,  8, 2>  TWO CTAs per SM, 64-column chunks, 256 TMEM columns (acc1 2 x 64 + acc2 <= 128), 97 KB of shared memory,
+//                 both k-blocks of a W1 chunk in one ring stage                                                  (C = 96, 128)
+// In the one-CTA shape the 16 warps run the LayerNorm prologue (load latency), the GELU passes (issue) and the output pass (HBM)
+// back to back while the tensor pipe and the memory system idle in turn (28-30 k clk per tile, 15 % tensor-pipe activity); two
+// resident CTAs interleave those phases on the SM's schedulers.
+constexpr int ML_SMEM_HALF = 112 * 1024;           // per CTA when two share an SM (227 KB - 2 x 1 KB reserved - static, halved)
 
 struct MlpParams {
   const float *x;
@@ -61,13 +65,13 @@ __device__ __forceinline__ void ml_fence_proxy_async() { asm volatile("fence.pro
 
 // LayerNorm of rows [m0, m0 + 128) into the resident A operand (same scheme as gemm_ln_tcgen05.cu / norm.cu)
 template <typename OutT, int LPR, int NV, int RI>
-__device__ __forceinline__ float ml_normalise_rows(const MlpParams &p, uint32_t a_base, long m0, int warp, int lane) {
+__device__ __forceinline__ float ml_normalise_rows(const MlpParams &p, uint32_t a_base, long m0, int warp, int lane, int n_warps) {
   constexpr int G = 32 / LPR;
   constexpr int RPW = G * RI;
   const int sub = lane % LPR, grp = lane / LPR;
   const int C = p.C;
   float amax = 0.0f;
-  for (int r0 = warp * RPW; r0 < ML_BM; r0 += ML_EPI_WARPS * RPW) {
+  for (int r0 = warp * RPW; r0 < ML_BM; r0 += n_warps * RPW) {
     float4 v[RI][NV];
     float s[RI], q[RI];
 #pragma unroll
@@ -127,12 +131,12 @@ __device__ __forceinline__ float ml_normalise_rows(const MlpParams &p, uint32_t 
 
 // (out of line, like the output epilogue below: both run once per tile, and inlined next to the hidden epilogue they make it spill)
 template <typename OutT>
-__device__ __noinline__ float ml_normalise(const MlpParams &p, uint32_t a_base, long m0, int warp, int lane) {
+__device__ __noinline__ float ml_normalise(const MlpParams &p, uint32_t a_base, long m0, int warp, int lane, int n_warps) {
   switch (p.C) {
-    case 96: return ml_normalise_rows<OutT, 8, 3, 2>(p, a_base, m0, warp, lane);
-    case 128: return ml_normalise_rows<OutT, 8, 4, 2>(p, a_base, m0, warp, lane);
-    case 192: return ml_normalise_rows<OutT, 16, 3, 2>(p, a_base, m0, warp, lane);
-    default: return ml_normalise_rows<OutT, 16, 4, 2>(p, a_base, m0, warp, lane);
+    case 96: return ml_normalise_rows<OutT, 8, 3, 2>(p, a_base, m0, warp, lane, n_warps);
+    case 128: return ml_normalise_rows<OutT, 8, 4, 2>(p, a_base, m0, warp, lane, n_warps);
+    case 192: return ml_normalise_rows<OutT, 16, 3, 2>(p, a_base, m0, warp, lane, n_warps);
+    default: return ml_normalise_rows<OutT, 16, 4, 2>(p, a_base, m0, warp, lane, n_warps);
   }
 }
 
@@ -142,7 +146,6 @@ __device__ __noinline__ float ml_normalise(const MlpParams &p, uint32_t a_base, 
 // loaded after the wait was the top non-barrier stall of the kernel).
 template <typename OutT>
 __device__ __forceinline__ float ml_hidden_epilogue(const float4 (&bias)[8], uint32_t h_base, uint32_t acc, int warp, int lane) {
-  static_assert(ML_EPI_GROUPS * 32 == ML_HC, "one 32-column unit per warp");
   const int quad = warp & 3, c0 = (warp >> 2) * 32;
   const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
   const uint32_t row = static_cast<uint32_t>(quad * 32 + lane);
@@ -171,12 +174,12 @@ __device__ __forceinline__ float ml_hidden_epilogue(const float4 (&bias)[8], uin
 
 // epi2: one warp's share of the 128 x C fc2 accumulator: + b2 + residual -> fp32 out, through a 4 KB swizzled staging tile so
 // that residual loads and output stores are full 128-byte row segments
-__device__ __noinline__ void ml_output_epilogue(const MlpParams &p, uint32_t st_base, uint32_t acc, int warp, int lane, long m0) {
+__device__ __noinline__ void ml_output_epilogue(const MlpParams &p, uint32_t st_base, uint32_t acc, int warp, int lane, long m0, int n_groups) {
   const int quad = warp & 3, grp = warp >> 2;
   const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
   const long row0 = m0 + quad * 32;
   const int c4 = lane & 7;
-  for (int c0 = grp * 32; c0 < p.C; c0 += 32 * ML_EPI_GROUPS) {
+  for (int c0 = grp * 32; c0 < p.C; c0 += 32 * n_groups) {
     const int col = c0 + c4 * 4;
     float4 res[8];
 #pragma unroll
@@ -209,8 +212,19 @@ __device__ __noinline__ void ml_output_epilogue(const MlpParams &p, uint32_t st_
   }
 }
 
-__global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                                                                    const MlpParams p) {
+// (Register files are per scheduler partition, 16 K registers each, and a CTA's warps are dealt round-robin: the 10 warps of the
+// two-per-SM shape put 3 on a partition, so two CTAs need 6 x 32 x regs <= 16384, i.e. 80 registers -- the bound is declared as
+// 384 threads x 2 to make ptxas target that, the kernel is launched with 320.)
+template <int ML_HC, int ML_EPI_WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__(MIN_CTAS == 2 ? 384 : (ML_EPI_WARPS + 2) * 32, MIN_CTAS) mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1,
+                                                                                         const __grid_constant__ CUtensorMap tmW2, const MlpParams p) {
+  constexpr int ML_EPI_GROUPS = ML_EPI_WARPS / 4;
+  static_assert(ML_EPI_GROUPS * 32 == ML_HC, "one 32-column unit of a hidden chunk per epilogue warp");
+  constexpr int ML_H_KB = ML_HC / 64;                       // k-blocks of one hidden chunk (the A operand of fc2)
+  constexpr int ML_H_BYTES = ML_H_KB * ML_KB_BYTES;         // one hidden chunk: 128 rows x HC columns x 16 bit
+  static_assert(2 * ML_H_BYTES >= ML_EPI_WARPS * 4096, "epi2 staging (4 KB per warp) lives in the two hidden-chunk buffers");
+  constexpr bool kGroupW1 = ML_HC == 64;                    // all k-blocks of a W1 chunk share one ring stage (8 KB each)
+  constexpr uint32_t ML_TMEM_COLS = ML_HC == 64 ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * ML_MAX_STAGES + 11];
   __shared__ uint32_t tmem_slot;
@@ -250,7 +264,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __gri
     fence_barrier_init();
   }
   if (warp == ML_EPI_WARPS + 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ML_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -274,12 +288,24 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __gri
       __syncwarp();
       if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
     };
+    auto load_w1 = [&](int chunk) {
+      if constexpr (kGroupW1) {
+        mbar_wait(w_empty0 + 8 * s, ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(w_full0 + 8 * s, static_cast<uint32_t>(p.nkb) * w1_bytes);
+          for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(ring + s * p.stage_bytes + kb * w1_bytes, &tmW1, w_full0 + 8 * s, kb * 64, chunk * ML_HC);
+        }
+        __syncwarp();
+        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+      } else {
+        for (int kb = 0; kb < p.nkb; ++kb) load(&tmW1, w1_bytes, kb * 64, chunk * ML_HC);
+      }
+    };
     for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < p.nkb; ++kb) load(&tmW1, w1_bytes, kb * 64, 0);                                   // MMA1(0)
+      load_w1(0);                                                                                             // MMA1(0)
       for (int j = 0; j < n; ++j) {
-        if (j + 1 < n)
-          for (int kb = 0; kb < p.nkb; ++kb) load(&tmW1, w1_bytes, kb * 64, (j + 1) * ML_HC);                // MMA1(j+1)
-        for (int kb = 0; kb < 2; ++kb) load(&tmW2, w2_bytes, j * ML_HC + kb * 64, 0);                         // MMA2(j)
+        if (j + 1 < n) load_w1(j + 1);                                                                        // MMA1(j+1)
+        for (int kb = 0; kb < ML_H_KB; ++kb) load(&tmW2, w2_bytes, j * ML_HC + kb * 64, 0);                   // MMA2(j)
       }
     }
   } else if (warp == ML_EPI_WARPS + 1) {
@@ -293,12 +319,19 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __gri
       mbar_wait(acc1_empty0 + 8 * slot, aph ^ 1);
       tc_fence_after();
       const uint32_t d = tmem_base + slot * ML_HC;
-      for (int kb = 0; kb < p.nkb; ++kb) {
+      if constexpr (kGroupW1) {
         mbar_wait(w_full0 + 8 * s, ph);
         tc_fence_after();
+      }
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        if constexpr (!kGroupW1) {
+          mbar_wait(w_full0 + 8 * s, ph);
+          tc_fence_after();
+        }
         const uint64_t adesc = make_kmajor_sw128_desc(a_base + kb * ML_KB_BYTES);
-        const uint64_t bdesc = make_kmajor_sw128_desc(ring + s * p.stage_bytes);
+        const uint64_t bdesc = make_kmajor_sw128_desc(ring + s * p.stage_bytes + (kGroupW1 ? kb * ML_HC * 128 : 0));
         const bool tail = (kb + 1) * 64 > p.C;
+        const bool release = !kGroupW1 || kb + 1 == p.nkb;
         if (elect_one()) {
           umma_bf16(d, adesc, bdesc, p.idesc1, kb > 0 ? 1u : 0u);
           umma_bf16(d, adesc + 2, bdesc + 2, p.idesc1, 1u);
@@ -306,10 +339,10 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __gri
             umma_bf16(d, adesc + 4, bdesc + 4, p.idesc1, 1u);
             umma_bf16(d, adesc + 6, bdesc + 6, p.idesc1, 1u);
           }
-          umma_commit(w_empty0 + 8 * s);
+          if (release) umma_commit(w_empty0 + 8 * s);
         }
         __syncwarp();
-        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+        if (release && ++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
       }
       if (elect_one()) umma_commit(acc1_full0 + 8 * slot);
       __syncwarp();
@@ -328,7 +361,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __gri
           mbar_wait(acc2_empty, (ti & 1) ^ 1);                    // the previous tile's output has left the accumulator
           tc_fence_after();
         }
-        for (int kb = 0; kb < 2; ++kb) {
+        for (int kb = 0; kb < ML_H_KB; ++kb) {
           mbar_wait(w_full0 + 8 * s, ph);
           tc_fence_after();
           const uint64_t adesc = make_kmajor_sw128_desc(h_base + hs * ML_H_BYTES + kb * ML_KB_BYTES);
@@ -365,7 +398,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __gri
       mt[0] = clock64();
 #endif
       // (every fc1 MMA of the previous tile has completed: this warp waited for its last acc1_full)
-      amax = fmaxf(amax, p.f16 ? ml_normalise<__half>(p, a_base, m0, warp, lane) : ml_normalise<__nv_bfloat16>(p, a_base, m0, warp, lane));
+      amax = fmaxf(amax, p.f16 ? ml_normalise<__half>(p, a_base, m0, warp, lane, ML_EPI_WARPS) : ml_normalise<__nv_bfloat16>(p, a_base, m0, warp, lane, ML_EPI_WARPS));
       ml_fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
@@ -403,10 +436,10 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __gri
 #ifdef ML_TIMING
       mt[10] = clock64();
 #endif
-      ml_output_epilogue(p, st_base, acc2, warp, lane, m0);
+      ml_output_epilogue(p, st_base, acc2, warp, lane, m0, ML_EPI_GROUPS);
 #ifdef ML_TIMING
       mt[11] = clock64();
-      if (blockIdx.x == 0 && (warp == 0 || warp == 15) && lane == 0 && ti >= 1 && ti < 4)
+      if (blockIdx.x == 0 && (warp == 0 || warp == ML_EPI_WARPS - 1) && lane == 0 && ti >= 1 && ti < 4)
         printf("tile %u warp %d: prologue %lld | c0 wait %lld work %lld | c1 wait %lld work %lld | c2 wait %lld work %lld | c3 wait %lld work %lld | wait acc2 %lld | epi2 %lld | total %lld\n",
                ti, warp, mt[1] - mt[0], mt[2] - mt[1], mt[3] - mt[2], mt[4] - mt[3], mt[5] - mt[4], mt[6] - mt[5], mt[7] - mt[6], mt[8] - mt[7], mt[9] - mt[8],
                mt[10] - mt[9], mt[11] - mt[10], mt[11] - mt[0]);
@@ -420,10 +453,54 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_tc_kernel(const __gri
 
   tc_fence_before();
   __syncthreads();
-  if (warp == ML_EPI_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  if (warp == ML_EPI_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ML_TMEM_COLS) : "memory");
 }
 
 bool mlp_fused_supported(int C) { return C == 96 || C == 128 || C == 192 || C == 256; }
+
+// shape policy: 0 / 1 = the one-CTA shape (default), 2 = two CTAs per SM where it fits (C <= 128).  Environment MUMPY_MLP_SHAPE.
+// Measured (B = 32 stage-0 shapes, ncu: 19.4 of the 20 theoretical warps resident): the two-per-SM shape takes the same time, 256-262
+// vs 255-261 us at M = 301056, C = 128 -- every phase of a CTA simply takes twice as long (prologue 7 -> 13 k clk, output pass
+// 7.5 -> 17 k clk, -DML_TIMING): the SM's 16 epilogue warps are the limit in either arrangement, not the phase order.
+static int g_mlp_shape = -1;
+
+template <int HC, int EW, int MIN_CTAS>
+static int launch_mlp_fused(MlpParams &p, const void *W1, const void *W2, int C, cudaStream_t st) {
+  p.n_chunks = 4 * C / HC;
+  p.idesc1 = make_idesc_16_f32(ML_BM, HC, p.f16 != 0);
+  p.idesc2 = make_idesc_16_f32(ML_BM, C, p.f16 != 0);
+  const int w2_bytes = C * 128;                                             // one 64-column k-block of W2: C rows
+  const int w1_bytes = (HC == 64 ? p.nkb : 1) * HC * 128;                   // HC = 64: every k-block of the W1 chunk in one stage
+  p.stage_bytes = (uint32_t)(w2_bytes > w1_bytes ? w2_bytes : w1_bytes);
+  p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
+  const int fixed = 1024 + p.nkb * ML_KB_BYTES + 2 * (HC / 64) * ML_KB_BYTES;
+  const int budget = MIN_CTAS == 2 ? ML_SMEM_HALF : ML_SMEM_TOTAL;
+  int stages = (budget - fixed) / (int)p.stage_bytes;
+  if (stages > ML_MAX_STAGES) stages = ML_MAX_STAGES;
+  MUMPY_REQUIRE(stages >= 2, "mlp_fused: shared memory budget (C=%d)", C);
+  p.stages = stages;
+  CUtensorMap tmW1, tmW2;
+  int rc = tc_encode_2d_16(&tmW1, W1, p.f16 != 0, (uint64_t)C, (uint64_t)4 * C, (uint64_t)C, 64, HC);
+  if (rc) return rc;
+  rc = tc_encode_2d_16(&tmW2, W2, p.f16 != 0, (uint64_t)4 * C, (uint64_t)C, (uint64_t)4 * C, 64, (uint32_t)C);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_tc_kernel<HC, EW, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget);
+    // (without the carve-out preference the driver sizes the shared-memory partition for ONE CTA of the two-per-SM shape)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused_tc_kernel<HC, EW, MIN_CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(mlp_fused_tc_kernel): %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long slots = (long)tc_num_sms() * MIN_CTAS;
+  const int smem = fixed + p.stages * (int)p.stage_bytes;
+  const unsigned grid = (unsigned)(p.num_tiles < slots ? p.num_tiles : slots);
+  launch_kernel(mlp_fused_tc_kernel<HC, EW, MIN_CTAS>, grid, (EW + 2) * 32, smem, st, tmW1, tmW2, p);
+  return launch_status("mlp_fused_tc_kernel");
+}
 
 int mlp_fused_16(const float *x, const float *gamma, const float *beta, float eps, const void *W1, const float *b1, const void *W2, const float *b2,
                  float *out, long M, int C, int w_dtype, cudaStream_t st) {
@@ -434,6 +511,10 @@ int mlp_fused_16(const float *x, const float *gamma, const float *beta, float ep
   MUMPY_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(W1) |
                   reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(W2) | reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                 "mlp_fused: all buffers must be 16-byte aligned");
+  if (g_mlp_shape < 0) {
+    const char *v = getenv("MUMPY_MLP_SHAPE");
+    g_mlp_shape = v ? atoi(v) : 0;
+  }
   MlpParams p = {};
   p.x = x;
   p.gamma = gamma;
@@ -445,38 +526,10 @@ int mlp_fused_16(const float *x, const float *gamma, const float *beta, float ep
   p.num_tiles = cdiv(M, ML_BM);
   p.C = C;
   p.nkb = (C + 63) / 64;
-  p.n_chunks = 4 * C / ML_HC;
   p.f16 = w_dtype == MUMPY_F16;
   p.eps = eps;
-  p.idesc1 = make_idesc_16_f32(ML_BM, ML_HC, p.f16 != 0);
-  p.idesc2 = make_idesc_16_f32(ML_BM, C, p.f16 != 0);
-  const int w2_bytes = C * 128;
-  p.stage_bytes = (uint32_t)(w2_bytes > ML_HC * 128 ? w2_bytes : ML_HC * 128);
-  p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
-  const int fixed = 1024 + p.nkb * ML_KB_BYTES + 2 * ML_H_BYTES;
-  int stages = (ML_SMEM_TOTAL - fixed) / (int)p.stage_bytes;
-  if (stages > ML_MAX_STAGES) stages = ML_MAX_STAGES;
-  MUMPY_REQUIRE(stages >= 2, "mlp_fused: shared memory budget (C=%d)", C);
-  p.stages = stages;
-  CUtensorMap tmW1, tmW2;
-  rc = tc_encode_2d_16(&tmW1, W1, p.f16 != 0, (uint64_t)C, (uint64_t)4 * C, (uint64_t)C, 64, ML_HC);
-  if (rc) return rc;
-  rc = tc_encode_2d_16(&tmW2, W2, p.f16 != 0, (uint64_t)4 * C, (uint64_t)C, (uint64_t)4 * C, 64, (uint32_t)C);
-  if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM_TOTAL);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(mlp_fused_tc_kernel): %s", cudaGetErrorString(e));
-      return MUMPY_ERR_CUDA;
-    }
-    attr_set = true;
-  }
-  const int sms = tc_num_sms();
-  const int smem = fixed + p.stages * (int)p.stage_bytes;
-  const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
-  launch_kernel(mlp_fused_tc_kernel, grid, ML_THREADS, smem, st, tmW1, tmW2, p);
-  return launch_status("mlp_fused_tc_kernel");
+  if (C <= 128 && g_mlp_shape == 2) return launch_mlp_fused<64, 8, 2>(p, W1, W2, C, st);
+  return launch_mlp_fused<128, 16, 1>(p, W1, W2, C, st);
 }
 
 }  // namespace mumpy
