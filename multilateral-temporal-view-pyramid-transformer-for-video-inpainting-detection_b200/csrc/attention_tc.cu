@@ -117,7 +117,20 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int half = tid >> 6, p = tid & 63;
+#ifdef WTC_TIMING
+  const long long t_entry = clock64();
+  unsigned long long g_entry;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_entry));
+#endif
 
+  // Tensor memory first: the SM does not start the next CTA of a kernel that allocates tensor memory until this one has given up
+  // its allocation permit (tools/cta_launch_bench.cu: CTAs 2, 3, 4 of an SM enter 0.9 / 1.7 / 2.4 us after the first when the
+  // allocation follows ~1 us of prologue, all within 64 ns of each other without tensor memory) -- with four CTAs per SM the
+  // zero fill and table staging below used to delay the fourth CTA by three prologues.
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(WTC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   for (int i = tid; i < WTC_TILE_BYTES / 16; i += WTC_THREADS) reinterpret_cast<uint4 *>(gen)[i] = make_uint4(0, 0, 0, 0);
   // bias table (TBL, heads) -> shared [heads][TBL] x log2(e).  Coalesced 16-byte reads, four in flight per thread: the former
   // transposing loop issued one dependent 4-byte load per iteration (21 L2 round trips, ~8 us before a CTA's first tile)
@@ -168,10 +181,6 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
     fence_barrier_init();
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(WTC_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   fence_proxy_async_smem();          // the zero fill is read by the MMAs
   tc_fence_before();
@@ -247,7 +256,13 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
 
   // Everything above touches only shared / tensor memory and the (constant) bias table: under programmatic dependent launch it
   // overlaps the tail of the kernel that produces qkv; the first read of qkv comes after this wait.
+#ifdef WTC_TIMING
+  const long long t_prologue = clock64();
+#endif
   pdl_grid_sync();
+#ifdef WTC_TIMING
+  const long long t_released = clock64();
+#endif
   const int t_begin = blockIdx.x * per_cta;
   const int t_end = min(n_tiles, t_begin + per_cta);
   RowState cur;
@@ -306,29 +321,49 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
 #pragma unroll
     for (int e = 0; e < 32; ++e) pk[e] = 0u;
     if (cur.valid) {
+      // Packed fp32x2 arithmetic (FFMA2 / FADD2) on key pairs (2e, 2e+1): the same roundings and the same four interleaved partial
+      // sums as the scalar form, two thirds of its issue slots (ncu: the kernel is bound by its instruction stream at ~3.6 warps
+      // per scheduler).  Key N (odd window sizes) is a pad: -1e30 leaves the maximum alone and its probability is exactly zero.
       const float *tb = tbl_all + cur.h * TBL + a_i;
-      float s[N];
+      constexpr int NP = (N + 1) / 2;
+      float2 s2[NP];
 #pragma unroll
-      for (int j = 0; j < N; ++j) s[j] = fmaf(__uint_as_float(j < 32 ? s_lo[j & 31] : s_hi[j & 31]), kC, tb[-a_of(j)]);
+      for (int e = 0; e < NP; ++e) {
+        const int j = 2 * e;
+        const float r0 = __uint_as_float(j < 32 ? s_lo[j & 31] : s_hi[j & 31]);
+        if (j + 1 < N) {
+          const float r1 = __uint_as_float(j + 1 < 32 ? s_lo[(j + 1) & 31] : s_hi[(j + 1) & 31]);
+          s2[e] = __ffma2_rn(make_float2(r0, r1), make_float2(kC, kC), make_float2(tb[-a_of(j)], tb[-a_of(j + 1)]));
+        } else {
+          s2[e] = make_float2(fmaf(r0, kC, tb[-a_of(j)]), -1e30f);
+        }
+      }
       if (cur.masked) {
 #pragma unroll
         for (int j = 0; j < N; ++j)
-          if ((cur.mbits >> j) & 1ull) s[j] += -100.0f * kLog2e;
+          if ((cur.mbits >> j) & 1ull) {
+            if (j & 1) s2[j >> 1].y += -100.0f * kLog2e;
+            else s2[j >> 1].x += -100.0f * kLog2e;
+          }
       }
       // four interleaved partial maxima / sums: the reductions are dependent chains, and a CTA has one warp per scheduler
-      float m4[4] = {s[0], s[1], s[2], s[3]};
+      float m4[4] = {s2[0].x, s2[0].y, s2[1].x, s2[1].y};
 #pragma unroll
-      for (int j = 4; j < N; ++j) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
-      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        s[j] = ex2_approx(s[j] - m);
-        sum4[j & 3] += s[j];
+      for (int e = 2; e < NP; ++e) {
+        m4[(2 * e) & 3] = fmaxf(m4[(2 * e) & 3], s2[e].x);
+        m4[(2 * e + 1) & 3] = fmaxf(m4[(2 * e + 1) & 3], s2[e].y);
       }
-      inv = 1.0f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const float2 nm = make_float2(-m, -m);
+      float2 sum2[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
 #pragma unroll
-      for (int e = 0; 2 * e < N; ++e) pk[e] = pack2<T>(s[2 * e], 2 * e + 1 < N ? s[2 * e + 1 < N ? 2 * e + 1 : 0] : 0.0f);
+      for (int e = 0; e < NP; ++e) {
+        const float2 d = __fadd2_rn(s2[e], nm);
+        const float2 pr = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+        sum2[e & 1] = __fadd2_rn(sum2[e & 1], pr);
+        pk[e] = pack2<T>(pr.x, pr.y);
+      }
+      inv = 1.0f / ((sum2[0].x + sum2[0].y) + (sum2[1].x + sum2[1].y));
     }
     // P goes into this thread's own lane of tensor memory (columns 64-95, inside the S block the row has finished reading):
     // the PV MMAs take their A operand from there, so the probabilities never touch shared memory.
@@ -387,12 +422,22 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     if (has_next) issue_v(nxt);       // (same warp, same rows: ordered after the staging reads)
     WTC_T(7);
 #ifdef WTC_TIMING
-    if (blockIdx.x == 0 && tid == 0 && tile < t_begin + 4)
+    if (false && blockIdx.x == 0 && tid == 0 && tile < t_begin + 4)
       printf("tile %d: sync1 %lld  S %lld  scatter %lld  softmax %lld  sync2 %lld  PV %lld  store %lld\n", tile, ts_[1] - ts_[0], ts_[2] - ts_[1], ts_[3] - ts_[2], ts_[4] - ts_[3], ts_[5] - ts_[4], ts_[6] - ts_[5], ts_[7] - ts_[6]);
 #endif
     tc_fence_before();      // (the barrier at the top of the next iteration orders these accumulator reads before the next S)
     cur = nxt;
   }
+#ifdef WTC_TIMING
+  if ((blockIdx.x % 64 == 0 || blockIdx.x == gridDim.x - 1) && tid == 0) {
+    unsigned long long g_exit;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_exit));
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    printf("cta %d sm %u: entry %llu ns  exit %llu ns | prologue %lld  pdl wait %lld  tiles %lld clk (%d tiles)\n", blockIdx.x, smid, g_entry % 10000000ull, g_exit % 10000000ull,
+           t_prologue - t_entry, t_released - t_prologue, clock64() - t_released, t_end - t_begin);
+  }
+#endif
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();

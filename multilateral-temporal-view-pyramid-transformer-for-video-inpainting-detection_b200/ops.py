@@ -212,8 +212,12 @@ def set_fused_mlp(enabled: bool):
     FUSED_MLP = bool(enabled)
 
 
+# widths that take the fused kernel (the kernel supports 96, 128, 192 and 256)
+FUSED_MLP_WIDTHS = tuple(int(v) for v in os.environ.get("MUMPY_FUSED_MLP_WIDTHS", "96,128,192,256").split(",") if v)
+
+
 def mlp_fused_fits(C) -> bool:
-    return FUSED_MLP and tensor_cores() and C in (96, 128, 192, 256)
+    return FUSED_MLP and tensor_cores() and C in (96, 128, 192, 256) and C in FUSED_MLP_WIDTHS
 
 
 def mlp_fused(x, gamma, beta, eps, w1, b1, w2, b2):
