@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmumpy_b200.so")
+# MUMPY_LIB: another build of the same ABI (development A/B runs on one box); the product always loads the in-tree library
+LIB_PATH = os.environ.get("MUMPY_LIB") or os.path.join(_HERE, "libmumpy_b200.so")
 
 _lib = None
 

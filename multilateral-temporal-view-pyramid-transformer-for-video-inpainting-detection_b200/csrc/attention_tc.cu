@@ -207,6 +207,10 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     bool valid, masked;
     unsigned long long mbits;
   };
+  // canvas rows of the four tokens this lane gathers for the tile located last (lane>>2 + 8 * pass of the warp's 32 rows; -1 = dead
+  // row): refreshed by shuffle only when the window pair changes, i.e. once per `heads` tiles instead of 12 times per tile
+  const int lane = tid & 31;
+  int grow[4] = {-1, -1, -1, -1};
   auto locate = [&](int pair, int h, RowState &rs) {
     rs.h = h;
     if (pair == rs.pair) return;
@@ -229,22 +233,23 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
       const unsigned long long same_c = last_c ? (i_c1 ? c1 : ~c1) : ~0ull;
       rs.mbits = ~(same_r & same_c);
     }
+    const int enc = rs.valid ? (int)rs.row : -1;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) grow[pass] = __shfl_sync(0xffffffffu, enc, pass * 8 + (lane >> 2));
   };
   // Gather: a warp fetches the q / k / v segments of its own 32 rows, four lanes per row (64 contiguous bytes, 8 rows per
   // instruction) -- the token row of the lane's gather row comes from its owner by shuffle.  Destination rows are 64 B with
   // 16-byte chunks XOR (row >> 1) & 3: the SWIZZLE_64B pattern for a 64-byte row pitch.
-  const int lane = tid & 31;
   const uint32_t g_chunk = static_cast<uint32_t>(lane & 3);
+  const uint32_t g_dst = static_cast<uint32_t>((tid & 32) + (lane >> 2));          // pass 0 row inside the window's 64-row tile (+8 per pass)
+  const long row_pitch = 3l * C;
   auto gather = [&](const RowState &rs, int which, uint32_t tile_base) {       // which: 0 q, 1 k, 2 v (element offset which * C)
-    const int enc = rs.valid ? (int)rs.row : -1;
+    const T *src0 = qkv + which * C + rs.h * 32 + g_chunk * 8;
 #pragma unroll
     for (int pass = 0; pass < 4; ++pass) {
-      const int r_in_warp = pass * 8 + (lane >> 2);
-      const int row = __shfl_sync(0xffffffffu, enc, r_in_warp);
-      if (row >= 0) {
-        const uint32_t r = static_cast<uint32_t>((tid & 32) + r_in_warp);      // row inside the window's 64-row tile
-        const T *src = qkv + (long)row * 3 * C + which * C + rs.h * 32 + g_chunk * 8;
-        wtc_cp_async_16(tile_base + r * 64 + ((g_chunk ^ ((r >> 1) & 3)) << 4), src);
+      if (grow[pass] >= 0) {
+        const uint32_t r = g_dst + pass * 8;
+        wtc_cp_async_16(tile_base + r * 64 + ((g_chunk ^ ((r >> 1) & 3)) << 4), src0 + grow[pass] * row_pitch);
       }
     }
   };
@@ -278,7 +283,8 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
   }
   uint32_t phase = 0;
 #ifdef WTC_TIMING
-  long long ts_[8];
+  long long ts_[11];
+  long long acc_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
   for (int tile = t_begin; tile < t_end; ++tile) {
     // Software pipeline: the next tile's q/k gather is issued as soon as S is complete (it lands during the softmax), its v
@@ -393,6 +399,7 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     phase ^= 1;
     uint32_t o[32];
     tmem_ld32(t_row + half * 32, o);
+    WTC_T(8);
     // The row's 32 outputs go through this warp's rows of the V tile (PV is complete, the next v gather not yet issued) so that
     // the global stores use the gather's mapping: four lanes write the 64 contiguous bytes of one token.
     if (cur.valid) {
@@ -419,17 +426,25 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
       }
     }
     __syncwarp();
+    WTC_T(9);
     if (has_next) issue_v(nxt);       // (same warp, same rows: ordered after the staging reads)
     WTC_T(7);
 #ifdef WTC_TIMING
-    if (false && blockIdx.x == 0 && tid == 0 && tile < t_begin + 4)
-      printf("tile %d: sync1 %lld  S %lld  scatter %lld  softmax %lld  sync2 %lld  PV %lld  store %lld\n", tile, ts_[1] - ts_[0], ts_[2] - ts_[1], ts_[3] - ts_[2], ts_[4] - ts_[3], ts_[5] - ts_[4], ts_[6] - ts_[5], ts_[7] - ts_[6]);
+    if (tile > t_begin) {
+      acc_[0] += ts_[1] - ts_[0]; acc_[1] += ts_[2] - ts_[1]; acc_[2] += ts_[3] - ts_[2]; acc_[3] += ts_[4] - ts_[3]; acc_[4] += ts_[5] - ts_[4];
+      acc_[5] += ts_[6] - ts_[5]; acc_[6] += ts_[8] - ts_[6]; acc_[7] += ts_[9] - ts_[8]; acc_[8] += ts_[7] - ts_[9]; acc_[9] += 1;
+    }
 #endif
     tc_fence_before();      // (the barrier at the top of the next iteration orders these accumulator reads before the next S)
     cur = nxt;
   }
 #ifdef WTC_TIMING
-  if ((blockIdx.x % 64 == 0 || blockIdx.x == gridDim.x - 1) && tid == 0) {
+  if ((blockIdx.x % 97 == 5) && (tid == 0 || tid == 127) && acc_[9] > 0) {
+    const long long n_ = acc_[9];
+    printf("cta %d tid %d: per tile (avg of %lld): gather wait+sync %lld | S mma %lld | issue qk %lld | softmax %lld | sync2 %lld | PV mma %lld | ld O %lld | stage+store %lld | issue v %lld\n", blockIdx.x,
+           tid, n_, acc_[0] / n_, acc_[1] / n_, acc_[2] / n_, acc_[3] / n_, acc_[4] / n_, acc_[5] / n_, acc_[6] / n_, acc_[7] / n_, acc_[8] / n_);
+  }
+  if (false) {
     unsigned long long g_exit;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_exit));
     unsigned smid;
