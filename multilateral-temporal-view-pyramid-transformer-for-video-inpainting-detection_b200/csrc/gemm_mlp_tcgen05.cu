@@ -55,6 +55,7 @@ struct MlpParams {
   int nkb;            // 64-column k-blocks of the A operand (C = 96: the second holds 32 columns)
   int n_chunks;       // 4C / 128
   int stages;
+  int a_bufs, acc2_bufs;      // pipelined shape: A operand / fc2 accumulator buffers (2 when C <= 128)
   int f16;
   uint32_t stage_bytes;
   uint32_t idesc1, idesc2;
@@ -65,7 +66,8 @@ __device__ __forceinline__ void ml_fence_proxy_async() { asm volatile("fence.pro
 
 // LayerNorm of rows [m0, m0 + 128) into the resident A operand (same scheme as gemm_ln_tcgen05.cu / norm.cu)
 template <typename OutT, int LPR, int NV, int RI>
-__device__ __forceinline__ float ml_normalise_rows(const MlpParams &p, uint32_t a_base, long m0, int warp, int lane, int n_warps) {
+__device__ __forceinline__ float ml_normalise_rows(const MlpParams &p, uint32_t a_base, long m0, int warp, int lane, int n_warps, const float *gamma,
+                                                   const float *beta) {
   constexpr int G = 32 / LPR;
   constexpr int RPW = G * RI;
   const int sub = lane % LPR, grp = lane / LPR;
@@ -110,7 +112,7 @@ __device__ __forceinline__ float ml_normalise_rows(const MlpParams &p, uint32_t 
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
       const int i = sub + LPR * u;
-      const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma) + i), b4 = __ldg(reinterpret_cast<const float4 *>(p.beta) + i);
+      const float4 g4 = *(reinterpret_cast<const float4 *>(gamma) + i), b4 = *(reinterpret_cast<const float4 *>(beta) + i);
       const uint32_t col_off = static_cast<uint32_t>(i >> 4) * ML_KB_BYTES + static_cast<uint32_t>(i & 1) * 8u;
       const uint32_t chunk = static_cast<uint32_t>(i & 15) >> 1;
 #pragma unroll
@@ -131,12 +133,12 @@ __device__ __forceinline__ float ml_normalise_rows(const MlpParams &p, uint32_t 
 
 // (out of line, like the output epilogue below: both run once per tile, and inlined next to the hidden epilogue they make it spill)
 template <typename OutT>
-__device__ __noinline__ float ml_normalise(const MlpParams &p, uint32_t a_base, long m0, int warp, int lane, int n_warps) {
+__device__ __noinline__ float ml_normalise(const MlpParams &p, uint32_t a_base, long m0, int warp, int lane, int n_warps, const float *gamma, const float *beta) {
   switch (p.C) {
-    case 96: return ml_normalise_rows<OutT, 8, 3, 2>(p, a_base, m0, warp, lane, n_warps);
-    case 128: return ml_normalise_rows<OutT, 8, 4, 2>(p, a_base, m0, warp, lane, n_warps);
-    case 192: return ml_normalise_rows<OutT, 16, 3, 2>(p, a_base, m0, warp, lane, n_warps);
-    default: return ml_normalise_rows<OutT, 16, 4, 2>(p, a_base, m0, warp, lane, n_warps);
+    case 96: return ml_normalise_rows<OutT, 8, 3, 2>(p, a_base, m0, warp, lane, n_warps, gamma, beta);
+    case 128: return ml_normalise_rows<OutT, 8, 4, 2>(p, a_base, m0, warp, lane, n_warps, gamma, beta);
+    case 192: return ml_normalise_rows<OutT, 16, 3, 2>(p, a_base, m0, warp, lane, n_warps, gamma, beta);
+    default: return ml_normalise_rows<OutT, 16, 4, 2>(p, a_base, m0, warp, lane, n_warps, gamma, beta);
   }
 }
 
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(MIN_CTAS == 2 ? 384 : (ML_EPI_WARPS + 2) * 32,
       mt[0] = clock64();
 #endif
       // (every fc1 MMA of the previous tile has completed: this warp waited for its last acc1_full)
-      amax = fmaxf(amax, p.f16 ? ml_normalise<__half>(p, a_base, m0, warp, lane, ML_EPI_WARPS) : ml_normalise<__nv_bfloat16>(p, a_base, m0, warp, lane, ML_EPI_WARPS));
+      amax = fmaxf(amax, p.f16 ? ml_normalise<__half>(p, a_base, m0, warp, lane, ML_EPI_WARPS, p.gamma, p.beta) : ml_normalise<__nv_bfloat16>(p, a_base, m0, warp, lane, ML_EPI_WARPS, p.gamma, p.beta));
       ml_fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
@@ -456,9 +458,405 @@ __global__ void __launch_bounds__(MIN_CTAS == 2 ? 384 : (ML_EPI_WARPS + 2) * 32,
   if (warp == ML_EPI_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ML_TMEM_COLS) : "memory");
 }
 
+// =====================================================================================================================
+// Pipelined shape (default): the same arithmetic with the three kinds of epilogue work on SEPARATE warp groups and two tiles in
+// flight.  In the kernel above one group of 16 warps runs, per 128-row tile, the LayerNorm prologue (global-load latency), the
+// GELU passes (issue / MUFU) and the output pass (global-load latency + HBM) strictly one after the other: 28-31 k clk per tile
+// of which the tensor pipe works 4 k (-DML_TIMING).  Here
+//     warps  0- 7  GELU group    hidden chunk c: two (quadrant, 32-column) units per warp, biases from shared memory
+//     warps  8-11  output group  tile i-1: acc2[(i-1)&1] + b2 + x -> out       (a lane quadrant each, every column unit)
+//     warps 12-17  LayerNorm     tile i+1: rows -> A[(i+1)&1]  (rows prefetched into L2 a tile earlier by the producer warp)
+//     warp  18     TMA producer, warp 19 MMA issuer (one continuous chunk stream: MMA1 of the next chunk -- also across the
+//                  tile boundary -- is issued before MMA2 of this one)
+// so each group's latency hides behind the other groups' work on neighbouring tiles.  20 warps = 640 threads keep 96 registers per
+// thread (22 or more warps round up to 24 in the register file: 80 registers and spills in the GELU loop).  Measured at M = 301056,
+// C = 128 (serial shape 255-260 us): LayerNorm 4 / GELU 8 warps 215 us (LayerNorm group saturated, 17.7 k clk per tile), 8 / 8
+// 203 us, all 16 compute warps alternating GELU and the next tile's LayerNorm 240-252 us (the two are serial again).
+// Double-buffered A operand and fc2
+// accumulator where they fit (C <= 128: 2 x 32 KB, 2 x 128 TMEM columns next to the two fc1 accumulators); single buffers for
+// C = 192 / 256 (the groups still overlap within and across the tile boundary, the LayerNorm of tile i+1 then starts when the
+// last MMA1 of tile i has read A).  Same k-block order, same per-element arithmetic: bit-identical to the kernel above.
+constexpr int MP_GELU_WARPS = 8, MP_OUT_WARPS = 4, MP_LN_WARPS = 6;
+constexpr int MP_WARP_OUT = MP_GELU_WARPS, MP_WARP_LN = MP_WARP_OUT + MP_OUT_WARPS, MP_WARP_TMA = MP_WARP_LN + MP_LN_WARPS, MP_WARP_MMA = MP_WARP_TMA + 1;
+constexpr int MP_THREADS = (MP_WARP_MMA + 1) * 32;
+constexpr int MP_HC = 128;
+constexpr int MP_H_BYTES = 2 * ML_KB_BYTES;
+constexpr int MP_STAGING_BYTES = MP_OUT_WARPS * 4096;
+
+// tcgen05.ld of 32 accumulator columns without the wait (the caller issues several, then one tcgen05.wait::ld)
+__device__ __forceinline__ void mp_tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// one (quadrant, 32-column) unit of a hidden chunk (accumulator columns already in v): ml_hidden_epilogue's arithmetic with the bias
+// read from shared memory
+template <typename OutT>
+__device__ __forceinline__ float mp_hidden_unit(const uint32_t (&v)[32], const float *bias_s, uint32_t h_base, int quad, int c0, int lane) {
+  const uint32_t row = static_cast<uint32_t>(quad * 32 + lane);
+  float amax = 0.0f;
+  const uint32_t kb_base = h_base + static_cast<uint32_t>(c0 >> 6) * ML_KB_BYTES + row * 128u;
+  const uint32_t chunk0 = static_cast<uint32_t>(c0 & 63) >> 3;
+  const float4 *b4 = reinterpret_cast<const float4 *>(bias_s);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
+    float2 f[4];
+    f[0] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(ba.x, ba.y)));
+    f[1] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(ba.z, ba.w)));
+    f[2] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bb.x, bb.y)));
+    f[3] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bb.z, bb.w)));
+    if constexpr (is_half_t<OutT>::value) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) amax = fmaxf(amax, fmaxf(fabsf(f[h].x), fabsf(f[h].y)));
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(kb_base + (((chunk0 + g) ^ (row & 7u)) << 4)), "r"(pack2<OutT>(f[0].x, f[0].y)),
+                 "r"(pack2<OutT>(f[1].x, f[1].y)), "r"(pack2<OutT>(f[2].x, f[2].y)), "r"(pack2<OutT>(f[3].x, f[3].y))
+                 : "memory");
+  }
+  return amax;
+}
+
+// output pass of one lane quadrant over every 32-column unit (ml_output_epilogue with b2 in shared memory): the residual rows of
+// the NEXT unit are requested before this unit's accumulator is read, so their latency hides behind the staging round trip
+__device__ __forceinline__ void mp_output_quadrant(const MlpParams &p, const float *b2_s, uint32_t st_base, uint32_t acc, int quad, int lane, long m0) {
+  const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
+  const long row0 = m0 + quad * 32;
+  const int c4 = lane & 7;
+  for (int c0 = 0; c0 < p.C; c0 += 32) {
+    const int col = c0 + c4 * 4;
+    float4 res[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long gm = row0 + i * 4 + (lane >> 3);
+      res[i] = gm < p.M ? *reinterpret_cast<const float4 *>(p.x + gm * p.C + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t v[32];
+    tmem_ld32(lane_addr + c0, v);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b = *reinterpret_cast<const float4 *>(b2_s + c0 + 4 * g);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + lane * 128 + ((g ^ (lane & 7)) << 4)), "f"(__uint_as_float(v[4 * g]) + b.x),
+                   "f"(__uint_as_float(v[4 * g + 1]) + b.y), "f"(__uint_as_float(v[4 * g + 2]) + b.z), "f"(__uint_as_float(v[4 * g + 3]) + b.w)
+                   : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      const long gm = row0 + r;
+      float4 o;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(st_base + r * 128 + ((c4 ^ (r & 7)) << 4)));
+      if (gm < p.M) {
+        o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w;
+        *reinterpret_cast<float4 *>(p.out + gm * p.C + col) = o;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(MP_THREADS, 1) mlp_pipe_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                                                                   const MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * ML_MAX_STAGES + 16];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t a_base = (raw + 1023u) & ~1023u;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.nkb) * ML_KB_BYTES;
+  const uint32_t h_base = a_base + static_cast<uint32_t>(p.a_bufs) * a_bytes;
+  const uint32_t stage_base = h_base + 2 * MP_H_BYTES;                      // output staging, 4 KB per output warp
+  const uint32_t bias_base = stage_base + MP_STAGING_BYTES;                 // b1 (4C floats) | b2 (C) | gamma (C) | beta (C)
+  const uint32_t ring = (bias_base + static_cast<uint32_t>(7 * p.C) * 4u + 1023u) & ~1023u;
+  float *b1_s = reinterpret_cast<float *>(smem_raw + (bias_base - raw));
+  float *b2_s = b1_s + 4 * p.C;
+  float *g_s = b2_s + p.C;
+  const uint32_t w_full0 = smem_u32(&bars[0]);
+  const uint32_t w_empty0 = smem_u32(&bars[ML_MAX_STAGES]);
+  const uint32_t bb = smem_u32(&bars[2 * ML_MAX_STAGES]);
+  const uint32_t a_full0 = bb, a_empty0 = bb + 16, acc1_full0 = bb + 32, acc1_empty0 = bb + 48, h_full0 = bb + 64, h_empty0 = bb + 80, acc2_full0 = bb + 96,
+                 acc2_empty0 = bb + 112;                                   // two barriers each
+
+  if (warp == MP_WARP_MMA) {          // tensor memory first (see attention_tc.cu: the SM holds back later CTAs until the permit is relinquished)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == MP_WARP_TMA && lane == 0) {
+    prefetch_tensormap(&tmW1);
+    prefetch_tensormap(&tmW2);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(w_full0 + 8 * s, 1);
+      mbar_init(w_empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_full0 + 8 * s, MP_LN_WARPS);
+      mbar_init(a_empty0 + 8 * s, 1);
+      mbar_init(acc1_full0 + 8 * s, 1);
+      mbar_init(acc1_empty0 + 8 * s, MP_GELU_WARPS);
+      mbar_init(h_full0 + 8 * s, MP_GELU_WARPS);
+      mbar_init(h_empty0 + 8 * s, 1);
+      mbar_init(acc2_full0 + 8 * s, 1);
+      mbar_init(acc2_empty0 + 8 * s, MP_OUT_WARPS);
+    }
+    fence_barrier_init();
+  }
+  // the biases are parameters, not a predecessor's output: staged ahead of the dependency wait
+  for (int i = threadIdx.x; i < 7 * p.C; i += MP_THREADS)
+    b1_s[i] = i < 4 * p.C ? __ldg(p.b1 + i) : (i < 5 * p.C ? __ldg(p.b2 + (i - 4 * p.C)) : (i < 6 * p.C ? __ldg(p.gamma + (i - 5 * p.C)) : __ldg(p.beta + (i - 6 * p.C))));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t acc2_0 = tmem_base + 2 * MP_HC;                  // acc1[0] | acc1[1] | acc2[0] (| acc2[1] at +128 when C <= 128)
+  pdl_grid_sync();
+
+  const int n = p.n_chunks;
+  const uint32_t A = static_cast<uint32_t>(p.a_bufs), Q = static_cast<uint32_t>(p.acc2_bufs);
+  const uint32_t n_my = blockIdx.x < p.num_tiles ? static_cast<uint32_t>((p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+  const bool ahead = A == 2;          // MMA1 of the next tile's first chunk goes ahead of this tile's last MMA2 only with two A buffers
+
+  if (warp == MP_WARP_TMA) {
+    // ------------------------------------------------ TMA producer: weight tiles in the MMA warp's consumption order ----
+    uint32_t s = 0, ph = 0;
+    const uint32_t w1_bytes = MP_HC * 128u, w2_bytes = static_cast<uint32_t>(p.C) * 128u;
+    auto load = [&](const CUtensorMap *map, uint32_t bytes, int kx, int ry) {
+      mbar_wait(w_empty0 + 8 * s, ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(w_full0 + 8 * s, bytes);
+        tma_load_2d(ring + s * p.stage_bytes, map, w_full0 + 8 * s, kx, ry);
+      }
+      __syncwarp();
+      if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+    };
+    auto load_w1 = [&](int chunk) {
+      for (int kb = 0; kb < p.nkb; ++kb) load(&tmW1, w1_bytes, kb * 64, chunk * MP_HC);
+    };
+    // the rows of a tile are contiguous (128 x C floats): a bulk L2 prefetch a tile period ahead of the LayerNorm that reads them
+    // turns its exposed global-load latency from HBM (2-4 k clk under load) into an L2 hit
+    auto prefetch_rows = [&](uint32_t i) {
+      if (i < n_my && elect_one()) {
+        const long m0 = (static_cast<long>(blockIdx.x) + static_cast<long>(i) * gridDim.x) * ML_BM;
+        const long rows = p.M - m0 < ML_BM ? p.M - m0 : ML_BM;
+        const uint32_t bytes = static_cast<uint32_t>(rows * p.C * 4);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.x + m0 * p.C), "r"(bytes) : "memory");
+      }
+      __syncwarp();
+    };
+    prefetch_rows(1);
+    for (uint32_t i = 0; i < n_my; ++i) {
+      prefetch_rows(i + 2);
+      if (i == 0 || !ahead) load_w1(0);
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) load_w1(j + 1);
+        else if (ahead && i + 1 < n_my) load_w1(0);
+        for (int kb = 0; kb < 2; ++kb) load(&tmW2, w2_bytes, j * MP_HC + kb * 64, 0);
+      }
+    }
+  } else if (warp == MP_WARP_MMA) {
+    // ------------------------------------------------ MMA issuer ---------------------------------------------------------
+    uint32_t s = 0, ph = 0;
+    uint32_t c1 = 0, c2 = 0;          // fc1 / fc2 chunks issued so far
+    auto mma1 = [&](uint32_t i, int j) {          // fc1 chunk j of this CTA's i-th tile
+      const uint32_t ab = i % A;
+      if (j == 0) {
+        mbar_wait(a_full0 + 8 * ab, (i / A) & 1);
+        tc_fence_after();
+      }
+      const uint32_t slot = c1 & 1, aph = (c1 >> 1) & 1;
+      mbar_wait(acc1_empty0 + 8 * slot, aph ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + slot * MP_HC;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(w_full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint64_t adesc = make_kmajor_sw128_desc(a_base + ab * a_bytes + kb * ML_KB_BYTES);
+        const uint64_t bdesc = make_kmajor_sw128_desc(ring + s * p.stage_bytes);
+        const bool tail = (kb + 1) * 64 > p.C;
+        if (elect_one()) {
+          umma_bf16(d, adesc, bdesc, p.idesc1, kb > 0 ? 1u : 0u);
+          umma_bf16(d, adesc + 2, bdesc + 2, p.idesc1, 1u);
+          if (!tail) {
+            umma_bf16(d, adesc + 4, bdesc + 4, p.idesc1, 1u);
+            umma_bf16(d, adesc + 6, bdesc + 6, p.idesc1, 1u);
+          }
+          umma_commit(w_empty0 + 8 * s);
+        }
+        __syncwarp();
+        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+      }
+      if (elect_one()) {
+        umma_commit(acc1_full0 + 8 * slot);
+        if (j == n - 1) umma_commit(a_empty0 + 8 * ab);          // every MMA that reads this tile's A operand has been issued
+      }
+      __syncwarp();
+      ++c1;
+    };
+    for (uint32_t i = 0; i < n_my; ++i) {
+      if (i == 0 || !ahead) mma1(i, 0);
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) mma1(i, j + 1);
+        else if (ahead && i + 1 < n_my) mma1(i + 1, 0);
+        const uint32_t hs = c2 & 1, hph = (c2 >> 1) & 1;
+        mbar_wait(h_full0 + 8 * hs, hph);                         // GELU(fc1 chunk) is in shared memory
+        tc_fence_after();
+        const uint32_t qb = i % Q;
+        if (j == 0) {
+          mbar_wait(acc2_empty0 + 8 * qb, ((i / Q) & 1) ^ 1);     // the output group has drained this accumulator
+          tc_fence_after();
+        }
+        const uint32_t acc2 = acc2_0 + qb * 128;
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait(w_full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(h_base + hs * MP_H_BYTES + kb * ML_KB_BYTES);
+          const uint64_t bdesc = make_kmajor_sw128_desc(ring + s * p.stage_bytes);
+          if (elect_one()) {
+            umma_bf16(acc2, adesc, bdesc, p.idesc2, (j > 0 || kb > 0) ? 1u : 0u);
+            umma_bf16(acc2, adesc + 2, bdesc + 2, p.idesc2, 1u);
+            umma_bf16(acc2, adesc + 4, bdesc + 4, p.idesc2, 1u);
+            umma_bf16(acc2, adesc + 6, bdesc + 6, p.idesc2, 1u);
+            umma_commit(w_empty0 + 8 * s);
+          }
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+        }
+        if (elect_one()) {
+          umma_commit(h_empty0 + 8 * hs);
+          if (j == n - 1) umma_commit(acc2_full0 + 8 * qb);
+        }
+        __syncwarp();
+        ++c2;
+      }
+    }
+  } else if (warp >= MP_WARP_LN) {
+    // ------------------------------------------------ LayerNorm group: one tile ahead --------------------------------------
+    const int lw = warp - MP_WARP_LN;
+    float amax = 0.0f;
+#ifdef ML_TIMING
+    long long tw_ = 0, tb_ = 0;
+#endif
+    for (uint32_t i = 0; i < n_my; ++i) {
+      const long m0 = (static_cast<long>(blockIdx.x) + static_cast<long>(i) * gridDim.x) * ML_BM;
+      const uint32_t ab = i % A;
+#ifdef ML_TIMING
+      const long long tq0 = clock64();
+#endif
+      mbar_wait(a_empty0 + 8 * ab, ((i / A) & 1) ^ 1);              // the MMAs of the tile that used this buffer have completed
+#ifdef ML_TIMING
+      const long long tq1 = clock64();
+#endif
+      const uint32_t dst = a_base + ab * a_bytes;
+      amax = fmaxf(amax, p.f16 ? ml_normalise<__half>(p, dst, m0, lw, lane, MP_LN_WARPS, g_s, g_s + p.C) : ml_normalise<__nv_bfloat16>(p, dst, m0, lw, lane, MP_LN_WARPS, g_s, g_s + p.C));
+      ml_fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full0 + 8 * ab);
+#ifdef ML_TIMING
+      if (i > 0) { tw_ += tq1 - tq0; tb_ += clock64() - tq1; }
+#endif
+    }
+#ifdef ML_TIMING
+    if (blockIdx.x == 3 && lane == 0 && n_my > 1) printf("LN warp %d: per tile wait %lld work %lld\n", lw, tw_ / (n_my - 1), tb_ / (n_my - 1));
+#endif
+    f16_guard(amax);
+  } else if (warp >= MP_WARP_OUT) {
+    // ------------------------------------------------ output group -----------------------------------------------------------
+    const int quad = warp & 3;
+    const uint32_t st_base = stage_base + static_cast<uint32_t>(warp - MP_WARP_OUT) * 4096u;
+#ifdef ML_TIMING
+    long long tw_ = 0, tb_ = 0;
+#endif
+    for (uint32_t i = 0; i < n_my; ++i) {
+      const long m0 = (static_cast<long>(blockIdx.x) + static_cast<long>(i) * gridDim.x) * ML_BM;
+      const uint32_t qb = i % Q;
+#ifdef ML_TIMING
+      const long long tq0 = clock64();
+#endif
+      mbar_wait(acc2_full0 + 8 * qb, (i / Q) & 1);
+      tc_fence_after();
+#ifdef ML_TIMING
+      const long long tq1 = clock64();
+#endif
+      mp_output_quadrant(p, b2_s, st_base, acc2_0 + qb * 128, quad, lane, m0);
+#ifdef ML_TIMING
+      if (i > 0) { tw_ += tq1 - tq0; tb_ += clock64() - tq1; }
+#endif
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_empty0 + 8 * qb);
+    }
+#ifdef ML_TIMING
+    if (blockIdx.x == 3 && lane == 0 && n_my > 1) printf("OUT warp %d: per tile wait %lld work %lld\n", warp - MP_WARP_OUT, tw_ / (n_my - 1), tb_ / (n_my - 1));
+#endif
+  } else {
+    // ------------------------------------------------ GELU group ---------------------------------------------------------------
+    const int quad = warp & 3, u0 = warp >> 2;          // units u0 and u0 + 2 of the chunk's four 32-column units
+    float amax = 0.0f;
+#ifdef ML_TIMING
+    long long tw_ = 0, tb_ = 0;
+#endif
+    const uint32_t total = n_my * static_cast<uint32_t>(n);
+    int j = 0;
+    for (uint32_t c = 0; c < total; ++c) {
+      const uint32_t slot = c & 1, cph = (c >> 1) & 1;
+#ifdef ML_TIMING
+      const long long tq0 = clock64();
+#endif
+      mbar_wait(acc1_full0 + 8 * slot, cph);
+      mbar_wait(h_empty0 + 8 * slot, cph ^ 1);                   // fc2 of the chunk two back has read H[slot]
+      tc_fence_after();
+#ifdef ML_TIMING
+      const long long tq1 = clock64();
+#endif
+      // both units' accumulator columns are requested before either is used: one tensor-memory round trip per chunk, not two
+      const uint32_t acc1 = tmem_base + slot * MP_HC + (static_cast<uint32_t>(quad * 32) << 16);
+      uint32_t va[32], vb[32];
+      mp_tmem_ld32_nowait(acc1 + u0 * 32, va);
+      mp_tmem_ld32_nowait(acc1 + (u0 + 2) * 32, vb);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const float *bj = b1_s + j * MP_HC;
+      const uint32_t hb = h_base + slot * MP_H_BYTES;
+      const float a0 = p.f16 ? mp_hidden_unit<__half>(va, bj + u0 * 32, hb, quad, u0 * 32, lane) : mp_hidden_unit<__nv_bfloat16>(va, bj + u0 * 32, hb, quad, u0 * 32, lane);
+      const float a1 = p.f16 ? mp_hidden_unit<__half>(vb, bj + (u0 + 2) * 32, hb, quad, (u0 + 2) * 32, lane)
+                             : mp_hidden_unit<__nv_bfloat16>(vb, bj + (u0 + 2) * 32, hb, quad, (u0 + 2) * 32, lane);
+      amax = fmaxf(amax, fmaxf(a0, a1));
+      tc_fence_before();
+      ml_fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(acc1_empty0 + 8 * slot);
+        mbar_arrive(h_full0 + 8 * slot);
+      }
+      if (++j == n) j = 0;
+#ifdef ML_TIMING
+      if (c >= (uint32_t)n) { tw_ += tq1 - tq0; tb_ += clock64() - tq1; }
+#endif
+    }
+#ifdef ML_TIMING
+    if (blockIdx.x == 3 && lane == 0 && n_my > 1 && (warp & 3) == 0) printf("GELU warp %d: per tile wait %lld work %lld\n", warp, tw_ / (n_my - 1), tb_ / (n_my - 1));
+#endif
+    f16_guard(amax);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MP_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 bool mlp_fused_supported(int C) { return C == 96 || C == 128 || C == 192 || C == 256; }
 
-// shape policy: 0 / 1 = the one-CTA shape (default), 2 = two CTAs per SM where it fits (C <= 128).  Environment MUMPY_MLP_SHAPE.
+// shape policy: 0 = the pipelined shape (default), 1 = the serial one-CTA shape, 2 = serial, two CTAs per SM where it fits (C <= 128).
+// Environment MUMPY_MLP_SHAPE.
 // Measured (B = 32 stage-0 shapes, ncu: 19.4 of the 20 theoretical warps resident): the two-per-SM shape takes the same time, 256-262
 // vs 255-261 us at M = 301056, C = 128 -- every phase of a CTA simply takes twice as long (prologue 7 -> 13 k clk, output pass
 // 7.5 -> 17 k clk, -DML_TIMING): the SM's 16 epilogue warps are the limit in either arrangement, not the phase order.
@@ -502,6 +900,40 @@ static int launch_mlp_fused(MlpParams &p, const void *W1, const void *W2, int C,
   return launch_status("mlp_fused_tc_kernel");
 }
 
+static int launch_mlp_pipe(MlpParams &p, const void *W1, const void *W2, int C, cudaStream_t st) {
+  p.n_chunks = 4 * C / MP_HC;
+  p.idesc1 = make_idesc_16_f32(ML_BM, MP_HC, p.f16 != 0);
+  p.idesc2 = make_idesc_16_f32(ML_BM, C, p.f16 != 0);
+  p.a_bufs = p.acc2_bufs = C <= 128 ? 2 : 1;
+  const int w2_bytes = C * 128;
+  p.stage_bytes = (uint32_t)(w2_bytes > MP_HC * 128 ? w2_bytes : MP_HC * 128);
+  p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
+  const int fixed = 1024 + p.a_bufs * p.nkb * ML_KB_BYTES + 2 * MP_H_BYTES + MP_STAGING_BYTES + ((7 * C * 4 + 1023) & ~1023);
+  int stages = (ML_SMEM_TOTAL - fixed) / (int)p.stage_bytes;
+  if (stages > ML_MAX_STAGES) stages = ML_MAX_STAGES;
+  MUMPY_REQUIRE(stages >= 2, "mlp_fused(pipelined): shared memory budget (C=%d)", C);
+  p.stages = stages;
+  CUtensorMap tmW1, tmW2;
+  int rc = tc_encode_2d_16(&tmW1, W1, p.f16 != 0, (uint64_t)C, (uint64_t)4 * C, (uint64_t)C, 64, MP_HC);
+  if (rc) return rc;
+  rc = tc_encode_2d_16(&tmW2, W2, p.f16 != 0, (uint64_t)4 * C, (uint64_t)C, (uint64_t)4 * C, 64, (uint32_t)C);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_pipe_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM_TOTAL);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(mlp_pipe_tc_kernel): %s", cudaGetErrorString(e));
+      return MUMPY_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long sms = tc_num_sms();
+  const int smem = fixed + p.stages * (int)p.stage_bytes;
+  const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
+  launch_kernel(mlp_pipe_tc_kernel, grid, MP_THREADS, smem, st, tmW1, tmW2, p);
+  return launch_status("mlp_pipe_tc_kernel");
+}
+
 int mlp_fused_16(const float *x, const float *gamma, const float *beta, float eps, const void *W1, const float *b1, const void *W2, const float *b2,
                  float *out, long M, int C, int w_dtype, cudaStream_t st) {
   int rc = resolve_driver_entry_points();
@@ -528,6 +960,7 @@ int mlp_fused_16(const float *x, const float *gamma, const float *beta, float ep
   p.nkb = (C + 63) / 64;
   p.f16 = w_dtype == MUMPY_F16;
   p.eps = eps;
+  if (g_mlp_shape == 0) return launch_mlp_pipe(p, W1, W2, C, st);
   if (C <= 128 && g_mlp_shape == 2) return launch_mlp_fused<64, 8, 2>(p, W1, W2, C, st);
   return launch_mlp_fused<128, 16, 1>(p, W1, W2, C, st);
 }
