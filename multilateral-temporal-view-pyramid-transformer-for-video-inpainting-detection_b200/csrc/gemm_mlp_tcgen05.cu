@@ -159,10 +159,11 @@ __device__ __forceinline__ float ml_hidden_epilogue(const float4 (&bias)[8], uin
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float2 f[4];
-    f[0] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(bias[2 * g].x, bias[2 * g].y)));
-    f[1] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(bias[2 * g].z, bias[2 * g].w)));
-    f[2] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bias[2 * g + 1].x, bias[2 * g + 1].y)));
-    f[3] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bias[2 * g + 1].z, bias[2 * g + 1].w)));
+    f[0] = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(bias[2 * g].x, bias[2 * g].y));
+    f[1] = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(bias[2 * g].z, bias[2 * g].w));
+    f[2] = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bias[2 * g + 1].x, bias[2 * g + 1].y));
+    f[3] = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bias[2 * g + 1].z, bias[2 * g + 1].w));
+    gelu_fast2_x4(f);
     if constexpr (is_half_t<OutT>::value) {
 #pragma unroll
       for (int h = 0; h < 4; ++h) amax = fmaxf(amax, fmaxf(fabsf(f[h].x), fabsf(f[h].y)));
@@ -510,10 +511,11 @@ __device__ __forceinline__ float mp_hidden_unit(const uint32_t (&v)[32], const f
   for (int g = 0; g < 4; ++g) {
     const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
     float2 f[4];
-    f[0] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(ba.x, ba.y)));
-    f[1] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(ba.z, ba.w)));
-    f[2] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bb.x, bb.y)));
-    f[3] = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bb.z, bb.w)));
+    f[0] = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(ba.x, ba.y));
+    f[1] = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(ba.z, ba.w));
+    f[2] = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bb.x, bb.y));
+    f[3] = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bb.z, bb.w));
+    gelu_fast2_x4(f);
     if constexpr (is_half_t<OutT>::value) {
 #pragma unroll
       for (int h = 0; h < 4; ++h) amax = fmaxf(amax, fmaxf(fabsf(f[h].x), fabsf(f[h].y)));

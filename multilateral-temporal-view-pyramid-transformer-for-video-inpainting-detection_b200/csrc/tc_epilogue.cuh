@@ -45,11 +45,10 @@ __device__ __forceinline__ float epilogue16_tile(uint16_t *__restrict__ out, lon
         f[2 * h + 1] = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4 * h + 2]), __uint_as_float(v[8 * g + 4 * h + 3])), make_float2(b.z, b.w));
       }
       uint32_t w[4];
+      if (ACT == 1) gelu_fast2_x4(f);          // four interleaved dependency chains (tc_common.cuh)
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        if (ACT == 1) {
-          f[h] = gelu_fast2(f[h]);
-        } else if (ACT == 2) {
+        if (ACT == 2) {
           f[h].x = apply_act(f[h].x, act_code);
           f[h].y = apply_act(f[h].y, act_code);
         }

@@ -213,7 +213,7 @@ def set_fused_mlp(enabled: bool):
 
 
 # widths that take the fused kernel (the kernel supports 96, 128, 192 and 256)
-FUSED_MLP_WIDTHS = tuple(int(v) for v in os.environ.get("MUMPY_FUSED_MLP_WIDTHS", "96,128,192,256").split(",") if v)
+FUSED_MLP_WIDTHS = tuple(int(v) for v in os.environ.get("MUMPY_FUSED_MLP_WIDTHS", "96,128,256").split(",") if v)
 
 
 def mlp_fused_fits(C) -> bool:
