@@ -615,8 +615,9 @@ struct TileChoice {
   int bn;
   bool pair;
 };
-// CTA-pair policy: 0 never (default: in the forward the 1-CTA kernel measured as fast or faster -- round-1 bench 18.4 vs
-// 18.8 ms/step -- because both variants are bound by load latency x bytes in flight, not by L2 bytes), 1 cost model decides,
+// CTA-pair policy: 0 never, 1 the cost model decides (default since the issue loops run converged under elect.sync: same-box A/B
+// of the whole batch-32 step, tools/ab_env.sh: 2428-2449 clips/s against 2398 with 0 and 2430 with 2, although the serial sum
+// of kernel times is 2 % higher -- the pairs load half of every weight tile per CTA, which pays when three lanes share L2),
 // 2 whenever legal.  Environment MUMPY_TC_PAIR or mumpy_set_gemm_pair_mode().
 static int g_dbg_pair = -1;
 
@@ -626,7 +627,7 @@ static TileChoice pick_tile(long M, int N, int nkb, bool has_res, bool gelu) {
   }
   if (g_dbg_pair < 0) {
     const char *v = getenv("MUMPY_TC_PAIR");
-    g_dbg_pair = v ? atoi(v) : 0;
+    g_dbg_pair = v ? atoi(v) : 1;
   }
   static const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
   const double t_chunk = 550.0 + (has_res ? 250.0 : 0.0) + (gelu ? 400.0 : 0.0);
