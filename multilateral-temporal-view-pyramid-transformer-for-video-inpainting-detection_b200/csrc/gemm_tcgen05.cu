@@ -640,6 +640,7 @@ static TileChoice pick_tile(long M, int N, int nkb, bool has_res, bool gelu) {
     if (N % c == 0 && c > widest_div) widest_div = c;
   for (int pair = 0; pair < 2; ++pair) {
     if (pair && (g_dbg_pair == 0 || g_num_sms < 2)) continue;
+    if (pair && g_dbg_pair == 3 && nkb < 16) continue;          // 3: cost model, long reductions (K >= 1024) only
     const long mt = cdiv(M, pair ? 2 * TC_BM : TC_BM);
     const long slots = pair ? g_num_sms / 2 : g_num_sms;
     for (int c : cands) {                            // descending: ties go to the wider tile
@@ -668,7 +669,7 @@ static TileChoice pick_tile(long M, int N, int nkb, bool has_res, bool gelu) {
 }
 
 void set_gemm_tile_override(int bn) { g_dbg_bn = bn < 0 ? 0 : bn; }
-void set_gemm_pair_mode(int mode) { g_dbg_pair = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+void set_gemm_pair_mode(int mode) { g_dbg_pair = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
 
 template <typename... KArgs, typename... Args>
 static void launch_pair_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args &&...args) {

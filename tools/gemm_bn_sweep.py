@@ -38,6 +38,7 @@ def timed(fn, reps=5):
     return min(ts)
 
 
+total_auto = total_best = 0.0
 for M, N, K, act, out16, res in SHAPES:
     a = torch.randn((M, K), device=dev).bfloat16()
     w = (torch.randn((N, K), device=dev) / K ** 0.5).bfloat16()
@@ -47,14 +48,22 @@ for M, N, K, act, out16, res in SHAPES:
     out = torch.empty((M, N), dtype=odt, device=dev)
     row = []
     lib.mumpy_set_gemm_tile(0)
+    ops.set_gemm_pair_mode(1)
     t_auto = timed(lambda: ops.linear(a, w, bias, r, act=act, out_dtype=odt, out=out))
-    for bn in (256, 192, 128, 96, 64, 48, 32):
-        if N % bn:
-            continue
-        lib.mumpy_set_gemm_tile(bn)
-        row.append((timed(lambda: ops.linear(a, w, bias, r, act=act, out_dtype=odt, out=out)), bn))
+    for pm in (0, 2):
+        ops.set_gemm_pair_mode(pm)
+        for bn in (256, 192, 128, 96, 64, 48, 32):
+            if N % bn:
+                continue
+            lib.mumpy_set_gemm_tile(bn)
+            row.append((timed(lambda: ops.linear(a, w, bias, r, act=act, out_dtype=odt, out=out)), bn, pm))
     lib.mumpy_set_gemm_tile(0)
+    ops.set_gemm_pair_mode(1)
     best = min(row)
-    print("M=%6d N=%4d K=%4d act=%d %s%s  auto %6.1f us | best BN=%3d %6.1f us | %s" % (
-        M, N, K, act, "16" if out16 else "32", "+res" if res else "    ", t_auto, best[1], best[0],
-        "  ".join("%d:%.1f" % (bn, t) for t, bn in sorted(row, key=lambda x: -x[1]))))
+    total_auto += t_auto
+    total_best += best[0]
+    print("M=%6d N=%4d K=%4d act=%d %s%s  auto %6.1f us | best BN=%3d%s %6.1f us | 1-CTA %s | pair %s" % (
+        M, N, K, act, "16" if out16 else "32", "+res" if res else "    ", t_auto, best[1], "p" if best[2] else " ", best[0],
+        "  ".join("%d:%.1f" % (bn, t) for t, bn, pm in sorted(row, key=lambda x: -x[1]) if pm == 0),
+        "  ".join("%d:%.1f" % (bn, t) for t, bn, pm in sorted(row, key=lambda x: -x[1]) if pm == 2)), flush=True)
+print("sum over the shapes: cost model %.1f us, per-shape optimum %.1f us" % (total_auto, total_best))

@@ -21,10 +21,21 @@ for w in want:
             print("%-70s %s %s" % (h, vals[i], units[i]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-if len(rows) > 2:
-    h2, data = rows[1], rows[2:]
+hdr_rows = [i for i, r in enumerate(rows) if "# Samples" in r]
+if hdr_rows:
+    h2 = rows[hdr_rows[0]]
+    data = [r for r in rows[hdr_rows[0] + 1:] if len(r) == len(h2)]
     iS, iSrc = h2.index("# Samples"), h2.index("Source")
     stall = [i for i, h in enumerate(h2) if h.startswith("stall_") and "Not Issued" not in h]
+    # (reports with several source views list every instruction once per view: keep the first occurrence of an address)
+    iA = h2.index("Address") if "Address" in h2 else None
+    if iA is not None:
+        seen, uniq = set(), []
+        for r in data:
+            if r[iA] not in seen:
+                seen.add(r[iA])
+                uniq.append(r)
+        data = uniq
     tot = sum(int(r[iS]) for r in data if r[iS].isdigit())
     agg = sorted(((sum(int(r[i]) for r in data if r[i].isdigit()), h2[i]) for i in stall), reverse=True)
     print("\nwarp-state samples: %d; by reason: %s" % (tot, ", ".join("%s %d" % (n, c) for c, n in agg[:8])))
