@@ -63,7 +63,8 @@ int mumpy_set_pdl(int enabled);
  * Synchronous (cudaMemcpyToSymbol); call once per device, outside stream capture. */
 int mumpy_set_f16_overflow_flag(unsigned int *flag_dev);
 /* CTA-pair (tcgen05 cta_group::2, 256 x BN tiles on a (2,1,1) cluster) policy of the bf16 GEMM / implicit-GEMM convolution:
- * 0 never, 1 the tile cost model decides (default), 2 whenever the shape allows.  Environment: MUMPY_TC_PAIR. */
+ * 0 never, 1 the tile cost model decides, 2 whenever the shape allows, 3 cost model for K >= 1024 only, 4 (default) cost model
+ * except for 16-bit outputs without residual (they keep the lean 1-CTA kernel).  Environment: MUMPY_TC_PAIR. */
 int mumpy_set_gemm_pair_mode(int mode);
 /* Tuning aid: force the GEMM tile width (a divisor of N; 0 = the cost model decides).  Environment: MUMPY_TC_BN. */
 int mumpy_set_gemm_tile(int bn);

@@ -615,19 +615,21 @@ struct TileChoice {
   int bn;
   bool pair;
 };
-// CTA-pair policy: 0 never, 1 the cost model decides (default since the issue loops run converged under elect.sync: same-box A/B
-// of the whole batch-32 step, tools/ab_env.sh: 2428-2449 clips/s against 2398 with 0 and 2430 with 2, although the serial sum
-// of kernel times is 2 % higher -- the pairs load half of every weight tile per CTA, which pays when three lanes share L2),
-// 2 whenever legal.  Environment MUMPY_TC_PAIR or mumpy_set_gemm_pair_mode().
+// CTA-pair policy: 0 never, 1 the cost model decides, 2 whenever legal, 3 cost model for K >= 1024 only, 4 (default) cost model
+// except that 16-bit outputs without residual keep the lean 16-warp 1-CTA kernel (the pair kernel has no lean form).  Same-box
+// A/B runs of the whole batch-32 step (tools/ab_env.sh, profiles/r2_ab_runs.txt): 0: 2398, 1: 2418-2449, 2: 2430, 3: 2402,
+// 4: 2436-2437 against 2423-2432 for 1 on that box -- although the pairs rarely win in isolation (tools/gemm_bn_sweep.py) and the
+// serial sum of kernel times is higher with 1: each CTA of a pair loads half of every weight tile, which pays when three lanes
+// share L2.  Environment MUMPY_TC_PAIR or mumpy_set_gemm_pair_mode().
 static int g_dbg_pair = -1;
 
-static TileChoice pick_tile(long M, int N, int nkb, bool has_res, bool gelu) {
+static TileChoice pick_tile(long M, int N, int nkb, bool has_res, bool gelu, bool lean_ok = false) {
   if (g_dbg_bn < 0) {
     g_dbg_bn = env_int("MUMPY_TC_BN");
   }
   if (g_dbg_pair < 0) {
     const char *v = getenv("MUMPY_TC_PAIR");
-    g_dbg_pair = v ? atoi(v) : 1;
+    g_dbg_pair = v ? atoi(v) : 4;
   }
   static const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
   const double t_chunk = 550.0 + (has_res ? 250.0 : 0.0) + (gelu ? 400.0 : 0.0);
@@ -641,6 +643,7 @@ static TileChoice pick_tile(long M, int N, int nkb, bool has_res, bool gelu) {
   for (int pair = 0; pair < 2; ++pair) {
     if (pair && (g_dbg_pair == 0 || g_num_sms < 2)) continue;
     if (pair && g_dbg_pair == 3 && nkb < 16) continue;          // 3: cost model, long reductions (K >= 1024) only
+    if (pair && g_dbg_pair == 4 && lean_ok) continue;           // 4: cost model, but the 16-bit outputs keep the lean 1-CTA kernel
     const long mt = cdiv(M, pair ? 2 * TC_BM : TC_BM);
     const long slots = pair ? g_num_sms / 2 : g_num_sms;
     for (int c : cands) {                            // descending: ties go to the wider tile
@@ -669,7 +672,7 @@ static TileChoice pick_tile(long M, int N, int nkb, bool has_res, bool gelu) {
 }
 
 void set_gemm_tile_override(int bn) { g_dbg_bn = bn < 0 ? 0 : bn; }
-void set_gemm_pair_mode(int mode) { g_dbg_pair = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
+void set_gemm_pair_mode(int mode) { g_dbg_pair = mode < 0 ? 0 : (mode > 4 ? 4 : mode); }
 
 template <typename... KArgs, typename... Args>
 static void launch_pair_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args &&...args) {
@@ -780,7 +783,8 @@ int linear_bf16(const void *A, long lda, const void *W, const float *bias, const
   p.M = M;
   p.N = N;
   p.K = K;
-  const TileChoice tc = pick_tile(M, N, (K + TC_BK - 1) / TC_BK, residual != nullptr, act == MUMPY_ACT_GELU);
+  const bool lean_ok = out_dtype != MUMPY_F32 && !residual && !aux && (act == MUMPY_ACT_NONE || act == MUMPY_ACT_GELU);
+  const TileChoice tc = pick_tile(M, N, (K + TC_BK - 1) / TC_BK, residual != nullptr, act == MUMPY_ACT_GELU, lean_ok);
   p.BN = tc.bn;
   p.act = act;
   p.out_bf16 = (out_dtype != MUMPY_F32);

@@ -568,5 +568,6 @@ def set_attention_tc(enabled: bool):
 
 
 def set_gemm_pair_mode(mode: int):
-    """CTA-pair (cta_group::2) policy of the tensor-core GEMM: 0 never, 1 cost model (default), 2 whenever legal."""
+    """CTA-pair (cta_group::2) policy of the tensor-core GEMM: 0 never, 1 cost model, 2 whenever legal, 3 cost model for K >= 1024,
+    4 (default) cost model except for the 16-bit outputs that have the lean 1-CTA kernel."""
     _lib.check(_lib.load().mumpy_set_gemm_pair_mode(int(mode)), "mumpy_set_gemm_pair_mode")

@@ -41,7 +41,7 @@ def pair_mode(request):
     ops = _ops()
     ops.set_gemm_pair_mode(request.param)
     yield request.param
-    ops.set_gemm_pair_mode(1)          # the library default (cost model)
+    ops.set_gemm_pair_mode(4)          # the library default
 
 
 @pytest.mark.parametrize("pair_mode", [0, 2], indirect=True)
