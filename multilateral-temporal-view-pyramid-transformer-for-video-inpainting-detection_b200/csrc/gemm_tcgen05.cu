@@ -693,7 +693,7 @@ static void launch_pair_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-static bool g_attr_set[7] = {false, false, false, false, false, false, false};
+static bool g_attr_set[8] = {false, false, false, false, false, false, false, false};
 static int g_dbg_lean = -1;      // MUMPY_TC_LEAN=0 keeps the 12-warp kernel for 16-bit outputs (A/B runs)
 
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p, bool pair, cudaStream_t st) {
@@ -723,12 +723,12 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
   if (stages < 1) stages = 1;
   p.stages = stages;
   // lean variant: plain linear, 16-bit output, no residual / side output, activation none or GELU
-  const bool lean = !p.conv && p.Wout == 0 && !pair && p.k_splits == 1 && p.out_bf16 && !p.residual && !p.aux && (p.act == MUMPY_ACT_NONE || p.act == MUMPY_ACT_GELU) &&
+  const bool lean = !p.conv && p.Wout == 0 && p.k_splits == 1 && p.out_bf16 && !p.residual && !p.aux && (p.act == MUMPY_ACT_NONE || p.act == MUMPY_ACT_GELU) &&
                     g_dbg_lean != 0;
   const int epi_smem = lean ? TC_EPI_WARPS_LEAN * (EPI16_STAGING + 512) : TC_EPI_WARPS * (32 * 128 + 512);
   const int smem = stages * stage_bytes + 1024 + epi_smem;
   const bool ts = !p.conv && p.Wout > 0;      // FAF pass: transposed / split store (geometry in the convolution fields)
-  const int which = ts ? 6 : lean ? 5 : p.k_splits > 1 ? 4 : (p.conv ? 1 : 0) + (pair ? 2 : 0);      // split-K: conv, single-CTA tiles only
+  const int which = ts ? 6 : lean ? (pair ? 7 : 5) : p.k_splits > 1 ? 4 : (p.conv ? 1 : 0) + (pair ? 2 : 0);      // split-K: conv, single-CTA tiles only
   if (!g_attr_set[which]) {
     const int max_smem = TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * (32 * 128 + 512);
     cudaError_t e;
@@ -739,6 +739,7 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
       case 3: e = cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
       case 4: e = cudaFuncSetAttribute(gemm_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
       case 5: e = cudaFuncSetAttribute(gemm_tc_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
+      case 7: e = cudaFuncSetAttribute(gemm_tc_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
       default: e = cudaFuncSetAttribute(gemm_tc_kernel<false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); break;
     }
     if (e != cudaSuccess) {
@@ -755,6 +756,7 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p
     case 3: launch_pair_kernel(gemm_tc_kernel<true, true>, 2 * groups, TC_THREADS, smem, st, tmA, tmB, p); break;
     case 4: launch_kernel(gemm_tc_kernel<true, false, true>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
     case 5: launch_kernel(gemm_tc_kernel<false, false, false, true>, groups, TC_THREADS_LEAN, smem, st, tmA, tmB, p); break;
+    case 7: launch_pair_kernel(gemm_tc_kernel<false, true, false, true>, 2 * groups, TC_THREADS_LEAN, smem, st, tmA, tmB, p); break;
     default: launch_kernel(gemm_tc_kernel<false, false, false, false, true>, groups, TC_THREADS, smem, st, tmA, tmB, p); break;
   }
   return launch_status("gemm_tc_kernel");
