@@ -221,7 +221,7 @@ def kernel_section(peaks, device, dt=None):
         t = timed(lambda: faf.frame(x, 1), reps=3)
         flops = B * 3 * 8 * 2 * 224 ** 3
         byts = B * 224 * 224 * (3 * 4 + 9 * 4)
-        out.append({"kernel": "mumpy_faf16 (4 tcgen05 GEMM passes on split bf16 operands + 5 repack kernels, B=64)", "bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        out.append({"kernel": "mumpy_faf16 (input split + 4 tcgen05 GEMM passes on split 16-bit operands, transposes / band masks in their epilogues, B=64)", "bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3, "dense_tflops_fp32": flops / t / 1e12})
         del x
         # (ii-b) loader front end: PIL-exact bicubic resize of 64 native-resolution DAVIS frames (480 x 854 RGB uint8) to 224 x 224
@@ -263,6 +263,20 @@ def kernel_section(peaks, device, dt=None):
             out.append({"kernel": "gemm_tc_kernel %s M=%d N=%d K=%d" % (name, M, N, K), "bound": "hbm" if flops / byts < 250 else "tensor",
                         "tflops": flops / t / 1e12, "tensor_frac": flops / t / 1e12 / peaks["bf16_tflops"], "gbs": byts / t / 1e9,
                         "hbm_frac": byts / t / 1e9 / peaks["hbm_gbs"], "ms": t * 1e3})
+        # the whole x + Mlp(LN(x)) of that block in one kernel (mumpy_mlp_fused, pipelined shape): algorithmic traffic = the fp32 stream in
+        # and out (the hidden activations never leave the SM), flops = both GEMMs
+        x32 = torch.randn((M, 128), device=device)
+        g1, b1 = torch.ones(128, device=device), torch.zeros(128, device=device)
+        w1 = (torch.randn((512, 128), device=device) / 128 ** 0.5).to(dt)
+        w2 = (torch.randn((128, 512), device=device) / 512 ** 0.5).to(dt)
+        bb1, bb2 = torch.zeros(512, device=device), torch.zeros(128, device=device)
+        t = timed(lambda: ops.mlp_fused(x32, g1, b1, 1e-5, w1, bb1, w2, bb2))
+        flops = 2.0 * M * 128 * 512 * 2
+        byts = 2 * 4 * M * 128
+        out.append({"kernel": "mlp_pipe_tc_kernel LN + fc1 + GELU + fc2 + residual M=%d C=128" % M, "bound": "hbm", "tflops": flops / t / 1e12,
+                    "tensor_frac": flops / t / 1e12 / peaks["bf16_tflops"], "gbs": byts / t / 1e9, "hbm_frac": byts / t / 1e9 / peaks["hbm_gbs"],
+                    "ms": t * 1e3, "note": "limited by the GELU warps' MUFU / FMA / ALU pipes, not by HBM or the tensor pipe (DESIGN section 3)"})
+        del x32
         # stage-2 shape (the 40%-of-FLOPs shape): M = 64*588, C = 512
         M = B * 588
         for name, N, K in (("qkv", 1536, 512), ("fc1+GELU", 2048, 512), ("fc2", 512, 2048)):

@@ -97,6 +97,10 @@ int mumpy_ln_linear_supported(int N, int K);
  * W2 (C,4C) row-major of `w_dtype`, b1 (4C), b2 (C) fp32.  C in {96,128,192,256} (mumpy_mlp_fused_supported returns 1); wider
  * blocks run mumpy_layernorm / mumpy_ln_linear + mumpy_linear.  Bit-identical to the unfused kernels. */
 int mumpy_mlp_fused_supported(int C);
+/* Kernel shape of mumpy_mlp_fused: 0 (default) the pipelined one (GELU / output / LayerNorm warp groups on neighbouring tiles),
+ * 1 the serial one (one group of 16 warps runs the three phases back to back), 2 the serial one with two CTAs per SM where it fits
+ * (C <= 128).  All three give bit-identical results.  Environment: MUMPY_MLP_SHAPE. */
+int mumpy_set_mlp_fused_shape(int shape);
 int mumpy_mlp_fused(const float *x, const float *gamma, const float *beta, float eps, const void *W1, const float *b1, const void *W2,
                     const float *b2, float *out, long M, int C, int w_dtype, void *stream);
 /* CTA-pair policy of mumpy_ln_linear (two adjacent 128-row tiles on a (2,1,1) cluster, tcgen05 cta_group::2, each CTA streaming half of

@@ -27,6 +27,7 @@ SIGNATURES = {
     "mumpy_linear_dual": [vp, cl, vp, vp, vp, vp, vp, cl, cl, ci, ci, ci, ci, vp],
     "mumpy_layernorm": [vp, vp, vp, vp, ci, cl, ci, cf, vp],
     "mumpy_mlp_fused_supported": [ci],
+    "mumpy_set_mlp_fused_shape": [ci],
     "mumpy_mlp_fused": [vp, vp, vp, cf, vp, vp, vp, vp, vp, cl, ci, ci, vp],
     "mumpy_ln_linear_supported": [ci, ci],
     "mumpy_set_ln_linear_pair_mode": [ci],

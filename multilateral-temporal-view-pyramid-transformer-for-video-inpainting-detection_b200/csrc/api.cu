@@ -44,6 +44,7 @@ int linear_bf16(const void *A, long lda, const void *W, const float *bias, const
                 long M, int N, int K, int ab_dtype, int out_dtype, int act, cudaStream_t st);
 
 bool mlp_fused_supported(int C);
+void set_mlp_fused_shape(int shape);
 int mlp_fused_16(const float *x, const float *gamma, const float *beta, float eps, const void *W1, const float *b1, const void *W2, const float *b2,
                  float *out, long M, int C, int w_dtype, cudaStream_t st);
 bool ln_linear_supported(int N, int K);
@@ -173,6 +174,10 @@ extern "C" int mumpy_linear(const void *A, long lda, const void *W, const float 
 }
 
 extern "C" int mumpy_mlp_fused_supported(int C) { return mlp_fused_supported(C) ? 1 : 0; }
+extern "C" int mumpy_set_mlp_fused_shape(int shape) {
+  set_mlp_fused_shape(shape);
+  return MUMPY_OK;
+}
 
 extern "C" int mumpy_mlp_fused(const float *x, const float *gamma, const float *beta, float eps, const void *W1, const float *b1, const void *W2,
                                const float *b2, float *out, long M, int C, int w_dtype, void *stream) {

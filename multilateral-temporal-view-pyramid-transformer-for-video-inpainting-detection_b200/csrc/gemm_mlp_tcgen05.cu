@@ -863,6 +863,7 @@ bool mlp_fused_supported(int C) { return C == 96 || C == 128 || C == 192 || C ==
 // vs 255-261 us at M = 301056, C = 128 -- every phase of a CTA simply takes twice as long (prologue 7 -> 13 k clk, output pass
 // 7.5 -> 17 k clk, -DML_TIMING): the SM's 16 epilogue warps are the limit in either arrangement, not the phase order.
 static int g_mlp_shape = -1;
+void set_mlp_fused_shape(int shape) { g_mlp_shape = shape < 0 ? 0 : (shape > 2 ? 2 : shape); }
 
 template <int HC, int EW, int MIN_CTAS>
 static int launch_mlp_fused(MlpParams &p, const void *W1, const void *W2, int C, cudaStream_t st) {

@@ -73,6 +73,11 @@ def _prep(*tensors):
             raise _lib.MumpyError("tensors on different devices")
     lib = _lib.load()
     if dev != _bound_device:
+        if _bound_device is not None:
+            # the library caches per-function attributes (opt-in shared-memory sizes, SM counts) once per process, and they are
+            # per device: the supported deployment is one process per GPU (torchrun), as bench.py and evaluate.py run it
+            raise _lib.MumpyError("libmumpy_b200 is bound to cuda:%d in this process; use one process per GPU (got a tensor on cuda:%d)"
+                                  % (_bound_device, dev))
         _lib.check(lib.mumpy_init(dev), "mumpy_init")
         if dev not in _overflow_flags:
             _overflow_flags[dev] = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", dev))
@@ -214,6 +219,11 @@ def set_fused_mlp(enabled: bool):
 
 # widths that take the fused kernel (the kernel supports 96, 128, 192 and 256)
 FUSED_MLP_WIDTHS = tuple(int(v) for v in os.environ.get("MUMPY_FUSED_MLP_WIDTHS", "96,128,256").split(",") if v)
+
+
+def set_mlp_fused_shape(shape: int):
+    """Kernel shape of mlp_fused: 0 pipelined (default), 1 serial, 2 serial with two CTAs per SM (C <= 128); bit-identical results."""
+    _lib.check(_lib.load().mumpy_set_mlp_fused_shape(int(shape)), "mumpy_set_mlp_fused_shape")
 
 
 def mlp_fused_fits(C) -> bool:

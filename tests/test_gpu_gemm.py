@@ -178,9 +178,19 @@ def test_fused_ln_forward_is_bit_identical():
         ops.set_fused_ln(was, widths=was_w)
 
 
+@pytest.fixture
+def mlp_shape(request):
+    """Kernel shape of mumpy_mlp_fused for one test: 0 pipelined (default), 1 serial, 2 serial with two CTAs per SM."""
+    ops = _ops()
+    ops.set_mlp_fused_shape(request.param)
+    yield request.param
+    ops.set_mlp_fused_shape(0)
+
+
+@pytest.mark.parametrize("mlp_shape", [0, 1, 2], indirect=True)
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("M,C", [(3136, 96), (9408 + 17, 128), (784, 192), (2352, 256), (130, 128), (1, 96), (128 * 300 + 5, 128), (128 * 160, 256)])
-def test_mlp_fused(M, C, dt):
+def test_mlp_fused(M, C, dt, mlp_shape):
     """mumpy_mlp_fused (LayerNorm -> fc1 -> GELU -> fc2 -> + x in one kernel, hidden activations in shared / tensor memory only)
     against (1) the oracle's fp32 arithmetic on operands rounded where the kernel rounds them and (2) the three unfused kernels,
     which it must reproduce bit for bit (same statistics arithmetic, same k-block order in both GEMMs)."""
