@@ -152,6 +152,9 @@ int mumpy_patchify16(const float *x, void *out, int out_dtype, int B, int T, int
  * `frame`; dct (S,S) fp32 DCT-II matrix; ws fp32 workspace of 5*B*3*S*S floats; out (B,9,S,S) fp32,
  * channel = band*3 + rgb; band k keeps lo_k <= i+j <= hi_k, band_lo_hi6 = HOST array {lo0,hi0,lo1,hi1,lo2,hi2}
  * (read during the call; the only non-device pointer in this ABI). */
+/* Workspace sizes: floats of mumpy_faf's `ws`, bytes of mumpy_faf16's `ws16`. */
+long mumpy_faf_workspace_floats(int B, int S);
+long mumpy_faf16_workspace_bytes(int B, int S);
 int mumpy_faf(const float *x, const float *dct, float *ws, float *out, int B, int T, int frame, int S,
               const int *band_lo_hi6, void *stream);
 
@@ -212,6 +215,8 @@ int mumpy_im2col_nhwc(const float *in, long ld_in, void *out, int out_dtype, int
  * stats_ws: 2*B*groups*(1 + nchunks) floats, nchunks = ceil(HW / min(64, 12288 / C, HW)).
  * quad_mean != 0: the output holds the mean of every 4 consecutive activated channels (C/4 per pixel; decoder.py:140-143 DAP =
  * PixelShuffle(2) -> AvgPool2d(2), which commutes with the bilinear upsample that follows) -- ld_out / out_col then count those. */
+/* Floats of mumpy_groupnorm_nhwc's caller-owned `stats_ws` for a (B, HW, C) map with `groups` groups. */
+long mumpy_groupnorm_workspace_floats(int B, int HW, int C, int groups);
 int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *stats_ws, float *out,
                          long ld_out, int out_col, int B, int HW, int C, int groups, float eps, int act, int quad_mean, void *stream);
 /* out[..., col:col+Cout] = resample(in) (* mul) (+ add); mul/add are (B,Ho,Wo,Cout) fp32 contiguous or NULL.  out is fp32

@@ -37,6 +37,9 @@ SIGNATURES = {
     "mumpy_mha_short": [vp, vp, ci, cl, ci, ci, ci, vp],
     "mumpy_tokenize": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
     "mumpy_patchify16": [vp, vp, ci, ci, ci, ci, ci, vp],
+    "mumpy_faf_workspace_floats": [ci, ci],
+    "mumpy_faf16_workspace_bytes": [ci, ci],
+    "mumpy_groupnorm_workspace_floats": [ci, ci, ci, ci],
     "mumpy_faf": [vp, vp, vp, vp, ci, ci, ci, ci, ctypes.POINTER(ci), vp],
     "mumpy_faf16": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ctypes.POINTER(ci), ci, vp],
     "mumpy_cva_offsets": [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
@@ -80,6 +83,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch
         fn.argtypes = argtypes
         fn.restype = ci
+    for name in ("mumpy_faf_workspace_floats", "mumpy_faf16_workspace_bytes", "mumpy_groupnorm_workspace_floats"):
+        getattr(lib, name).restype = cl          # size queries return a count, not a status
     lib.mumpy_last_error.argtypes = []
     lib.mumpy_last_error.restype = ctypes.c_char_p
     _lib = lib

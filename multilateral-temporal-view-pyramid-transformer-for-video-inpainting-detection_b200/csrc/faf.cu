@@ -142,6 +142,10 @@ static int faf_repack(const RepackParams &p, int n_img, int dtype, cudaStream_t 
 
 using namespace mumpy;
 
+// workspace sizes of the two FAF entry points (floats of `ws` / bytes of `ws16`), so that callers do not repeat the layout
+extern "C" long mumpy_faf_workspace_floats(int B, int S) { return B > 0 && S > 0 ? 5l * B * 3 * S * S : 0; }
+extern "C" long mumpy_faf16_workspace_bytes(int B, int S) { return B > 0 && S > 0 ? 2l * 9 * B * S * 3 * S * 2 : 0; }
+
 extern "C" int mumpy_faf(const float *x, const float *dct, float *ws, float *out, int B, int T, int frame, int S,
                          const int *band_lo_hi6, void *stream) {
   MUMPY_REQUIRE(x && dct && ws && out && band_lo_hi6 && B > 0 && frame >= 0 && frame < T, "faf: bad arguments");

@@ -492,6 +492,17 @@ extern "C" int mumpy_patch_merge_norm(const float *x, const float *gamma, const 
   return launch_ln(mr, gamma, beta, out, out_dtype, rows, C, eps, as_stream(stream));
 }
 
+// floats of the caller-owned stats_ws of mumpy_groupnorm_nhwc: 2 B groups statistics + 2 B groups nchunks partial sums (the
+// chunking below); callers size the buffer with this instead of repeating the formula
+extern "C" long mumpy_groupnorm_workspace_floats(int B, int HW, int C, int groups) {
+  if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C > GN_SMEM_FLOATS) return 0;
+  int pix = GN_SMEM_FLOATS / C;
+  if (pix > 64) pix = 64;
+  if (pix > HW) pix = HW;
+  const long nchunks = cdiv(HW, pix);
+  return 2l * B * groups * (1 + nchunks);
+}
+
 extern "C" int mumpy_groupnorm_nhwc(const float *x, const float *gamma, const float *beta, float *stats_ws, float *out,
                                     long ld_out, int out_col, int B, int HW, int C, int groups, float eps, int act,
                                     int quad_mean, void *stream) {

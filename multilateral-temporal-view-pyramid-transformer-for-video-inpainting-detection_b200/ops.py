@@ -292,7 +292,7 @@ def patchify16(x, kt, dtype=None):
 
 def faf(x, dct, bands, frame=1):
     B, T, _, S, _ = x.shape
-    ws = torch.empty((5 * B * 3 * S * S,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((_lib.load().mumpy_faf_workspace_floats(B, S),), dtype=torch.float32, device=x.device)
     out = torch.empty((B, 9, S, S), dtype=torch.float32, device=x.device)
     lib, st = _prep(x, dct, ws, out)
     arr = (ctypes.c_int * 6)(*[int(v) for lohi in bands for v in lohi])
@@ -305,7 +305,7 @@ def faf(x, dct, bands, frame=1):
 def faf16(x, dcat, dtcat, bands, frame=1):
     """Tensor-core FAF (16-bit modes): dcat / dtcat (S, 3S) = [D_hi | D_lo | D_hi] for D and D^T in the operand type."""
     B, T, _, S, _ = x.shape
-    ws16 = torch.empty((2, 9 * B * S, 3 * S), dtype=dcat.dtype, device=x.device)      # the four passes ping-pong between the halves
+    ws16 = torch.empty((_lib.load().mumpy_faf16_workspace_bytes(B, S) // 2,), dtype=dcat.dtype, device=x.device)      # the four passes ping-pong between two halves
     out = torch.empty((B, 9, S, S), dtype=torch.float32, device=x.device)
     lib, st = _prep(x, dcat, dtcat, ws16, out)
     arr = (ctypes.c_int * 6)(*[int(v) for lohi in bands for v in lohi])
@@ -416,9 +416,10 @@ def groupnorm_nhwc(x, gamma, beta, B, HW, C, groups, act, eps=1e-5, out=None, ld
     Co = C // 4 if quad_mean else C
     if out is None:
         out = torch.empty(tuple(x.shape[:-1]) + (Co,), dtype=torch.float32, device=x.device)
-    pix = max(1, min(64, 12288 // C, HW))
-    nchunks = (HW + pix - 1) // pix
-    stats = torch.empty((2 * B * groups * (1 + nchunks),), dtype=torch.float32, device=x.device)
+    n_ws = _lib.load().mumpy_groupnorm_workspace_floats(B, HW, C, groups)      # the library's own layout (statistics + chunk partials)
+    if n_ws <= 0:
+        raise _lib.MumpyError("groupnorm_nhwc: unsupported shape B=%d HW=%d C=%d groups=%d" % (B, HW, C, groups))
+    stats = torch.empty((n_ws,), dtype=torch.float32, device=x.device)
     lib, st = _prep(x, gamma, beta, stats, out)
     global launch_count
     launch_count += 2            # partial statistics + finalize + apply

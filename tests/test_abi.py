@@ -12,7 +12,7 @@ def header_prototypes():
     src = open(os.path.join(ROOT, "include", "mumpy_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = {}
-    for m in re.finditer(r"(?:int|const char \*)\s*\*?(mumpy_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"(?:int|long|const char \*)\s*\*?(mumpy_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
     return protos
@@ -64,3 +64,14 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), os.path.join(dp, f)
                 assert "mumpy_oracle" not in text and "ref_harness" not in text, os.path.join(dp, f)
+
+
+def test_workspace_size_queries(lib):
+    """The caller-owned workspaces are sized by the library itself (no GPU call): statistics + per-chunk partial sums of GroupNorm,
+    the five fp32 image sets of the fp32 FAF, the two ping-pong halves of the 16-bit FAF."""
+    h = lib.load()
+    assert h.mumpy_groupnorm_workspace_floats(2, 112 * 112, 128, 32) == 2 * 2 * 32 * (1 + (112 * 112 + 63) // 64)
+    assert h.mumpy_groupnorm_workspace_floats(1, 10, 1024, 32) == 2 * 1 * 32 * (1 + 1)            # 12 pixels fit a chunk, HW = 10 -> one chunk
+    assert h.mumpy_groupnorm_workspace_floats(0, 10, 64, 8) == 0
+    assert h.mumpy_faf_workspace_floats(4, 224) == 5 * 4 * 3 * 224 * 224
+    assert h.mumpy_faf16_workspace_bytes(4, 224) == 2 * 9 * 4 * 224 * 3 * 224 * 2
