@@ -45,6 +45,9 @@ __device__ __forceinline__ void wtc_cp_async_16(uint32_t dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void wtc_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void wtc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// waits until at most the most recent commit group of this thread is still in flight
+__device__ __forceinline__ void wtc_cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -279,7 +282,9 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
   if (t_begin < t_end) {
     locate(t_begin / heads, t_begin % heads, cur);
     issue_qk(cur);
+    wtc_cp_async_commit();
     issue_v(cur);
+    wtc_cp_async_commit();
   }
   uint32_t phase = 0;
 #ifdef WTC_TIMING
@@ -296,7 +301,10 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
       const bool wrap = cur.h + 1 == heads;            // heads of one window pair are consecutive tiles
       locate(cur.pair + (wrap ? 1 : 0), wrap ? 0 : cur.h + 1, nxt);
     }
-    wtc_cp_async_wait_all();
+    // q / k of this tile (the older commit group) must have landed; its v (the newest group, issued at the very end of the previous
+    // tile) is only needed by the PV MMAs and is awaited there -- it used to be the exposed part of this wait (~1000 clk per tile
+    // on the stage-0 canvas)
+    wtc_cp_async_wait_but_one();
     fence_proxy_async_smem();
     __syncthreads();
     WTC_T(1);
@@ -316,7 +324,10 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     mbar_wait(bar_s, phase);
     tc_fence_after();
     WTC_T(2);
-    if (has_next) issue_qk(nxt);
+    if (has_next) {
+      issue_qk(nxt);
+      wtc_cp_async_commit();
+    }
     WTC_T(3);
     // ---- softmax of this thread's row (exp2 domain)
     uint32_t s_lo[32], s_hi[32];
@@ -375,6 +386,9 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     // the PV MMAs take their A operand from there, so the probabilities never touch shared memory.
     tmem_st32(t_row + WTC_P_COL, pk);
     WTC_T(4);
+    // v of this tile: every group but the next tile's q / k gather (the newest one, when there is a next tile)
+    if (has_next) wtc_cp_async_wait_but_one(); else wtc_cp_async_wait_all();
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     WTC_T(5);
@@ -427,7 +441,10 @@ __global__ void __launch_bounds__(WTC_THREADS, 4) window_attention_tc_kernel(con
     }
     __syncwarp();
     WTC_T(9);
-    if (has_next) issue_v(nxt);       // (same warp, same rows: ordered after the staging reads)
+    if (has_next) {
+      issue_v(nxt);                   // (same warp, same rows: ordered after the staging reads)
+      wtc_cp_async_commit();
+    }
     WTC_T(7);
 #ifdef WTC_TIMING
     if (tile > t_begin) {
