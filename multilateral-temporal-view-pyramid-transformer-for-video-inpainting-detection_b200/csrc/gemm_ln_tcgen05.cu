@@ -3,11 +3,11 @@
 // i.e. norm1 -> qkv (swinTransformer.py:266 + :142) and norm2 -> fc1 + GELU (:305 + :47-48) of every Swin block whose
 // width fits (K = C in {96, 128, 192, 256, 384, 512}).  The normalised operand never exists in global memory:
 //
-//   * a work item is (128-row tile, group of `ng` N-tiles).  The 12 epilogue warps first normalise the item's 128 rows
+//   * a work item is (128-row tile, group of `ng` N-tiles).  The 16 epilogue warps first normalise the item's 128 rows
 //     (exact two-pass fp32 statistics, the arithmetic of layernorm_vec_kernel: same lanes-per-row split, same summation
 //     order, so the operand is bit-identical to the unfused path) and write them as 16-bit K-major SWIZZLE_128B tiles
 //     straight into shared memory -- the whole 128 x K A operand stays resident (K = 512: 128 KB) for all N-tiles of the item;
-//   * warp 12 streams only the weight tiles (BN x 64) through a TMA / mbarrier ring, warp 13 issues tcgen05.mma
+//   * warp 16 streams only the weight tiles (BN x 64) through a TMA / mbarrier ring, warp 17 issues tcgen05.mma
 //     (M = 128, N = BN, K = 16) into double-buffered TMEM accumulators, the epilogue warps drain them (bias, GELU, 16-bit
 //     pack through a 2 KB per-warp swizzled staging tile, 64-byte coalesced row segments).
 //
@@ -29,7 +29,7 @@ int tc_num_sms();
 constexpr int LG_BM = 128;
 constexpr int LG_BK = 64;
 constexpr int LG_MAX_STAGES = 8;
-constexpr int LG_EPI_WARPS = 12;
+constexpr int LG_EPI_WARPS = 16;                   // (12 until round 2: 16 normalise 32 rows per round -- 4 rounds instead of 6 -- and drain the GELU tiles faster: fc1 57.3 -> 56.4 us, qkv 44.5 -> 43.9 us at M = 18816, K = 512; 96 registers)
 constexpr int LG_EPI_GROUPS = LG_EPI_WARPS / 4;
 constexpr int LG_THREADS = (LG_EPI_WARPS + 2) * 32;
 constexpr int LG_STAGING = EPI16_STAGING;           // per-warp staging tile: 32 rows x 32 columns of 16-bit outputs
