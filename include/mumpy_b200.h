@@ -136,6 +136,9 @@ int mumpy_window_attention(const void *qkv, const float *bias, const float *mask
 
 /* Attention.forward core for short sequences (blocks.py:64-70): qkv (Bn*N, 3C) -> out (Bn*N, C), N <= 8. */
 int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, int N, int C, int heads, void *stream);
+/* The attention map of the same call, softmax(q k^T d^-1/2): probs (Bn, heads, N, N) fp32 -- what Attention.forward returns next to x
+ * (blocks.py:66-68,74) and Block.forward(return_attention=True) returns alone (:88-89).  Diagnostic, not on the hot path. */
+int mumpy_mha_short_probs(const void *qkv, float *probs, int dtype, long Bn, int N, int C, int heads, void *stream);
 
 /* CrossThreeViewTokenize, one view (multiTemporalViewEncoder.py:605-618): Conv3d(3->C, k=s=(kt,4,4)) + LayerNorm.
  * x (B,T,3,S,S) fp32; w_kc (3*kt*16, C) fp32 = weight.reshape(C,-1).T; out (B, To*(S/4)^2, C) fp32, To = T/kt. */
@@ -180,6 +183,11 @@ int mumpy_cva_sample(const void *x2, int x2_dtype, const float *pix, void *sampl
  *         qidx(j) = j mod N1 (reference, batch-global) or the same map applied inside each clip. */
 int mumpy_cva_attention(const float *q, const void *kv, int kv_dtype, void *o, int out_dtype, int B, int TH1,
                         int TH2, int W, int C, int heads, int ws, int per_clip_pairing, void *stream);
+/* The attention map of mumpy_cva_attention: probs (N2, heads, P, P) fp32 = the reference's (N1, r * heads, P, P) view
+ * (deformableAttention.py:364,389,399; returned by SwinDAttention.forward and by CVAModule.forward(return_attention=True),
+ * multiTemporalViewEncoder.py:134-137).  Diagnostic, not on the hot path. */
+int mumpy_cva_attention_probs(const float *q, const void *kv, int kv_dtype, float *probs, int B, int TH1, int TH2, int W, int C,
+                              int heads, int ws, int per_clip_pairing, void *stream);
 /* residual: x_new[b,l,:] = h[b,l,:] + h[b, canvas(l/P, l%P), :] + reinterpret(y)[b,l,:]
  *         (deformableAttention.py:403 raw reshape; multiTemporalViewEncoder.py:138,284-286). y (N1*P, C) fp32. */
 int mumpy_cva_residual(const float *h, const float *y, float *x_new, int B, int TH1, int W, int C, int ws,

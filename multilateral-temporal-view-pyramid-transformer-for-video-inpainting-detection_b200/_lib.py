@@ -35,6 +35,7 @@ SIGNATURES = {
     "mumpy_patch_merge_norm": [vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
     "mumpy_window_attention": [vp, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_mha_short": [vp, vp, ci, cl, ci, ci, ci, vp],
+    "mumpy_mha_short_probs": [vp, vp, ci, cl, ci, ci, ci, vp],
     "mumpy_tokenize": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp],
     "mumpy_patchify16": [vp, vp, ci, ci, ci, ci, ci, vp],
     "mumpy_faf_workspace_floats": [ci, ci],
@@ -45,6 +46,7 @@ SIGNATURES = {
     "mumpy_cva_offsets": [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_cva_sample": [vp, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_cva_attention": [vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],
+    "mumpy_cva_attention_probs": [vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_cva_residual": [vp, vp, vp, ci, ci, ci, ci, ci, vp],
     "mumpy_gather_rows": [vp, ci, vp, ci, cl, ci, ci, ci, ci, ci, ci, ci, ci, vp],
     "mumpy_conv2d_nhwc": [vp, cl, vp, vp, vp, cl, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp],

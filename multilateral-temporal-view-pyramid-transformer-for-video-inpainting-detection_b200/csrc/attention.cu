@@ -359,6 +359,109 @@ extern "C" int mumpy_mha_short(const void *qkv, void *out, int dtype, long Bn, i
   return launch_status("mha_short");
 }
 
+// ---- attention maps (diagnostic outputs of the reference: blocks.py:66-68,88-89; deformableAttention.py:364,389,399; the hot path never
+// materialises them).  Plain fp32 arithmetic on the same q / k operands the fused kernels read. -------------------------------------
+template <typename T>
+__device__ __forceinline__ float probs_load(const T *p) { return to_f32(*p); }
+template <>
+__device__ __forceinline__ float probs_load<float>(const float *p) { return *p; }
+
+// softmax(q k^T * d^-1/2) of short sequences: probs (Bn, heads, N, N) fp32 from qkv (Bn, N, 3C); one thread per (sequence, head, row)
+template <typename T>
+__global__ void __launch_bounds__(128) mha_short_probs_kernel(const T *__restrict__ qkv, float *__restrict__ probs, long n_rows, int N, int C, int heads) {
+  pdl_grid_sync();
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_rows) return;
+  const int i = (int)(gid % N);
+  const long bh = gid / N;
+  const int h = (int)(bh % heads);
+  const long bn = bh / heads;
+  const int d = C / heads;
+  const float scale = 1.0f / sqrtf((float)d);
+  const T *q = qkv + (bn * N + i) * 3 * C + h * d;
+  float sc[8];
+  float m = -3.0e38f;
+  for (int j = 0; j < N; ++j) {
+    const T *k = qkv + (bn * N + j) * 3 * C + C + h * d;
+    float a = 0.0f;
+    for (int e = 0; e < d; ++e) a = fmaf(probs_load(q + e), probs_load(k + e), a);
+    sc[j] = a * scale;
+    m = fmaxf(m, sc[j]);
+  }
+  float sum = 0.0f;
+  for (int j = 0; j < N; ++j) {
+    sc[j] = expf(sc[j] - m);
+    sum += sc[j];
+  }
+  float *o = probs + gid * N;
+  for (int j = 0; j < N; ++j) o[j] = sc[j] / sum;
+}
+
+// deformable cross-view attention map: probs (N2, heads, P, P) fp32 (= the reference's (N1, r * heads, P, P) view) from the canvas-ordered
+// fp32 queries and the window-major sampled k (kv rows of 2C, k first); one thread per (kv window, head, query pixel)
+template <typename T>
+__global__ void __launch_bounds__(64) cva_attention_probs_kernel(const float *__restrict__ q, const T *__restrict__ kv, float *__restrict__ probs, int N1, int TH1,
+                                                                int W, int C, int heads, int ws, int r, int per_clip) {
+  pdl_grid_sync();
+  const int P = ws * ws;
+  const int j = blockIdx.x, h = blockIdx.y, i = threadIdx.x;
+  if (i >= P) return;
+  const int nW1 = (TH1 / ws) * (W / ws);
+  const int qw = cva_query_window(j, r, N1, nW1, per_clip);
+  const long qb = qw / nW1;
+  const int qn = qw - (int)qb * nW1;
+  const long L1 = (long)TH1 * W;
+  const float *qrow = q + (qb * L1 + window_token_row(qn, i, TH1, W, ws, 0)) * C + h * 32;
+  float qv[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) qv[e] = qrow[e];
+  float *o = probs + (((long)j * heads + h) * P + i) * P;
+  float m = -3.0e38f;
+  for (int p = 0; p < P; ++p) {
+    const T *k = kv + ((long)j * P + p) * 2 * C + h * 32;
+    float a = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) a = fmaf(qv[e], probs_load(k + e), a);
+    a *= 0.17677669529663687f;
+    o[p] = a;
+    m = fmaxf(m, a);
+  }
+  float sum = 0.0f;
+  for (int p = 0; p < P; ++p) {
+    const float e = expf(o[p] - m);
+    o[p] = e;
+    sum += e;
+  }
+  const float inv = 1.0f / sum;
+  for (int p = 0; p < P; ++p) o[p] *= inv;
+}
+
+extern "C" int mumpy_mha_short_probs(const void *qkv, float *probs, int dtype, long Bn, int N, int C, int heads, void *stream) {
+  MUMPY_REQUIRE(qkv && probs && Bn > 0 && N > 0 && N <= 8 && heads > 0 && C % heads == 0, "mha_short_probs: bad arguments (N=%d)", N);
+  cudaStream_t st = as_stream(stream);
+  const long n_rows = Bn * heads * N;
+  const unsigned grid = (unsigned)cdiv(n_rows, 128);
+  if (dtype == MUMPY_F16) launch_kernel(mha_short_probs_kernel<__half>, grid, 128, 0, st, static_cast<const __half *>(qkv), probs, n_rows, N, C, heads);
+  else if (dtype == MUMPY_BF16) launch_kernel(mha_short_probs_kernel<__nv_bfloat16>, grid, 128, 0, st, static_cast<const __nv_bfloat16 *>(qkv), probs, n_rows, N, C, heads);
+  else launch_kernel(mha_short_probs_kernel<float>, grid, 128, 0, st, static_cast<const float *>(qkv), probs, n_rows, N, C, heads);
+  return launch_status("mha_short_probs");
+}
+
+extern "C" int mumpy_cva_attention_probs(const float *q, const void *kv, int kv_dtype, float *probs, int B, int TH1, int TH2, int W, int C, int heads, int ws,
+                                         int per_clip_pairing, void *stream) {
+  MUMPY_REQUIRE(q && kv && probs && B > 0 && heads > 0 && C % heads == 0 && C / heads == 32, "cva_attention_probs: bad arguments (head dim must be 32)");
+  MUMPY_REQUIRE(TH1 % ws == 0 && TH2 % TH1 == 0 && W % ws == 0 && ws * ws <= 64, "cva_attention_probs: bad window geometry");
+  const int N1 = B * (TH1 / ws) * (W / ws);
+  const int r = TH2 / TH1;
+  dim3 grid((unsigned)(N1 * r), (unsigned)heads);
+  cudaStream_t st = as_stream(stream);
+  if (kv_dtype == MUMPY_F16) launch_kernel(cva_attention_probs_kernel<__half>, grid, 64, 0, st, q, static_cast<const __half *>(kv), probs, N1, TH1, W, C, heads, ws, r, per_clip_pairing);
+  else if (kv_dtype == MUMPY_BF16)
+    launch_kernel(cva_attention_probs_kernel<__nv_bfloat16>, grid, 64, 0, st, q, static_cast<const __nv_bfloat16 *>(kv), probs, N1, TH1, W, C, heads, ws, r, per_clip_pairing);
+  else launch_kernel(cva_attention_probs_kernel<float>, grid, 64, 0, st, q, static_cast<const float *>(kv), probs, N1, TH1, W, C, heads, ws, r, per_clip_pairing);
+  return launch_status("cva_attention_probs");
+}
+
 extern "C" int mumpy_cva_attention(const float *q, const void *kv, int kv_dtype, void *o, int out_dtype, int B, int TH1, int TH2,
                                    int W, int C, int heads, int ws, int per_clip_pairing, void *stream) {
   MUMPY_REQUIRE(q && kv && o && B > 0 && C % heads == 0 && C / heads == 32, "cva_attention: bad arguments (head dim must be 32)");

@@ -41,8 +41,10 @@ class CVAModule(nn.Module):
         self.drop_path = nn.Identity()
 
     def forward(self, x1, x2, mask=None, return_attention=False):
-        """x1 (N1,P,C), x2 (N2,P,C) windows -> (x1 + y, None)   (:134-139)."""
+        """x1 (N1,P,C), x2 (N2,P,C) windows -> (x1 + y, attn), or attn alone with return_attention   (:134-139)."""
         y, attn = self.crossattn(x1, x2)
+        if return_attention:
+            return attn
         return ops.add(x1.contiguous().float(), y), attn
 
 

@@ -49,16 +49,20 @@ class Attention(PackedModule):
     def unwrapped(self):
         return self
 
-    def fused(self, xn, Bn, N, C, residual=None):
+    def fused(self, xn, Bn, N, C, residual=None, want_attn=False):
         qkv = ops.linear(xn, self._gemm_weight("qkv", self.qkv.weight), self.qkv.bias, out_dtype=ops.act_dtype())
+        if want_attn:
+            # the softmax map itself (blocks.py:66-68): a diagnostic output, computed by its own small kernel from the same q / k
+            self.attn_map = ops.mha_short_probs(qkv, Bn, N, C, self.heads)
         ao = ops.mha_short(qkv, Bn, N, C, self.heads)
         return ops.linear(ao, self._gemm_weight("proj", self.proj.weight), self.proj.bias, residual=residual)
 
     def forward(self, x, mask=None):
-        """Returns (x, attn); the attention map is not materialised by the fused kernel (attn is None)."""
+        """Returns (x, attn) like the reference (blocks.py:54-74): attn (B, heads, N, N) fp32."""
         require_inference(self)
         B, N, C = x.shape
-        return self.fused(as_operand(x.contiguous()), B, N, C), None
+        y = self.fused(as_operand(x.contiguous()), B, N, C, want_attn=True)
+        return y, self.attn_map
 
 
 class Block(PackedModule):
@@ -72,11 +76,12 @@ class Block(PackedModule):
 
     def forward(self, x, mask=None, return_attention=False):
         require_inference(self)
-        if return_attention:
-            raise NotImplementedError("attention maps are not materialised by the fused kernels")
         B, N, C = x.shape
         x = x.contiguous()
         xn = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        if return_attention:                                     # blocks.py:88-89: the map of this block's attention, nothing else
+            qkv = ops.linear(xn, self.attn._gemm_weight("qkv", self.attn.qkv.weight), self.attn.qkv.bias, out_dtype=ops.act_dtype())
+            return ops.mha_short_probs(qkv, B, N, C, self.attn.heads)
         x = self.attn.fused(xn, B, N, C, residual=x)
         xn = ops.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         return self.mlp.fused(xn, residual=x)

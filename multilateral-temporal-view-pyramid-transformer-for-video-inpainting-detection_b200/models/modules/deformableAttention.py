@@ -79,7 +79,7 @@ class SwinDAttention(PackedModule):
                                      self.conv_offset[3].weight.detach().reshape(2, cg).contiguous()))
 
     # ---- canvas form used by CrossSwinBlock ------------------------------------------------------------------
-    def canvas_forward(self, h, x2p, B, TH1, TH2, W, per_clip_pairing=False):
+    def canvas_forward(self, h, x2p, B, TH1, TH2, W, per_clip_pairing=False, want_attn=False):
         """h (B,TH1*W,C) fp32 query canvas, x2p (B,TH2*W,C) fp32 key/value canvas (after `pre`).
         Returns proj_out's token-major result y (N1*P, C) fp32; the raw reshape of :403 is applied by
         ops.cva_residual, which consumes y."""
@@ -91,19 +91,21 @@ class SwinDAttention(PackedModule):
         samp = ops.cva_sample(x2p, pix, B, TH1, TH2, W, C, self.n_groups, ws, per_clip_pairing, ops.act_dtype())
         kv = ops.linear(samp, self._kv_weight(), self._kv_bias(), out_dtype=ops.act_dtype())
         o = ops.cva_attention(q, kv, B, TH1, TH2, W, C, self.n_heads, ws, per_clip_pairing)
-        return ops.linear(o, self._gemm_weight("out", self.proj_out.weight, (C, C)), self.proj_out.bias)
+        y = ops.linear(o, self._gemm_weight("out", self.proj_out.weight, (C, C)), self.proj_out.bias)
+        if want_attn:          # the reference's second result (:399,405): (N1, r * heads, P, P), from the same q / sampled k
+            return y, ops.cva_attention_probs(q, kv, B, TH1, TH2, W, C, self.n_heads, ws, per_clip_pairing)
+        return y
 
     def forward(self, x1, x2, return_attention=False):
-        """x1 (N1, ws*ws, C) query windows, x2 (N2, ws*ws, C) key/value windows -> (x (N1, ws*ws, C), None)."""
+        """x1 (N1, ws*ws, C) query windows, x2 (N2, ws*ws, C) key/value windows -> (x (N1, ws*ws, C), attn (N1, r*heads, P, P)) like the
+        reference (:324-405; `return_attention` is accepted and ignored there too)."""
         require_inference(self)
-        if return_attention:
-            raise NotImplementedError("attention maps are not materialised by the fused kernels")
         N1, P, C = x1.shape
         N2 = x2.shape[0]
         ws = self.ws
         x1 = x1.contiguous().float()
         x2 = x2.contiguous().float()
         # a stack of n windows is an (n*ws) x ws canvas whose windows are exactly the inputs, in order
-        y = self.canvas_forward(x1.view(1, N1 * P, C), x2.view(1, N2 * P, C), 1, N1 * ws, N2 * ws, ws)
+        y, attn = self.canvas_forward(x1.view(1, N1 * P, C), x2.view(1, N2 * P, C), 1, N1 * ws, N2 * ws, ws, want_attn=True)
         zero = torch.zeros_like(x1).view(1, N1 * P, C)
-        return ops.cva_residual(zero, y, 1, N1 * ws, ws, C, ws).view(N1, P, C), None
+        return ops.cva_residual(zero, y, 1, N1 * ws, ws, C, ws).view(N1, P, C), attn

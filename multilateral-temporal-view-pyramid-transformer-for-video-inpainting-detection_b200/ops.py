@@ -267,6 +267,14 @@ def mha_short(qkv, Bn, N, C, heads):
     return out
 
 
+def mha_short_probs(qkv, Bn, N, C, heads):
+    """Attention map of mha_short: (Bn, heads, N, N) fp32 (diagnostic output of blocks.py:66-68)."""
+    probs = torch.empty((Bn, heads, N, N), dtype=torch.float32, device=qkv.device)
+    lib, st = _prep(qkv, probs)
+    _lib.check(lib.mumpy_mha_short_probs(_p(qkv), _p(probs), code(qkv.dtype), Bn, N, C, heads, st), "mumpy_mha_short_probs")
+    return probs
+
+
 # ------------------------------------------------------------------------------------------------ front end
 def tokenize(x, w_kc, bias, gamma, beta, kt, eps=1e-5):
     B, T, _, S, _ = x.shape
@@ -342,6 +350,17 @@ def cva_attention(q, kv, B, TH1, TH2, W, C, heads, ws, per_clip):
     _lib.check(lib.mumpy_cva_attention(_p(q), _p(kv), code(kv.dtype), _p(out), code(out.dtype), B, TH1, TH2, W, C, heads,
                                        ws, int(per_clip), st), "mumpy_cva_attention")
     return out
+
+
+def cva_attention_probs(q, kv, B, TH1, TH2, W, C, heads, ws, per_clip):
+    """Attention map of cva_attention in the reference's layout (N1, r * heads, P, P) fp32 (deformableAttention.py:364,389,399)."""
+    N1 = B * (TH1 // ws) * (W // ws)
+    r = TH2 // TH1
+    probs = torch.empty((N1, r * heads, ws * ws, ws * ws), dtype=torch.float32, device=q.device)
+    lib, st = _prep(q, kv, probs)
+    _lib.check(lib.mumpy_cva_attention_probs(_p(q), _p(kv), code(kv.dtype), _p(probs), B, TH1, TH2, W, C, heads, ws, int(per_clip), st),
+               "mumpy_cva_attention_probs")
+    return probs
 
 
 def cva_residual(h, y, B, TH1, W, C, ws):

@@ -271,7 +271,7 @@ def bilinear_sample_zeros(img, py, px):
     return out
 
 
-def swin_dattention(sd, pre, x1w, x2w, nH, ws=7, groups=3, clip_windows=None):
+def swin_dattention(sd, pre, x1w, x2w, nH, ws=7, groups=3, clip_windows=None, return_attn=False):
     """x1w (N1,P,C) query windows, x2w (N2=r*N1,P,C) key/value windows (already through `pre`).
 
     out[i] = raw_reshape( proj_out( sum_t A(x1w[q(i,t)], x2w[r*i+t]) ) ),  q(i,t) = (r*i+t) mod N1
@@ -327,7 +327,10 @@ def swin_dattention(sd, pre, x1w, x2w, nH, ws=7, groups=3, clip_windows=None):
     o = o.reshape(N1, r, P, C).sum(1)                                                         # :394-395
     y = linear(o, sd[pre + "proj_out.weight"].reshape(C, C), sd[pre + "proj_out.bias"])       # (N1,P,C) token-major
     # :403 `.reshape(B, H*W, C)` of a (B,C,H,W) tensor: reinterpret channel-major memory, no transpose
-    return y.transpose(1, 2).contiguous().reshape(N1, P, C)
+    out = y.transpose(1, 2).contiguous().reshape(N1, P, C)
+    if return_attn:                                                                           # :399 (N2*nH,P,P) -> (N1, r*nH, P, P)
+        return out, attn.reshape(N1, r * nH, P, P)
+    return out
 
 
 # a8. CrossSwinBlock.forward: multiTemporalViewEncoder.py:228-291 (+ CVAModule :134-139), SURVEY A4
@@ -385,12 +388,14 @@ def stages(sd, toks, cfg, pre="base.layers.layers.", per_clip_pairing=False):
 
 
 # a13. Block / Attention / FeedForward: models/modules/blocks.py:37-92 on (B*n, 3, 768)  
-def vit_block(sd, pre, x, heads):
+def vit_block(sd, pre, x, heads, return_attention=False):
     Bn, N, C = x.shape
     d = C // heads
     xn = layer_norm(x, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
     qkv = linear(xn, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"]).reshape(Bn, N, 3, heads, d).permute(2, 0, 3, 1, 4)
     attn = torch.softmax((qkv[0] @ qkv[1].transpose(-2, -1)) * (d ** -0.5), dim=-1)
+    if return_attention:                                                                      # blocks.py:88-89
+        return attn
     y = (attn @ qkv[2]).transpose(1, 2).reshape(Bn, N, C)
     x = x + linear(y, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
     return x + mlp(sd, pre + "mlp.", layer_norm(x, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"]))

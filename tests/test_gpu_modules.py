@@ -90,6 +90,58 @@ def test_vit_block(mods):
     assert util.maxabs(m(x.cuda()), f["outputs"]["y"]) < TOL
 
 
+@pytest.fixture(scope="module")
+def attn_maps():
+    return util.golden("attn_maps.pt")
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("fp16", 3e-3)])
+@pytest.mark.parametrize("name", ["sda_r3", "sda_r1"])
+def test_swin_dattention_attention_map(attn_maps, name, mode, tol):
+    """SwinDAttention.forward's second result (deformableAttention.py:399,405) against the map captured from the reference."""
+    import mumpy_b200
+    from mumpy_b200.models.modules.deformableAttention import SwinDAttention
+    f = attn_maps[name]
+    mumpy_b200.set_precision(mode)
+    m = _build(SwinDAttention, f["ctor"])
+    x1 = util.seeded_input(f["x1_shape"], f["input_seed"])
+    x2 = util.seeded_input(f["x2_shape"], f["input_seed"] + 100)
+    _, attn = m(x1.cuda(), x2.cuda())
+    assert attn.dtype == torch.float32 and tuple(attn.shape) == tuple(f["attn"].shape)
+    assert util.maxabs(attn, f["attn"]) < tol
+    assert util.maxabs(attn.sum(-1), torch.ones(attn.shape[:-1])) < 1e-5
+
+
+def test_cva_module_return_attention(attn_maps):
+    """CVAModule.forward(return_attention=True) returns the map alone (multiTemporalViewEncoder.py:134-137)."""
+    from mumpy_b200.models.encoder.multiTemporalViewEncoder import CVAModule
+    f = attn_maps["cva_module"]
+    m = _build(CVAModule, f["ctor"])
+    x1 = util.seeded_input(f["x1_shape"], f["input_seed"])
+    x2 = util.seeded_input(f["x2_shape"], f["input_seed"] + 100)
+    attn = m(x1.cuda(), x2.cuda(), return_attention=True)
+    assert util.maxabs(attn, f["attn"]) < 2e-5
+    y, attn2 = m(x1.cuda(), x2.cuda())
+    assert torch.equal(attn, attn2) and tuple(y.shape) == tuple(x1.shape)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("fp16", 3e-3)])
+def test_vit_block_return_attention(attn_maps, mode, tol):
+    """Block.forward(return_attention=True) (blocks.py:86-89) and Attention.forward's second result (:66-74)."""
+    import mumpy_b200
+    from mumpy_b200.models.modules.blocks import Block
+    f = attn_maps["vit_block"]
+    mumpy_b200.set_precision(mode)
+    m = _build(Block, f["ctor"])
+    x = util.seeded_input(f["input_shape"], f["input_seed"]).cuda()
+    attn = m(x, return_attention=True)
+    assert attn.dtype == torch.float32 and tuple(attn.shape) == tuple(f["attn"].shape)
+    assert util.maxabs(attn, f["attn"]) < tol
+    xn = torch.nn.functional.layer_norm(x, (x.shape[-1],), m.norm1.weight, m.norm1.bias, m.norm1.eps)
+    y, attn2 = m.attn(xn)
+    assert tuple(y.shape) == tuple(x.shape) and util.maxabs(attn2, f["attn"]) < max(tol, 1e-4)
+
+
 def test_tokenize(mods):
     from mumpy_b200.models.encoder.multiTemporalViewEncoder import CrossThreeViewTokenize
     from mumpy_b200.models.factory.modelFactory import default_view_configs

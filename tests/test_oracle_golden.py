@@ -65,3 +65,36 @@ def test_modules_match_reference_capture():
         lg, xf = orc.decoder_forward(dec_sd, final_x, view_x, ff)
         assert util.maxabs(lg, d["outputs"]["logits"]) < TOL
         assert util.maxabs(xf[:, :, ::4, ::4], d["outputs"]["x_feats_sub"]) < TOL
+
+
+def test_attention_maps_match_reference_capture():
+    """The oracle's attention maps (return_attn / return_attention) against the maps captured from the reference
+    (oracle/make_golden_attn.py): SwinDAttention's second result, CVAModule(return_attention=True), Block(return_attention=True)."""
+    maps = util.golden("attn_maps.pt")
+    with torch.no_grad():
+        for name in ("sda_r3", "sda_r1"):
+            f = maps[name]
+            sd = wts.from_manifest({k: list(v) for k, v in _sda_shapes(f["ctor"]).items()})
+            x1 = util.seeded_input(f["x1_shape"], f["input_seed"])
+            x2 = util.seeded_input(f["x2_shape"], f["input_seed"] + 100)
+            _, attn = orc.swin_dattention(sd, "", x1, x2, f["ctor"]["n_heads"], return_attn=True)
+            assert util.maxabs(attn, f["attn"]) < 1e-5
+        f = maps["vit_block"]
+        C, hid = f["ctor"]["dim"], f["ctor"]["mlp_dim"]
+        shapes = {"norm1.weight": [C], "norm1.bias": [C], "norm2.weight": [C], "norm2.bias": [C], "attn.qkv.weight": [3 * C, C], "attn.qkv.bias": [3 * C],
+                  "attn.proj.weight": [C, C], "attn.proj.bias": [C], "mlp.fc1.weight": [hid, C], "mlp.fc1.bias": [hid], "mlp.fc2.weight": [C, hid],
+                  "mlp.fc2.bias": [C]}
+        attn = orc.vit_block(wts.from_manifest(shapes), "", util.seeded_input(f["input_shape"], f["input_seed"]), f["ctor"]["heads"], return_attention=True)
+        assert util.maxabs(attn, f["attn"]) < 1e-5
+
+
+def _sda_shapes(ctor):
+    """state_dict shapes of SwinDAttention(dim1, n_heads, 0.0, n_groups=3) (deformableAttention.py:218-300)."""
+    C, g = ctor["dim1"], ctor["n_groups"]
+    cg = C // g
+    shapes = {"conv_offset.0.weight": (cg, 1, 5, 5), "conv_offset.0.bias": (cg,), "conv_offset.1.norm.weight": (cg,), "conv_offset.1.norm.bias": (cg,),
+              "conv_offset.3.weight": (2, cg, 1, 1)}
+    for n in ("proj_q", "proj_k", "proj_v", "proj_out"):
+        shapes[n + ".weight"] = (C, C, 1, 1)
+        shapes[n + ".bias"] = (C,)
+    return shapes
