@@ -475,6 +475,21 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const
       if (p < N) rows[p] = qb * L1 + token_row<WS>(wr, wc, p, TH1, W, 0);
     }
     __syncwarp();
+    // k / v: already in operand precision -- asynchronous 16-byte copies straight into the tiles (no registers), in flight while
+    // the q rows below are loaded, converted and stored (ncu: the kernel waited on its global loads at 17 % occupancy)
+    const T *kvb = kv + ((long)j * N) * 2 * C + h * 32;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t tile = which == 0 ? sK : sV;
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int p = pass * 8 + (lane >> 2);
+        const int chunk = lane & 3;
+        if (p < N) cp_async_16(tile + tile_off(p, chunk), kvb + (long)p * 2 * C + which * C + chunk * 8);
+        else *reinterpret_cast<uint4 *>((which == 0 ? tk : tv) + tile_off(p, chunk)) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    cp_async_commit();
     // q: fp32 canvas rows -> bf16 tile
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
@@ -488,19 +503,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) cva_attention_mma_kernel(const
       }
       *reinterpret_cast<uint4 *>(tq + tile_off(p, chunk)) = v;
     }
-    const T *kvb = kv + ((long)j * N) * 2 * C + h * 32;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      uint8_t *tile = which == 0 ? tk : tv;
-#pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        const int p = pass * 8 + (lane >> 2);
-        const int chunk = lane & 3;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (p < N) v = __ldg(reinterpret_cast<const uint4 *>(kvb + (long)p * 2 * C + which * C + chunk * 8));
-        *reinterpret_cast<uint4 *>(tile + tile_off(p, chunk)) = v;
-      }
-    }
+    cp_async_wait<0>();
     __syncwarp();
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
