@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) faf_repack_kernel(const RepackParams p) {
 }
 
 int linear_faf_pass(const void *A, const void *W, void *out, long M, int K, int S, int imgs_per_band, int bands, const int *lo_hi6, int final_pass,
-                    int ab_dtype, cudaStream_t st);
+                    int ab_dtype, cudaStream_t st, int in_sparse = 0);
 
 static int faf_repack(const RepackParams &p, int n_img, int dtype, cudaStream_t st) {
   dim3 grid(1, (unsigned)cdiv(p.R, 32), (unsigned)n_img);
@@ -206,8 +206,15 @@ extern "C" int mumpy_faf16(const float *x, const void *dcat, const void *dtcat, 
   rc = linear_faf_pass(ws_b, dcat, ws_a, (long)n_img * S, 3 * S, S, n_img, 3, lohi, 0, dtype, st);
   if (rc) return rc;
   // G3: U[(band,img,k'), j] = sum_k (F o Xf)[k',k] D[k,j]          -> rows (band, img, j), columns k'
-  rc = linear_faf_pass(ws_a, dtcat, ws_b, 3l * n_img * S, 3 * S, S, 3 * n_img, 1, nullptr, 0, dtype, st);
+  // (passes 3 and 4 skip the k-blocks that the band masks zeroed: 6 / 7 / 11 of 11 blocks for the low / middle / high band at S = 224;
+  //  MUMPY_FAF_SPARSE=0 multiplies them all)
+  static int faf_sparse = -1;
+  if (faf_sparse < 0) {
+    const char *v = getenv("MUMPY_FAF_SPARSE");
+    faf_sparse = (v && v[0] == '0') ? 0 : 1;
+  }
+  rc = linear_faf_pass(ws_a, dtcat, ws_b, 3l * n_img * S, 3 * S, S, 3 * n_img, 1, lohi, 0, dtype, st, faf_sparse);
   if (rc) return rc;
   // G4: Y^T[(band,img,j), i] = sum_k' U[k',j] D[k',i]              -> out (B, 9, S, S), channel = band*3 + rgb, element (i, j)
-  return linear_faf_pass(ws_b, dtcat, out, 3l * n_img * S, 3 * S, S, n_img, 1, nullptr, 1, dtype, st);
+  return linear_faf_pass(ws_b, dtcat, out, 3l * n_img * S, 3 * S, S, n_img, 1, lohi, 1, dtype, st, faf_sparse);
 }

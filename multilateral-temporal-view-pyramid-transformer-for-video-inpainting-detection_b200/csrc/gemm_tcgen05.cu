@@ -258,7 +258,7 @@ __device__ __forceinline__ void faf_ts_epilogue(const TcParams &p, uint32_t acc,
   const int quad = warp & 3, grp = warp >> 2;
   const uint32_t lane_addr = acc + (static_cast<uint32_t>(quad * 32) << 16);
   const long m = m0 + quad * 32 + lane;
-  const int S = p.Wout, n_img = p.Hout, bands = p.kw;
+  const int S = p.Wout, n_img = p.Hout, bands = p.kw & 0xff;          // (bit 8 of kw: band-limited INPUT, see faf_kblock_mask)
   const bool valid = m < p.M;
   const int img = valid ? static_cast<int>(m / S) : 0;
   const int r = valid ? static_cast<int>(m - (long)img * S) : 0;
@@ -299,6 +299,27 @@ __device__ __forceinline__ void faf_ts_epilogue(const TcParams &p, uint32_t acc,
     }
   }
   if (is_half_t<T16>::value) f16_guard(amax);
+}
+
+// FAF passes 3 and 4 (kTS kernels, TcParams::kw bit 8 set): the A operand's rows are (band, image, r) -- three bands of M / 3 rows --
+// and band b's rows are zero outside columns [0, hi_b] of each of the three K segments ([hi | hi | lo], S columns each): the masked
+// DCT coefficients of dct.py:66-68 vanish for k + k' > hi_b.  Returns the 64-column k-blocks that can hold non-zeros for the rows
+// [m0, m0 + 128) (bit kb set = load and multiply it); a tile that straddles two bands takes the wider one's.
+__device__ __forceinline__ uint32_t faf_kblock_mask(const TcParams &p, long m0, int nkb) {
+  if (!(p.kw & 0x100) || nkb > 32) return 0xffffffffu;
+  const long rpb = p.M / 3;
+  long band = (m0 + TC_BM - 1) / rpb;
+  if (band > 2) band = 2;
+  const int hi = band == 0 ? (p.lower_w >> 16) : (band == 1 ? (p.lower_h >> 16) : (p.cblocks >> 16));
+  const int S = p.Wout;
+  uint32_t mask = 0;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int c0 = kb * TC_BK, c1 = c0 + TC_BK - 1;
+    bool need = false;
+    for (int seg = 0; seg < 3; ++seg) need = need || (c1 >= seg * S && c0 <= seg * S + hi);
+    if (need) mask |= 1u << kb;
+  }
+  return mask;
 }
 
 // kPair: the two CTAs of a (2,1,1) cluster (one TPC) work on one 256 x BN tile with tcgen05.mma.cta_group::2: CTA r loads
@@ -395,7 +416,9 @@ __global__ void __launch_bounds__(kLean ? TC_THREADS_LEAN : TC_THREADS, 1) gemm_
           cn = static_cast<int>(r / p.Hout);
         }
         int tap = kConv ? kb0 / p.cblocks : 0, cb = kConv ? kb0 - tap * p.cblocks : 0;
+        const uint32_t kmask = kTS ? faf_kblock_mask(p, m0, nkb) : 0xffffffffu;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (kTS && !((kmask >> (kb & 31)) & 1u)) continue;          // an all-zero k-block of a band-limited FAF operand
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t sa = tiles + s * stage_bytes;
           if (elect_one()) {
@@ -439,18 +462,23 @@ __global__ void __launch_bounds__(kLean ? TC_THREADS_LEAN : TC_THREADS, 1) gemm_
 #ifdef GEMM_TIMING
         if (t < 8) gt_tile[t][1] = clock64();
 #endif
+        const uint32_t kmask = kTS ? faf_kblock_mask(p, (tile_s / p.tiles_n) * TC_BM, nkb) : 0xffffffffu;
+        bool first_kb = true;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (kTS && !((kmask >> (kb & 31)) & 1u)) continue;          // (the producer skips the same k-blocks)
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
           const uint32_t sa = tiles + s * stage_bytes;
           const uint64_t adesc = make_kmajor_sw128_desc(sa);
           const uint64_t bdesc = make_kmajor_sw128_desc(sa + a_bytes);
+          const bool accumulate = kTS ? !first_kb : kb > kb0;
+          first_kb = false;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
               // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr>>4) field
-              if (kPair) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (kPair) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (accumulate || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (accumulate || k > 0) ? 1u : 0u);
             }
             if (kPair) umma_commit_pair(empty0 + 8 * s); else umma_commit(empty0 + 8 * s);      // frees the smem slot(s) once these MMAs have read them
           }
@@ -802,7 +830,7 @@ int linear_bf16(const void *A, long lda, const void *W, const float *bias, const
 // One pass of the tensor-core FAF (faf.cu): out(transposed per S x S image, band masked, split) = A . W^T.
 // A (M = images * S, K) and W (S, K) 16-bit K-major.  final_pass: fp32 result into the (B, 9, S, S) output instead.
 int linear_faf_pass(const void *A, const void *W, void *out, long M, int K, int S, int imgs_per_band, int bands, const int *lo_hi6, int final_pass,
-                    int ab_dtype, cudaStream_t st) {
+                    int ab_dtype, cudaStream_t st, int in_sparse) {
   int rc = resolve_driver_entry_points();
   if (rc) return rc;
   MUMPY_REQUIRE(S % 8 == 0 && K % 8 == 0 && S < 65536 && M % S == 0, "faf pass: S, K multiples of 8 and M a multiple of S required");
@@ -819,7 +847,7 @@ int linear_faf_pass(const void *A, const void *W, void *out, long M, int K, int 
   p.out_bf16 = final_pass ? 0 : 1;
   p.Wout = S;
   p.Hout = imgs_per_band;
-  p.kw = bands;
+  p.kw = bands | ((in_sparse && lo_hi6 && M % 3 == 0) ? 0x100 : 0);          // bit 8: A rows are (band, image, r), band-limited (faf_kblock_mask)
   p.lower_w = lo_hi6 ? (lo_hi6[0] | (lo_hi6[1] << 16)) : 0;
   p.lower_h = lo_hi6 ? (lo_hi6[2] | (lo_hi6[3] << 16)) : 0;
   p.cblocks = lo_hi6 ? (lo_hi6[4] | (lo_hi6[5] << 16)) : 0;
